@@ -1,0 +1,172 @@
+r"""
+ctypes binding of ``libglue_b200.so`` (C ABI declared in ``include/glue_b200.h``).
+
+There is no CPU fallback: if the shared library has not been built, or a kernel
+is asked to run on a non-CUDA tensor, the caller gets a ``RuntimeError``.
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+import torch
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libglue_b200.so")
+
+# Every symbol include/glue_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = (
+    "glue_abi_version",
+    "glue_arch",
+    "glue_error_string",
+    "glue_graphconv_csr",
+    "glue_csr_build_workspace_bytes",
+    "glue_csr_build",
+    "glue_graphdec_workspace_bytes",
+    "glue_graphdec_bce_fwd",
+    "glue_graphdec_bwd",
+    "glue_graphdec_bwd_scaled",
+    "glue_decoder_workspace_bytes",
+    "glue_decoder_nll_fwd_bwd",
+    "glue_decoder_nll_fwd",
+    "glue_decoder_log_prob",
+    "glue_decoder_mean",
+)
+
+FAMILY = {"NB": 0, "ZINB": 1, "Normal": 2, "ZILN": 3}
+
+
+class DecoderArgs(ctypes.Structure):
+    """Mirror of ``struct glue_decoder_args``."""
+
+    _fields_ = [
+        ("family", c_int32),
+        ("B", c_int32),
+        ("F", c_int32),
+        ("K", c_int32),
+        ("n_batches", c_int32),
+        ("reduce", c_int32),
+        ("u", c_void_p),
+        ("v", c_void_p),
+        ("vidx", c_void_p),
+        ("b", c_void_p),
+        ("row_order", c_void_p),
+        ("l", c_void_p),
+        ("x", c_void_p),
+        ("scale_lin", c_void_p),
+        ("bias", c_void_p),
+        ("disp", c_void_p),
+        ("zi_logits", c_void_p),
+        ("wmat", c_void_p),
+        ("loss", c_void_p),
+        ("grad_u", c_void_p),
+        ("grad_v", c_void_p),
+        ("grad_scale_lin", c_void_p),
+        ("grad_bias", c_void_p),
+        ("grad_disp", c_void_p),
+        ("grad_zi_logits", c_void_p),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_size_t),
+    ]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    lib.glue_abi_version.restype = c_int32
+    lib.glue_abi_version.argtypes = []
+    lib.glue_arch.restype = c_char_p
+    lib.glue_arch.argtypes = []
+    lib.glue_error_string.restype = c_char_p
+    lib.glue_error_string.argtypes = [c_int32]
+
+    lib.glue_graphconv_csr.restype = c_int32
+    lib.glue_graphconv_csr.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]
+    lib.glue_csr_build_workspace_bytes.restype = c_size_t
+    lib.glue_csr_build_workspace_bytes.argtypes = [c_int64, c_int64]
+    lib.glue_csr_build.restype = c_int32
+    lib.glue_csr_build.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_size_t, c_void_p]
+
+    lib.glue_graphdec_workspace_bytes.restype = c_size_t
+    lib.glue_graphdec_workspace_bytes.argtypes = [c_int64, c_int64]
+    lib.glue_graphdec_bce_fwd.restype = c_int32
+    lib.glue_graphdec_bce_fwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.glue_graphdec_bwd.restype = c_int32
+    lib.glue_graphdec_bwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.glue_graphdec_bwd_scaled.restype = c_int32
+    lib.glue_graphdec_bwd_scaled.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_size_t, c_void_p]
+
+    lib.glue_decoder_workspace_bytes.restype = c_size_t
+    lib.glue_decoder_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
+    for name in ("glue_decoder_nll_fwd_bwd", "glue_decoder_nll_fwd"):
+        fn = getattr(lib, name)
+        fn.restype = c_int32
+        fn.argtypes = [POINTER(DecoderArgs), c_void_p]
+    for name in ("glue_decoder_log_prob", "glue_decoder_mean"):
+        fn = getattr(lib, name)
+        fn.restype = c_int32
+        fn.argtypes = [POINTER(DecoderArgs), c_void_p, c_void_p]
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the native library; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"glue_b200: native library {LIB_PATH} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C glue_b200/csrc`. There is no CPU fallback."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        if handle.glue_abi_version() != 1:
+            raise RuntimeError("glue_b200: ABI version mismatch, rebuild the native library")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    """Turn a non-zero return code into ``RuntimeError`` (the ABI never throws)."""
+    if code != 0:
+        msg = lib().glue_error_string(code).decode()
+        raise RuntimeError(f"glue_b200.{what} failed with code {code}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (``None`` -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    """All given tensors must live on one CUDA device: the hot path has no CPU branch."""
+    device = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "glue_b200 kernels run on CUDA (sm_100a) tensors only; got a "
+                f"{t.device} tensor. There is no CPU fallback."
+            )
+        if device is None:
+            device = t.device
+        elif t.device != device:
+            raise RuntimeError("glue_b200: tensors on different devices")
+    if device is None:
+        raise RuntimeError("glue_b200: no tensor given")
+    return device
+
+
+def current_stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

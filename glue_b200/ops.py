@@ -1,0 +1,387 @@
+r"""
+``torch.autograd.Function`` wrappers around the native kernels.
+
+Each op states which reference computation it replaces; parity tests live in
+``tests/test_ops_gpu.py``.  PyTorch is used here for device memory, streams and
+autograd bookkeeping only -- all arithmetic happens in ``libglue_b200.so``.
+"""
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FAMILY, DecoderArgs, check, current_stream, ptr, require_cuda
+
+# ------------------------------------------------------------------ workspace
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"glue_b200: `{name}` must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        raise TypeError(f"glue_b200: `{name}` must be int64, got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------ CSR
+
+
+class GraphCSR:
+    r"""
+    Guidance graph in the two CSR layouts the GraphConv kernel consumes:
+    rows = edge targets (forward) and rows = edge sources (backward).
+
+    Layout definition (bit-exact with the numpy recipe of ``oracle/sampling.py``):
+    stable sort of the edges by row key, ``indptr = cumsum(bincount(key))``,
+    ``col`` int32, ``val = esgn * enorm`` fp32 exactly as ``scglue/models/nn.py:53``,
+    multi-edges kept.
+    """
+
+    def __init__(self, eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor, vnum: int):
+        device = require_cuda(eidx, enorm, esgn)
+        eidx, enorm, esgn = _i64(eidx, "eidx"), _f32(enorm, "enorm"), _f32(esgn, "esgn")
+        if eidx.dim() != 2 or eidx.shape[0] != 2:
+            raise ValueError("`eidx` must have shape [2, n_edges]")
+        n_edges = eidx.shape[1]
+        if enorm.shape != (n_edges,) or esgn.shape != (n_edges,):
+            raise ValueError("`enorm` / `esgn` must have shape [n_edges]")
+        self.vnum, self.n_edges, self.device = int(vnum), n_edges, device
+        val = esgn * enorm  # same rounding as the reference (nn.py:53)
+        self.fwd = self._build(eidx[1], eidx[0], val)
+        self.bwd = self._build(eidx[0], eidx[1], val)
+
+    def _build(self, key, other, val) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        L = _lib.lib()
+        dev = self.device
+        indptr = torch.empty(self.vnum + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(self.n_edges, dtype=torch.int32, device=dev)
+        out_val = torch.empty(self.n_edges, dtype=torch.float32, device=dev)
+        nbytes = L.glue_csr_build_workspace_bytes(self.n_edges, self.vnum)
+        ws = _workspace(nbytes, dev)
+        key, other = key.contiguous(), other.contiguous()
+        check(L.glue_csr_build(ptr(key), ptr(other), ptr(val), self.n_edges, self.vnum, ptr(indptr),
+                               ptr(col), ptr(out_val), ptr(ws), ws.numel(), current_stream(dev)),
+              "csr_build")
+        return indptr, col, out_val
+
+
+_CSR_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CSR_CACHE_SIZE = 8
+
+
+def csr_for(eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor, vnum: int) -> GraphCSR:
+    r"""Cached :class:`GraphCSR` for a ``(eidx, enorm, esgn)`` triple.  The graph encoder
+    is called with the same full-graph tensors every step (``scglue.py:328``); the key
+    holds storage address + version counter, and the cache keeps the tensors alive so an
+    address cannot be recycled under it."""
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (eidx, enorm, esgn)) + (vnum,)
+    hit = _CSR_CACHE.get(key)
+    if hit is not None:
+        _CSR_CACHE.move_to_end(key)
+        return hit[0]
+    csr = GraphCSR(eidx, enorm, esgn, vnum)
+    _CSR_CACHE[key] = (csr, eidx, enorm, esgn)
+    while len(_CSR_CACHE) > _CSR_CACHE_SIZE:
+        _CSR_CACHE.popitem(last=False)
+    return csr
+
+
+# ------------------------------------------------------------------ GraphConv
+
+
+def _spmm(csr_part, inp: torch.Tensor) -> torch.Tensor:
+    indptr, col, val = csr_part
+    out = torch.empty_like(inp)
+    check(_lib.lib().glue_graphconv_csr(ptr(indptr), ptr(col), ptr(val), ptr(inp), ptr(out),
+                                        inp.shape[0], inp.shape[1], current_stream(inp.device)),
+          "graphconv_csr")
+    return out
+
+
+class _GraphConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp: torch.Tensor, csr: GraphCSR) -> torch.Tensor:
+        ctx.csr = csr
+        return _spmm(csr.fwd, inp)
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        return _spmm(ctx.csr.bwd, _f32(grad_out, "grad_out")), None
+
+
+def graph_conv(inp: torch.Tensor, csr: GraphCSR) -> torch.Tensor:
+    r"""``res[t] = sum_{e: tidx_e = t} esgn_e enorm_e inp[sidx_e]`` -- replaces the
+    gather + ``scatter_add_`` of ``scglue/models/nn.py:52-57`` (and its backward)."""
+    require_cuda(inp)
+    inp = _f32(inp, "input")
+    if inp.dim() != 2 or inp.shape[0] != csr.vnum:
+        raise ValueError("`input` must have shape [n_vertices, n_features]")
+    return _GraphConvFn.apply(inp, csr)
+
+
+# -------------------------------------------------------------- graph decoder
+
+
+def _graphdec_ws(n_edges: int, vnum: int, device) -> torch.Tensor:
+    return _workspace(_lib.lib().glue_graphdec_workspace_bytes(n_edges, vnum), device)
+
+
+class _GraphNllFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, eidx, esgn, ewt):
+        dev = v.device
+        n_edges, (vnum, k) = eidx.shape[1], v.shape
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(n_edges, dtype=torch.float32, device=dev)
+        ws = _graphdec_ws(n_edges, vnum, dev)
+        check(_lib.lib().glue_graphdec_bce_fwd(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), n_edges, vnum, k, ptr(loss), None, None,
+            ptr(coef), ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bce_fwd")
+        ctx.save_for_backward(v, eidx, esgn, coef)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        v, eidx, esgn, coef = ctx.saved_tensors
+        dev = v.device
+        n_edges, (vnum, k) = eidx.shape[1], v.shape
+        grad_v = torch.empty_like(v)
+        ws = _graphdec_ws(n_edges, vnum, dev)
+        up = _f32(grad_out, "grad_out")
+        check(_lib.lib().glue_graphdec_bwd_scaled(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(coef), ptr(up), n_edges, vnum, k, ptr(grad_v),
+            ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bwd")
+        return grad_v, None, None, None
+
+
+class _GraphLogitsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, eidx, esgn, ewt_dummy):
+        dev = v.device
+        n_edges, (vnum, k) = eidx.shape[1], v.shape
+        logits = torch.empty(n_edges, dtype=torch.float32, device=dev)
+        ws = _graphdec_ws(n_edges, vnum, dev)
+        check(_lib.lib().glue_graphdec_bce_fwd(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(ewt_dummy), n_edges, vnum, k, None, ptr(logits), None,
+            None, ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bce_fwd")
+        ctx.save_for_backward(v, eidx, esgn)
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        v, eidx, esgn = ctx.saved_tensors
+        dev = v.device
+        n_edges, (vnum, k) = eidx.shape[1], v.shape
+        grad_v = torch.empty_like(v)
+        ws = _graphdec_ws(n_edges, vnum, dev)
+        coef = _f32(grad_logits, "grad_logits")
+        check(_lib.lib().glue_graphdec_bwd(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(coef), n_edges, vnum, k, ptr(grad_v), ptr(ws),
+            ws.numel(), current_stream(dev)), "graphdec_bwd")
+        return grad_v, None, None, None
+
+
+def _graph_args(v, eidx, esgn, ewt=None):
+    require_cuda(v, eidx, esgn, ewt)
+    v, eidx, esgn = _f32(v, "v"), _i64(eidx, "eidx"), _f32(esgn, "esgn")
+    if eidx.dim() != 2 or eidx.shape[0] != 2 or esgn.shape != (eidx.shape[1],):
+        raise ValueError("`eidx` must be [2, n_edges] and `esgn` [n_edges]")
+    if eidx.shape[1] == 0:
+        raise ValueError("empty edge minibatch")
+    if ewt is not None:
+        ewt = _f32(ewt, "ewt")
+        if ewt.shape != esgn.shape:
+            raise ValueError("`ewt` must be [n_edges]")
+    return v, eidx, esgn, ewt
+
+
+def graph_nll(v, eidx, esgn, ewt) -> torch.Tensor:
+    r"""Balanced Bernoulli NLL of the sampled edges -- replaces ``GraphDecoder.forward``
+    + ``Bernoulli.log_prob`` + the pos/neg averaging of ``scglue/models/scglue.py:331-338``
+    (without its ``.item()`` host sync)."""
+    return _GraphNllFn.apply(*_graph_args(v, eidx, esgn, ewt))
+
+
+def graph_logits(v, eidx, esgn) -> torch.Tensor:
+    r"""``esgn * <v[sidx], v[tidx]>`` (``scglue/models/sc.py:57-58``), differentiable in ``v``."""
+    v, eidx, esgn, _ = _graph_args(v, eidx, esgn)
+    return _GraphLogitsFn.apply(v, eidx, esgn, esgn)
+
+
+# --------------------------------------------------------------- data decoder
+
+
+class DecoderCall:
+    r"""Argument marshalling for one ``glue_decoder_*`` call (keeps tensors alive)."""
+
+    def __init__(self, family: str, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits,
+                 reduce: str = "nanmean"):
+        dev = require_cuda(u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits)
+        if family not in FAMILY:
+            raise ValueError(f"unknown decoder family {family!r}")
+        self.family, self.device = family, dev
+        self.u, self.v = _f32(u, "u"), _f32(v, "v")
+        self.vidx = None if vidx is None else _i64(vidx, "vidx")
+        self.b = None if b is None else _i64(b, "b")
+        self.l = None if l is None else _f32(l, "l").reshape(-1)
+        self.x = None if x is None else _f32(x, "x")
+        self.scale_lin, self.bias, self.disp = (
+            _f32(scale_lin, "scale_lin"), _f32(bias, "bias"), _f32(disp, "disp"))
+        self.zi = None if zi_logits is None else _f32(zi_logits, "zi_logits")
+        self.B, self.K = self.u.shape
+        self.n_batches, self.F = self.scale_lin.shape
+        self.reduce = {"nanmean": 0, "mean": 1}[reduce]
+        if self.v.dim() != 2 or self.v.shape[1] != self.K:
+            raise ValueError("`u` and `v` must share the latent dimension")
+        if self.K > 64:
+            raise ValueError("glue_b200 decoders support latent_dim <= 64")
+        if self.vidx is None and self.v.shape[0] != self.F:
+            raise ValueError("`v` must have one row per feature")
+        if self.vidx is not None and self.vidx.shape != (self.F,):
+            raise ValueError("`vidx` must have one entry per feature")
+        if self.x is not None and self.x.shape != (self.B, self.F):
+            raise ValueError("`x` must have shape [n_cells, n_features]")
+        if family in ("NB", "ZINB") and (self.l is None or self.l.numel() != self.B):
+            raise ValueError("NB / ZINB decoders need the library size `l` [n_cells, 1]")
+        if family in ("ZINB", "ZILN") and self.zi is None:
+            raise ValueError("zero-inflated decoders need `zi_logits`")
+        for name, t in (("bias", self.bias), ("disp", self.disp), ("zi_logits", self.zi)):
+            if t is not None and t.shape != self.scale_lin.shape:
+                raise ValueError(f"`{name}` must have shape [n_batches, n_features]")
+        # cells sorted by batch index so that every CTA sees each parameter row as one run
+        self.row_order = None
+        if self.n_batches > 1 and self.b is not None:
+            self.row_order = torch.sort(self.b, stable=True).indices.to(torch.int32)
+        nbytes = _lib.lib().glue_decoder_workspace_bytes(
+            FAMILY[family], self.B, self.F, self.K, self.n_batches)
+        self.ws = _workspace(nbytes, dev)
+
+    def args(self, **out) -> DecoderArgs:
+        a = DecoderArgs()
+        a.family, a.B, a.F, a.K = FAMILY[self.family], self.B, self.F, self.K
+        a.n_batches, a.reduce = self.n_batches, self.reduce
+        a.u, a.v, a.vidx, a.b = ptr(self.u), ptr(self.v), ptr(self.vidx), ptr(self.b)
+        a.row_order, a.l, a.x = ptr(self.row_order), ptr(self.l), ptr(self.x)
+        a.scale_lin, a.bias, a.disp = ptr(self.scale_lin), ptr(self.bias), ptr(self.disp)
+        a.zi_logits = ptr(self.zi)
+        a.workspace, a.workspace_bytes = ptr(self.ws), self.ws.numel()
+        for key, t in out.items():
+            setattr(a, key, ptr(t))
+        return a
+
+    def grad_buffers(self):
+        dev = self.device
+        gu = torch.empty_like(self.u)
+        # rows of the latent table that are not features of this modality get zero gradient
+        gv = torch.zeros_like(self.v) if self.vidx is not None else torch.empty_like(self.v)
+        gs, gb, gd = (torch.empty_like(self.scale_lin) for _ in range(3))
+        gz = None if self.zi is None else torch.empty_like(self.zi)
+        return gu, gv, gs, gb, gd, gz
+
+    def stream(self) -> int:
+        return current_stream(self.device)
+
+
+class _DecoderNllFn(torch.autograd.Function):
+    r"""``-log_prob(x).(nan)mean()`` with every gradient produced by the same launch
+    sequence (the ``[B, F]`` logits never reach HBM)."""
+
+    @staticmethod
+    def forward(ctx, u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family, reduce,
+                unit_upstream):
+        call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce)
+        loss = torch.empty((), dtype=torch.float32, device=call.device)
+        need_grad = any(t is not None and t.requires_grad
+                        for t in (u, v, scale_lin, bias, disp, zi_logits))
+        L = _lib.lib()
+        if need_grad:
+            gu, gv, gs, gb, gd, gz = call.grad_buffers()
+            a = call.args(loss=loss, grad_u=gu, grad_v=gv, grad_scale_lin=gs, grad_bias=gb,
+                          grad_disp=gd, grad_zi_logits=gz)
+            check(L.glue_decoder_nll_fwd_bwd(ctypes.byref(a), call.stream()), "decoder_nll_fwd_bwd")
+            ctx.grads = (gu, gv, gs, gb, gd, gz)
+        else:
+            a = call.args(loss=loss)
+            check(L.glue_decoder_nll_fwd(ctypes.byref(a), call.stream()), "decoder_nll_fwd")
+            ctx.grads = None
+        ctx.unit_upstream = unit_upstream
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.grads is None:
+            raise RuntimeError("decoder_nll: no input required grad at forward time")
+        grads = ctx.grads
+        ctx.grads = None
+        if not ctx.unit_upstream:
+            live = [g for g in grads if g is not None]
+            torch._foreach_mul_(live, grad_out)
+        return (*grads, None, None, None, None, None, None, None)
+
+
+def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
+                x=None, vidx=None, reduce: str = "nanmean", unit_upstream: bool = False):
+    r"""Fused data decoder + negative log-likelihood.
+
+    Replaces ``-u2x(u, v, b, l).log_prob(x).nanmean()`` (``scglue/models/scglue.py:342-347``;
+    ``reduce="mean"`` is the ``PairedSCGLUETrainer`` variant, ``scglue.py:603``).  With
+    ``vidx`` given, ``v`` is the full vertex table and ``v[vidx]`` is gathered inside the
+    kernel (saves the ``[F, K]`` gather and its ``index_put_`` backward).
+    ``unit_upstream=True`` promises that this loss enters the final objective with
+    coefficient exactly 1, so backward hands the gradients over without rescaling."""
+    if x is None:
+        raise ValueError("`x` is required")
+    return _DecoderNllFn.apply(u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family,
+                               reduce, unit_upstream)
+
+
+class _DecoderLogProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family):
+        call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits)
+        out = torch.empty(call.B, call.F, dtype=torch.float32, device=call.device)
+        a = call.args()
+        check(_lib.lib().glue_decoder_log_prob(ctypes.byref(a), ptr(out), call.stream()),
+              "decoder_log_prob")
+        ctx.call = call
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        call = ctx.call
+        wmat = _f32(grad_out, "grad_out")
+        gu, gv, gs, gb, gd, gz = call.grad_buffers()
+        a = call.args(wmat=wmat, grad_u=gu, grad_v=gv, grad_scale_lin=gs, grad_bias=gb,
+                      grad_disp=gd, grad_zi_logits=gz)
+        check(_lib.lib().glue_decoder_nll_fwd_bwd(ctypes.byref(a), call.stream()),
+              "decoder_nll_fwd_bwd")
+        return gu, gv, gs, gb, gd, gz, None, None, None, None, None
+
+
+def decoder_log_prob(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
+                     x=None, vidx=None) -> torch.Tensor:
+    r"""Materialised ``u2x(u, v, b, l).log_prob(x)`` ``[B, F]`` for API users; its backward
+    runs the fused kernels with the incoming gradient as per-element weights."""
+    return _DecoderLogProbFn.apply(u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family)
+
+
+@torch.no_grad()
+def decoder_mean(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
+                 vidx=None) -> torch.Tensor:
+    r"""Mean of the decoded distribution ``[B, F]`` (``decode_data``, ``scglue.py:1355``)."""
+    call = DecoderCall(family, u, v, vidx, b, l, None, scale_lin, bias, disp, zi_logits)
+    out = torch.empty(call.B, call.F, dtype=torch.float32, device=call.device)
+    a = call.args()
+    check(_lib.lib().glue_decoder_mean(ctypes.byref(a), ptr(out), call.stream()), "decoder_mean")
+    return out

@@ -1,0 +1,164 @@
+/*
+ * glue_b200.h -- C ABI of the B200-native SCGLUE hot path (libglue_b200.so, sm_100a).
+ *
+ * This is the drop-in boundary.  The reference (gao-lab/GLUE, scglue 0.4.1) is
+ * pure Python: its "operator interface" for this path is the set of
+ * torch.nn.Module.forward methods listed below.  Each entry point replaces the
+ * ATen op sequence behind one of them and is bound from Python with ctypes
+ * (glue_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to memory owned by the caller; the
+ *     library never allocates, frees, synchronises or keeps state between calls;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - tensors are dense row-major fp32 unless noted; indices are int64 where the
+ *     reference uses int64 (eidx, b, vidx) and int32 inside the CSR;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     GLUE_E_* argument error.  glue_error_string() decodes both.
+ *   - one process drives one GPU; calls on different streams are re-entrant.
+ */
+#ifndef GLUE_B200_H
+#define GLUE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLUE_B200_ABI_VERSION 1
+
+#define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
+#define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */
+#define GLUE_E_WORKSPACE (-3)   /* workspace too small                            */
+#define GLUE_E_ALIGN (-4)       /* pointer not aligned as documented              */
+
+int glue_abi_version(void);
+/* "sm_100a" -- the only architecture the library is compiled for. */
+const char *glue_arch(void);
+const char *glue_error_string(int code);
+
+/* ------------------------------------------------------------------------- *
+ * GraphConv  --  replaces scglue/models/nn.py:26-57 (GraphConv.forward) and,
+ * called with the transposed CSR, its autograd backward.
+ *
+ *   out[r, :] = sum_{e in [indptr[r], indptr[r+1])} val[e] * in[col[e], :]
+ *
+ * CSR rows are edge targets (forward) or edge sources (backward), edges keep
+ * their original relative order inside a row, val = esgn * enorm.  One warp per
+ * row, vectorised row gathers, no atomics => bit-reproducible.
+ * `in`/`out`: [n_rows, K] with 8-byte aligned rows when K is even.
+ * ------------------------------------------------------------------------- */
+int glue_graphconv_csr(const int32_t *indptr, const int32_t *col, const float *val,
+                       const float *in, float *out, int64_t n_rows, int32_t K, void *stream);
+
+/* Device CSR build (stable counting sort by `key`); bit-exact with
+ * argsort(key, kind="stable") / bincount / cumsum.
+ *   key, other : [E] int64 (row key, column payload), val: [E]
+ *   indptr: [n_rows+1] int32, col: [E] int32, out_val: [E]
+ * `workspace` must hold glue_csr_build_workspace_bytes(E, n_rows) bytes. */
+size_t glue_csr_build_workspace_bytes(int64_t E, int64_t n_rows);
+int glue_csr_build(const int64_t *key, const int64_t *other, const float *val, int64_t E,
+                   int64_t n_rows, int32_t *indptr, int32_t *col, float *out_val,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * GraphDecoder + Bernoulli log-prob + pos/neg balanced mean -- replaces
+ * scglue/models/sc.py:54-59 and scglue/models/scglue.py:331-338.
+ *
+ *   logit[e] = esgn[e] * <v[eidx[0,e]], v[eidx[1,e]]>
+ *   nll[e]   = softplus(logit[e]) - ewt[e] * logit[e]
+ *   out_loss[0] = ( sum_{ewt==0} nll / max(n_neg,1) + sum_{ewt!=0} nll / max(n_pos,1) )
+ *                 / ((n_pos>0) + (n_neg>0))                (no host sync)
+ *
+ * eidx: [2, E] int64 (row 0 sources, row 1 targets).  Optional outputs (NULL to
+ * skip): out_logits [E], out_nll [E], out_coef [E] = d out_loss / d logit[e].
+ * workspace: glue_graphdec_workspace_bytes(E, V).
+ * ------------------------------------------------------------------------- */
+size_t glue_graphdec_workspace_bytes(int64_t E, int64_t V);
+int glue_graphdec_bce_fwd(const float *v, const int64_t *eidx, const float *esgn,
+                          const float *ewt, int64_t E, int64_t V, int32_t K, float *out_loss,
+                          float *out_logits, float *out_nll, float *out_coef, void *workspace,
+                          size_t workspace_bytes, void *stream);
+/* Backward of the above w.r.t. v by segmented reduction over the edge
+ * incidence list sorted by vertex (deterministic, no float atomics):
+ *   grad_v[w, :] = sum_{e: s_e = w} coef[e] esgn[e] v[t_e] + sum_{e: t_e = w} coef[e] esgn[e] v[s_e]
+ * `coef` is any per-edge upstream d L / d logit[e]; every row of grad_v [V, K] is
+ * written (zeros for untouched vertices). */
+int glue_graphdec_bwd(const float *v, const int64_t *eidx, const float *esgn, const float *coef,
+                      int64_t E, int64_t V, int32_t K, float *grad_v, void *workspace,
+                      size_t workspace_bytes, void *stream);
+/* Same, with every coefficient multiplied by the device scalar upstream[0]
+ * (autograd's d L / d out_loss) so that no extra pass over grad_v is needed. */
+int glue_graphdec_bwd_scaled(const float *v, const int64_t *eidx, const float *esgn,
+                             const float *coef, const float *upstream, int64_t E, int64_t V,
+                             int32_t K, float *grad_v, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused data decoders -- replace forward + log_prob + (nan)mean + backward of
+ *   NB     scglue/models/sc.py:372-397 + torch NegativeBinomial.log_prob
+ *   ZINB   scglue/models/sc.py:447-478 + scglue/models/prob.py:144-153
+ *   Normal scglue/models/sc.py:280-308 + torch Normal.log_prob
+ *   ZILN   scglue/models/sc.py:340-369 + scglue/models/prob.py:110-118
+ * and the reduction at scglue/models/scglue.py:342-347.
+ *
+ *   a[i,j]  = softplus(scale_lin[b_i,j]) * <u_i, v_j> + bias[b_i,j]
+ *   NB/ZINB: mu = softmax_j(a) * l_i ; NB(theta=exp(log_theta[b_i,j]), logits=log(mu+1e-7)-log_theta)
+ *   Normal/ZILN: loc = a ; std = softplus(std_lin[b_i,j]) + 1e-7
+ * The [B,F] logit matrix lives only in registers / shared memory.
+ * ------------------------------------------------------------------------- */
+enum glue_decoder_family { GLUE_NB = 0, GLUE_ZINB = 1, GLUE_NORMAL = 2, GLUE_ZILN = 3 };
+
+typedef struct glue_decoder_args {
+    int32_t family;    /* enum glue_decoder_family                                   */
+    int32_t B;         /* rows (cells) in this call                                  */
+    int32_t F;         /* features                                                   */
+    int32_t K;         /* latent dimension, 1..64                                    */
+    int32_t n_batches; /* rows of the per-feature parameter tables                   */
+    int32_t reduce;    /* 0: mean over non-NaN x (nanmean)  1: plain mean            */
+    /* inputs */
+    const float *u;           /* [B, K]                                              */
+    const float *v;           /* [n_vrows, K] feature-latent table                   */
+    const int64_t *vidx;      /* [F] row of `v` holding feature j; NULL = identity   */
+    const int64_t *b;         /* [B] parameter row per cell; NULL = all zero         */
+    const int32_t *row_order; /* [B] cells sorted by b (stable); NULL = identity.
+                                 Required when b has more than one distinct value.   */
+    const float *l;           /* [B] library size (NB/ZINB); NULL for Normal/ZILN    */
+    const float *x;           /* [B, F] observations                                 */
+    const float *scale_lin;   /* [n_batches, F]                                      */
+    const float *bias;        /* [n_batches, F]                                      */
+    const float *disp;        /* [n_batches, F] log_theta (NB/ZINB) or std_lin       */
+    const float *zi_logits;   /* [n_batches, F] (ZINB/ZILN) else NULL                */
+    const float *wmat;        /* optional [B, F] upstream d L / d log_prob; when
+                                 non-NULL the objective is L = sum wmat*log_prob and
+                                 `reduce`/`loss` are ignored                         */
+    /* outputs (any may be NULL when its gradient is not wanted) */
+    float *loss;           /* [1]  -mean(log_prob)                                   */
+    float *grad_u;         /* [B, K]                                                 */
+    float *grad_v;         /* [n_vrows, K]; only rows vidx[0..F) are written         */
+    float *grad_scale_lin; /* [n_batches, F] (all rows written)                      */
+    float *grad_bias;
+    float *grad_disp;
+    float *grad_zi_logits;
+    void *workspace; /* glue_decoder_workspace_bytes()                               */
+    size_t workspace_bytes;
+} glue_decoder_args;
+
+size_t glue_decoder_workspace_bytes(int32_t family, int32_t B, int32_t F, int32_t K,
+                                    int32_t n_batches);
+/* loss and all gradients of loss in one call (training step). */
+int glue_decoder_nll_fwd_bwd(const glue_decoder_args *args, void *stream);
+/* loss only (validation / get_losses). */
+int glue_decoder_nll_fwd(const glue_decoder_args *args, void *stream);
+/* Materialising variants for API users of Distribution.log_prob / .mean
+ * (scglue/models/scglue.py:1355 decode_data): out is [B, F]. */
+int glue_decoder_log_prob(const glue_decoder_args *args, float *out, void *stream);
+int glue_decoder_mean(const glue_decoder_args *args, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLUE_B200_H */

@@ -1,0 +1,293 @@
+"""GPU parity tests of the native kernels (through the C ABI) against the CPU oracle and
+the golden vectors generated from the reference.  Tolerance for floating point: 1e-4
+max-norm relative (BASELINE.json north_star); integer / index outputs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampling
+from oracle import scglue_cpu as oc
+from tests.util import assert_close, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops(native_lib):
+    from glue_b200 import ops as _ops
+    return _ops
+
+
+def _cuda(x):
+    return torch.as_tensor(x).to(DEV)
+
+
+# --------------------------------------------------------------------------- CSR
+@pytest.mark.parametrize("V,E", [(37, 200), (5000, 40000), (52000, 100000)])
+def test_csr_build_bit_exact(ops, V, E):
+    rs = np.random.RandomState(V)
+    eidx, ewt, esgn = random_graph(rs, V, E, loops=(V != 37))
+    eidx[:, : E // 10] = eidx[:, E // 10: 2 * (E // 10)]  # multi-edges
+    enorm = sampling.normalize_edges(eidx, ewt)
+    csr = ops.GraphCSR(_cuda(eidx), _cuda(enorm), _cuda(esgn), V)
+    for got, want in ((csr.fwd, sampling.csr_forward(eidx, enorm, esgn, V)),
+                      (csr.bwd, sampling.csr_transposed(eidx, enorm, esgn, V))):
+        for g, w in zip(got, want):
+            assert g.dtype == torch.as_tensor(w).dtype
+            assert np.array_equal(g.cpu().numpy(), w)
+
+
+def test_csr_golden(ops, golden):
+    g = golden("graph")
+    V = len(g["vertices"])
+    csr = ops.GraphCSR(_cuda(g["eidx"]), _cuda(g["enorm_keepvar"]), _cuda(g["esgn"]), V)
+    want = sampling.csr_forward(g["eidx"], g["enorm_keepvar"], g["esgn"], V)
+    for got, w in zip(csr.fwd, want):
+        assert np.array_equal(got.cpu().numpy(), w)
+
+
+# --------------------------------------------------------------------- GraphConv
+@pytest.mark.parametrize("V,E,K", [(37, 200, 50), (5000, 40000, 50), (3000, 20000, 16),
+                                   (1000, 5000, 7), (52000, 100000, 50), (800, 3000, 128)])
+def test_graphconv_vs_oracle(ops, V, E, K):
+    rs = np.random.RandomState(K + V)
+    eidx, ewt, esgn = random_graph(rs, V, E)
+    enorm = sampling.normalize_edges(eidx, ewt)
+    inp = torch.randn(V, K, generator=torch.Generator().manual_seed(1))
+    gout = torch.randn(V, K, generator=torch.Generator().manual_seed(2))
+    ref_in = inp.clone().requires_grad_(True)
+    ref = oc.graph_conv(ref_in, torch.as_tensor(eidx), torch.as_tensor(enorm), torch.as_tensor(esgn))
+    (ref_gin,) = torch.autograd.grad(ref, ref_in, gout)
+
+    csr = ops.GraphCSR(_cuda(eidx), _cuda(enorm), _cuda(esgn), V)
+    x = inp.to(DEV).requires_grad_(True)
+    out = ops.graph_conv(x, csr)
+    (gin,) = torch.autograd.grad(out, x, gout.to(DEV))
+    assert_close(out, ref, 1e-6, "graphconv fwd")
+    assert_close(gin, ref_gin, 1e-6, "graphconv bwd")
+    # atomic-free => run-to-run bit identical
+    assert torch.equal(out, ops.graph_conv(x, csr))
+
+
+def test_graphconv_golden(ops, golden):
+    g, m = golden("graph"), golden("modules")
+    V = m["gc_in"].shape[0]
+    csr = ops.GraphCSR(_cuda(g["eidx"]), _cuda(g["enorm_keepvar"]), _cuda(g["esgn"]), V)
+    x = _cuda(m["gc_in"]).requires_grad_(True)
+    out = ops.graph_conv(x, csr)
+    (gin,) = torch.autograd.grad(out, x, _cuda(m["gc_gout"]))
+    assert_close(out, m["gc_out"], 1e-6, "graphconv fwd vs reference")
+    assert_close(gin, m["gc_gin"], 1e-6, "graphconv bwd vs reference")
+
+
+def test_graphconv_isolated_vertices(ops):
+    V, K = 64, 50
+    eidx = np.array([[0, 1, 2], [5, 5, 7]], dtype=np.int64)
+    ewt = np.array([0.3, 0.6, 1.0], dtype=np.float32)
+    esgn = np.array([1.0, -1.0, 1.0], dtype=np.float32)
+    enorm = sampling.normalize_edges(eidx, ewt)
+    csr = ops.GraphCSR(_cuda(eidx), _cuda(enorm), _cuda(esgn), V)
+    x = torch.randn(V, K)
+    out = ops.graph_conv(x.to(DEV), csr)
+    ref = oc.graph_conv(x, torch.as_tensor(eidx), torch.as_tensor(enorm), torch.as_tensor(esgn))
+    assert torch.equal(out.cpu() == 0, ref == 0)
+    assert_close(out, ref, 1e-6)
+
+
+# ----------------------------------------------------------------- graph decoder
+@pytest.mark.parametrize("V,E,K,pos_frac", [(60, 333, 50, 0.1), (5000, 36000, 50, 1 / 11),
+                                            (400, 1000, 16, 0.0), (400, 1000, 7, 1.0)])
+def test_graph_nll_vs_oracle(ops, V, E, K, pos_frac):
+    rs = np.random.RandomState(E)
+    eidx = rs.randint(0, V, (2, E)).astype(np.int64)
+    eidx[1, :5] = eidx[0, :5]  # self loops
+    esgn = np.where(rs.rand(E) < 0.3, -1.0, 1.0).astype(np.float32)
+    ewt = (rs.rand(E) < pos_frac).astype(np.float32)
+    v = torch.randn(V, K, generator=torch.Generator().manual_seed(3)) * 0.4
+    ref_v = v.clone().requires_grad_(True)
+    ref = oc.graph_nll(ref_v, torch.as_tensor(eidx), torch.as_tensor(esgn), torch.as_tensor(ewt))
+    (ref_g,) = torch.autograd.grad(ref, ref_v)
+
+    dv = v.to(DEV).requires_grad_(True)
+    loss = ops.graph_nll(dv, _cuda(eidx), _cuda(esgn), _cuda(ewt))
+    (g,) = torch.autograd.grad(3.0 * loss, dv)
+    assert_close(loss, ref, TOL, "graph nll")
+    assert_close(g, 3.0 * ref_g, TOL, "graph nll grad")
+    logits = ops.graph_logits(dv, _cuda(eidx), _cuda(esgn))
+    assert_close(logits, oc.graph_decoder_logits(v, torch.as_tensor(eidx), torch.as_tensor(esgn)),
+                 1e-5, "graph logits")
+    loss2 = ops.graph_nll(dv, _cuda(eidx), _cuda(esgn), _cuda(ewt))
+    (g2,) = torch.autograd.grad(3.0 * loss2, dv)
+    assert torch.equal(g, g2), "segmented-reduction backward must be deterministic"
+
+
+def test_graph_decoder_golden(ops, golden):
+    g, m = golden("graph"), golden("modules")
+    v = _cuda(m["gd_v"]).requires_grad_(True)
+    eidx, ewt, esgn = _cuda(g["samp0_eidx"]), _cuda(g["samp0_ewt"]), _cuda(g["samp0_esgn"])
+    loss = ops.graph_nll(v, eidx, esgn, ewt)
+    (gv,) = torch.autograd.grad(loss, v)
+    assert_close(loss, m["gd_nll"], TOL, "graph nll vs reference")
+    assert_close(gv, m["gd_gv"], TOL, "graph nll grad vs reference")
+    logits = ops.graph_logits(v, eidx, esgn)
+    assert_close(logits, m["gd_logits"], 1e-5)
+    logp = torch.distributions.Bernoulli(logits=logits).log_prob(ewt)
+    (gv2,) = torch.autograd.grad(logp.sum(), v)
+    ref_v = torch.as_tensor(m["gd_v"]).requires_grad_(True)
+    ref_lp = torch.distributions.Bernoulli(logits=oc.graph_decoder_logits(
+        ref_v, torch.as_tensor(g["samp0_eidx"]), torch.as_tensor(g["samp0_esgn"]))).log_prob(
+        torch.as_tensor(g["samp0_ewt"]))
+    (ref_g2,) = torch.autograd.grad(ref_lp.sum(), ref_v)
+    assert_close(logp, m["gd_logp"], 1e-5)
+    assert_close(gv2, ref_g2, TOL, "logits backward")
+
+
+# ------------------------------------------------------------------ data decoder
+PARAM_NAMES = {"NB": ("scale_lin", "bias", "log_theta"),
+               "ZINB": ("scale_lin", "bias", "log_theta", "zi_logits"),
+               "Normal": ("scale_lin", "bias", "std_lin"),
+               "ZILN": ("scale_lin", "bias", "std_lin", "zi_logits")}
+
+
+def _decoder_case(family, B, F, K, nb, seed, nan_frac=0.0, extra_rows=0):
+    gen = torch.Generator().manual_seed(seed)
+    u = torch.randn(B, K, generator=gen) * 0.5
+    v = torch.randn(F + extra_rows, K, generator=gen) * 0.5
+    b = torch.randint(0, nb, (B,), generator=gen)
+    params = {n: torch.randn(nb, F, generator=gen) * 0.5 for n in PARAM_NAMES[family]}
+    if family in ("NB", "ZINB"):
+        x = torch.poisson(torch.rand(B, F, generator=gen) * 2.0, generator=gen)
+        x[0, : min(4, F)] = torch.tensor([40.0, 13.0, 0.0, 200.0])[: min(4, F)]
+        l = x.sum(dim=1, keepdim=True) + 1.0
+    elif family == "Normal":
+        x, l = torch.randn(B, F, generator=gen) * 2.0, None
+    else:
+        x = torch.exp(torch.randn(B, F, generator=gen)) * (torch.rand(B, F, generator=gen) > 0.4)
+        l = None
+    if nan_frac:
+        x[torch.rand(B, F, generator=gen) < nan_frac] = float("nan")
+    vidx = torch.randperm(F + extra_rows, generator=gen)[:F] if extra_rows else None
+    return u, v, b, l, x, params, vidx
+
+
+def _oracle_nll(family, u, v, b, l, x, params, vidx, reduce):
+    u, v = u.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    st = {f"u2x.m.{k}": p.clone().requires_grad_(True) for k, p in params.items()}
+    vv = v if vidx is None else v[vidx]
+    lp = oc.DECODER_LOG_PROB[family](st, "u2x.m.", u, vv, b, l, torch.nan_to_num(x, nan=1.0))
+    if reduce == "nanmean":
+        mask = ~torch.isnan(x)
+        loss = -(lp * mask).sum() / mask.sum()
+    else:
+        loss = -lp.mean()
+    grads = torch.autograd.grad(loss, [u, v] + list(st.values()))
+    return loss, lp, grads
+
+
+def _device_nll(ops, family, u, v, b, l, x, params, vidx, reduce, scale=1.0):
+    d = lambda t: None if t is None else t.to(DEV)
+    du, dv = d(u).requires_grad_(True), d(v).requires_grad_(True)
+    dp = [d(params[n]).requires_grad_(True) for n in PARAM_NAMES[family]]
+    zi = dp[3] if len(dp) == 4 else None
+    loss = ops.decoder_nll(family, du, dv, dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x),
+                           vidx=d(vidx), reduce=reduce)
+    grads = torch.autograd.grad(scale * loss, [du, dv] + dp)
+    return loss, grads
+
+
+CASES = [
+    # family, B, F, K, n_batches, nan_frac, extra_rows, reduce
+    ("NB", 9, 23, 50, 3, 0.0, 0, "mean"),
+    ("NB", 128, 2000, 50, 1, 0.0, 0, "nanmean"),
+    ("NB", 128, 700, 50, 1, 0.0, 300, "nanmean"),
+    ("NB", 200, 1500, 50, 4, 0.0, 0, "mean"),
+    ("NB", 33, 129, 10, 2, 0.0, 0, "nanmean"),
+    ("NB", 64, 400, 64, 1, 0.0, 0, "nanmean"),
+    ("ZINB", 128, 2000, 50, 20, 0.0, 0, "nanmean"),
+    ("ZINB", 17, 95, 50, 1, 0.0, 7, "mean"),
+    ("Normal", 128, 1000, 50, 3, 0.05, 0, "nanmean"),
+    ("Normal", 40, 333, 16, 1, 0.0, 0, "mean"),
+    ("ZILN", 128, 1000, 50, 2, 0.05, 0, "nanmean"),
+    ("ZILN", 300, 260, 50, 1, 0.0, 40, "mean"),
+    ("NB", 1, 5, 50, 1, 0.0, 0, "nanmean"),
+]
+
+
+@pytest.mark.parametrize("family,B,F,K,nb,nan_frac,extra,reduce", CASES)
+def test_decoder_nll_vs_oracle(ops, family, B, F, K, nb, nan_frac, extra, reduce):
+    case = _decoder_case(family, B, F, K, nb, seed=B * 1000 + F, nan_frac=nan_frac, extra_rows=extra)
+    ref_loss, _, ref_grads = _oracle_nll(family, *case, reduce)
+    loss, grads = _device_nll(ops, family, *case, reduce, scale=2.5)
+    assert_close(loss, ref_loss, TOL, f"{family} nll")
+    names = ["u", "v"] + list(PARAM_NAMES[family])
+    for n, g, rg in zip(names, grads, ref_grads):
+        assert_close(g, 2.5 * rg, TOL, f"{family} d/d{n}")
+    loss2, grads2 = _device_nll(ops, family, *case, reduce, scale=2.5)
+    assert torch.equal(loss, loss2) and all(torch.equal(a, b) for a, b in zip(grads, grads2)), \
+        "decoder must be run-to-run deterministic"
+
+
+@pytest.mark.parametrize("family", ["NB", "ZINB", "Normal", "ZILN"])
+def test_decoder_golden(ops, golden, family):
+    m = golden("modules")
+    xkey = {"NB": "dd_counts", "ZINB": "dd_counts", "Normal": "dd_cont", "ZILN": "dd_poscont"}[family]
+    u, v = _cuda(m["dd_u"]).requires_grad_(True), _cuda(m["dd_v"]).requires_grad_(True)
+    b, l, x = _cuda(m["dd_b"]), _cuda(m["dd_l"]), _cuda(m[xkey])
+    ps = [_cuda(m[f"dd_{family}_p_{n}"]).requires_grad_(True) for n in PARAM_NAMES[family]]
+    zi = ps[3] if len(ps) == 4 else None
+    use_l = l if family in ("NB", "ZINB") else None
+    # fused NLL + gradients vs what the reference's autograd produced
+    loss = ops.decoder_nll(family, u, v, ps[0], ps[1], ps[2], zi, b=b, l=use_l, x=x, reduce="mean")
+    grads = torch.autograd.grad(loss, [u, v] + ps)
+    assert_close(loss, -m[f"dd_{family}_logp"].mean(), TOL, "nll vs reference")
+    assert_close(grads[0], m[f"dd_{family}_gu"], TOL, "d/du vs reference")
+    assert_close(grads[1], m[f"dd_{family}_gv"], TOL, "d/dv vs reference")
+    for n, g in zip(PARAM_NAMES[family], grads[2:]):
+        assert_close(g, m[f"dd_{family}_g_{n}"], TOL, f"d/d{n} vs reference")
+    # materialised log_prob / mean
+    logp = ops.decoder_log_prob(family, u, v, ps[0], ps[1], ps[2], zi, b=b, l=use_l, x=x)
+    ref_lp = torch.as_tensor(m[f"dd_{family}_logp"])
+    assert (logp.cpu() - ref_lp).abs().max().item() <= 1e-4 * max(1.0, ref_lp.abs().max().item())
+    mean = ops.decoder_mean(family, u, v, ps[0], ps[1], ps[2], zi, b=b, l=use_l)
+    assert_close(mean, m[f"dd_{family}_mean"], TOL, "mean vs reference")
+    # autograd through the materialised log_prob (per-element upstream weights)
+    w = torch.rand(logp.shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+    g2 = torch.autograd.grad((logp * w).sum(), [u, v] + ps)
+    cu, cv = torch.as_tensor(m["dd_u"]).requires_grad_(True), torch.as_tensor(m["dd_v"]).requires_grad_(True)
+    st = {f"u2x.m.{n}": torch.as_tensor(m[f"dd_{family}_p_{n}"]).requires_grad_(True)
+          for n in PARAM_NAMES[family]}
+    lp_cpu = oc.DECODER_LOG_PROB[family](st, "u2x.m.", cu, cv, torch.as_tensor(m["dd_b"]),
+                                        torch.as_tensor(m["dd_l"]) if use_l is not None else None,
+                                        torch.as_tensor(m[xkey]))
+    ref_g2 = torch.autograd.grad((lp_cpu * w.cpu()).sum(), [cu, cv] + list(st.values()))
+    for g, rg in zip(g2, ref_g2):
+        assert_close(g, rg, TOL, "log_prob backward")
+
+
+@pytest.mark.parametrize("family,F", [("NB", 50000), ("ZINB", 50000), ("Normal", 48000)])
+def test_decoder_full_size_properties(ops, family, F):
+    """BASELINE-size (B=128, F=50k) checks that do not need the slow oracle everywhere:
+    fused loss == mean of the materialised log_prob; gradients agree with the oracle on
+    a feature sub-range for Normal (separable) and are deterministic for all."""
+    B, K = 128, 50
+    case = _decoder_case(family, B, F, K, 1, seed=99)
+    u, v, b, l, x, params, vidx = case
+    loss, grads = _device_nll(ops, family, *case, "nanmean")
+    d = lambda t: None if t is None else t.to(DEV)
+    dp = [d(params[n]) for n in PARAM_NAMES[family]]
+    zi = dp[3] if len(dp) == 4 else None
+    logp = ops.decoder_log_prob(family, d(u), d(v), dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x))
+    assert_close(loss, -logp.double().mean().float(), TOL, "fused loss vs materialised mean")
+    ref_loss, _, ref_grads = _oracle_nll(family, *case, "nanmean")
+    assert_close(loss, ref_loss, TOL)
+    for g, rg in zip(grads, ref_grads):
+        assert_close(g, rg, TOL, f"{family} full-size gradient")
+
+
+def test_decoder_rejects_cpu_tensors(ops):
+    u, v = torch.randn(4, 50), torch.randn(6, 50)
+    p = torch.zeros(1, 6)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.decoder_nll("NB", u, v, p, p, p, l=torch.ones(4, 1), x=torch.ones(4, 6))
