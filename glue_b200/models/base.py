@@ -1,0 +1,250 @@
+r"""
+Training loop, model persistence and the plugin interface
+(API of ``scglue/models/base.py``, without the pytorch-ignite dependency).
+
+The reference wires two ``ignite.engine.Engine`` objects (``base.py:117-214``); here a
+small event-driven :class:`Engine` provides the same hooks (``state.epoch``,
+``state.metrics``, ``terminate()``, per-epoch validation, plugins).  Two deliberate
+differences, both to keep the GPU queue free of host synchronisation:
+
+* running loss averages are accumulated **on the device** and read back once per epoch
+  (ignite's ``Average`` reads every step);
+* the non-finite-loss check (``TerminateOnNan``) therefore fires at the end of the
+  offending epoch instead of at the offending iteration.
+"""
+
+import os
+import pathlib
+import tempfile
+import time
+from collections import defaultdict
+from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional
+
+import dill
+import torch
+
+from ..utils import DelayedKeyboardInterrupt, config, logged
+
+# ----------------------------------------------------------------------- engine
+
+STARTED, EPOCH_STARTED, ITERATION_COMPLETED = "started", "epoch_started", "iteration_completed"
+EPOCH_COMPLETED, COMPLETED, TERMINATE = "epoch_completed", "completed", "terminate"
+
+
+class EngineState:
+    def __init__(self) -> None:
+        self.epoch = 0
+        self.iteration = 0
+        self.max_epochs = 0
+        self.output: Optional[Mapping[str, torch.Tensor]] = None
+        self.metrics: Dict[str, float] = {}
+        self.times: Dict[str, float] = {}
+
+
+class Engine:
+    r"""Runs ``step(engine, batch)`` over a loader for a number of epochs and fires events."""
+
+    def __init__(self, step: Callable[["Engine", Any], Mapping[str, torch.Tensor]],
+                 tracked: Optional[List[str]] = None) -> None:
+        self.step = step
+        self.tracked = list(tracked or [])
+        self.state = EngineState()
+        self.should_terminate = False
+        self._handlers: Dict[str, List[Callable]] = defaultdict(list)
+
+    def add_event_handler(self, event: str, handler: Callable, *args, **kwargs) -> None:
+        self._handlers[event].append(lambda engine: handler(engine, *args, **kwargs))
+
+    def on(self, event: str):
+        def deco(fn):
+            self.add_event_handler(event, fn)
+            return fn
+        return deco
+
+    def fire(self, event: str) -> None:
+        for handler in self._handlers[event]:
+            handler(self)
+
+    def terminate(self) -> None:
+        self.should_terminate = True
+
+    def run(self, loader: Iterable, max_epochs: int = 1) -> EngineState:
+        r"""Run (or resume: epochs continue from ``state.epoch``) until ``max_epochs``."""
+        state = self.state
+        state.max_epochs = max_epochs
+        if state.epoch == 0:
+            self.fire(STARTED)
+        while state.epoch < max_epochs and not self.should_terminate:
+            state.epoch += 1
+            tic = time.time()
+            self.fire(EPOCH_STARTED)
+            sums: Dict[str, torch.Tensor] = {}
+            count = 0
+            for batch in loader:
+                state.iteration += 1
+                state.output = self.step(self, batch)
+                for key in self.tracked:
+                    val = state.output[key].detach()
+                    sums[key] = val.clone() if key not in sums else sums[key] + val
+                count += 1
+                self.fire(ITERATION_COMPLETED)
+                if self.should_terminate:
+                    break
+            if sums:  # one device->host read per epoch
+                keys = list(sums)
+                host = (torch.stack([sums[k].float() for k in keys]) / max(count, 1)).tolist()
+                state.metrics = dict(zip(keys, host))
+            state.times["EPOCH_COMPLETED"] = time.time() - tic
+            self.fire(EPOCH_COMPLETED)
+            state.times["EPOCH_COMPLETED"] = time.time() - tic
+        self.fire(TERMINATE if self.should_terminate else COMPLETED)
+        return state
+
+
+# ---------------------------------------------------------------------- trainer
+
+
+@logged
+class Trainer:
+    r"""Abstract trainer: ``train_step`` / ``val_step`` + :meth:`fit` / :meth:`get_losses`."""
+
+    def __init__(self, net: torch.nn.Module) -> None:
+        self.net = net
+        self.required_losses: List[str] = []
+
+    def train_step(self, engine: Engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        raise NotImplementedError  # pragma: no cover
+
+    def val_step(self, engine: Engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        raise NotImplementedError  # pragma: no cover
+
+    def report_metrics(self, train_state: EngineState, val_state: Optional[EngineState]) -> None:
+        if train_state.epoch % config.PRINT_LOSS_INTERVAL:
+            return
+        fmt = lambda m: {k: float(f"{v:.3f}") for k, v in m.items()}
+        self.logger.info("[Epoch %d] train=%s, val=%s, %.1fs elapsed", train_state.epoch,
+                         fmt(train_state.metrics), fmt(val_state.metrics) if val_state else None,
+                         train_state.times["EPOCH_COMPLETED"])
+
+    def fit(self, train_loader: Iterable, val_loader: Optional[Iterable] = None,
+            max_epochs: int = 100, random_seed: int = 0,
+            directory: Optional[os.PathLike] = None,
+            plugins: Optional[List["TrainingPlugin"]] = None) -> None:
+        r"""Training loop with per-epoch validation and plugins (``base.py:117-214``)."""
+        directory = pathlib.Path(directory or tempfile.mkdtemp(prefix=config.TMP_PREFIX))
+        self.logger.info('Using training directory: "%s"', directory)
+        train_engine = Engine(self.train_step, self.required_losses)
+        val_engine = Engine(self.val_step, self.required_losses) if val_loader else None
+
+        @train_engine.on(EPOCH_COMPLETED)
+        def _nonfinite_guard(engine):  # TerminateOnNan, at epoch granularity
+            if any(v != v or v in (float("inf"), float("-inf"))
+                   for v in engine.state.metrics.values()):
+                self.logger.warning("Non-finite loss encountered, terminating training...")
+                engine.terminate()
+
+        if val_engine:
+            @train_engine.on(EPOCH_COMPLETED)
+            def _validate(engine):
+                val_engine.run(val_loader, max_epochs=engine.state.epoch)
+
+        @train_engine.on(EPOCH_COMPLETED)
+        def _report(engine):
+            self.report_metrics(engine.state, val_engine.state if val_engine else None)
+
+        for plugin in plugins or []:
+            plugin.attach(net=self.net, trainer=self, train_engine=train_engine,
+                          val_engine=val_engine, train_loader=train_loader,
+                          val_loader=val_loader, directory=directory)
+
+        torch.manual_seed(random_seed)
+        try:
+            train_engine.run(train_loader, max_epochs=max_epochs)
+        except KeyboardInterrupt:
+            if not config.ALLOW_TRAINING_INTERRUPTION:
+                raise
+            self.logger.info("Stopping training due to user interrupt...")
+            train_engine.terminate()
+            train_engine.fire(TERMINATE)
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+    def get_losses(self, loader: Iterable) -> Mapping[str, float]:
+        engine = Engine(self.val_step, self.required_losses)
+        engine.run(loader, max_epochs=1)
+        return engine.state.metrics
+
+    def state_dict(self) -> Mapping[str, Any]:
+        return {}
+
+    def load_state_dict(self, state_dict: Mapping[str, Any]) -> None:
+        pass
+
+
+# ------------------------------------------------------------------------ model
+
+
+@logged
+class Model:
+    r"""Abstract model: owns a network, builds a trainer in :meth:`compile`, trains in
+    :meth:`fit`, persists with ``dill`` (``base.py:261-388``)."""
+
+    NET_TYPE = torch.nn.Module
+    TRAINER_TYPE = Trainer
+
+    def __init__(self, *args, **kwargs) -> None:
+        self._net = self.NET_TYPE(*args, **kwargs)
+        self._trainer: Optional[Trainer] = None
+
+    @property
+    def net(self) -> torch.nn.Module:
+        return self._net
+
+    @property
+    def trainer(self) -> Trainer:
+        if self._trainer is None:
+            raise RuntimeError("No trainer has been registered! Please call `.compile()` first.")
+        return self._trainer
+
+    def compile(self, *args, **kwargs) -> None:
+        if self._trainer:
+            self.logger.warning("`compile` has already been called. "
+                                "Previous trainer will be overwritten!")
+        self._trainer = self.TRAINER_TYPE(self.net, *args, **kwargs)
+
+    def fit(self, *args, **kwargs) -> None:
+        self.trainer.fit(*args, **kwargs)
+
+    def get_losses(self, *args, **kwargs) -> Mapping[str, float]:
+        return self.trainer.get_losses(*args, **kwargs)
+
+    def save(self, fname: os.PathLike) -> None:
+        r"""``dill`` the model with the trainer stripped and the network moved to CPU."""
+        fname = pathlib.Path(fname)
+        trainer_backup, device_backup = self._trainer, self.net.device
+        self._trainer, self.net.device = None, torch.device("cpu")
+        try:
+            with fname.open("wb") as f:
+                dill.dump(self, f, protocol=4, byref=False, recurse=True)
+        finally:
+            self.net.device = device_backup
+            self._trainer = trainer_backup
+
+    @staticmethod
+    def load(fname: os.PathLike) -> "Model":
+        fname = pathlib.Path(fname)
+        with fname.open("rb") as f:
+            model = dill.load(f)
+        from .nn import autodevice
+        model.net.device = autodevice()
+        return model
+
+
+@logged
+class TrainingPlugin:
+    r"""Plugin interface (``base.py:391-428``): ``attach`` receives the engines and loaders."""
+
+    def attach(self, net: torch.nn.Module, trainer: Trainer, train_engine: Engine,
+               val_engine: Optional[Engine], train_loader: Iterable,
+               val_loader: Optional[Iterable], directory: pathlib.Path) -> None:
+        raise NotImplementedError  # pragma: no cover

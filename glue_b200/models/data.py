@@ -1,0 +1,597 @@
+r"""
+Datasets, samplers and loaders (API of ``scglue/models/data.py``).
+
+The index streams are the reference's, bit for bit: cell order comes from legacy
+``numpy.random.RandomState(seed + epoch)`` permutations plus ``rs.choice`` random fill
+for unpaired rows (``data.py:372-392,617-620``), edge minibatches from
+``GraphDataset.propose_shuffle`` (``data.py:794-820``), and block-level shuffling is done
+by the real ``torch.utils.data`` sampler classes with the same generator seeding
+(``glue.py:580-625``).  What changes is where the bytes live: with ``to_device`` the count
+matrices / representations / sampled edges stay resident in HBM and a minibatch is a
+device-side row gather driven by a few hundred host-generated indices, instead of a host
+densify + 26 MB H2D copy per step (``data.py:397-436``, ``scglue.py:276-289``).
+"""
+
+import copy
+import functools
+import operator
+import threading
+import uuid
+from math import ceil
+from typing import Any, List, Mapping, Optional, Tuple
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import scipy.sparse
+import torch
+
+from ..num import vertex_degrees
+from ..utils import config, get_rs, logged
+from .nn import get_default_numpy_dtype
+
+DATA_CONFIG = Mapping[str, Any]
+
+
+# --------------------------------------------------------------------------- base
+
+
+@logged
+class Dataset(torch.utils.data.Dataset):
+    r"""
+    Dataset with seed-driven custom shuffling.  ``shuffle()`` number ``n`` (0-based) of a
+    dataset object uses seed ``random_seed + n`` (``data.py:99-112``); ``propose_shuffle`` is
+    a pure function of the seed, so proposing the next shuffle ahead of time on a
+    background thread (instead of the reference's worker process) cannot change results.
+    """
+
+    def __init__(self, getitem_size: int = 1) -> None:
+        super().__init__()
+        self.getitem_size = getitem_size
+        self.shuffle_seed: Optional[int] = None
+        self._lookahead: Optional[Tuple[int, threading.Thread, list]] = None
+        self._num_workers = 0
+
+    def prepare_shuffle(self, num_workers: int = 1, random_seed: int = 0) -> None:
+        self.clean()
+        self.shuffle_seed = random_seed
+        self._num_workers = num_workers
+        if num_workers:
+            self._spawn(self.shuffle_seed)
+
+    def _spawn(self, seed: int) -> None:
+        box: list = []
+        thread = threading.Thread(target=lambda: box.append(self.propose_shuffle(seed)),
+                                  daemon=True)
+        thread.start()
+        self._lookahead = (seed, thread, box)
+
+    def shuffle(self) -> None:
+        if self.shuffle_seed is None:
+            raise RuntimeError("`prepare_shuffle` must be called before `shuffle`")
+        if self._lookahead is not None and self._lookahead[0] == self.shuffle_seed:
+            _, thread, box = self._lookahead
+            thread.join()
+            shuffled = box[0] if box else self.propose_shuffle(self.shuffle_seed)
+        else:
+            shuffled = self.propose_shuffle(self.shuffle_seed)
+        self.accept_shuffle(shuffled)
+        self.shuffle_seed += 1
+        if self._num_workers:
+            self._spawn(self.shuffle_seed)
+
+    def propose_shuffle(self, seed: int) -> Any:
+        raise NotImplementedError  # pragma: no cover
+
+    def accept_shuffle(self, shuffled: Any) -> None:
+        raise NotImplementedError  # pragma: no cover
+
+    def clean(self) -> None:
+        if getattr(self, "_lookahead", None) is not None:
+            self._lookahead[1].join()
+        self._lookahead = None
+
+    @property
+    def has_workers(self) -> bool:
+        return self._lookahead is not None
+
+
+# ------------------------------------------------------------------------- arrays
+
+
+def _rows(a, idx: np.ndarray) -> np.ndarray:
+    block = a[idx]
+    return block.toarray() if scipy.sparse.issparse(block) else np.asarray(block)
+
+
+@logged
+class ArrayDataset(Dataset):
+    r"""Unpaired arrays; shorter arrays are recycled; sparse rows densified on fetch
+    (``data.py:190-300``)."""
+
+    def __init__(self, *arrays, getitem_size: int = 1) -> None:
+        super().__init__(getitem_size=getitem_size)
+        self.arrays = arrays
+
+    @property
+    def arrays(self):
+        return self._arrays
+
+    @arrays.setter
+    def arrays(self, arrays) -> None:
+        self.sizes = [a.shape[0] for a in arrays]
+        if min(self.sizes) == 0:
+            raise ValueError("Empty array is not allowed!")
+        self.size = max(self.sizes)
+        self.view_idx = [np.arange(s) for s in self.sizes]
+        self.shuffle_idx = self.view_idx
+        self._arrays = arrays
+
+    def __len__(self) -> int:
+        return ceil(self.size / self.getitem_size)
+
+    def __getitem__(self, index: int) -> List[torch.Tensor]:
+        pos = np.arange(index * self.getitem_size, min((index + 1) * self.getitem_size, self.size))
+        return [torch.as_tensor(_rows(a, self.shuffle_idx[i][np.mod(pos, self.sizes[i])]))
+                for i, a in enumerate(self.arrays)]
+
+    def propose_shuffle(self, seed: int) -> List[np.ndarray]:
+        rs = get_rs(seed)
+        return [rs.permutation(v) for v in self.view_idx]
+
+    def accept_shuffle(self, shuffled: List[np.ndarray]) -> None:
+        self.shuffle_idx = shuffled
+
+    def random_split(self, fractions: List[float], random_state=None) -> List["ArrayDataset"]:
+        _check_fractions(fractions)
+        rs = get_rs(random_state)
+        cuts = np.cumsum(fractions)
+        subs = [ArrayDataset(*self.arrays, getitem_size=self.getitem_size) for _ in fractions]
+        for j, view in enumerate(self.view_idx):
+            view = rs.permutation(view)
+            pieces = np.split(view, np.round(cuts * view.size).astype(int)[:-1])
+            for sub, piece in zip(subs, pieces):
+                sub.sizes[j] = len(piece)
+                sub.view_idx[j] = piece
+                sub.shuffle_idx[j] = piece
+        return subs
+
+
+def _check_fractions(fractions: List[float]) -> None:
+    if min(fractions) <= 0:
+        raise ValueError("Fractions should be greater than 0!")
+    if sum(fractions) != 1:
+        raise ValueError("Fractions do not sum to 1!")
+
+
+# ------------------------------------------------------------------------ AnnData
+
+
+@logged
+class AnnDataset(Dataset):
+    r"""
+    Dataset over configured AnnData-like objects with partial pairing (``data.py:303-664``).
+
+    A *view row* is one cell id of the union over all modalities; each view row maps to one
+    row per modality (``shuffle_idx [n, n_modalities]``) plus a pairing mask
+    (``shuffle_pmsk``) that is ``False`` where the modality does not contain that cell and a
+    substitute row was filled in.
+
+    Items are ``[x_k..., xrep_k..., xbch_k..., xlbl_k..., xdwt_k..., pmsk]`` like the
+    reference.  After :meth:`to_device` the per-modality arrays are device tensors and an
+    item is a device-side row gather.
+    """
+
+    def __init__(self, adatas, data_configs: List[DATA_CONFIG], mode: str = "train",
+                 getitem_size: int = 1) -> None:
+        super().__init__(getitem_size=getitem_size)
+        if mode not in ("train", "eval"):
+            raise ValueError("Invalid `mode`!")
+        self.mode = mode
+        self.device: Optional[torch.device] = None
+        self.device_data = None
+        self.adatas = adatas
+        self.data_configs = data_configs
+
+    @property
+    def adatas(self):
+        return self._adatas
+
+    @adatas.setter
+    def adatas(self, adatas) -> None:
+        self.sizes = [adata.shape[0] for adata in adatas]
+        if min(self.sizes) == 0:
+            raise ValueError("Empty dataset is not allowed!")
+        self._adatas = adatas
+
+    @property
+    def data_configs(self):
+        return self._data_configs
+
+    @data_configs.setter
+    def data_configs(self, data_configs) -> None:
+        if len(data_configs) != len(self.adatas):
+            raise ValueError("Number of data configs must match the number of datasets!")
+        self.data_idx, self.extracted_data = self._extract_data(data_configs)
+        self.view_idx = (pd.concat([idx.to_series() for idx in self.data_idx])
+                         .drop_duplicates().to_numpy())
+        self.size = self.view_idx.size
+        self.shuffle_idx, self.shuffle_pmsk = self._get_idx_pmsk(self.view_idx)
+        self.nan_sparse = [cfg["nan_sparse"] for cfg in data_configs]
+        self._data_configs = data_configs
+
+    # -- view rows -> per-modality rows ------------------------------------------------
+    def _get_idx_pmsk(self, view_idx: np.ndarray, random_fill: bool = False,
+                      random_state=None) -> Tuple[np.ndarray, np.ndarray]:
+        rs = get_rs(random_state) if random_fill else None
+        cols, masks = [], []
+        for data_idx in self.data_idx:
+            idx = data_idx.get_indexer(view_idx)
+            present = idx >= 0
+            n_missing = present.size - present.sum()
+            if random_fill:
+                fill = rs.choice(idx[present], n_missing, replace=True)
+            else:
+                fill = idx[present][np.mod(np.arange(n_missing), present.sum())]
+            idx[~present] = fill
+            cols.append(idx)
+            masks.append(present)
+        return np.stack(cols, axis=1), np.stack(masks, axis=1)
+
+    def __len__(self) -> int:
+        return ceil(self.size / self.getitem_size)
+
+    def __getitem__(self, index: int) -> List[torch.Tensor]:
+        s = slice(index * self.getitem_size, min((index + 1) * self.getitem_size, self.size))
+        if self.device is not None:  # indices only; gathered once per batch in `fetch_device`
+            return [torch.as_tensor(self.shuffle_idx[s]), torch.as_tensor(self.shuffle_pmsk[s])]
+        rows, pmsk = self.shuffle_idx[s].T, self.shuffle_pmsk[s]
+        items = [torch.as_tensor(self._index_array(data, idx, nan_sparse))
+                 for group in self.extracted_data
+                 for idx, data, nan_sparse in zip(rows, group, self.nan_sparse)]
+        items.append(torch.as_tensor(pmsk))
+        return items
+
+    @staticmethod
+    def _index_array(arr, idx: np.ndarray, nan_sparse: bool) -> np.ndarray:
+        arr = arr[idx]
+        if scipy.sparse.issparse(arr):
+            if nan_sparse:  # structural zeros mean "not measured"
+                coo = arr.tocoo()
+                dense = np.full(coo.shape, np.nan, dtype=coo.dtype)
+                dense[coo.row, coo.col] = coo.data
+                return dense
+            return arr.toarray()
+        return np.asarray(arr)
+
+    # -- device residency ----------------------------------------------------------------
+    def to_device(self, device: torch.device) -> "AnnDataset":
+        r"""Upload the per-modality arrays once; minibatches become device row gathers."""
+        device = torch.device(device)
+        total = 0
+        for group in self.extracted_data:
+            for arr in group:
+                total += int(np.prod(arr.shape)) * 4
+        if total > config.DEVICE_DATA_BUDGET_BYTES:
+            raise MemoryError(
+                f"dense device-resident data would need {total / 2**30:.1f} GiB "
+                f"(> DEVICE_DATA_BUDGET_BYTES); keep the dataset on the host")
+        dev_groups = []
+        for group in self.extracted_data:
+            dev_group = []
+            for arr, nan_sparse in zip(group, self.nan_sparse):
+                dense = self._index_array(arr, slice(None), nan_sparse) \
+                    if scipy.sparse.issparse(arr) else np.asarray(arr)
+                dev_group.append(torch.as_tensor(dense).to(device))
+            dev_groups.append(dev_group)
+        self.device_data = dev_groups
+        self.device = device
+        return self
+
+    def fetch_device(self, rows: torch.Tensor, pmsk: torch.Tensor) -> List[torch.Tensor]:
+        r"""``rows [B, n_modalities]`` (host, int64) -> reference-format item on the device."""
+        rows_dev = rows.to(self.device, non_blocking=True)
+        items = [data.index_select(0, rows_dev[:, k])
+                 for group in self.device_data for k, data in enumerate(group)]
+        items.append(pmsk.to(self.device, non_blocking=True))
+        return items
+
+    # -- extraction (data.py:438-608) ----------------------------------------------------
+    def _extract_data(self, data_configs):
+        pairs = list(zip(self.adatas, data_configs))
+        xuid = [self._extract_xuid(a, c) for a, c in pairs]
+        xrep = [self._extract_xrep(a, c) for a, c in pairs]
+        default = get_default_numpy_dtype()
+        if self.mode == "eval":
+            x = [np.empty((a.shape[0], 0), dtype=default) if r.size else self._extract_x(a, c)
+                 for (a, c), r in zip(pairs, xrep)]
+            xbch = xlbl = [np.empty((a.shape[0], 0), dtype=int) for a in self.adatas]
+            xdwt = [np.empty((a.shape[0], 0), dtype=default) for a in self.adatas]
+        else:
+            x = [self._extract_x(a, c) for a, c in pairs]
+            xbch = [self._extract_xbch(a, c) for a, c in pairs]
+            xlbl = [self._extract_xlbl(a, c) for a, c in pairs]
+            xdwt = [self._extract_xdwt(a, c) for a, c in pairs]
+        return xuid, (x, xrep, xbch, xlbl, xdwt)
+
+    @staticmethod
+    def _extract_x(adata, cfg):
+        features, use_layer = cfg["features"], cfg["use_layer"]
+        if not np.array_equal(adata.var_names, features):
+            adata = adata[:, features]
+        if use_layer:
+            if use_layer not in adata.layers:
+                raise ValueError(f"Configured data layer '{use_layer}' "
+                                 f"cannot be found in input data!")
+            x = adata.layers[use_layer]
+        else:
+            x = adata.X
+        default = get_default_numpy_dtype(np.iscomplexobj(x))
+        if x.dtype.type is not default:
+            if not (isinstance(x, np.ndarray) or scipy.sparse.issparse(x)):
+                raise RuntimeError(f"User is responsible for ensuring a {default} dtype "
+                                   f"when using backed data!")
+            x = x.astype(default)
+        return x.tocsr() if scipy.sparse.issparse(x) else x
+
+    @staticmethod
+    def _extract_xrep(adata, cfg):
+        default = get_default_numpy_dtype()
+        use_rep, rep_dim = cfg["use_rep"], cfg["rep_dim"]
+        if not use_rep:
+            return np.empty((adata.shape[0], 0), dtype=default)
+        if use_rep not in adata.obsm:
+            raise ValueError(f"Configured data representation '{use_rep}' "
+                             f"cannot be found in input data!")
+        xrep = np.asarray(adata.obsm[use_rep]).astype(default)
+        if xrep.shape[1] != rep_dim:
+            raise ValueError(f"Input representation dimensionality {xrep.shape[1]} "
+                             f"does not match the configured {rep_dim}!")
+        return xrep
+
+    @staticmethod
+    def _extract_xbch(adata, cfg):
+        use_batch, batches = cfg["use_batch"], cfg["batches"]
+        if not use_batch:
+            return np.zeros(adata.shape[0], dtype=int)
+        if use_batch not in adata.obs:
+            raise ValueError(f"Configured data batch '{use_batch}' "
+                             f"cannot be found in input data!")
+        return pd.Index(batches).get_indexer(adata.obs[use_batch])
+
+    @staticmethod
+    def _extract_xlbl(adata, cfg):
+        use_cell_type, cell_types = cfg["use_cell_type"], cfg["cell_types"]
+        if not use_cell_type:
+            return -np.ones(adata.shape[0], dtype=int)
+        if use_cell_type not in adata.obs:
+            raise ValueError(f"Configured cell type '{use_cell_type}' "
+                             f"cannot be found in input data!")
+        return pd.Index(cell_types).get_indexer(adata.obs[use_cell_type])
+
+    @staticmethod
+    def _extract_xdwt(adata, cfg):
+        default = get_default_numpy_dtype()
+        use_dsc_weight = cfg["use_dsc_weight"]
+        if not use_dsc_weight:
+            return np.ones(adata.shape[0], dtype=default)
+        if use_dsc_weight not in adata.obs:
+            raise ValueError(f"Configured discriminator sample weight '{use_dsc_weight}' "
+                             f"cannot be found in input data!")
+        xdwt = np.asarray(adata.obs[use_dsc_weight]).astype(default)
+        return xdwt / (xdwt.sum() / xdwt.size)
+
+    @staticmethod
+    def _extract_xuid(adata, cfg) -> pd.Index:
+        if cfg["use_obs_names"]:
+            xuid = np.asarray(adata.obs_names)
+        else:  # unpaired: every cell gets an id that collides with nothing
+            xuid = np.array([uuid.uuid4().hex for _ in range(adata.shape[0])])
+        if len(set(xuid)) != xuid.size:
+            raise ValueError("Non-unique cell ID!")
+        return pd.Index(xuid)
+
+    # -- shuffling ------------------------------------------------------------------------
+    def propose_shuffle(self, seed: int):
+        rs = get_rs(seed)
+        return self._get_idx_pmsk(rs.permutation(self.view_idx), random_fill=True, random_state=rs)
+
+    def accept_shuffle(self, shuffled) -> None:
+        self.shuffle_idx, self.shuffle_pmsk = shuffled
+
+    def random_split(self, fractions: List[float], random_state=None) -> List["AnnDataset"]:
+        _check_fractions(fractions)
+        rs = get_rs(random_state)
+        view = rs.permutation(self.view_idx)
+        pieces = np.split(view, np.round(np.cumsum(fractions) * view.size).astype(int)[:-1])
+        subs = []
+        for piece in pieces:
+            sub = copy.copy(self)
+            sub._lookahead = None
+            sub.view_idx, sub.size = piece, piece.size
+            sub.shuffle_idx, sub.shuffle_pmsk = sub._get_idx_pmsk(piece)
+            subs.append(sub)
+        return subs
+
+
+# -------------------------------------------------------------------------- graph
+
+
+@logged
+class GraphDataset(Dataset):
+    r"""
+    Guidance-graph dataset with negative sampling (``data.py:667-828``).
+
+    Per graph epoch: draw ``round(sum(ewt))`` positive edges with replacement
+    (``p = ewt / sum``), and for each ``neg_samples`` corrupted copies whose target is
+    redrawn from the degree-weighted vertex distribution until ``(src, tgt, sign)`` is not a
+    real edge; positives get weight 1, negatives 0; then permute.  The draw sequence on the
+    legacy ``RandomState`` is the reference's, hence the edge stream is bit-identical; only
+    the membership test is vectorised (sorted int64 keys + ``searchsorted`` instead of a
+    Python ``set`` of tuples).
+    """
+
+    def __init__(self, graph: nx.Graph, vertices: pd.Index, neg_samples: int = 1,
+                 weighted_sampling: bool = True, deemphasize_loops: bool = True,
+                 getitem_size: int = 1) -> None:
+        super().__init__(getitem_size=getitem_size)
+        self.eidx, self.ewt, self.esgn = self.graph2triplet(graph, vertices)
+        self.vnum = int(self.eidx.max()) + 1
+        self._edge_keys = np.unique(self._key(self.eidx[0], self.eidx[1], self.esgn))
+        if weighted_sampling:
+            keep = (self.eidx[0] != self.eidx[1]) if deemphasize_loops \
+                else np.ones(self.ewt.size, dtype=bool)
+            degree = vertex_degrees(self.eidx[:, keep], self.ewt[keep], vnum=self.vnum,
+                                    direction="both")
+        else:
+            degree = np.ones(self.vnum, dtype=self.ewt.dtype)
+        total = degree.sum()
+        self.vprob = degree / total if total \
+            else np.ones(self.vnum, dtype=self.ewt.dtype) / self.vnum
+        effective = self.ewt.sum()
+        self.eprob = self.ewt / effective
+        self.effective_enum = round(effective)
+        self.neg_samples = neg_samples
+        self.size = self.effective_enum * (1 + self.neg_samples)
+        self.samp_eidx = self.samp_ewt = self.samp_esgn = None
+        self.device: Optional[torch.device] = None
+
+    def _key(self, src, dst, sgn) -> np.ndarray:
+        return (src.astype(np.int64) * self.vnum + dst.astype(np.int64)) * 2 + (sgn > 0)
+
+    def _is_edge(self, src, dst, sgn) -> np.ndarray:
+        keys = self._key(src, dst, sgn)
+        pos = np.searchsorted(self._edge_keys, keys)
+        pos[pos == self._edge_keys.size] = 0
+        return self._edge_keys[pos] == keys
+
+    @staticmethod
+    def graph2triplet(graph: nx.Graph, vertices: pd.Index):
+        r"""``(eidx int64 [2,E], ewt, esgn)`` in ``MultiDiGraph`` edge order; undirected input
+        becomes bi-directed, multi-edges are kept (``data.py:733-779``)."""
+        directed = nx.MultiDiGraph(graph)
+        dtype = get_default_numpy_dtype()
+        src, dst, weight, sign = [], [], [], []
+        for (s, t, *_), attr in dict(directed.edges).items():
+            src.append(s), dst.append(t)
+            weight.append(attr["weight"]), sign.append(attr["sign"])
+        vertices = pd.Index(vertices)
+        eidx = np.stack([vertices.get_indexer(src), vertices.get_indexer(dst)]).astype(np.int64)
+        if eidx.min() < 0:
+            raise ValueError("Missing vertices!")
+        ewt = np.asarray(weight).astype(dtype)
+        if ewt.min() <= 0 or ewt.max() > 1:
+            raise ValueError("Invalid edge weight!")
+        esgn = np.asarray(sign).astype(dtype)
+        if set(esgn).difference({-1, 1}):
+            raise ValueError("Invalid edge sign!")
+        return eidx, ewt, esgn
+
+    def to_device(self, device: torch.device) -> "GraphDataset":
+        self.device = torch.device(device)
+        return self
+
+    def __len__(self) -> int:
+        return ceil(self.size / self.getitem_size)
+
+    def __getitem__(self, index: int) -> List[torch.Tensor]:
+        s = slice(index * self.getitem_size, min((index + 1) * self.getitem_size, self.size))
+        return [self.samp_eidx[:, s], self.samp_ewt[s], self.samp_esgn[s]]
+
+    def propose_shuffle(self, seed: int):
+        rs = get_rs(seed)
+        pick = rs.choice(self.ewt.size, self.effective_enum, replace=True, p=self.eprob)
+        p_src, p_dst, p_sgn = self.eidx[0][pick], self.eidx[1][pick], self.esgn[pick]
+        p_wt = np.ones_like(self.ewt[pick])
+        n_src = np.tile(p_src, self.neg_samples)
+        n_sgn = np.tile(p_sgn, self.neg_samples)
+        n_wt = np.zeros(p_wt.size * self.neg_samples, dtype=p_wt.dtype)
+        n_dst = rs.choice(self.vnum, p_dst.size * self.neg_samples, replace=True, p=self.vprob)
+        clash = np.where(self._is_edge(n_src, n_dst, n_sgn))[0]
+        while clash.size:  # NOTE: does not terminate on (near-)complete graphs, as in the reference
+            redraw = rs.choice(self.vnum, clash.size, replace=True, p=self.vprob)
+            n_dst[clash] = redraw
+            clash = clash[self._is_edge(n_src[clash], redraw, n_sgn[clash])]
+        idx = np.stack([np.concatenate([p_src, n_src]), np.concatenate([p_dst, n_dst])])
+        wt, sgn = np.concatenate([p_wt, n_wt]), np.concatenate([p_sgn, n_sgn])
+        perm = rs.permutation(idx.shape[1])
+        return idx[:, perm], wt[perm], sgn[perm]
+
+    def accept_shuffle(self, shuffled) -> None:
+        eidx, ewt, esgn = (torch.as_tensor(np.ascontiguousarray(a)) for a in shuffled)
+        if self.device is not None:  # one upload per graph epoch; minibatches are slices
+            eidx, ewt, esgn = (t.to(self.device, non_blocking=True) for t in (eidx, ewt, esgn))
+        self.samp_eidx, self.samp_ewt, self.samp_esgn = eidx, ewt, esgn
+
+
+# ------------------------------------------------------------------------ loaders
+
+
+class DataLoader(torch.utils.data.DataLoader):
+    r"""
+    ``torch.utils.data.DataLoader`` that re-shuffles its dataset (new cell permutation / new
+    negative samples) at every ``iter()`` and concatenates the fetched blocks
+    (``data.py:831-859``).  For device-resident :class:`AnnDataset` s the blocks carry row
+    indices only and the batch is gathered on the device here.
+    """
+
+    def __init__(self, dataset: Dataset, reshuffle: Optional[bool] = None, **kwargs) -> None:
+        super().__init__(dataset, **kwargs)
+        # `reshuffle` lets callers that pass an explicit `batch_sampler` keep the
+        # re-shuffle-at-iter behaviour that `shuffle=True` implies
+        self.shuffle = kwargs.get("shuffle", False) if reshuffle is None else reshuffle
+        if isinstance(dataset, GraphDataset):
+            self.collate_fn = self._collate_graph
+        elif isinstance(dataset, AnnDataset) and dataset.device is not None:
+            self.collate_fn = functools.partial(self._collate_device, dataset)
+        else:
+            self.collate_fn = self._collate
+
+    def __iter__(self):
+        if self.shuffle:
+            self.dataset.shuffle()
+        return super().__iter__()
+
+    @staticmethod
+    def _collate(batch):
+        return tuple(torch.cat(parts, dim=0) for parts in zip(*batch))
+
+    @staticmethod
+    def _collate_graph(batch):
+        eidx, ewt, esgn = zip(*batch)
+        return torch.cat(eidx, dim=1), torch.cat(ewt, dim=0), torch.cat(esgn, dim=0)
+
+    @staticmethod
+    def _collate_device(dataset: AnnDataset, batch):
+        rows, pmsk = (torch.cat(parts, dim=0) for parts in zip(*batch))
+        return tuple(dataset.fetch_device(rows, pmsk))
+
+
+class ParallelDataLoader:
+    r"""Iterate several loaders in lock-step, optionally cycling the shorter ones
+    (``data.py:862-902``)."""
+
+    def __init__(self, *data_loaders, cycle_flags: Optional[List[bool]] = None) -> None:
+        cycle_flags = cycle_flags or [False] * len(data_loaders)
+        if len(cycle_flags) != len(data_loaders):
+            raise ValueError("Invalid cycle flags!")
+        self.cycle_flags = cycle_flags
+        self.data_loaders = list(data_loaders)
+        self.num_loaders = len(self.data_loaders)
+        self.iterators = None
+
+    def __iter__(self) -> "ParallelDataLoader":
+        self.iterators = [iter(loader) for loader in self.data_loaders]
+        return self
+
+    def _next(self, i: int):
+        try:
+            return next(self.iterators[i])
+        except StopIteration:
+            if not self.cycle_flags[i]:
+                raise
+            self.iterators[i] = iter(self.data_loaders[i])
+            return next(self.iterators[i])
+
+    def __next__(self):
+        return functools.reduce(operator.add, [self._next(i) for i in range(self.num_loaders)])

@@ -1,0 +1,671 @@
+r"""
+SCGLUE network, trainers and public model classes (API of ``scglue/models/scglue.py``).
+
+``SCGLUETrainer.compute_losses`` evaluates the same objective as the reference
+(``scglue.py:292-376``; paired variant ``scglue.py:550-701``) but routes the three hot
+sub-computations through the sm_100a kernels:
+
+* graph encoder propagation  -> CSR GraphConv (forward + transposed-CSR backward);
+* graph reconstruction loss  -> gather-dot + fused BCE + pos/neg balancing, no host sync;
+* data reconstruction losses -> fused decoder NLL, gathering ``v[idx_k]`` inside the kernel
+  and producing every gradient in the forward launch sequence.
+"""
+
+import copy
+from itertools import chain
+from math import ceil
+from typing import Callable, List, Mapping, Optional, Tuple, Union
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import torch
+import torch.distributions as D
+import torch.nn.functional as F
+
+from ..num import normalize_edges
+from ..utils import AUTO, config, logged
+from . import sc
+from .base import Model
+from .data import AnnDataset, ArrayDataset, DataLoader, GraphDataset
+from .glue import GLUE, GLUETrainer
+from .nn import freeze_running_stats
+
+# ---------------------------------------------------------- prob-model registry
+
+_ENCODER_MAP: Mapping[str, type] = {}
+_DECODER_MAP: Mapping[str, type] = {}
+
+
+def register_prob_model(prob_model: str, encoder: type, decoder: type) -> None:
+    r"""
+    Register a data encoder / decoder pair under a ``prob_model`` name
+    (extension point of the reference, ``scglue.py:36-61`` / ``docs/dev.rst``).
+    """
+    _ENCODER_MAP[prob_model] = encoder
+    _DECODER_MAP[prob_model] = decoder
+
+
+register_prob_model("Normal", sc.VanillaDataEncoder, sc.NormalDataDecoder)
+register_prob_model("ZIN", sc.VanillaDataEncoder, sc.ZINDataDecoder)
+register_prob_model("ZILN", sc.VanillaDataEncoder, sc.ZILNDataDecoder)
+register_prob_model("NB", sc.NBDataEncoder, sc.NBDataDecoder)
+register_prob_model("ZINB", sc.NBDataEncoder, sc.ZINBDataDecoder)
+register_prob_model("Bernoulli", sc.VanillaDataEncoder, sc.BernoulliDataDecoder)
+
+
+# ---------------------------------------------------------------------- network
+
+
+class SCGLUE(GLUE):
+    r"""GLUE network for single-cell multi-omics integration, with an optional cell-type
+    classifier ``u2c`` (``scglue.py:67-103``)."""
+
+    def __init__(self, g2v, v2g, x2u, u2x, idx, du, prior, u2c=None) -> None:
+        super().__init__(g2v, v2g, x2u, u2x, idx, du, prior)
+        self.u2c = u2c.to(self.device) if u2c else None
+
+
+def _kl_to_prior(q: D.Normal, prior: D.Normal) -> torch.Tensor:
+    return D.kl_divergence(q, prior).sum(dim=1).mean()
+
+
+# --------------------------------------------------------------------- trainers
+
+
+@logged
+class SCGLUETrainer(GLUETrainer):
+    r"""
+    Trainer for :class:`SCGLUE` (``scglue.py:159-420``).  One ``train_step`` = one
+    discriminator update followed by one generator (VAE) update.
+    """
+
+    BURNIN_NOISE_EXAG: float = 1.5  # burn-in noise exaggeration
+
+    def __init__(self, net: SCGLUE, lam_data: float = None, lam_kl: float = None,
+                 lam_graph: float = None, lam_align: float = None, lam_sup: float = None,
+                 dsc_steps: int = None, normalize_u: bool = None,
+                 modality_weight: Mapping[str, float] = None, optim: str = None,
+                 lr: float = None, **kwargs) -> None:
+        super().__init__(net, lam_data=lam_data, lam_kl=lam_kl, lam_graph=lam_graph,
+                         lam_align=lam_align, dsc_steps=dsc_steps,
+                         modality_weight=modality_weight, optim=optim, lr=lr, **kwargs)
+        for name, val in dict(lam_sup=lam_sup, normalize_u=normalize_u).items():
+            if val is None:
+                raise ValueError(f"`{name}` must be specified!")
+        self.lam_sup, self.normalize_u = lam_sup, normalize_u
+        self.freeze_u = False
+        if net.u2c:
+            self.required_losses.append("sup_loss")
+            self.vae_optim = self._make_optim(self._vae_modules() + [net.u2c])
+        # `noise(shape_like, tag)` supplies standard-normal draws; tests inject host noise
+        self.noise: Callable[[torch.Tensor, str], torch.Tensor] = \
+            lambda like, tag: torch.randn_like(like)
+
+    @property
+    def freeze_u(self) -> bool:
+        r"""Whether cell embeddings (encoders + discriminator) are frozen."""
+        return self._freeze_u
+
+    @freeze_u.setter
+    def freeze_u(self, freeze_u: bool) -> None:
+        self._freeze_u = freeze_u
+        for p in chain(self.net.x2u.parameters(), self.net.du.parameters()):
+            p.requires_grad_(not freeze_u)
+
+    # -- data formatting -------------------------------------------------------------------
+    PAIRED = False
+
+    def format_data(self, data: List[torch.Tensor]):
+        r"""
+        Split the flat loader output ``[x.., xrep.., xbch.., xlbl.., xdwt.., (pmsk,) eidx, ewt,
+        esgn]`` (``scglue.py:255-290``) into per-modality dicts on the compute device.
+        Host tensors are copied (pinned + ``non_blocking``); device-resident batches pass
+        through untouched.
+        """
+        device, keys = self.net.device, self.net.keys
+        K = len(keys)
+        move = lambda t: t.to(device, non_blocking=True)
+        groups = [dict(zip(keys, map(move, data[i * K:(i + 1) * K]))) for i in range(5)]
+        x, xrep, xbch, xlbl, xdwt = groups
+        rest = data[5 * K:]
+        pmsk = move(rest[0])
+        eidx, ewt, esgn = (move(t) for t in rest[1:])
+        xflag = {k: torch.full((x[k].shape[0],), i, dtype=torch.int64, device=device)
+                 for i, k in enumerate(keys)}
+        if self.PAIRED:
+            return x, xrep, xbch, xlbl, xdwt, xflag, pmsk, eidx, ewt, esgn
+        return x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn
+
+    # -- shared pieces of the objective ----------------------------------------------------
+    def _encode(self, x, xrep, dsc_only: bool):
+        net = self.net
+        u, l = {}, {}
+        for k in net.keys:
+            u[k], l[k] = net.x2u[k](x[k], xrep[k], lazy_normalizer=dsc_only)
+        usamp = {k: u[k].mean + self.noise(u[k].mean, f"u_{k}") * u[k].stddev for k in net.keys}
+        if self.normalize_u:
+            usamp = {k: F.normalize(usamp[k], dim=1) for k in net.keys}
+        return u, l, usamp
+
+    def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int):
+        net = self.net
+        u_cat = torch.cat([u[k].mean for k in net.keys])
+        xbch_cat = torch.cat([xbch[k] for k in net.keys])
+        xdwt_cat = torch.cat([xdwt[k] for k in net.keys])
+        xflag_cat = torch.cat([xflag[k] for k in net.keys])
+        anneal = max(1 - (epoch - 1) / self.align_burnin, 0) if self.align_burnin else 0
+        if anneal:
+            with torch.no_grad():  # D.Normal(0, std).sample(): not differentiated through
+                jitter = self.noise(u_cat, "burnin") * u_cat.std(dim=0)
+            u_cat = u_cat + (anneal * self.BURNIN_NOISE_EXAG) * jitter
+        dsc_loss = F.cross_entropy(net.du(u_cat, xbch_cat), xflag_cat, reduction="none")
+        dsc_loss = (dsc_loss * xdwt_cat).sum() / xdwt_cat.numel()
+        return u_cat, dsc_loss
+
+    def _supervision(self, u_cat, xlbl):
+        net = self.net
+        if not net.u2c:
+            return torch.zeros((), device=net.device)
+        xlbl_cat = torch.cat([xlbl[k] for k in net.keys])
+        labelled = xlbl_cat >= 0  # masked mean without boolean indexing (static shapes)
+        ce = F.cross_entropy(net.u2c(u_cat), xlbl_cat.clamp(min=0), reduction="none")
+        return (ce * labelled).sum() / labelled.sum().clamp(min=1)
+
+    def _graph_terms(self, eidx, ewt, esgn, prior):
+        net = self.net
+        v = net.g2v(self.eidx, self.enorm, self.esgn)
+        vsamp = v.mean + self.noise(v.mean, "v") * v.stddev
+        g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+        g_kl = _kl_to_prior(v, prior) / vsamp.shape[0]
+        return vsamp, g_nll, g_kl
+
+    def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str) -> torch.Tensor:
+        r"""``-u2x[k](usamp, vsamp[idx_k], xbch, l).log_prob(x).<reduce>()``; kernel-backed
+        decoders take the whole vertex table and gather ``idx_k`` rows themselves."""
+        net = self.net
+        decoder, idx = net.u2x[k], getattr(net, f"{k}_idx")
+        if isinstance(decoder, sc._FusedDecoder):
+            return decoder(usamp, vsamp, xbch, l, vidx=idx).nll(x, reduce=reduce)
+        log_prob = decoder(usamp, vsamp[idx], xbch, l).log_prob(x)
+        return -(log_prob.nanmean() if reduce == "nanmean" else log_prob.mean())
+
+    DATA_REDUCE = "nanmean"  # scglue.py:345
+
+    def compute_losses(self, data, epoch: int, dsc_only: bool = False
+                       ) -> Mapping[str, torch.Tensor]:
+        net = self.net
+        x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
+        u, l, usamp = self._encode(x, xrep, dsc_only)
+        prior = net.prior()
+        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
+        if dsc_only:
+            return {"dsc_loss": self.lam_align * dsc_loss}
+        sup_loss = self._supervision(u_cat, xlbl)
+        vsamp, g_nll, g_kl = self._graph_terms(eidx, ewt, esgn, prior)
+        g_elbo = g_nll + self.lam_kl * g_kl
+        x_nll = {k: self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE)
+                 for k in net.keys}
+        x_kl = {k: _kl_to_prior(u[k], prior) / x[k].shape[1] for k in net.keys}
+        x_elbo = {k: x_nll[k] + self.lam_kl * x_kl[k] for k in net.keys}
+        x_elbo_sum = sum(self.modality_weight[k] * x_elbo[k] for k in net.keys)
+        vae_loss = (self.lam_data * x_elbo_sum + self.lam_graph * len(net.keys) * g_elbo
+                    + self.lam_sup * sup_loss)
+        extra = self._extra_losses(data, usamp, vsamp, l)
+        for weight, term in extra.values():
+            vae_loss = vae_loss + weight * term
+        gen_loss = vae_loss - self.lam_align * dsc_loss
+        losses = {"dsc_loss": dsc_loss, "vae_loss": vae_loss, "gen_loss": gen_loss,
+                  "g_nll": g_nll, "g_kl": g_kl, "g_elbo": g_elbo}
+        losses.update({name: term for name, (_, term) in extra.items()})
+        for k in net.keys:
+            losses.update({f"x_{k}_nll": x_nll[k], f"x_{k}_kl": x_kl[k],
+                           f"x_{k}_elbo": x_elbo[k]})
+        if net.u2c:
+            losses["sup_loss"] = sup_loss
+        return losses
+
+    def _extra_losses(self, data, usamp, vsamp, l) -> Mapping[str, Tuple[float, torch.Tensor]]:
+        return {}
+
+    # -- steps -------------------------------------------------------------------------------
+    def train_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        self.net.train()
+        data = self.format_data(data)
+        epoch = engine.state.epoch
+        if self.freeze_u:
+            self.net.x2u.apply(freeze_running_stats)
+            self.net.du.apply(freeze_running_stats)
+        else:  # discriminator step
+            for _ in range(self.dsc_steps):
+                losses = self.compute_losses(data, epoch, dsc_only=True)
+                self.net.zero_grad(set_to_none=True)
+                losses["dsc_loss"].backward()  # already scaled by lam_align
+                self._sync_grads("dsc")
+                self.dsc_optim.step()
+        losses = self.compute_losses(data, epoch)  # generator step
+        self.net.zero_grad(set_to_none=True)
+        losses["gen_loss"].backward()
+        self._sync_grads("vae")
+        self.vae_optim.step()
+        return losses
+
+    @torch.no_grad()
+    def val_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        self.net.eval()
+        return self.compute_losses(self.format_data(data), engine.state.epoch)
+
+    def __repr__(self) -> str:
+        indent = lambda o: repr(o).replace("    ", "  ").replace("\n", "\n  ")
+        return (f"{type(self).__name__}(\n  lam_graph: {self.lam_graph}\n"
+                f"  lam_align: {self.lam_align}\n  vae_optim: {indent(self.vae_optim)}\n"
+                f"  dsc_optim: {indent(self.dsc_optim)}\n  freeze_u: {self.freeze_u}\n)")
+
+
+@logged
+class PairedSCGLUETrainer(SCGLUETrainer):
+    r"""
+    Trainer for partially paired data (``scglue.py:423-701``): adds joint-cross,
+    real-cross and cosine losses over the cells observed in several modalities.  Subsets are
+    taken by compacting row indices on the device (``nonzero``), which needs one host read
+    of the subset sizes per step -- as in the reference, whose boolean-mask indexing does the
+    same implicitly.
+    """
+
+    PAIRED = True
+    DATA_REDUCE = "mean"  # scglue.py:603
+
+    def __init__(self, net: SCGLUE, lam_data: float = None, lam_kl: float = None,
+                 lam_graph: float = None, lam_align: float = None, lam_sup: float = None,
+                 lam_joint_cross: float = None, lam_real_cross: float = None,
+                 lam_cos: float = None, dsc_steps: int = None, normalize_u: bool = None,
+                 modality_weight: Mapping[str, float] = None, optim: str = None,
+                 lr: float = None, **kwargs) -> None:
+        super().__init__(net, lam_data=lam_data, lam_kl=lam_kl, lam_graph=lam_graph,
+                         lam_align=lam_align, lam_sup=lam_sup, dsc_steps=dsc_steps,
+                         normalize_u=normalize_u, modality_weight=modality_weight, optim=optim,
+                         lr=lr, **kwargs)
+        for name, val in dict(lam_joint_cross=lam_joint_cross, lam_real_cross=lam_real_cross,
+                              lam_cos=lam_cos).items():
+            if val is None:
+                raise ValueError(f"`{name}` must be specified!")
+        self.lam_joint_cross, self.lam_real_cross, self.lam_cos = (
+            lam_joint_cross, lam_real_cross, lam_cos)
+        self.required_losses += ["joint_cross_loss", "real_cross_loss", "cos_loss"]
+
+    def compute_losses(self, data, epoch: int, dsc_only: bool = False):
+        x, xrep, xbch, xlbl, xdwt, xflag, pmsk, eidx, ewt, esgn = data
+        self._pmsk = pmsk
+        return super().compute_losses((x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn),
+                                      epoch, dsc_only=dsc_only)
+
+    def _extra_losses(self, data, usamp, vsamp, l):
+        net = self.net
+        x, xrep, xbch, *_ = data
+        keys = net.keys
+        device = net.device
+        pmsk = self._pmsk.T  # [n_modalities, B]
+        zero = torch.zeros((), device=device)
+        ustack = torch.stack([usamp[k] for k in keys])
+        pstack = pmsk.unsqueeze(2).expand_as(ustack)
+        umean = (ustack * pstack).sum(dim=0) / pstack.sum(dim=0)
+        if self.normalize_u:
+            umean = F.normalize(umean, dim=1)
+
+        # row subsets: observed in modality k, and observed in both of an ordered pair
+        pair_masks = {(i, j): pmsk[i] & pmsk[j]
+                      for i in range(len(keys)) for j in range(len(keys)) if i != j}
+        all_masks = list(pmsk) + list(pair_masks.values())
+        counts = torch.stack([m.sum() for m in all_masks]).tolist()  # the one host read
+        single_n = counts[:len(keys)]
+        pair_n = dict(zip(pair_masks, counts[len(keys):]))
+        rows_of = lambda m: m.nonzero(as_tuple=True)[0]
+
+        def subset_nll(k, usrc, rows):
+            lk = None if l[k] is None else l[k][rows]
+            return self._data_nll(k, usrc[rows], vsamp, xbch[k][rows], lk, x[k][rows], "mean")
+
+        joint = zero
+        if self.lam_joint_cross:
+            for i, k in enumerate(keys):
+                if single_n[i]:
+                    joint = joint + self.modality_weight[k] * subset_nll(k, umean, rows_of(pmsk[i]))
+        real = zero
+        if self.lam_real_cross:
+            for i, kt in enumerate(keys):
+                acc = zero
+                for j, ks in enumerate(keys):
+                    if i != j and pair_n[(j, i)]:
+                        acc = acc + subset_nll(kt, usamp[ks], rows_of(pair_masks[(j, i)]))
+                real = real + self.modality_weight[kt] * acc
+        cos = zero
+        if self.lam_cos:
+            for i, k in enumerate(keys):
+                if single_n[i]:
+                    rows = rows_of(pmsk[i])
+                    cos = cos + (1 - F.cosine_similarity(ustack[i][rows], umean[rows]).mean())
+        return {"joint_cross_loss": (self.lam_joint_cross, joint),
+                "real_cross_loss": (self.lam_real_cross, real),
+                "cos_loss": (self.lam_cos, cos)}
+
+
+# ------------------------------------------------------------------- public API
+
+
+@logged
+class SCGLUEModel(Model):
+    r"""
+    GLUE model for single-cell multi-omics data integration (``scglue.py:707-1362``).
+
+    Parameters
+    ----------
+    adatas
+        Configured datasets indexed by modality name (see ``configure_dataset``)
+    vertices
+        Guidance-graph vertices; must cover the features of every modality
+    latent_dim, h_depth, h_dim, dropout
+        Latent size (<= 64 for the fused decoders) and encoder / discriminator MLP shape
+    disc_norm
+        Standardise discriminator inputs
+    shared_batches
+        Batches are shared across modalities (discriminator sees the batch one-hot)
+    random_seed
+        Seed for initialisation and all sampling
+    """
+
+    NET_TYPE = SCGLUE
+    TRAINER_TYPE = SCGLUETrainer
+
+    GRAPH_BATCHES: int = 32  # graph minibatches per graph epoch
+    # optimisation progress (learning rate * iterations) behind the AUTO rules
+    ALIGN_BURNIN_PRG: float = 8.0
+    MAX_EPOCHS_PRG: float = 48.0
+    PATIENCE_PRG: float = 4.0
+    REDUCE_LR_PATIENCE_PRG: float = 2.0
+
+    def __init__(self, adatas: Mapping[str, "AnnData"], vertices: List[str], latent_dim: int = 50,
+                 h_depth: int = 2, h_dim: int = 256, dropout: float = 0.2,
+                 disc_norm: bool = False, shared_batches: bool = False,
+                 random_seed: int = 0) -> None:
+        self.vertices = pd.Index(vertices)
+        self.random_seed = random_seed
+        torch.manual_seed(self.random_seed)
+
+        # construction order fixes the RNG stream of the default initialisers:
+        # g2v, v2g, then per modality encoder + decoder, then du, prior, u2c (scglue.py:767-841)
+        g2v = sc.GraphEncoder(self.vertices.size, latent_dim)
+        v2g = sc.GraphDecoder()
+        self.modalities, idx, x2u, u2x, all_ct = {}, {}, {}, {}, set()
+        for k, adata in adatas.items():
+            if config.ANNDATA_KEY not in adata.uns:
+                raise ValueError(f"The '{k}' dataset has not been configured. "
+                                 f"Please call `configure_dataset` first!")
+            cfg = copy.deepcopy(adata.uns[config.ANNDATA_KEY])
+            if cfg["rep_dim"] and cfg["rep_dim"] < latent_dim:
+                self.logger.warning("It is recommended that `use_rep` dimensionality "
+                                    "be equal or larger than `latent_dim`.")
+            feature_idx = self.vertices.get_indexer(cfg["features"]).astype(np.int64)
+            if feature_idx.min() < 0:
+                raise ValueError("Not all modality features exist in the graph!")
+            idx[k] = torch.as_tensor(feature_idx)
+            x2u[k] = _ENCODER_MAP[cfg["prob_model"]](
+                cfg["rep_dim"] or len(cfg["features"]), latent_dim, h_depth=h_depth, h_dim=h_dim,
+                dropout=dropout)
+            cfg["batches"] = pd.Index([]) if cfg["batches"] is None else pd.Index(cfg["batches"])
+            u2x[k] = _DECODER_MAP[cfg["prob_model"]](
+                len(cfg["features"]), n_batches=max(cfg["batches"].size, 1))
+            all_ct = all_ct.union(set() if cfg["cell_types"] is None else cfg["cell_types"])
+            self.modalities[k] = cfg
+        all_ct = pd.Index(all_ct).sort_values()
+        for cfg in self.modalities.values():
+            cfg["cell_types"] = all_ct
+        if shared_batches:
+            batch_sets = [cfg["batches"] for cfg in self.modalities.values()]
+            for batches in batch_sets:
+                if not np.array_equal(batches, batch_sets[0]):
+                    raise RuntimeError("Batches must match when using `shared_batches`!")
+            du_n_batches = batch_sets[0].size
+        else:
+            du_n_batches = 0
+        du = sc.Discriminator(latent_dim, len(self.modalities), n_batches=du_n_batches,
+                              h_depth=h_depth, h_dim=h_dim, dropout=dropout, norm=disc_norm)
+        prior = sc.Prior()
+        super().__init__(g2v, v2g, x2u, u2x, idx, du, prior,
+                         u2c=None if all_ct.empty else sc.Classifier(latent_dim, all_ct.size))
+
+    # -- cell embedding freezing / model adoption -------------------------------------------
+    def freeze_cells(self) -> None:
+        self.trainer.freeze_u = True
+
+    def unfreeze_cells(self) -> None:
+        self.trainer.freeze_u = False
+
+    def adopt_pretrained_model(self, source: "SCGLUEModel", submodule: Optional[str] = None
+                               ) -> None:
+        r"""Copy every parameter / buffer that exists in ``source`` with the same name and
+        shape (``scglue.py:855-887``)."""
+        def descend(obj, dotted):
+            for part in dotted.split("."):
+                obj = getattr(obj, part)
+            return obj
+        src, dst = source.net, self.net
+        if submodule:
+            src, dst = descend(src, submodule), descend(dst, submodule)
+        for name, target in chain(dst.named_parameters(), dst.named_buffers()):
+            try:
+                value = descend(src, name)
+            except AttributeError:
+                self.logger.warning("Missing: %s", name)
+                continue
+            if value.shape != target.shape:
+                self.logger.warning("Shape mismatch: %s", name)
+                continue
+            with torch.no_grad():
+                target.data.copy_(value.data.to(device=target.device, dtype=target.dtype))
+
+    # -- compile / fit ----------------------------------------------------------------------
+    def compile(self, lam_data: float = 1.0, lam_kl: float = 1.0, lam_graph: float = 0.02,
+                lam_align: float = 0.05, lam_sup: float = 0.02, dsc_steps: int = 1,
+                normalize_u: bool = False, modality_weight: Optional[Mapping[str, float]] = None,
+                lr: float = 2e-3, **kwargs) -> None:
+        r"""Create the trainer (RMSprop on both parameter groups, ``scglue.py:889-942``)."""
+        if modality_weight is None:
+            modality_weight = {k: 1.0 for k in self.net.keys}
+        super().compile(lam_data=lam_data, lam_kl=lam_kl, lam_graph=lam_graph,
+                        lam_align=lam_align, lam_sup=lam_sup, dsc_steps=dsc_steps,
+                        normalize_u=normalize_u, modality_weight=modality_weight,
+                        optim="RMSprop", lr=lr, **kwargs)
+
+    def _auto(self, name: str, value, progress: float, batch_per_epoch: float):
+        if value != AUTO:
+            return value
+        value = max(ceil(progress / self.trainer.lr / batch_per_epoch), ceil(progress))
+        self.logger.info("Setting `%s` = %d", name, value)
+        return value
+
+    def fit(self, adatas: Mapping[str, "AnnData"], graph: nx.Graph, neg_samples: int = 10,
+            val_split: float = 0.1, data_batch_size: int = 128,
+            graph_batch_size: Union[int, str] = AUTO, align_burnin: Union[int, str] = AUTO,
+            safe_burnin: bool = True, max_epochs: Union[int, str] = AUTO,
+            patience: Optional[Union[int, str]] = AUTO,
+            reduce_lr_patience: Optional[Union[int, str]] = AUTO,
+            wait_n_lrs: int = 1, directory=None, device_resident: bool = True) -> None:
+        r"""
+        Fit the model (``scglue.py:944-1055``).  ``device_resident`` keeps count matrices and
+        the sampled edge stream in HBM (falls back to host-side fetching when they exceed
+        ``config.DEVICE_DATA_BUDGET_BYTES``); the minibatch index streams are unchanged.
+        """
+        data = AnnDataset([adatas[k] for k in self.net.keys],
+                          [self.modalities[k] for k in self.net.keys], mode="train")
+        from ..graph import check_graph
+        check_graph(graph, adatas.values(), cov="ignore", attr="error", loop="warn", sym="warn")
+        graph = GraphDataset(graph, self.vertices, neg_samples=neg_samples,
+                             weighted_sampling=True, deemphasize_loops=True)
+        if device_resident and self.net.device.type == "cuda":
+            try:
+                data.to_device(self.net.device)
+                graph.to_device(self.net.device)
+            except MemoryError as e:
+                self.logger.warning("%s", e)
+        batch_per_epoch = data.size * (1 - val_split) / data_batch_size
+        if graph_batch_size == AUTO:
+            graph_batch_size = ceil(graph.size / self.GRAPH_BATCHES)
+            self.logger.info("Setting `graph_batch_size` = %d", graph_batch_size)
+        align_burnin = self._auto("align_burnin", align_burnin, self.ALIGN_BURNIN_PRG,
+                                  batch_per_epoch)
+        max_epochs = self._auto("max_epochs", max_epochs, self.MAX_EPOCHS_PRG, batch_per_epoch)
+        patience = self._auto("patience", patience, self.PATIENCE_PRG, batch_per_epoch)
+        reduce_lr_patience = self._auto("reduce_lr_patience", reduce_lr_patience,
+                                        self.REDUCE_LR_PATIENCE_PRG, batch_per_epoch)
+        if self.trainer.freeze_u:
+            self.logger.info("Cell embeddings are frozen")
+        super().fit(data, graph, val_split=val_split, data_batch_size=data_batch_size,
+                    graph_batch_size=graph_batch_size, align_burnin=align_burnin,
+                    safe_burnin=safe_burnin, max_epochs=max_epochs, patience=patience,
+                    reduce_lr_patience=reduce_lr_patience, wait_n_lrs=wait_n_lrs,
+                    random_seed=self.random_seed, directory=directory)
+
+    @torch.no_grad()
+    def get_losses(self, adatas: Mapping[str, "AnnData"], graph: nx.Graph, neg_samples: int = 10,
+                   data_batch_size: int = 128, graph_batch_size: Union[int, str] = AUTO
+                   ) -> Mapping[str, float]:
+        r"""Loss values on the given data (``scglue.py:1057-1108``)."""
+        data = AnnDataset([adatas[k] for k in self.net.keys],
+                          [self.modalities[k] for k in self.net.keys], mode="train")
+        graph = GraphDataset(graph, self.vertices, neg_samples=neg_samples,
+                             weighted_sampling=True, deemphasize_loops=True)
+        if graph_batch_size == AUTO:
+            graph_batch_size = ceil(graph.size / self.GRAPH_BATCHES)
+        return super().get_losses(data, graph, data_batch_size=data_batch_size,
+                                  graph_batch_size=graph_batch_size,
+                                  random_seed=self.random_seed)
+
+    # -- inference ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_graph(self, graph: nx.Graph, n_sample: Optional[int] = None) -> np.ndarray:
+        r"""Vertex (feature) embeddings ``[V, K]``, or ``[V, n_sample, K]`` samples
+        (``scglue.py:1110-1149``).  One GraphConv + two 50x50 GEMMs."""
+        self.net.eval()
+        graph = GraphDataset(graph, self.vertices)
+        device = self.net.device
+        enorm = torch.as_tensor(normalize_edges(graph.eidx, graph.ewt), device=device)
+        esgn = torch.as_tensor(graph.esgn, device=device)
+        eidx = torch.as_tensor(graph.eidx, device=device)
+        v = self.net.g2v(eidx, enorm, esgn)
+        if n_sample:
+            return torch.cat([v.sample((1,)).cpu() for _ in range(n_sample)]
+                             ).permute(1, 0, 2).numpy()
+        return v.mean.detach().cpu().numpy()
+
+    def _eval_loader(self, key: str, adata, batch_size: int) -> DataLoader:
+        data = AnnDataset([adata], [self.modalities[key]], mode="eval", getitem_size=batch_size)
+        pin = config.DATALOADER_PIN_MEMORY and not config.CPU_ONLY and torch.cuda.is_available()
+        return DataLoader(data, batch_size=1, shuffle=False,
+                          num_workers=config.DATALOADER_NUM_WORKERS, pin_memory=pin,
+                          drop_last=False, persistent_workers=False)
+
+    @torch.no_grad()
+    def encode_data(self, key: str, adata, batch_size: int = 128,
+                    n_sample: Optional[int] = None) -> np.ndarray:
+        r"""Cell embeddings ``[N, K]`` (posterior means) or ``[N, n_sample, K]`` samples
+        (``scglue.py:1151-1208``)."""
+        self.net.eval()
+        encoder, device = self.net.x2u[key], self.net.device
+        result = []
+        for x, xrep, *_ in self._eval_loader(key, adata, batch_size):
+            u = encoder(x.to(device, non_blocking=True), xrep.to(device, non_blocking=True),
+                        lazy_normalizer=True)[0]
+            if n_sample:
+                result.append(u.sample((n_sample,)).cpu().permute(1, 0, 2))
+            else:
+                result.append(u.mean.detach().cpu())
+        return torch.cat(result).numpy()
+
+    @torch.no_grad()
+    def classify_data(self, key: str, adata, batch_size: int = 128) -> pd.DataFrame:
+        r"""Cell-type probabilities from the linear classifier (``scglue.py:1210-1262``)."""
+        self.net.eval()
+        encoder, classifier, device = self.net.x2u[key], self.net.u2c, self.net.device
+        if classifier is None:
+            raise RuntimeError("The model was built without cell type supervision!")
+        result = []
+        for x, xrep, *_ in self._eval_loader(key, adata, batch_size):
+            u = encoder(x.to(device, non_blocking=True), xrep.to(device, non_blocking=True),
+                        lazy_normalizer=True)[0]
+            result.append(classifier(u.mean).softmax(dim=-1).cpu())
+        return pd.DataFrame(torch.cat(result).numpy(), index=adata.obs_names,
+                            columns=self.modalities[key]["cell_types"])
+
+    @torch.no_grad()
+    def decode_data(self, source_key: str, target_key: str, adata, graph: nx.Graph,
+                    target_libsize: Optional[Union[float, np.ndarray]] = None,
+                    target_batch: Optional[np.ndarray] = None, batch_size: int = 128
+                    ) -> np.ndarray:
+        r"""Cross-modality imputation: encode with ``source_key``, decode with
+        ``target_key`` (mean of the decoded distribution, ``scglue.py:1264-1356``)."""
+        l = target_libsize or 1.0
+        if not isinstance(l, np.ndarray):
+            l = np.asarray(l)
+        l = l.squeeze()
+        if l.ndim == 0:
+            l = l[np.newaxis]
+        elif l.ndim > 1:
+            raise ValueError("`target_libsize` cannot be >1 dimensional")
+        if l.size == 1:
+            l = np.repeat(l, adata.shape[0])
+        if l.size != adata.shape[0]:
+            raise ValueError("`target_libsize` must have the same size as `adata`!")
+        l = l.reshape((-1, 1)).astype(np.float32)
+
+        use_batch = self.modalities[target_key]["use_batch"]
+        batches = self.modalities[target_key]["batches"]
+        if use_batch and target_batch is not None:
+            target_batch = np.asarray(target_batch)
+            if target_batch.size != adata.shape[0]:
+                raise ValueError("`target_batch` must have the same size as `adata`!")
+            b = batches.get_indexer(target_batch)
+        else:
+            b = np.zeros(adata.shape[0], dtype=int)
+
+        net, device = self.net, self.net.device
+        net.eval()
+        u = self.encode_data(source_key, adata, batch_size=batch_size)
+        v = torch.as_tensor(self.encode_graph(graph), device=device)
+        v = v[getattr(net, f"{target_key}_idx")].contiguous()
+        decoder = net.u2x[target_key]
+        result = []
+        for start in range(0, adata.shape[0], batch_size):
+            s = slice(start, start + batch_size)
+            u_ = torch.as_tensor(u[s], device=device)
+            b_ = torch.as_tensor(b[s], dtype=torch.int64, device=device)
+            l_ = torch.as_tensor(l[s], device=device)
+            result.append(decoder(u_, v, b_, l_).mean.detach().cpu())
+        return torch.cat(result).numpy()
+
+    def upgrade(self) -> None:
+        if hasattr(self, "domains"):
+            self.logger.warning("Upgrading model generated by older versions...")
+            self.modalities = getattr(self, "domains")
+            delattr(self, "domains")
+
+    def __repr__(self) -> str:
+        return (f"SCGLUE model with the following network and trainer:\n\n"
+                f"{repr(self.net)}\n\n{repr(self.trainer)}\n")
+
+
+@logged
+class PairedSCGLUEModel(SCGLUEModel):
+    r"""GLUE model for partially paired data (``scglue.py:1365-1459``); cells are paired
+    through ``obs_names`` when datasets are configured with ``use_obs_names=True``."""
+
+    TRAINER_TYPE = PairedSCGLUETrainer
+
+    def compile(self, lam_data: float = 1.0, lam_kl: float = 1.0, lam_graph: float = 0.02,
+                lam_align: float = 0.05, lam_sup: float = 0.02, lam_joint_cross: float = 0.02,
+                lam_real_cross: float = 0.02, lam_cos: float = 0.02, dsc_steps: int = 1,
+                normalize_u: bool = False, modality_weight: Optional[Mapping[str, float]] = None,
+                lr: float = 2e-3, **kwargs) -> None:
+        super().compile(lam_data=lam_data, lam_kl=lam_kl, lam_graph=lam_graph,
+                        lam_align=lam_align, lam_sup=lam_sup, lam_joint_cross=lam_joint_cross,
+                        lam_real_cross=lam_real_cross, lam_cos=lam_cos, dsc_steps=dsc_steps,
+                        normalize_u=normalize_u, modality_weight=modality_weight, lr=lr, **kwargs)
