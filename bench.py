@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the SCGLUE training step (BASELINE.json metric: train cells/s, with the
+fused NB decoder's fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one ``train_step`` (discriminator update + generator update, RMSprop) on one
+minibatch of 128 cells per modality.  Workload = BASELINE.json ``configs[1]``:
+PairedSCGLUE, RNA + ATAC, synthetic 10x-Multiome-PBMC shape (10 000 paired cells, 2 000
+HVGs, 50 000 peaks, 100 k-edge guidance graph + self-loops, NB decoders, 50-d latent).
+"A cell" = one view row (one RNA row + one ATAC row).
+
+``value``  : steps over minibatches already resident in HBM (device-resident pipeline).
+``e2e``    : the same steps through the reference-facing call ``trainer.train_step(engine,
+             host_batch)`` with pinned host tensors: H2D of the dense minibatch and a D2H read
+             of the loss are inside the timed region.
+``roofline``: the dominant kernel sequence (fused NB decoder fwd+bwd at F = 50 000) timed with
+             CUDA events inside the timed steps, algorithmic bytes / time vs the measured
+             HBM copy bandwidth.
+``cpu_baseline`` / ``--impl reference``: the CPU port of the reference's train_step
+             (``oracle/scglue_cpu.py``, pinned against the unmodified reference) on the
+             host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="cfg2_paired_scglue_pbmc", n_cells=10000, n_genes=2000, n_peaks=50000,
+                n_pairs=50000, latent_dim=50, h_dim=256, rep_dim=100, batch=128, neg_samples=10,
+                rna_rate=0.26, atac_rate=0.05, seed=0)
+
+
+# ----------------------------------------------------------------------- workload
+def make_workload(cfg):
+    """Seeded synthetic data: CSR fp32 counts, 100-d encoder inputs, bipartite guidance graph."""
+    import networkx as nx
+    import pandas as pd
+    import scipy.sparse
+
+    from glue_b200.anndata_lite import AnnData
+
+    rs = np.random.RandomState(cfg["seed"])
+    n = cfg["n_cells"]
+    cells = [f"cell{i}" for i in range(n)]
+    adatas = {}
+    for key, prefix, f, rate in (("rna", "g", cfg["n_genes"], cfg["rna_rate"]),
+                                 ("atac", "p", cfg["n_peaks"], cfg["atac_rate"])):
+        nnz = int(n * f * rate)
+        rows = rs.randint(0, n, nnz)
+        cols = rs.randint(0, f, nnz)
+        vals = (1 + rs.poisson(0.3, nnz)).astype(np.float32)
+        x = scipy.sparse.coo_matrix((vals, (rows, cols)), shape=(n, f)).tocsr()
+        x.sum_duplicates()
+        x = (x + scipy.sparse.csr_matrix((np.ones(n, np.float32), (np.arange(n), np.zeros(n, int))),
+                                         shape=(n, f))).tocsr().astype(np.float32)
+        names = [f"{prefix}{i}" for i in range(f)]
+        adatas[key] = AnnData(X=x, obs=pd.DataFrame(index=cells), var=pd.DataFrame(index=names),
+                              obsm={"X_rep": rs.randn(n, cfg["rep_dim"]).astype(np.float32)})
+    g = nx.Graph()
+    genes, peaks = list(adatas["rna"].var_names), list(adatas["atac"].var_names)
+    g.add_nodes_from(genes + peaks)
+    src, dst = rs.randint(0, len(genes), cfg["n_pairs"]), rs.randint(0, len(peaks), cfg["n_pairs"])
+    wts = rs.uniform(0.05, 1.0, cfg["n_pairs"])
+    g.add_edges_from((genes[s], peaks[t], {"weight": float(w), "sign": 1})
+                     for s, t, w in zip(src, dst, wts))
+    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in genes + peaks)
+    return adatas, g
+
+
+def build_model(cfg, adatas, graph):
+    from glue_b200 import models
+
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep",
+                                 use_obs_names=True)
+    model = models.PairedSCGLUEModel(adatas, sorted(graph.nodes), latent_dim=cfg["latent_dim"],
+                                     h_dim=cfg["h_dim"], random_seed=cfg["seed"])
+    model.compile()
+    return model
+
+
+def make_loaders(model, adatas, graph, cfg, device_resident):
+    """Datasets + loaders exactly as ``SCGLUEModel.fit`` / ``GLUETrainer.fit`` build them."""
+    from glue_b200.models.data import AnnDataset, GraphDataset
+    from glue_b200.utils import config
+
+    net, trainer = model.net, model.trainer
+    data = AnnDataset([adatas[k] for k in net.keys], [model.modalities[k] for k in net.keys],
+                      mode="train")
+    gds = GraphDataset(graph, model.vertices, neg_samples=cfg["neg_samples"],
+                       weighted_sampling=True, deemphasize_loops=True)
+    if device_resident:
+        data.to_device(net.device)
+        gds.to_device(net.device)
+    graph_batch = math.ceil(gds.size / model.GRAPH_BATCHES)
+    fetches = config.DATALOADER_FETCHES_PER_BATCH
+    data.getitem_size = max(1, round(cfg["batch"] / fetches))
+    gds.getitem_size = max(1, round(graph_batch / fetches))
+    data.prepare_shuffle(num_workers=0, random_seed=cfg["seed"])
+    gds.prepare_shuffle(num_workers=0, random_seed=cfg["seed"])
+    loader = trainer._loaders(data, gds, fetches, fetches, cfg["seed"], True, True, shard=True)
+    return gds, loader, graph_batch
+
+
+class _Engine:
+    class state:
+        epoch = 1
+
+
+# ------------------------------------------------------------------- clock sampling
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------- CPU oracle arm
+def cpu_step_runner(cfg, model, host_batches, gds, threads):
+    """Returns ``run(n) -> seconds`` executing n train steps of the CPU port of the reference."""
+    from glue_b200.num import normalize_edges
+    from oracle import scglue_cpu as oc
+
+    torch.set_num_threads(threads)
+    net = model.net
+    state = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    step_cfg = oc.StepConfig(net.keys, {k: "NB" for k in net.keys}, {k: True for k in net.keys},
+                             {k: 1 for k in net.keys}, paired=True, lam_joint_cross=0.02,
+                             lam_real_cross=0.02, lam_cos=0.02, align_burnin=57)
+    full = (torch.as_tensor(gds.eidx), torch.as_tensor(normalize_edges(gds.eidx, gds.ewt)),
+            torch.as_tensor(gds.esgn))
+    trainer = oc.CpuTrainer(step_cfg, state, full, lr=2e-3)
+    K = len(net.keys)
+
+    def to_batch(data):
+        data = [t.cpu() for t in data]
+        groups = [dict(zip(net.keys, data[i * K:(i + 1) * K])) for i in range(5)]
+        return dict(x=groups[0], xrep=groups[1], xbch=groups[2], xdwt=groups[4], pmsk=data[5 * K],
+                    eidx=data[5 * K + 1], ewt=data[5 * K + 2], esgn=data[5 * K + 3])
+
+    batches = [to_batch(b) for b in host_batches]
+
+    def run(n, offset=0):
+        tic = time.perf_counter()
+        for i in range(n):
+            trainer.train_step(batches[(offset + i) % len(batches)], epoch=1)
+        return time.perf_counter() - tic
+
+    return run
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(name):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(name)
+    return None
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(WORKLOAD)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        return run_reference(args, cfg)
+
+    import __graft_entry__ as entry
+    if local_rank == 0:
+        entry.build()
+    from glue_b200 import dist as gdist
+    from glue_b200 import ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    gdist.init_from_env()
+    if world > 1:
+        torch.distributed.barrier()
+    device = torch.device("cuda", local_rank)
+    warmup = max(args.warmup, 3)
+
+    adatas, graph = make_workload(cfg)
+    model = build_model(cfg, adatas, graph)
+    trainer, net = model.trainer, model.net
+    gds, dev_loader, graph_batch = make_loaders(model, adatas, graph, cfg, device_resident=True)
+    trainer.set_full_graph(gds)
+    trainer.align_burnin = max(math.ceil(8.0 / 2e-3 / (cfg["n_cells"] * 0.9 / cfg["batch"])), 8)  # AUTO rule
+
+    # pools of distinct minibatches: 8 x 27 MB of inputs per pass, i.e. larger than L2
+    pool_n = 8
+    it = iter(dev_loader)
+    dev_pool = [next(it) for _ in range(pool_n)]
+    _, host_loader, _ = make_loaders(model, adatas, graph, cfg, device_resident=False)
+    it = iter(host_loader)
+    host_pool = [[t.pin_memory() for t in next(it)] for _ in range(pool_n)]
+    h2d = sum(t.numel() * t.element_size() for t in host_pool[0])
+    e_mb = int(dev_pool[0][-1].numel())
+
+    def sync():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(device)
+
+    def timed(fn, steps):
+        sync()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(steps):
+            fn(i)
+        stop.record()
+        sync()
+        ms = start.elapsed_time(stop)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # --- device-resident steps -------------------------------------------------------
+    step_dev = lambda i: trainer.train_step(_Engine, dev_pool[i % pool_n])
+    for i in range(warmup):
+        step_dev(i)
+    launches0 = ops.kernel_launches()
+    ops.TIMER.enabled = True
+    ops.TIMER.reset()
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(step_dev, args.steps)
+    ops.TIMER.enabled = False
+    launches = ops.kernel_launches() - launches0
+    ktimes = ops.TIMER.summary()
+    cells = cfg["batch"] * args.steps * world
+    value = cells / (ms * 1e-3)
+
+    # --- end to end: host batches through the reference-facing call -----------------------
+    def step_e2e(i):
+        losses = trainer.train_step(_Engine, host_pool[i % pool_n])
+        return float(losses["vae_loss"])  # D2H read of the step's result
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = cells / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+
+    # --- roofline of the dominant kernel sequence ------------------------------------------
+    B, K, F = cfg["batch"], cfg["latent_dim"], cfg["n_peaks"]
+    dom = f"decoder_fwd_bwd_NB_F{F}_B{B}"
+    alg_bytes = B * F * 4 + 2 * F * K * 4 + 2 * 3 * 1 * F * 4 + 2 * B * K * 4 + 16 * B
+    peak, peak_src = peaks()
+    roof = {"bound": "hbm", "kernel": "fused NB decoder fwd+bwd (ATAC, B=128, F=50000)",
+            "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+            "traffic": traffic_from_profile(dom), "peak_source": peak_src,
+            "algorithmic_bytes": alg_bytes}
+    if dom in ktimes:
+        n_calls, total_ms = ktimes[dom]
+        us = total_ms * 1e3 / n_calls
+        roof.update(achieved=alg_bytes / (us * 1e-6) / 1e9, launch_us=us, calls=n_calls,
+                    share_of_step=total_ms / ms)
+        roof["frac"] = roof["achieved"] / peak
+    kernels = {name: {"calls": n, "us_per_call": t * 1e3 / n, "share_of_step": t / ms}
+               for name, (n, t) in sorted(ktimes.items())}
+
+    # --- CPU baseline (bounded sample of the same workload) --------------------------------
+    cpu = None
+    if not args.skip_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        run = cpu_step_runner(cfg, model, host_pool, gds, cores)
+        run(1)
+        n_cpu = 5
+        secs = run(n_cpu, offset=1)
+        cpu = {"value": cfg["batch"] * n_cpu / secs, "unit": "cells/s", "cores": cores,
+               "kind": "port", "ms_per_step": secs * 1e3 / n_cpu,
+               "sample": f"{n_cpu} train steps (1 warm-up) of the same workload, "
+                         f"torch CPU, {cores} threads"}
+
+    out = {
+        "metric": "train_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["name"], "cells": cfg["n_cells"], "genes": cfg["n_genes"],
+                   "peaks": cfg["n_peaks"], "graph_edges": int(gds.eidx.shape[1]),
+                   "edge_minibatch": e_mb, "batch_per_gpu": cfg["batch"],
+                   "global_batch": cfg["batch"] * world, "latent_dim": K,
+                   "parallelism": f"dp{world}",
+                   "l2": f"inputs cycle through {pool_n} minibatches (8 x 27 MB > 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+
+
+def run_reference(args, cfg):
+    """The reference's CPU path (port pinned against the unmodified reference) on host cores."""
+    from glue_b200.utils import config
+    config.CPU_ONLY = True
+    adatas, graph = make_workload(cfg)
+    model = build_model(cfg, adatas, graph)
+    gds, host_loader, _ = make_loaders(model, adatas, graph, cfg, device_resident=False)
+    it = iter(host_loader)
+    host_pool = [next(it) for _ in range(8)]
+    cores = os.cpu_count() or 1
+    run = cpu_step_runner(cfg, model, host_pool, gds, cores)
+    warmup = max(1, min(args.warmup, 3))
+    steps = max(1, min(args.steps, 40))  # bounded: ~1 s per step on 8+ cores
+    run(warmup)
+    secs = run(steps, offset=warmup)
+    value = cfg["batch"] * steps / secs
+    sample = (f"{steps} train steps ({warmup} warm-up) of the same workload; CPU port of the "
+              f"reference train_step, torch CPU, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "train_cells_per_s", "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": secs * 1e3 / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": cfg["name"], "batch_per_gpu": cfg["batch"]},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    main()

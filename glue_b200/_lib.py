@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     "glue_abi_version",
     "glue_arch",
     "glue_error_string",
+    "glue_kernel_launches",
     "glue_graphconv_csr",
     "glue_csr_build_workspace_bytes",
     "glue_csr_build",
@@ -80,6 +81,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_arch.argtypes = []
     lib.glue_error_string.restype = c_char_p
     lib.glue_error_string.argtypes = [c_int32]
+    lib.glue_kernel_launches.restype = ctypes.c_ulonglong
+    lib.glue_kernel_launches.argtypes = []
 
     lib.glue_graphconv_csr.restype = c_int32
     lib.glue_graphconv_csr.argtypes = [

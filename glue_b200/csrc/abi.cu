@@ -1,5 +1,11 @@
 // Library identification and error decoding for libglue_b200 (sm_100a).
+#include <atomic>
+
 #include "common.cuh"
+
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void glue_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long glue_kernel_launches(void) { return g_launches.load(); }
 
 extern "C" int glue_abi_version(void) { return GLUE_B200_ABI_VERSION; }
 

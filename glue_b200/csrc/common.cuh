@@ -8,8 +8,12 @@
 
 #define GLUE_EPS 1e-7f  // scglue/num.py:12
 
+// Diagnostic only: number of kernels this library has launched in this process.
+extern "C" void glue_count_launch_(void);
+
 #define GLUE_CHECK_LAUNCH()                      \
     do {                                         \
+        glue_count_launch_();                    \
         cudaError_t e__ = cudaPeekAtLastError(); \
         if (e__ != cudaSuccess) return (int)e__; \
     } while (0)

@@ -15,6 +15,49 @@ import torch
 from . import _lib
 from ._lib import FAMILY, DecoderArgs, check, current_stream, ptr, require_cuda
 
+# ------------------------------------------------------------------- profiling
+
+
+class KernelTimer:
+    r"""Optional CUDA-event bracketing of native calls (used by ``bench.py`` to time the
+    dominant kernel sequence *inside* the timed training steps, on the launching stream)."""
+
+    def __init__(self) -> None:
+        self.enabled = False
+        self.records = []  # (name, start_event, end_event)
+
+    def start(self, name: str, device):
+        if not self.enabled:
+            return None
+        ev = (name, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[1].record(torch.cuda.current_stream(device))
+        return ev
+
+    def stop(self, ev, device) -> None:
+        if ev is not None:
+            ev[2].record(torch.cuda.current_stream(device))
+            self.records.append(ev)
+
+    def summary(self):
+        r"""``{name: (n_calls, total_ms)}``; call after ``torch.cuda.synchronize()``."""
+        out = {}
+        for name, a, b in self.records:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+    def reset(self) -> None:
+        self.records = []
+
+
+TIMER = KernelTimer()
+
+
+def kernel_launches() -> int:
+    r"""Kernels launched by ``libglue_b200.so`` in this process so far."""
+    return int(_lib.lib().glue_kernel_launches())
+
+
 # ------------------------------------------------------------------ workspace
 
 
@@ -103,9 +146,11 @@ def csr_for(eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor, vnum: i
 def _spmm(csr_part, inp: torch.Tensor) -> torch.Tensor:
     indptr, col, val = csr_part
     out = torch.empty_like(inp)
+    ev = TIMER.start("graphconv", inp.device)
     check(_lib.lib().glue_graphconv_csr(ptr(indptr), ptr(col), ptr(val), ptr(inp), ptr(out),
                                         inp.shape[0], inp.shape[1], current_stream(inp.device)),
           "graphconv_csr")
+    TIMER.stop(ev, inp.device)
     return out
 
 
@@ -309,7 +354,9 @@ class _DecoderNllFn(torch.autograd.Function):
             gu, gv, gs, gb, gd, gz = call.grad_buffers()
             a = call.args(loss=loss, grad_u=gu, grad_v=gv, grad_scale_lin=gs, grad_bias=gb,
                           grad_disp=gd, grad_zi_logits=gz)
+            ev = TIMER.start(f"decoder_fwd_bwd_{family}_F{call.F}_B{call.B}", call.device)
             check(L.glue_decoder_nll_fwd_bwd(ctypes.byref(a), call.stream()), "decoder_nll_fwd_bwd")
+            TIMER.stop(ev, call.device)
             ctx.grads = (gu, gv, gs, gb, gd, gz)
         else:
             a = call.args(loss=loss)

@@ -39,6 +39,9 @@ int glue_abi_version(void);
 /* "sm_100a" -- the only architecture the library is compiled for. */
 const char *glue_arch(void);
 const char *glue_error_string(int code);
+/* Diagnostic: kernels launched by this library in this process so far (the one piece of
+ * process-wide state; it never influences results). */
+unsigned long long glue_kernel_launches(void);
 
 /* ------------------------------------------------------------------------- *
  * GraphConv  --  replaces scglue/models/nn.py:26-57 (GraphConv.forward) and,
