@@ -290,12 +290,12 @@ def main():
 
     # --- device-resident steps -------------------------------------------------------
     step_dev = lambda i: trainer.train_step(_Engine, dev_pool[i % pool_n])
-    for i in range(warmup):
-        step_dev(i)
-    launches0 = ops.kernel_launches()
-    ops.TIMER.enabled = True
-    ops.TIMER.reset()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:  # sampled from warm-up on (the timed region is short)
+        for i in range(warmup):
+            step_dev(i)
+        launches0 = ops.kernel_launches()
+        ops.TIMER.enabled = True
+        ops.TIMER.reset()
         ms = timed(step_dev, args.steps)
     ops.TIMER.enabled = False
     launches = ops.kernel_launches() - launches0
@@ -306,7 +306,7 @@ def main():
     # --- end to end: host batches through the reference-facing call -----------------------
     def step_e2e(i):
         losses = trainer.train_step(_Engine, host_pool[i % pool_n])
-        return float(losses["vae_loss"])  # D2H read of the step's result
+        return float(losses["vae_loss"].detach())  # D2H read of the step's result
 
     for i in range(3):
         step_e2e(i)

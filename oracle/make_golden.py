@@ -20,6 +20,8 @@ import numpy as np
 import pandas as pd
 import torch
 
+from tests.util import make_graph
+
 from . import refstub, sampling
 from . import scglue_cpu as oc
 
@@ -43,28 +45,9 @@ def _exact(a, b, what):
         raise AssertionError(f"oracle not bit-exact with reference on {what}")
 
 
-def make_graph(rs, n_rna, n_atac, n_extra, n_pairs, neg_sign_frac=0.0):
-    """Random bipartite guidance graph with self-loops, as an nx.Graph plus vertex list."""
-    rna = [f"g{i}" for i in range(n_rna)]
-    atac = [f"p{i}" for i in range(n_atac)]
-    extra = [f"z{i}" for i in range(n_extra)]
-    g = nx.Graph()
-    g.add_nodes_from(rna + atac + extra)
-    for _ in range(n_pairs):
-        a, b = rna[rs.randint(n_rna)], atac[rs.randint(n_atac)]
-        sign = -1 if rs.rand() < neg_sign_frac else 1
-        g.add_edge(a, b, weight=float(rs.uniform(0.05, 1.0)), sign=sign)
-    for e in extra[: n_extra // 2]:
-        g.add_edge(e, rna[rs.randint(n_rna)], weight=float(rs.uniform(0.05, 1.0)), sign=1)
-    for v in g.nodes:
-        g.add_edge(v, v, weight=1.0, sign=1)
-    vertices = sorted(g.nodes)
-    return g, vertices, rna, atac
-
-
 def golden_graph(ref):
-    rs = np.random.RandomState(7)
-    g, vertices, rna, atac = make_graph(rs, 12, 30, 6, 70, neg_sign_frac=0.25)
+    from tests.util import golden_graph as build
+    g, vertices, rna, atac = build()
     ds = ref.models.data.GraphDataset(g, pd.Index(vertices), neg_samples=3,
                                       weighted_sampling=True, deemphasize_loops=True)
     eidx, ewt, esgn = ds.eidx, ds.ewt, ds.esgn

@@ -1,0 +1,185 @@
+"""Host-side data logic: bit-exact negative sampling, pairing masks, loader semantics,
+rank-strided batches (mirrors the reference's tests/models/test_data.py where applicable)."""
+import networkx as nx
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse
+import torch
+
+from glue_b200 import models
+from glue_b200.anndata_lite import AnnData
+from glue_b200.dist import RankStridedBatches
+from glue_b200.models.data import (AnnDataset, ArrayDataset, DataLoader, GraphDataset,
+                                   ParallelDataLoader)
+from glue_b200.utils import config
+
+
+def _graph_from_golden(g):
+    from tests.util import golden_graph
+    graph, vertices, _, _ = golden_graph()
+    assert list(vertices) == list(g["vertices"])
+    return graph
+
+
+def test_graph_dataset_matches_reference_bit_exact(golden):
+    g = golden("graph")
+    ds = GraphDataset(_graph_from_golden(g), pd.Index(g["vertices"]), neg_samples=3)
+    assert np.array_equal(ds.eidx, g["eidx"]) and np.array_equal(ds.ewt, g["ewt"])
+    assert np.array_equal(ds.esgn, g["esgn"])
+    assert np.array_equal(ds.vprob, g["vprob"]) and np.array_equal(ds.eprob, g["eprob"])
+    assert ds.size == int(g["size"])
+    for seed in (0, 5):
+        eidx, ewt, esgn = ds.propose_shuffle(seed)
+        assert np.array_equal(eidx, g[f"samp{seed}_eidx"])
+        assert np.array_equal(ewt, g[f"samp{seed}_ewt"])
+        assert np.array_equal(esgn, g[f"samp{seed}_esgn"])
+    # shuffle n uses seed random_seed + n; background look-ahead does not change the stream
+    for workers in (0, 1):
+        ds.prepare_shuffle(num_workers=workers, random_seed=5)
+        ds.shuffle()
+        assert np.array_equal(ds.samp_eidx.numpy(), g["samp5_eidx"])
+        ds.clean()
+
+
+def test_negative_samples_are_never_true_edges(golden):
+    g = golden("graph")
+    ds = GraphDataset(_graph_from_golden(g), pd.Index(g["vertices"]), neg_samples=5)
+    eidx, ewt, esgn = ds.propose_shuffle(11)
+    true = {(i, j, s) for (i, j), s in zip(ds.eidx.T, ds.esgn)}
+    neg = ewt == 0
+    assert neg.sum() == 5 * (~neg).sum()
+    assert not any((i, j, s) in true for (i, j), s in zip(eidx[:, neg].T, esgn[neg]))
+    assert all((i, j, s) in true for (i, j), s in zip(eidx[:, ~neg].T, esgn[~neg]))
+
+
+def test_graph_dataset_validation():
+    vertices = pd.Index(["a", "b"])
+    for attrs, msg in (({"weight": 1.5, "sign": 1}, "weight"), ({"weight": 0.5, "sign": 2}, "sign")):
+        graph = nx.Graph()
+        graph.add_edge("a", "b", **attrs)
+        with pytest.raises(ValueError, match=msg):
+            GraphDataset(graph, vertices)
+    graph = nx.Graph()
+    graph.add_edge("a", "c", weight=0.5, sign=1)
+    with pytest.raises(ValueError, match="Missing vertices"):
+        GraphDataset(graph, vertices)
+
+
+def test_array_dataset_split_and_shuffle():
+    a, b = np.arange(100).reshape(50, 2), scipy.sparse.random(30, 4, 0.5, format="csr")
+    ds = ArrayDataset(a, b, getitem_size=7)
+    assert len(ds) == 8
+    item = ds[7]
+    assert item[0].shape == (1, 2) and item[1].shape == (1, 4)
+    train, val = ds.random_split([0.8, 0.2], random_state=0)
+    assert train.sizes == [40, 24] and val.sizes == [10, 6]
+    assert set(train.view_idx[0]).isdisjoint(val.view_idx[0])
+    train.prepare_shuffle(num_workers=0, random_seed=3)
+    train.shuffle()
+    assert sorted(train.shuffle_idx[0]) == sorted(train.view_idx[0])
+    with pytest.raises(ValueError):
+        ds.random_split([0.5, 0.6])
+    with pytest.raises(ValueError):
+        ArrayDataset(np.empty((0, 3)))
+
+
+def _paired_adatas():
+    rs = np.random.RandomState(0)
+    shared = [f"s{i}" for i in range(100)]
+    rna_names = shared + [f"r{i}" for i in range(50)]
+    atac_names = shared[::-1] + [f"a{i}" for i in range(20)]
+    rna = AnnData(X=rs.poisson(2, (150, 5)).astype(np.float32), obs=pd.DataFrame(index=rna_names),
+                  var=pd.DataFrame(index=[f"g{i}" for i in range(5)]),
+                  layers={"arange": np.tile(np.arange(150)[:, None], (1, 5)).astype(np.float32)})
+    atac = AnnData(X=scipy.sparse.csr_matrix(rs.poisson(1, (120, 6)).astype(np.float32)),
+                   obs=pd.DataFrame(index=atac_names),
+                   var=pd.DataFrame(index=[f"p{i}" for i in range(6)]),
+                   layers={"arange": scipy.sparse.csr_matrix(
+                       np.tile(np.array([shared.index(n) if n in shared else -1
+                                         for n in atac_names])[:, None] + 0.0, (1, 6)).astype(np.float32))})
+    return rna, atac, shared
+
+
+def test_anndataset_pairing_mask():
+    """Rows that are marked as paired must carry the same cell in every modality
+    (property checked by the reference's tests/models/test_data.py:40-96)."""
+    rna, atac, shared = _paired_adatas()
+    for a in (rna, atac):
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_layer="arange",
+                                 use_obs_names=True)
+    ds = AnnDataset([rna, atac], [rna.uns[config.ANNDATA_KEY], atac.uns[config.ANNDATA_KEY]],
+                    mode="train", getitem_size=16)
+    assert ds.size == 170  # 100 shared + 50 + 20
+    ds.prepare_shuffle(num_workers=0, random_seed=1)
+    ds.shuffle()
+    for i in range(len(ds)):
+        *arrays, pmsk = ds[i]
+        x_rna, x_atac = arrays[0], arrays[1]
+        both = pmsk[:, 0] & pmsk[:, 1]
+        # rna layer holds its own row number (shared cell i is row i); atac holds the shared index
+        assert torch.equal(x_rna[both, 0], x_atac[both, 0])
+        assert pmsk.any(dim=1).all()
+    train, val = ds.random_split([0.9, 0.1], random_state=0)
+    assert train.size + val.size == ds.size
+
+
+def test_anndataset_errors():
+    rna, atac, _ = _paired_adatas()
+    with pytest.raises(ValueError, match="highly variable"):
+        models.configure_dataset(rna, "NB")
+    with pytest.raises(ValueError, match="use_layer"):
+        models.configure_dataset(rna, "NB", use_highly_variable=False, use_layer="nope")
+    with pytest.raises(ValueError, match="use_rep"):
+        models.configure_dataset(rna, "NB", use_highly_variable=False, use_rep="nope")
+    with pytest.raises(ValueError, match="use_batch"):
+        models.configure_dataset(rna, "NB", use_highly_variable=False, use_batch="nope")
+    models.configure_dataset(rna, "NB", use_highly_variable=False)
+    with pytest.raises(ValueError, match="match the number"):
+        AnnDataset([rna, atac], [rna.uns[config.ANNDATA_KEY]])
+    with pytest.raises(ValueError, match="mode"):
+        AnnDataset([rna], [rna.uns[config.ANNDATA_KEY]], mode="xxx")
+
+
+def test_nan_sparse_densify():
+    x = scipy.sparse.csr_matrix(np.array([[0, 2.0, 0], [1.0, 0, 0]], dtype=np.float32))
+    dense = AnnDataset._index_array(x, np.array([1, 0]), nan_sparse=True)
+    assert np.isnan(dense).sum() == 4 and dense[0, 0] == 1.0 and dense[1, 1] == 2.0
+
+
+def test_parallel_loader_cycles_the_short_loader():
+    ds1, ds2 = ArrayDataset(np.arange(40).reshape(20, 2)), ArrayDataset(np.arange(6).reshape(3, 2))
+    for ds in (ds1, ds2):
+        ds.prepare_shuffle(num_workers=0, random_seed=0)
+    pl = ParallelDataLoader(DataLoader(ds1, batch_size=4, shuffle=True),
+                            DataLoader(ds2, batch_size=2, shuffle=True), cycle_flags=[False, True])
+    batches = list(pl)
+    assert len(batches) == 5 and all(len(b) == 2 for b in batches)
+    with pytest.raises(ValueError):
+        ParallelDataLoader(DataLoader(ds1, batch_size=4), cycle_flags=[True, False])
+
+
+def test_explicit_sampler_equals_shuffle_true():
+    """GLUETrainer._loaders builds RandomSampler/BatchSampler by hand; the batch stream must be
+    the one DataLoader(shuffle=True, generator=G) yields (what the reference constructs)."""
+    def stream(explicit):
+        ds = ArrayDataset(np.arange(90).reshape(45, 2), getitem_size=2)
+        ds.prepare_shuffle(num_workers=0, random_seed=4)
+        gen = torch.Generator().manual_seed(4)
+        if explicit:
+            bs = torch.utils.data.BatchSampler(
+                torch.utils.data.RandomSampler(ds, generator=gen), 4, True)
+            dl = DataLoader(ds, reshuffle=True, batch_sampler=bs, generator=gen)
+        else:
+            dl = DataLoader(ds, batch_size=4, shuffle=True, drop_last=True, generator=gen)
+        return [b[0].clone() for _ in range(3) for b in dl]
+    a, b = stream(True), stream(False)
+    assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_rank_strided_batches_partition_the_stream():
+    base = [[i] for i in range(11)]
+    parts = [list(RankStridedBatches(base, r, 4)) for r in range(4)]
+    assert all(len(p) == 2 for p in parts)  # 11 // 4, tail dropped so ranks stay in lock-step
+    flat = sorted(b[0] for p in parts for b in p)
+    assert flat == list(range(8))

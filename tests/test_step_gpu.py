@@ -93,23 +93,14 @@ def test_train_step_matches_reference(native_lib, golden, paired):
         if key in g:
             assert p.grad is not None, name
             assert_close(p.grad, g[key], TOL, f"gradient {name}")
-    # Post-step parameters.  RMSprop's first step is lr * g / (0.1 |g| + 1e-8): entries whose
-    # gradient is rounding noise (e.g. Linear biases in front of BatchNorm, whose true
-    # gradient is zero) get a full-size step in the direction of that noise, in the reference
-    # as much as here, so they are compared only where the reference gradient is significant.
+    from tests.util import assert_post_step_close
     for name, val in net.state_dict().items():
         want = g[f"final__{name}"]
         if not val.dtype.is_floating_point:
             assert np.array_equal(val.cpu().numpy(), want), name
             continue
         gref = g.get(f"dscgrad__{name}") if name.startswith("du.") else g.get(f"gengrad__{name}")
-        got = val.detach().cpu().numpy()
-        if gref is None:  # buffers (BatchNorm running statistics)
-            assert_close(got, want, TOL, f"post-step {name}")
-            continue
-        live = np.abs(gref) > max(1e-6, 1e-3 * np.abs(gref).max())
-        if live.any():
-            assert_close(got[live], want[live], TOL, f"post-step {name}")
+        assert_post_step_close(val.detach().cpu().numpy(), want, gref, TOL, f"post-step {name}")
 
 
 def test_short_fit_runs_and_learns(native_lib):
