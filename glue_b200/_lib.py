@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_nll_fwd",
     "glue_decoder_log_prob",
     "glue_decoder_mean",
+    "glue_tc_selftest",
 )
 
 FAMILY = {"NB": 0, "ZINB": 1, "Normal": 2, "ZILN": 3}
@@ -119,6 +120,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = c_int32
         fn.argtypes = [POINTER(DecoderArgs), c_void_p, c_void_p]
+
+
+    lib.glue_tc_selftest.restype = c_int32
+    lib.glue_tc_selftest.argtypes = [
+        c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+        ctypes.c_uint32, ctypes.c_uint32, POINTER(ctypes.c_uint32), POINTER(ctypes.c_uint32),
+        ctypes.c_uint32, c_void_p, c_void_p]
 
 
 def lib() -> ctypes.CDLL:

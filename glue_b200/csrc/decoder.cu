@@ -20,36 +20,15 @@
 //   pass B  (main)     : L, G-terms, c_i, A1, A2     reads x ONCE, v, u
 //   pass C  (softmax)  : the  -p_ij c_i  terms       reads v, u (no x)
 //   Normal family: only pass B (dL/da_ij = G_ij).
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "decoder_common.cuh"
 
 namespace glue {
 
 constexpr int TF = 128;  // features per tile == threads per CTA (thread <-> feature)
 constexpr int RC = 32;   // rows per chunk (x tile, G/P tiles)
 constexpr int RB = 128;  // rows whose u is resident in shared memory
-
-enum Mode { MODE_LOSS = 0, MODE_GRAD = 1, MODE_LOGP = 2, MODE_MEAN = 3 };
-
-struct DecWs {  // workspace carve-up (device pointers)
-    float* pmax;     // [ncta][B]
-    float* psum;     // [ncta][B]
-    float* lse;      // [B]
-    float* cpart;    // [ncta][B]
-    float* c;        // [B]
-    float* apart;    // [ncta][B][2][KP]
-    float* losspart; // [ncta]
-    int* badpart;    // [ncta]  number of NaN observations skipped
-    float* rescale;  // [1]  (B*F)/count when NaNs were skipped, else 1
-};
-
-struct DecParams {
-    glue_decoder_args a;
-    DecWs ws;
-    int ncta;
-    int feat_per_cta;
-    float w0;  // uniform weight -1/(B*F) when wmat == NULL
-    float* out;  // MODE_LOGP / MODE_MEAN
-};
 
 template <int KP>
 struct __align__(16) DecSmem {
@@ -67,116 +46,6 @@ struct __align__(16) DecSmem {
     float cw2[RC][4];
 };
 
-__host__ __device__ inline bool is_nb_family(int fam) { return fam == GLUE_NB || fam == GLUE_ZINB; }
-
-// Per-(batch row, feature) parameters, reloaded when the (sorted) batch index changes.
-struct FeatParams {
-    float s, sg;       // softplus(scale_lin), sigmoid(scale_lin)
-    float bias;
-    float disp;        // log_theta | std_lin
-    float th;          // exp(log_theta)          (NB family)
-    float std_inv, log_std, sg_std;  // Normal family
-    float zi, spz, sgz, ezi;          // zero inflation
-};
-
-template <int FAM>
-__device__ __forceinline__ FeatParams load_params(const glue_decoder_args& a, int bi, int j, bool jok) {
-    FeatParams p;
-    const int64_t off = (int64_t)bi * a.F + j;
-    const float sl = jok ? a.scale_lin[off] : 0.f;
-    p.s = softplusf(sl);
-    p.sg = sigmoidf(sl);
-    p.bias = jok ? a.bias[off] : 0.f;
-    p.disp = jok ? a.disp[off] : 0.f;
-    p.th = 1.f, p.std_inv = 1.f, p.log_std = 0.f, p.sg_std = 0.f;
-    if (FAM == GLUE_NB || FAM == GLUE_ZINB) {
-        p.th = expf(p.disp);
-    } else {
-        const float sd = softplusf(p.disp) + GLUE_EPS;
-        p.std_inv = 1.f / sd;
-        p.log_std = logf(sd);
-        p.sg_std = sigmoidf(p.disp);
-    }
-    p.zi = 0.f, p.spz = 0.f, p.sgz = 0.f, p.ezi = 0.f;
-    if (FAM == GLUE_ZINB || FAM == GLUE_ZILN) {
-        p.zi = jok ? a.zi_logits[off] : 0.f;
-        p.spz = softplusf(p.zi);
-        p.sgz = sigmoidf(p.zi);
-        p.ezi = expf(p.zi);
-    }
-    return p;
-}
-
-struct ElemOut {
-    float lp;    // log_prob
-    float g;     // d lp / d logp (NB family) or d lp / d loc (Normal family)
-    float gd;    // d lp / d disp
-    float gz;    // d lp / d zi_logits
-    float prob;  // softmax probability (NB family)
-    float mean;  // distribution mean
-};
-
-template <int FAM>
-__device__ __forceinline__ ElemOut element(const FeatParams& p, float a, float x, float lse, float l) {
-    ElemOut o;
-    o.gz = 0.f;
-    o.prob = 0.f;
-    if (FAM == GLUE_NB || FAM == GLUE_ZINB) {
-        const float logp = a - lse;
-        const float pr = expf(logp);
-        const float mu = pr * l;
-        const float m = mu + GLUE_EPS;
-        const float Lm = logf(m), Lt = logf(m + p.th);
-        float lg, dg;
-        nb_gamma_terms(x, p.th, lg, dg);
-        const float lp = p.th * (p.disp - Lt) + x * (Lm - Lt) + lg;
-        const float sig = m / (m + p.th);
-        const float d = x - (x + p.th) * sig;
-        const float tl = p.th * ((p.disp - Lt) + dg) - d;
-        float wnb = 1.f;
-        o.lp = lp;
-        if (FAM == GLUE_ZINB) {
-            if (fabsf(x) < GLUE_EPS) {
-                const float e1 = expf(lp);
-                const float E = e1 + p.ezi + GLUE_EPS;
-                o.lp = logf(E) - p.spz;
-                wnb = e1 / E;
-                o.gz = p.ezi / E - p.sgz;
-            } else {
-                o.lp = lp - p.spz;
-                o.gz = -p.sgz;
-            }
-        }
-        o.g = wnb * d * (mu / m);
-        o.gd = wnb * tl;
-        o.prob = pr;
-        o.mean = m;
-    } else {
-        if (FAM == GLUE_ZILN && fabsf(x) < GLUE_EPS) {
-            o.lp = p.zi - p.spz;
-            o.g = 0.f;
-            o.gd = 0.f;
-            o.gz = 1.f - p.sgz;
-        } else {
-            const float y = FAM == GLUE_ZILN ? logf(x) : x;
-            const float z = (y - a) * p.std_inv;
-            o.lp = -0.5f * z * z - p.log_std - 0.91893853320467274178f;
-            o.g = z * p.std_inv;
-            o.gd = (z * z - 1.f) * p.std_inv * p.sg_std;
-            if (FAM == GLUE_ZILN) {
-                o.lp -= y + p.spz;
-                o.gz = -p.sgz;
-            }
-        }
-        if (FAM == GLUE_ZILN) {
-            const float sd = 1.f / p.std_inv;
-            o.mean = expf(a + 0.5f * sd * sd);
-        } else {
-            o.mean = a;
-        }
-    }
-    return o;
-}
 
 // ---- staging helpers -------------------------------------------------------
 template <int KP>
@@ -310,23 +179,6 @@ __global__ void __launch_bounds__(TF, 1) dec_rowstats_kernel(DecParams p) {
             }
         }
     }
-}
-
-// one warp per row: lse_i = log sum_cta psum * exp(pmax - M) + M
-__global__ void dec_lse_kernel(DecWs ws, int ncta, int B) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= B) return;
-    float m = -INFINITY;
-    for (int c = lane; c < ncta; c += 32) m = fmaxf(m, ws.pmax[(int64_t)c * B + row]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int c = lane; c < ncta; c += 32) {
-        const float pm = ws.pmax[(int64_t)c * B + row];
-        if (pm > -INFINITY) s += ws.psum[(int64_t)c * B + row] * expf(pm - m);
-    }
-    s = warp_sum(s);
-    if (lane == 0) ws.lse[row] = m + logf(s);
 }
 
 // ---- pass B: main ----------------------------------------------------------
@@ -633,27 +485,6 @@ __global__ void __launch_bounds__(TF, 1) dec_softmax_bwd_kernel(DecParams p) {
     }
 }
 
-// ---- only does work when NaN observations were skipped (nanmean denominator) --
-__global__ void dec_rescale_kernel(DecParams p) {
-    const float ratio = p.ws.rescale[0];
-    if (ratio == 1.f) return;
-    const glue_decoder_args& a = p.a;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    if (a.grad_u)
-        for (int64_t i = tid; i < (int64_t)a.B * a.K; i += nth) a.grad_u[i] *= ratio;
-    if (a.grad_v)
-        for (int64_t i = tid; i < (int64_t)a.F * a.K; i += nth) {
-            const int64_t jj = i / a.K, k = i - jj * a.K;
-            const int64_t vr = a.vidx ? a.vidx[jj] : jj;
-            a.grad_v[vr * a.K + k] *= ratio;
-        }
-    float* tabs[4] = {a.grad_scale_lin, a.grad_bias, a.grad_disp, a.grad_zi_logits};
-    for (int q = 0; q < 4; ++q)
-        if (tabs[q])
-            for (int64_t i = tid; i < (int64_t)a.n_batches * a.F; i += nth) tabs[q][i] *= ratio;
-}
-
 // ======================================================================= host
 static int pick_kp(int K) {
     if (K <= 16) return 16;
@@ -784,11 +615,23 @@ static int run(const glue_decoder_args* args, int mode, float* out, cudaStream_t
     return 0;
 }
 
+// GLUE_B200_DECODER=v1 pins the CUDA-core kernels (A/B comparisons, tests of both paths)
+static bool force_v1() {
+    const char* e = getenv("GLUE_B200_DECODER");
+    return e && e[0] == 'v' && e[1] == '1';
+}
+
 static int dispatch(const glue_decoder_args* args, int mode, float* out, void* stream) {
     const int rc = validate(args, mode != MODE_MEAN);
     if (rc) return rc;
     if ((mode == MODE_LOGP || mode == MODE_MEAN) && !out) return GLUE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!force_v1() && tc_eligible(*args, mode)) {
+        DecParams p;
+        p.a = *args;
+        p.out = out;
+        return tc_run(p, mode, st);
+    }
     switch (pick_kp(args->K)) {
         case 16: return run<16>(args, mode, out, st);
         case 52: return run<52>(args, mode, out, st);
@@ -806,7 +649,9 @@ extern "C" size_t glue_decoder_workspace_bytes(int32_t family, int32_t B, int32_
     if (B <= 0 || F <= 0 || KP == 0) return 0;
     int ncta, per;
     glue::plan(a, ncta, per);
-    return glue::ws_layout(a, ncta, KP, nullptr, nullptr);
+    const size_t v1 = glue::ws_layout(a, ncta, KP, nullptr, nullptr);
+    const size_t v2 = glue::tc_workspace_bytes(a);
+    return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int glue_decoder_nll_fwd_bwd(const glue_decoder_args* args, void* stream) {

@@ -1,0 +1,170 @@
+// Blackwell (sm_100a) tensor-core plumbing used by the fused decoder: mbarrier, TMEM
+// allocation, tcgen05.mma / .ld / .commit wrappers, UMMA shared-memory descriptors and the
+// bf16 hi/lo operand staging into the 128-byte-swizzled canonical layouts.
+//
+// Operand tiles are [rows][64 bf16] = [rows][128 B] with the 16-byte chunks of every row
+// XOR-swizzled by (row & 7) (UMMA SWIZZLE_128B, 8-row x 128 B atoms, 1024 B aligned).  The same
+// bytes serve as a K-major operand (rows = M/N index, the 128 B = 64 K elements) and as an
+// MN-major operand (rows = K index, the 128 B = 64 M/N elements); only the descriptor differs.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace glue {
+namespace tc {
+
+constexpr uint32_t ROW_BYTES = 128;             // 64 bf16
+constexpr uint32_t OP_BYTES = 128 * ROW_BYTES;  // one [128 x 64] bf16 operand component: 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+        if (it > (1u << 24)) __trap();
+}
+
+// ---- fences --------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- TMEM ----------------------------------------------------------------------------------
+// One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread i of the warp gets TMEM lane (lane_base + i).
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr)
+        : "memory");
+}
+
+// ---- UMMA descriptors ------------------------------------------------------------------------
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in
+// [46,48), layout type SWIZZLE_128B (2) in [61,64).
+__host__ __device__ constexpr uint64_t smem_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint64_t base, uint32_t smem_addr) {
+    return base | (uint64_t)((smem_addr >> 4) & 0x3FFF);
+}
+// Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation
+// (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a/b_format BF16 = 1 @ [7,10) / [10,13),
+// a_major @ 15, b_major @ 16 (0 = K-major, 1 = MN-major), N >> 3 @ [17,23), M >> 4 @ [24,29).
+__host__ __device__ constexpr uint32_t instr_desc_bf16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once all tcgen05.mma issued so far by this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- bf16 hi/lo split --------------------------------------------------------------------------
+// x ~ hi + lo with |x - hi - lo| <= 2^-18 |x|; three products hi*hi + hi*lo + lo*hi reproduce
+// the fp32 product to ~2^-17.
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x (low 16 bits) = x0
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float r0 = x0 - __uint_as_float(hb << 16);
+    const float r1 = x1 - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    hi = hb;
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// byte offset of 16-byte chunk `ch` (0..7) of row `r` inside a [rows][128 B] swizzled tile
+__device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t ch) { return r * ROW_BYTES + ((ch ^ (r & 7u)) << 4); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Stage one fp32 row (K valid entries, K even, 8-byte aligned; src == nullptr -> zeros) as row
+// `r` of the hi and lo tiles.
+__device__ __forceinline__ void stage_row(uint32_t hi_base, uint32_t lo_base, uint32_t r, const float* __restrict__ src,
+                                          int K) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = ch * 8 + q * 2;
+            float2 val = make_float2(0.f, 0.f);
+            if (src != nullptr && k < K) val = __ldg(reinterpret_cast<const float2*>(src + k));
+            split2(val.x, val.y, h[q], l[q]);
+        }
+        const uint32_t off = swz(r, ch);
+        st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
+        st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
+    }
+}
+
+}  // namespace tc
+}  // namespace glue

@@ -161,6 +161,21 @@ int glue_decoder_nll_fwd(const glue_decoder_args *args, void *stream);
 int glue_decoder_log_prob(const glue_decoder_args *args, float *out, void *stream);
 int glue_decoder_mean(const glue_decoder_args *args, float *out, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
+ * M = 128) steps on caller-built shared-memory operand images and return the
+ * accumulator tile out[128][N].  a_img / b_img are device buffers copied
+ * verbatim into 1024-byte aligned shared memory; a_desc_base / b_desc_base are
+ * UMMA shared-memory descriptors without the start address; a_off / b_off are
+ * HOST arrays of nk start-address byte offsets.  tests/test_tc_gpu.py uses it to
+ * pin the operand layouts (K-major / MN-major, 128-byte swizzle) the fused
+ * decoder relies on against a plain matrix product.
+ * ------------------------------------------------------------------------- */
+int glue_tc_selftest(const void *a_img, uint32_t a_bytes, const void *b_img, uint32_t b_bytes,
+                     uint64_t a_desc_base, uint64_t b_desc_base, uint32_t idesc, uint32_t nk,
+                     const uint32_t *a_off, const uint32_t *b_off, uint32_t N, float *out,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif
