@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_log_prob",
     "glue_decoder_mean",
     "glue_tc_selftest",
+    "glue_tc_set_trace",
 )
 
 FAMILY = {"NB": 0, "ZINB": 1, "Normal": 2, "ZILN": 3}
@@ -127,6 +128,10 @@ def _declare(lib: ctypes.CDLL) -> None:
         c_void_p, ctypes.c_uint32, c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
         ctypes.c_uint32, ctypes.c_uint32, POINTER(ctypes.c_uint32), POINTER(ctypes.c_uint32),
         ctypes.c_uint32, c_void_p, c_void_p]
+
+
+    lib.glue_tc_set_trace.restype = None
+    lib.glue_tc_set_trace.argtypes = [c_void_p]
 
 
 def lib() -> ctypes.CDLL:

@@ -78,38 +78,78 @@ struct ElemOut {
     float mean;  // distribution mean
 };
 
-template <int FAM>
+// FAST selects the hardware approximations (ex2 / lg2 / rcp based, ~2^-21 relative error) used
+// by the tensor-core path; the CUDA-core path keeps the libdevice versions.
+template <bool FAST>
+__device__ __forceinline__ float exf(float x) { return FAST ? __expf(x) : expf(x); }
+template <bool FAST>
+__device__ __forceinline__ float lgf(float x) { return FAST ? __logf(x) : logf(x); }
+template <bool FAST>
+__device__ __forceinline__ float dvf(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+
+// rare path of nb_gamma_terms (non-integer or large counts), kept out of line
+static __device__ __noinline__ void nb_gamma_terms_slow(float x, float theta, float* lg, float* dg) {
+    *lg = lgammaf(theta + x) - lgammaf(theta) - lgammaf(1.f + x);
+    *dg = digammaf(theta + x) - digammaf(theta);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void nb_gamma_terms_t(float x, float theta, float& lg, float& dg) {
+    if (!FAST) {
+        nb_gamma_terms(x, theta, lg, dg);
+        return;
+    }
+    lg = 0.f, dg = 0.f;
+    if (x == 0.f) return;
+    if (x <= 12.f && x == floorf(x)) {
+        float prod = 1.f, h = 0.f, quot = 1.f;
+        const int n = (int)x;
+#pragma unroll 1
+        for (int m = 0; m < n; ++m) {
+            const float t = theta + (float)m;
+            prod *= t;
+            quot *= (float)(m + 1);
+            h += __fdividef(1.f, t);
+        }
+        lg = __logf(prod) - __logf(quot);
+        dg = h;
+        return;
+    }
+    nb_gamma_terms_slow(x, theta, &lg, &dg);
+}
+
+template <int FAM, bool FAST = false>
 __device__ __forceinline__ ElemOut element(const FeatParams& p, float a, float x, float lse, float l) {
     ElemOut o;
     o.gz = 0.f;
     o.prob = 0.f;
     if (FAM == GLUE_NB || FAM == GLUE_ZINB) {
         const float logp = a - lse;
-        const float pr = expf(logp);
+        const float pr = exf<FAST>(logp);
         const float mu = pr * l;
         const float m = mu + GLUE_EPS;
-        const float Lm = logf(m), Lt = logf(m + p.th);
+        const float Lm = lgf<FAST>(m), Lt = lgf<FAST>(m + p.th);
         float lg, dg;
-        nb_gamma_terms(x, p.th, lg, dg);
+        nb_gamma_terms_t<FAST>(x, p.th, lg, dg);
         const float lp = p.th * (p.disp - Lt) + x * (Lm - Lt) + lg;
-        const float sig = m / (m + p.th);
+        const float sig = dvf<FAST>(m, m + p.th);
         const float d = x - (x + p.th) * sig;
         const float tl = p.th * ((p.disp - Lt) + dg) - d;
         float wnb = 1.f;
         o.lp = lp;
         if (FAM == GLUE_ZINB) {
             if (fabsf(x) < GLUE_EPS) {
-                const float e1 = expf(lp);
+                const float e1 = exf<FAST>(lp);
                 const float E = e1 + p.ezi + GLUE_EPS;
-                o.lp = logf(E) - p.spz;
-                wnb = e1 / E;
-                o.gz = p.ezi / E - p.sgz;
+                o.lp = lgf<FAST>(E) - p.spz;
+                wnb = dvf<FAST>(e1, E);
+                o.gz = dvf<FAST>(p.ezi, E) - p.sgz;
             } else {
                 o.lp = lp - p.spz;
                 o.gz = -p.sgz;
             }
         }
-        o.g = wnb * d * (mu / m);
+        o.g = wnb * d * dvf<FAST>(mu, m);
         o.gd = wnb * tl;
         o.prob = pr;
         o.mean = m;
@@ -120,7 +160,7 @@ __device__ __forceinline__ ElemOut element(const FeatParams& p, float a, float x
             o.gd = 0.f;
             o.gz = 1.f - p.sgz;
         } else {
-            const float y = FAM == GLUE_ZILN ? logf(x) : x;
+            const float y = FAM == GLUE_ZILN ? lgf<FAST>(x) : x;
             const float z = (y - a) * p.std_inv;
             o.lp = -0.5f * z * z - p.log_std - 0.91893853320467274178f;
             o.g = z * p.std_inv;
@@ -132,7 +172,7 @@ __device__ __forceinline__ ElemOut element(const FeatParams& p, float a, float x
         }
         if (FAM == GLUE_ZILN) {
             const float sd = 1.f / p.std_inv;
-            o.mean = expf(a + 0.5f * sd * sd);
+            o.mean = exf<FAST>(a + 0.5f * sd * sd);
         } else {
             o.mean = a;
         }

@@ -18,9 +18,10 @@
 //   * the soft-max row statistics pass uses the transposed tile D[cell, feature] = U V^T so that
 //     max / sum-exp are per-thread reductions over TMEM columns.
 //
-// Warp roles (384 threads, 1 CTA / SM): warps 0-7 epilogue (warp w owns TMEM lanes
-// 32 (w & 3) .. +31 and one half of the cell columns), warp 8 issues tcgen05.mma (one lane),
-// warps 9-11 stage the v tiles (double buffered).  Pipelines are mbarrier based.
+// Warp roles (416 threads, 1 CTA / SM): warps 0-7 epilogue (warp w owns TMEM lanes
+// 32 (w & 3) .. +31 and one half of the cell columns), warps 8-11 stage the v tiles (double
+// buffered, one thread per row) and prefetch the step's observations into L2, warp 12 issues
+// tcgen05.mma (one lane).  Pipelines are mbarrier based.
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
 
@@ -29,12 +30,12 @@ using namespace tc;
 
 namespace {
 
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 416;
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_WARPS = 8;
-constexpr int MMA_WARP = 8;
-constexpr int PROD_T0 = 288;
-constexpr int PROD_THREADS = 96;
+constexpr int PROD_T0 = 256;  // warps 8-11: one producer thread per operand row
+constexpr int PROD_THREADS = 128;
+constexpr int MMA_WARP = 12;
 constexpr int NB_MAX = 24;  // parameter rows the row-statistics table holds per v stage
 
 constexpr uint32_t COL_ACC = 0;    // logits accumulators: 2 x 128 columns
@@ -49,6 +50,26 @@ constexpr uint64_t DESC_MN_X = smem_desc_base(16384, 1024);   // MN-major X: two
 constexpr uint32_t IDESC_FWD = instr_desc_bf16(128, 128, 0, 0);
 constexpr uint32_t IDESC_D1 = instr_desc_bf16(128, 64, 0, 1);
 constexpr uint32_t IDESC_D2 = instr_desc_bf16(128, 64, 1, 1);
+
+constexpr float LOG2EF = 1.4426950408889634074f;
+constexpr float LN2F = 0.69314718055994530942f;
+
+// hardware approximations (flush-to-zero forms: one MUFU each)
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct Bars {
     uint64_t v_full[2], v_empty[2], acc_full[2], acc_empty[2], x_full, x_empty, d1_full[2], d1_empty[2], d2_full;
@@ -83,12 +104,14 @@ struct TcParams {
     int ntiles;
     int cell0, ncell;  // cell block [cell0, cell0 + ncell) of the (sorted) minibatch, ncell <= 128
     int acc;           // outputs accumulate (a previous cell block already wrote them)
+    long long* trace;  // optional: clock64 stamps of CTA 0, [kernel 0..2][tile < 8][event < 16]
 };
 
-template <class T>
-__device__ __forceinline__ T& carve(uint8_t* raw) {
-    return *reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-}
+#define TC_TRACE(kern, it, ev)                                                              \
+    do {                                                                                    \
+        if (P.trace != nullptr && blockIdx.x == 0 && (it) < 8)                              \
+            P.trace[((kern) * 8 + (it)) * 16 + (ev)] = clock64();                           \
+    } while (0)
 
 __device__ __forceinline__ int orig_row(const glue_decoder_args& a, int pos) {
     return a.row_order ? a.row_order[pos] : pos;
@@ -124,12 +147,14 @@ __device__ __forceinline__ void issue_logits(uint32_t tmem_acc, const uint8_t* a
 // pass A: soft-max row statistics.  D[cell, feature] = U V^T; thread <-> cell.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    SmemStats& S = carve<SmemStats>(smem_raw);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemStats& S = *reinterpret_cast<SmemStats*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzled operand tiles need 1024 B alignment
     const glue_decoder_args& a = P.p.a;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int ntl = (P.ntiles - cta + ncta - 1) / ncta;
+    if (t == 0) TC_TRACE(0, 7, 2);
 
     if (t == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -152,13 +177,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    if (t == 0) TC_TRACE(0, 7, 0);
 
-    if (warp > MMA_WARP) {
+    if (warp >= PROD_T0 / 32 && warp < MMA_WARP) {
         const int pt = t - PROD_T0;
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1, f0 = (cta + it * ncta) * 128;
             mbar_wait(&S.bars.v_empty[s], ((it >> 1) & 1) ^ 1);
+            if (pt == 0) TC_TRACE(0, it, 0);
             produce_v_rows(a, S.v_hi[s], S.v_lo[s], f0, pt);
+            if (pt == 0) TC_TRACE(0, it, 12);
             for (int r = pt; r < 128; r += PROD_THREADS) {
                 const int j = f0 + r;
                 for (int b = 0; b < a.n_batches; ++b) {
@@ -172,6 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
             }
             fence_proxy_async();
             mbar_arrive(&S.bars.v_full[s]);
+            if (pt == 0) TC_TRACE(0, it, 1);
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -184,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
                 umma_commit(&S.bars.acc_full[s]);
             }
         }
-    } else {
+    } else if (warp < EPI_WARPS) {
         const int q = warp & 3, h = warp >> 2;
         const int cell = 32 * q + lane;
         const int my_b = S.bidx[cell];
@@ -194,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
             const int nvalid = min(128, a.F - f0);
             mbar_wait(&S.bars.acc_full[s], (it >> 1) & 1);
             tc_fence_after();
+            if (t == 0) TC_TRACE(0, it, 6);
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int c0 = 64 * h + 32 * cc;
@@ -221,6 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
                     }
                 }
             }
+            if (t == 0) TC_TRACE(0, it, 8);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -236,17 +267,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
     }
     tc_fence_before();
     __syncthreads();
+    if (t == 0) TC_TRACE(0, 7, 1);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass B (PHASE 0: likelihood + all G terms) and pass C (PHASE 1: the -p_ij c_i soft-max terms).
-// D[feature, cell] = V U^T; thread <-> feature.
+// D[feature, cell] = V U^T; thread <-> feature.  NB1: a single parameter row (n_batches == 1).
 // ---------------------------------------------------------------------------------------------
-template <int FAM, int PHASE, bool GRAD>
+template <int FAM, int PHASE, bool GRAD, bool NB1>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    SmemMain& S = carve<SmemMain>(smem_raw);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemMain& S = *reinterpret_cast<SmemMain*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzled operand tiles need 1024 B alignment
     const glue_decoder_args& a = P.p.a;
     constexpr bool NBF = (FAM == GLUE_NB || FAM == GLUE_ZINB);
     constexpr bool ZI = (FAM == GLUE_ZINB || FAM == GLUE_ZILN);
@@ -254,6 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int ntl = (P.ntiles - cta + ncta - 1) / ncta;
     const int ncell = P.ncell;
+    if (t == 0) TC_TRACE(1 + PHASE, 7, 2);
 
     if (t == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -278,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         S.bidx[t] = (ok && a.b) ? (int)a.b[orig] : 0;
         S.xoff[t] = (long long)orig * a.F;
         S.l[t] = (ok && a.l) ? a.l[orig] : 1.f;
-        S.lse[t] = (ok && NBF) ? P.p.ws.lse[pos] : 0.f;
+        S.lse[t] = (ok && NBF) ? P.p.ws.lse[pos] * LOG2EF : 0.f;  // base 2
         S.c[t] = (ok && PHASE == 1) ? P.p.ws.c[pos] : 0.f;
         S.c_acc[t] = 0.f;
     }
@@ -291,16 +325,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    if (t == 0) TC_TRACE(1 + PHASE, 7, 0);
 
-    if (warp > MMA_WARP) {
-        // ===== v tile producers =====
+    if (warp >= PROD_T0 / 32 && warp < MMA_WARP) {
+        // ===== v tile producers (one thread per row); x tile of the same step -> L2 =====
         const int pt = t - PROD_T0;
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1, f0 = (cta + it * ncta) * 128;
+            if (PHASE == 0 && pt < ncell) {
+                const float* px = a.x + S.xoff[pt] + f0;
+                const int nvalid = min(128, a.F - f0);
+                for (int o = 0; o < nvalid; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(px + nvalid - 1));
+            }
             mbar_wait(&S.bars.v_empty[s], ((it >> 1) & 1) ^ 1);
+            if (pt == 0) TC_TRACE(1 + PHASE, it, 0);
             produce_v_rows(a, S.v_hi[s], S.v_lo[s], f0, pt);
             fence_proxy_async();
             mbar_arrive(&S.bars.v_full[s]);
+            if (pt == 0) TC_TRACE(1 + PHASE, it, 1);
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
@@ -313,6 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 issue_logits(tmem_base + COL_ACC + s * 128, S.v_hi[s], S.v_lo[s], S.u_hi, S.u_lo);
                 umma_commit(&S.bars.acc_full[s]);
                 if (!GRAD) umma_commit(&S.bars.v_empty[s]);
+                TC_TRACE(1 + PHASE, it, 2);
             };
             issue_fwd(0);
             const uint32_t nks1 = (uint32_t)(ncell + 15) >> 4;  // K steps over cells
@@ -321,6 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 if (GRAD) {
                     const int s = it & 1;
                     mbar_wait(&S.bars.x_full, it & 1);
+                    TC_TRACE(1 + PHASE, it, 3);
                     mbar_wait(&S.bars.d1_empty[s], ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t xh = smem_u32(S.x_hi), xl = smem_u32(S.x_lo);
@@ -350,19 +395,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                                           smem_desc(DESC_MN1, bs[c] + ks * 2048), IDESC_D2, (it | c | ks) ? 1u : 0u);
                         umma_commit(&S.bars.x_empty);
                         umma_commit(&S.bars.v_empty[s]);
+                        TC_TRACE(1 + PHASE, it, 4);
                     }
                 }
             }
             if (GRAD) umma_commit(&S.bars.d2_full);
         }
-    } else {
+    } else if (warp < EPI_WARPS) {
         // ===== epilogue =====
         const int q = warp & 3, h = warp >> 2;
         const int frow = 32 * q + lane;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        const int nch = (ncell + 31) >> 5;
-        const int ch_begin = h == 0 ? 0 : (nch + 1) / 2;
-        const int ch_end = h == 0 ? (nch + 1) / 2 : nch;
+        // groups of 8 cells (= one 16-byte chunk of a coefficient-tile row); the two threads that
+        // share a feature split the groups in two contiguous halves
+        const int ngrp = (ncell + 7) >> 3;
+        const int g_begin = h == 0 ? 0 : (ngrp + 1) / 2;
+        const int g_end = h == 0 ? (ngrp + 1) / 2 : ngrp;
         const bool add_v = (PHASE == 1) || P.acc;
         float loss_acc = 0.f;
         int bad_acc = 0;
@@ -380,19 +428,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             if (lane == 0) mbar_arrive(&S.bars.d1_empty[s]);
             if (j < a.F && a.grad_v) {
                 const int64_t vr = a.vidx ? a.vidx[j] : (int64_t)j;
-                float* dst = a.grad_v + vr * a.K + 32 * h;
+                float2* dst = reinterpret_cast<float2*>(a.grad_v + vr * a.K + 32 * h);
+                float2 old[16];
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    if (32 * h + 2 * k2 < a.K) {
-                        float2 val = make_float2(__uint_as_float(r[2 * k2]), __uint_as_float(r[2 * k2 + 1]));
-                        float2* d2p = reinterpret_cast<float2*>(dst + 2 * k2);
-                        if (add_v) {
-                            const float2 old = *d2p;
-                            val.x += old.x, val.y += old.y;
-                        }
-                        *d2p = val;
-                    }
+                for (int k2 = 0; k2 < 16; ++k2) {  // every load before the first store
+                    old[k2] = make_float2(0.f, 0.f);
+                    if (add_v && 32 * h + 2 * k2 < a.K) old[k2] = dst[k2];
                 }
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2)
+                    if (32 * h + 2 * k2 < a.K)
+                        dst[k2] = make_float2(__uint_as_float(r[2 * k2]) + old[k2].x,
+                                              __uint_as_float(r[2 * k2 + 1]) + old[k2].y);
             }
         };
 
@@ -410,12 +457,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             int64_t pend_off = 0;
             float pend_b = 0.f, pend_s = 0.f, pend_d = 0.f, pend_z = 0.f;
             auto write_param = [&](int64_t off, float vb, float vs, float vd, float vz, bool add) {
-                if (a.grad_bias) a.grad_bias[off] = add ? a.grad_bias[off] + vb : vb;
-                if (a.grad_scale_lin) a.grad_scale_lin[off] = add ? a.grad_scale_lin[off] + vs : vs;
-                if (PHASE == 0) {
-                    if (a.grad_disp) a.grad_disp[off] = add ? a.grad_disp[off] + vd : vd;
-                    if (ZI && a.grad_zi_logits) a.grad_zi_logits[off] = add ? a.grad_zi_logits[off] + vz : vz;
+                const bool wd = PHASE == 0 && a.grad_disp, wz = PHASE == 0 && ZI && a.grad_zi_logits;
+                float ob = 0.f, os = 0.f, od = 0.f, oz = 0.f;
+                if (add) {  // every load before the first store
+                    if (a.grad_bias) ob = a.grad_bias[off];
+                    if (a.grad_scale_lin) os = a.grad_scale_lin[off];
+                    if (wd) od = a.grad_disp[off];
+                    if (wz) oz = a.grad_zi_logits[off];
                 }
+                if (a.grad_bias) a.grad_bias[off] = ob + vb;
+                if (a.grad_scale_lin) a.grad_scale_lin[off] = os + vs;
+                if (wd) a.grad_disp[off] = od + vd;
+                if (wz) a.grad_zi_logits[off] = oz + vz;
             };
             auto flush = [&]() {
                 if (GRAD && cur_b >= 0 && jok) {
@@ -424,55 +477,172 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                     if (h == 1 && !pend) {
                         pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
                     } else {
-                        write_param(off, gb, vs, gd, gz, (PHASE == 1) || P.acc || a.n_batches > 1 || h == 1);
+                        write_param(off, gb, vs, gd, gz, (PHASE == 1) || P.acc || !NB1 || h == 1);
                     }
                 }
                 gb = gs = gd = gz = 0.f;
             };
+            float s2 = 0.f, b2 = 0.f, lg1 = 0.f, dg1 = 0.f, lg2 = 0.f, dg2 = 0.f;
+            if (NB1) {
+                fp = load_params<FAM>(a, 0, j, jok);
+                cur_b = 0;
+                s2 = fp.s * LOG2EF, b2 = fp.bias * LOG2EF;  // logits in base 2
+                if (NBF && PHASE == 0) {  // log-gamma / digamma differences for counts 1 and 2
+                    const float ti = 1.f / fp.th;
+                    lg1 = fp.disp, dg1 = ti;
+                    lg2 = logf(fp.th * (fp.th + 1.f)) - 0.69314718055994530942f;
+                    dg2 = ti + 1.f / (fp.th + 1.f);
+                }
+            }
 
+            // observations of the first group are requested before the logits are waited for
+            float xn[8];
+            auto load_x = [&](int g) {
+#pragma unroll
+                for (int e8 = 0; e8 < 8; ++e8) {
+                    const int cell = 8 * g + e8;
+                    xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell) ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
+                }
+            };
+            load_x(g_begin);
+            if (t == 0) TC_TRACE(1 + PHASE, it, 5);
             mbar_wait(&S.bars.acc_full[s], (it >> 1) & 1);
             tc_fence_after();
+            if (t == 0) TC_TRACE(1 + PHASE, it, 6);
 #pragma unroll 1
-            for (int cc = ch_begin; cc < ch_end; ++cc) {
-                const int c0 = cc * 32;
-                uint32_t d[32];
-                tmem_ld32(tmem_base + lane_addr + COL_ACC + s * 128 + c0, d);
-                float xv[32];
-                if (PHASE == 0) {
-#pragma unroll
-                    for (int r = 0; r < 32; ++r)
-                        xv[r] = (jok && c0 + r < ncell) ? __ldg(a.x + S.xoff[c0 + r] + j) : 0.f;
+            for (int g = g_begin; g < g_end; ++g) {
+                const int c0 = g * 8;
+                uint32_t d[8];
+                tmem_ld8(tmem_base + lane_addr + COL_ACC + s * 128 + c0, d);
+                // per-cell scalars of the group (vector shared-memory loads)
+                float lsev[8], auxv[8];  // aux = library size (pass B) or c_i (pass C)
+                int bv[8];
+                {
+                    const float4 l0 = *reinterpret_cast<const float4*>(&S.lse[c0]);
+                    const float4 l1 = *reinterpret_cast<const float4*>(&S.lse[c0 + 4]);
+                    const float* auxp = PHASE == 0 ? S.l : S.c;
+                    const float4 a0 = *reinterpret_cast<const float4*>(&auxp[c0]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&auxp[c0 + 4]);
+                    lsev[0] = l0.x, lsev[1] = l0.y, lsev[2] = l0.z, lsev[3] = l0.w;
+                    lsev[4] = l1.x, lsev[5] = l1.y, lsev[6] = l1.z, lsev[7] = l1.w;
+                    auxv[0] = a0.x, auxv[1] = a0.y, auxv[2] = a0.z, auxv[3] = a0.w;
+                    auxv[4] = a1.x, auxv[5] = a1.y, auxv[6] = a1.z, auxv[7] = a1.w;
+                    if (!NB1) {
+                        const int4 b0 = *reinterpret_cast<const int4*>(&S.bidx[c0]);
+                        const int4 b1 = *reinterpret_cast<const int4*>(&S.bidx[c0 + 4]);
+                        bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
+                        bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
+                    }
                 }
-                tmem_ld_wait();
-                if (GRAD && cc == ch_begin) mbar_wait(&S.bars.x_empty, (it & 1) ^ 1);
-                float gch[32];
-                const uint32_t xh = smem_u32(S.x_hi) + (uint32_t)(c0 >> 6) * OP_BYTES;
-                const uint32_t xl = smem_u32(S.x_lo) + (uint32_t)(c0 >> 6) * OP_BYTES;
+                float xv[8];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float coef[8];
+                for (int e8 = 0; e8 < 8; ++e8) xv[e8] = xn[e8];
+                load_x(g + 1);
+                tmem_ld_wait();
+                if (GRAD && g == g_begin) {
+                    mbar_wait(&S.bars.x_empty, (it & 1) ^ 1);
+                    if (t == 0) TC_TRACE(1 + PHASE, it, 7);
+                }
+                float coef[8], gch[8];
+                if constexpr (NB1 && PHASE == 1) {
+                    // ---- pass C, straight-line over the 8 cells --------------------------------
 #pragma unroll
                     for (int e8 = 0; e8 < 8; ++e8) {
-                        const int r = 8 * g + e8;
-                        const int cell = c0 + r;
+                        const float dot = __uint_as_float(d[e8]);
+                        const float pr = ex2f(fmaf(s2, dot, b2) - lsev[e8]);
+                        float G = -(pr * auxv[e8]);
+                        G = (jok && c0 + e8 < ncell) ? G : 0.f;
+                        gb += G;
+                        gs = fmaf(G, dot, gs);
+                        coef[e8] = G * fp.s;
+                        gch[e8] = G;
+                    }
+                } else if constexpr (NB1 && NBF) {
+                    // ---- pass B, NB / ZINB, straight-line in three stages -------------------------
+                    float xs[8], dlt[8], xl[8], dd[8], ratio[8], lgv[8], dgv[8], Wv[8];
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const float dot = __uint_as_float(d[e8]);
+                        const float x = xv[e8];
+                        const bool isnan_x = x != x;
+                        bool valid = jok && (c0 + e8 < ncell);
+                        if (a.reduce == 0 && isnan_x) {
+                            bad_acc += valid ? 1 : 0;
+                            valid = false;
+                        }
+                        xs[e8] = isnan_x ? 0.f : x;
+                        Wv[e8] = valid ? P.p.w0 : 0.f;
+                        const float pr = ex2f(fmaf(s2, dot, b2) - lsev[e8]);
+                        const float mu = pr * auxv[e8];
+                        const float m = mu + GLUE_EPS, mt = m + fp.th;
+                        const float Lm = lg2f(m) * LN2F, Lt = lg2f(mt) * LN2F;
+                        const float r = rcpf(m * mt);  // 1/m = r mt, 1/(m + theta) = r m
+                        const float sig = (m * m) * r;
+                        ratio[e8] = mu * (r * mt);
+                        dlt[e8] = fp.disp - Lt;
+                        xl[e8] = Lm - Lt;
+                        dd[e8] = xs[e8] - (xs[e8] + fp.th) * sig;
+                        lgv[e8] = xs[e8] == 1.f ? lg1 : (xs[e8] == 2.f ? lg2 : 0.f);
+                        dgv[e8] = xs[e8] == 1.f ? dg1 : (xs[e8] == 2.f ? dg2 : 0.f);
+                    }
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8)  // counts other than 0, 1, 2: rare
+                        if (!(xs[e8] == 0.f || xs[e8] == 1.f || xs[e8] == 2.f)) {
+                            float lg_t, dg_t;  // (locals: the out-of-line slow path takes addresses)
+                            nb_gamma_terms_t<true>(xs[e8], fp.th, lg_t, dg_t);
+                            lgv[e8] = lg_t, dgv[e8] = dg_t;
+                        }
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const float dot = __uint_as_float(d[e8]);
+                        float lp = fmaf(fp.th, dlt[e8], fmaf(xs[e8], xl[e8], lgv[e8]));
+                        const float tl = fmaf(fp.th, dlt[e8] + dgv[e8], -dd[e8]);
+                        float wnb = 1.f, gzv = 0.f;
+                        if (FAM == GLUE_ZINB) {
+                            const float e1 = ex2f(lp * LOG2EF);
+                            const float E = e1 + fp.ezi + GLUE_EPS;
+                            const float rE = rcpf(E);
+                            const bool isz = fabsf(xs[e8]) < GLUE_EPS;
+                            lp = isz ? lg2f(E) * LN2F - fp.spz : lp - fp.spz;
+                            wnb = isz ? e1 * rE : 1.f;
+                            gzv = isz ? fp.ezi * rE - fp.sgz : -fp.sgz;
+                        }
+                        const float W = Wv[e8];
+                        loss_acc = fmaf(W, lp, loss_acc);
+                        float G = 0.f;
+                        if (GRAD) {
+                            G = W * (wnb * dd[e8] * ratio[e8]);
+                            gb += G;
+                            gs = fmaf(G, dot, gs);
+                            gd = fmaf(W, wnb * tl, gd);
+                            gz = fmaf(W, gzv, gz);
+                        }
+                        coef[e8] = G * fp.s;
+                        gch[e8] = G;
+                    }
+                } else {
+                    // ---- generic path: other families, several parameter rows ---------------------
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int cell = c0 + e8;
                         const bool cok = cell < ncell;  // warp-uniform
                         float G = 0.f, cf = 0.f;
-                        if (cok) {
-                            const int bi = S.bidx[cell];
-                            if (bi != cur_b) {
+                        if (NB1 || cok) {
+                            if (!NB1 && bv[e8] != cur_b) {
                                 flush();
-                                fp = load_params<FAM>(a, bi, j, jok);
-                                cur_b = bi;
+                                fp = load_params<FAM>(a, bv[e8], j, jok);
+                                cur_b = bv[e8];
                             }
-                            const float dot = __uint_as_float(d[r]);
+                            const float dot = __uint_as_float(d[e8]);
                             const float av = fmaf(fp.s, dot, fp.bias);
                             if (PHASE == 0) {
-                                const float x = xv[r];
-                                const ElemOut e = element<FAM>(fp, av, x, S.lse[cell], S.l[cell]);
-                                bool valid = jok;
+                                const float x = xv[e8];
+                                const float lse_nat = NBF ? lsev[e8] * LN2F : 0.f;
+                                const ElemOut e = element<FAM, true>(fp, av, x, lse_nat, auxv[e8]);
+                                bool valid = jok && cok;
                                 if (a.reduce == 0 && x != x) {
+                                    bad_acc += valid ? 1 : 0;
                                     valid = false;
-                                    bad_acc += jok ? 1 : 0;
                                 }
                                 const float W = valid ? P.p.w0 : 0.f;
                                 loss_acc += valid ? W * e.lp : 0.f;
@@ -485,45 +655,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                                     gz += valid ? W * e.gz : 0.f;
                                 }
                             } else {
-                                const float pr = jok ? expf(av - S.lse[cell]) : 0.f;
-                                const float w = pr * S.c[cell];
-                                G = -w;
+                                const float pr = (jok && cok) ? ex2f(av * LOG2EF - lsev[e8]) : 0.f;
+                                G = -(pr * auxv[e8]);
                                 cf = G * fp.s;
                                 gb += G;
                                 gs += G * dot;
                             }
                         }
                         coef[e8] = cf;
-                        gch[r] = G;
-                    }
-                    if (GRAD) {
-                        // coefficient tile -> shared memory (bf16 hi / lo): rows = features, 128 B = 64 cells
-                        uint32_t hh[4], ll[4];
-#pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) split2(coef[2 * e2], coef[2 * e2 + 1], hh[e2], ll[e2]);
-                        const uint32_t off = swz((uint32_t)frow, (uint32_t)(((c0 & 63) >> 3) + g));
-                        st_shared_v4(xh + off, hh[0], hh[1], hh[2], hh[3]);
-                        st_shared_v4(xl + off, ll[0], ll[1], ll[2], ll[3]);
+                        gch[e8] = G;
                     }
                 }
                 if (GRAD) {
+                    // coefficient tile -> shared memory (bf16 hi / lo): rows = features, 128 B = 64 cells
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) split2(coef[2 * e2], coef[2 * e2 + 1], hh[e2], ll[e2]);
+                    const uint32_t off = (uint32_t)(c0 >> 6) * OP_BYTES + swz((uint32_t)frow, (uint32_t)((c0 & 63) >> 3));
+                    st_shared_v4(smem_u32(S.x_hi) + off, hh[0], hh[1], hh[2], hh[3]);
+                    st_shared_v4(smem_u32(S.x_lo) + off, ll[0], ll[1], ll[2], ll[3]);
                     if (NBF && PHASE == 0) {
-                        // c_i partial: transpose-reduce the 32 x 32 (feature lane x cell) block over lanes
+                        // c_i partial: transpose-reduce the (32 feature lanes x 8 cells) block over lanes;
+                        // afterwards lane L holds the warp total of cell c0 + 4 bit4(L) + 2 bit3(L) + bit2(L)
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            const bool up = (lane & off) != 0;
+                        for (int off2 = 16, n = 4; n >= 1; off2 >>= 1, n >>= 1) {
+                            const bool up = (lane & off2) != 0;
 #pragma unroll
-                            for (int k = 0; k < off; ++k) {
-                                const float send = up ? gch[k] : gch[k + off];
-                                const float keep = up ? gch[k + off] : gch[k];
-                                gch[k] = keep + __shfl_xor_sync(FULL, send, off);
+                            for (int k = 0; k < n; ++k) {
+                                const float send = up ? gch[k] : gch[k + n];
+                                const float keep = up ? gch[k + n] : gch[k];
+                                gch[k] = keep + __shfl_xor_sync(FULL, send, off2);
                             }
                         }
-                        S.cw[it & 1][q][c0 + lane] = gch[0];
+                        float tot = gch[0];
+                        tot += __shfl_xor_sync(FULL, tot, 2);
+                        tot += __shfl_xor_sync(FULL, tot, 1);
+                        if ((lane & 3) == 0) S.cw[it & 1][q][c0 + (lane >> 2)] = tot;
                     }
                 }
             }
             flush();
+            if (t == 0) TC_TRACE(1 + PHASE, it, 8);
+            if (t == 128) TC_TRACE(1 + PHASE, it, 9);
             if (GRAD) fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -533,31 +706,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             }
             if (GRAD) {
                 named_bar_sync(1, EPI_THREADS);
+                if (t == 0) TC_TRACE(1 + PHASE, it, 10);
                 if (pend) write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
                 if (NBF && PHASE == 0 && t < ncell)
                     S.c_acc[t] += (S.cw[it & 1][0][t] + S.cw[it & 1][1][t]) + (S.cw[it & 1][2][t] + S.cw[it & 1][3][t]);
                 if (it > 0) readout_d1(it - 1);
+                if (t == 0) TC_TRACE(1 + PHASE, it, 11);
             }
         }
         if (GRAD) {
             readout_d1(ntl - 1);
+            if (t == 0) TC_TRACE(1 + PHASE, 6, 13);
             // d/du partial of this CTA: rows = cells
             mbar_wait(&S.bars.d2_full, 0);
             tc_fence_after();
+            if (t == 0) TC_TRACE(1 + PHASE, 6, 14);
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_addr + COL_D2 + 32 * h, r);
             tmem_ld_wait();
             float4* dst = reinterpret_cast<float4*>(P.p.ws.apart + ((int64_t)cta * 128 + frow) * 64 + 32 * h);
+            float4 old[8];
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-                float4 val = make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]),
-                                         __uint_as_float(r[4 * k4 + 2]), __uint_as_float(r[4 * k4 + 3]));
-                if (PHASE == 1) {
-                    const float4 old = dst[k4];
-                    val.x += old.x, val.y += old.y, val.z += old.z, val.w += old.w;
-                }
-                dst[k4] = val;
-            }
+            for (int k4 = 0; k4 < 8; ++k4) old[k4] = PHASE == 1 ? dst[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+                dst[k4] = make_float4(__uint_as_float(r[4 * k4]) + old[k4].x, __uint_as_float(r[4 * k4 + 1]) + old[k4].y,
+                                      __uint_as_float(r[4 * k4 + 2]) + old[k4].z,
+                                      __uint_as_float(r[4 * k4 + 3]) + old[k4].w);
+            if (t == 0) TC_TRACE(1 + PHASE, 6, 15);
             if (NBF && PHASE == 0) {
                 named_bar_sync(1, EPI_THREADS);
                 if (t < ncell) P.p.ws.cpart[(int64_t)cta * a.B + P.cell0 + t] = S.c_acc[t];
@@ -581,26 +757,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     }
     tc_fence_before();
     __syncthreads();
+    if (t == 0) TC_TRACE(1 + PHASE, 7, 1);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// c_i = sum over CTAs of the partials; loss and the nanmean rescale factor (1 block of 128 threads)
-__global__ void tc_finish_main_kernel(DecParams p, int ncta, int nbf, int grad) {
+// c_i = sum over CTAs of the partials (8 strided sub-sums per cell, combined in a fixed order);
+// loss and the nanmean rescale factor.  One block of 1024 threads.
+__global__ void __launch_bounds__(1024) tc_finish_main_kernel(DecParams p, int ncta, int nbf, int grad) {
     const glue_decoder_args& a = p.a;
     const int t = threadIdx.x;
-    if (grad && nbf)
-        for (int i = t; i < a.B; i += blockDim.x) {
-            float c = 0.f;
-            for (int q = 0; q < ncta; ++q) c += p.ws.cpart[(int64_t)q * a.B + i];
-            p.ws.c[i] = c;
-        }
-    if (t == 0) {
+    __shared__ float part[8][128];
+    __shared__ double lpart[32];
+    __shared__ long long bpart[32];
+    if (grad && nbf) {
+        const int i = t & 127, sub = t >> 7;
+        float c = 0.f;
+        if (i < a.B)
+            for (int q = sub; q < ncta; q += 8) c += p.ws.cpart[(int64_t)q * a.B + i];
+        part[sub][i] = c;
+    }
+    if (t < 32) {
         double loss = 0.0;
         long long bad = 0;
-        for (int q = 0; q < ncta; ++q) {
+        for (int q = t; q < ncta; q += 32) {
             loss += (double)p.ws.losspart[q];
             bad += p.ws.badpart[q];
         }
+        lpart[t] = loss, bpart[t] = bad;
+    }
+    __syncthreads();
+    if (grad && nbf && t < a.B && t < 128)
+        p.ws.c[t] = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) +
+                    ((part[4][t] + part[5][t]) + (part[6][t] + part[7][t]));
+    if (t == 0) {
+        double loss = 0.0;
+        long long bad = 0;
+        for (int q = 0; q < 32; ++q) loss += lpart[q], bad += bpart[q];
         const double total = (double)a.B * (double)a.F;
         const double ratio = bad > 0 ? total / (total - (double)bad) : 1.0;
         p.ws.rescale[0] = (float)ratio;
@@ -608,14 +800,18 @@ __global__ void tc_finish_main_kernel(DecParams p, int ncta, int nbf, int grad) 
     }
 }
 
-// d/du = sum over CTAs of the D2 partials; grid = B blocks (sorted position), 64 threads
-__global__ void tc_grad_u_kernel(DecParams p, int ncta) {
+// d/du = sum over CTAs of the D2 partials; grid = B blocks (sorted position), 256 threads =
+// 64 latent columns x 4 strided sub-sums combined in a fixed order
+__global__ void __launch_bounds__(256) tc_grad_u_kernel(DecParams p, int ncta) {
     const glue_decoder_args& a = p.a;
-    const int pos = blockIdx.x, k = threadIdx.x;
-    if (k >= a.K || !a.grad_u) return;
+    const int pos = blockIdx.x, k = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    __shared__ float part[4][64];
     float acc = 0.f;
-    for (int q = 0; q < ncta; ++q) acc += p.ws.apart[((int64_t)q * 128 + pos) * 64 + k];
-    a.grad_u[(int64_t)orig_row(a, pos) * a.K + k] = acc;
+    for (int q = sub; q < ncta; q += 4) acc += p.ws.apart[((int64_t)q * 128 + pos) * 64 + k];
+    part[sub][k] = acc;
+    __syncthreads();
+    if (sub == 0 && k < a.K && a.grad_u)
+        a.grad_u[(int64_t)orig_row(a, pos) * a.K + k] = (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
 }
 
 size_t tc_ws_layout(const glue_decoder_args& a, int ncta, char* base, DecWs* ws) {
@@ -644,12 +840,12 @@ int tc_grid(const glue_decoder_args& a, int& ntiles) {
     return ntiles < sm_count() ? ntiles : sm_count();
 }
 
-template <int FAM>
+template <int FAM, bool NB1>
 int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
-    const size_t smem = sizeof(SmemMain) + 1024;
+    const size_t smem = sizeof(SmemMain);
 #define GLUE_TC_LAUNCH(PH, GR)                                                                      \
     {                                                                                               \
-        auto k = tc_main_kernel<FAM, PH, GR>;                                                       \
+        auto k = tc_main_kernel<FAM, PH, GR, NB1>;                                                  \
         GLUE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k<<<ncta, NTHREADS, smem, st>>>(P);                                                         \
     }
@@ -661,7 +857,20 @@ int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t
     return 0;
 }
 
+template <bool NB1>
+int launch_family(int family, int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
+    if (phase == 1) return launch_phase<GLUE_NB, NB1>(1, true, P, ncta, st);  // pass C is family independent
+    switch (family) {
+        case GLUE_NB: return launch_phase<GLUE_NB, NB1>(0, grad, P, ncta, st);
+        case GLUE_ZINB: return launch_phase<GLUE_ZINB, NB1>(0, grad, P, ncta, st);
+        case GLUE_NORMAL: return launch_phase<GLUE_NORMAL, NB1>(0, grad, P, ncta, st);
+        default: return launch_phase<GLUE_ZILN, NB1>(0, grad, P, ncta, st);
+    }
+}
+
 }  // namespace
+
+static long long* g_trace = nullptr;
 
 size_t tc_workspace_bytes(const glue_decoder_args& a) {
     int ntiles;
@@ -689,7 +898,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     tc_ws_layout(a, ncta, (char*)a.workspace, &p.ws);
     p.ncta = ncta;
     p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F));
-    P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0;
+    P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
 
@@ -701,30 +910,26 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         if (a.grad_zi_logits) GLUE_CUDA(cudaMemsetAsync(a.grad_zi_logits, 0, tab, st));
     }
     if (nbf) {
-        const size_t smem = sizeof(SmemStats) + 1024;
+        const size_t smem = sizeof(SmemStats);
         GLUE_CUDA(cudaFuncSetAttribute(tc_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
         GLUE_CHECK_LAUNCH();
         dec_lse_kernel<<<(a.B * 32 + 255) / 256, 256, 0, st>>>(p.ws, 2 * ncta, a.B);
         GLUE_CHECK_LAUNCH();
     }
-    int rc = 0;
-    switch (a.family) {
-        case GLUE_NB: rc = launch_phase<GLUE_NB>(0, grad, P, ncta, st); break;
-        case GLUE_ZINB: rc = launch_phase<GLUE_ZINB>(0, grad, P, ncta, st); break;
-        case GLUE_NORMAL: rc = launch_phase<GLUE_NORMAL>(0, grad, P, ncta, st); break;
-        default: rc = launch_phase<GLUE_ZILN>(0, grad, P, ncta, st); break;
-    }
+    const bool nb1 = a.n_batches == 1;
+    int rc = nb1 ? launch_family<true>(a.family, 0, grad, P, ncta, st)
+                 : launch_family<false>(a.family, 0, grad, P, ncta, st);
     if (rc) return rc;
-    tc_finish_main_kernel<<<1, 128, 0, st>>>(p, ncta, nbf ? 1 : 0, grad ? 1 : 0);
+    tc_finish_main_kernel<<<1, 1024, 0, st>>>(p, ncta, nbf ? 1 : 0, grad ? 1 : 0);
     GLUE_CHECK_LAUNCH();
     if (grad) {
         if (nbf) {
-            rc = a.family == GLUE_NB ? launch_phase<GLUE_NB>(1, true, P, ncta, st)
-                                     : launch_phase<GLUE_ZINB>(1, true, P, ncta, st);
+            rc = nb1 ? launch_family<true>(a.family, 1, true, P, ncta, st)
+                     : launch_family<false>(a.family, 1, true, P, ncta, st);
             if (rc) return rc;
         }
-        tc_grad_u_kernel<<<a.B, 64, 0, st>>>(p, ncta);
+        tc_grad_u_kernel<<<a.B, 256, 0, st>>>(p, ncta);
         GLUE_CHECK_LAUNCH();
         if (a.reduce == 0) {
             dec_rescale_kernel<<<sm_count(), 256, 0, st>>>(p);
@@ -735,3 +940,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
 }
 
 }  // namespace glue
+
+// Diagnostic: device buffer of 3 * 8 * 16 int64 that receives clock64 stamps of CTA 0 of the
+// tensor-core decoder kernels (NULL switches tracing off).  Not part of the training path.
+extern "C" void glue_tc_set_trace(void* device_buffer) { glue::g_trace = (long long*)device_buffer; }

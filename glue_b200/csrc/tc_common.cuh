@@ -146,24 +146,32 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Stage one fp32 row (K valid entries, K even, 8-byte aligned; src == nullptr -> zeros) as row
-// `r` of the hi and lo tiles.
+// Stage one fp32 row (K valid entries, K even <= 64, 8-byte aligned; src == nullptr -> zeros) as
+// row `r` of the hi and lo tiles.  All loads are issued before the first store.
 __device__ __forceinline__ void stage_row(uint32_t hi_base, uint32_t lo_base, uint32_t r, const float* __restrict__ src,
                                           int K) {
+    float2 vals[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        vals[q] = make_float2(0.f, 0.f);
+        if (src != nullptr && 2 * q < K) vals[q] = __ldg(reinterpret_cast<const float2*>(src + 2 * q));
+    }
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = ch * 8 + q * 2;
-            float2 val = make_float2(0.f, 0.f);
-            if (src != nullptr && k < K) val = __ldg(reinterpret_cast<const float2*>(src + k));
-            split2(val.x, val.y, h[q], l[q]);
-        }
+        for (int q = 0; q < 4; ++q) split2(vals[4 * ch + q].x, vals[4 * ch + q].y, h[q], l[q]);
         const uint32_t off = swz(r, ch);
         st_shared_v4(hi_base + off, h[0], h[1], h[2], h[3]);
         st_shared_v4(lo_base + off, l[0], l[1], l[2], l[3]);
     }
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr)
+                 : "memory");
 }
 
 }  // namespace tc

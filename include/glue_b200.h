@@ -176,6 +176,10 @@ int glue_tc_selftest(const void *a_img, uint32_t a_bytes, const void *b_img, uin
                      const uint32_t *a_off, const uint32_t *b_off, uint32_t N, float *out,
                      void *stream);
 
+/* Diagnostic: device buffer of 3*8*16 int64 receiving clock64 stamps of CTA 0 of the tensor-core
+ * decoder kernels (pipeline timeline, tools/tc_trace.py); NULL switches it off (default). */
+void glue_tc_set_trace(void *device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,8 +113,8 @@ def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F,
     finally:
         os.environ.pop("GLUE_B200_DECODER")
     l2, g2 = _run_decoder(ops, family, case, "nanmean")
-    assert_close(l2, l1, 2e-5, "loss")
+    assert_close(l2, l1, 1e-4, "loss")
     for n, a, b in zip(["u", "v"] + list(PARAM_NAMES[family]), g2, g1):
-        assert_close(a, b, 5e-5, f"{family} d/d{n} (v2 vs v1)")
+        assert_close(a, b, 1e-4, f"{family} d/d{n} (v2 vs v1)")
     l3, g3 = _run_decoder(ops, family, case, "nanmean")
     assert torch.equal(l2, l3) and all(torch.equal(a, b) for a, b in zip(g2, g3)), "v2 must be deterministic"
