@@ -61,6 +61,7 @@ class DecoderArgs(ctypes.Structure):
         ("disp", c_void_p),
         ("zi_logits", c_void_p),
         ("wmat", c_void_p),
+        ("row_weight", c_void_p),
         ("loss", c_void_p),
         ("grad_u", c_void_p),
         ("grad_v", c_void_p),
@@ -146,7 +147,7 @@ def lib() -> ctypes.CDLL:
             )
         handle = ctypes.CDLL(LIB_PATH)
         _declare(handle)
-        if handle.glue_abi_version() != 1:
+        if handle.glue_abi_version() != 2:
             raise RuntimeError("glue_b200: ABI version mismatch, rebuild the native library")
         _lib = handle
     return _lib

@@ -24,6 +24,18 @@ extern "C" void glue_count_launch_(void);
         if (e__ != cudaSuccess) return (int)e__; \
     } while (0)
 
+// Opt a kernel instantiation in to > 48 KB of dynamic shared memory, once per process (the
+// call site is instantiated per kernel; the value is a per-function attribute).
+#define GLUE_SMEM_ONCE(kernel, bytes)                                                            \
+    do {                                                                                         \
+        static bool done__ = false;                                                              \
+        if (!done__) {                                                                           \
+            GLUE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)(bytes)));                                       \
+            done__ = true;                                                                       \
+        }                                                                                        \
+    } while (0)
+
 namespace glue {
 
 constexpr unsigned FULL = 0xffffffffu;

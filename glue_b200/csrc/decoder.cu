@@ -258,9 +258,10 @@ __global__ void __launch_bounds__(TF, 1) dec_main_kernel(DecParams p) {
                         if (jok) p.out[(int64_t)S.row[rr] * a.F + j] = MODE == MODE_LOGP ? e.lp : e.mean;
                         continue;
                     }
-                    float W = a.wmat ? (jok ? a.wmat[(int64_t)S.row[rr] * a.F + j] : 0.f) : p.w0;
+                    float W = a.wmat ? (jok ? a.wmat[(int64_t)S.row[rr] * a.F + j] : 0.f)
+                                     : (a.row_weight ? -a.row_weight[S.row[rr]] : p.w0);
                     bool valid = jok;
-                    if (a.reduce == 0 && xv != xv) {  // nanmean: NaN observations carry no weight
+                    if (a.reduce == 0 && !a.row_weight && xv != xv) {  // nanmean: NaN observations carry no weight
                         valid = false;
                         bad_acc += jok ? 1 : 0;
                     }
@@ -539,7 +540,7 @@ static int launch_main(int mode, const DecParams& p, int ncta, size_t smem, cuda
 #define GLUE_LAUNCH_MODE(M)                                                                          \
     case M: {                                                                                        \
         auto k = dec_main_kernel<KP, FAM, M>;                                                        \
-        GLUE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GLUE_SMEM_ONCE(k, smem); \
         k<<<ncta, TF, smem, st>>>(p);                                                                \
         break;                                                                                       \
     }
@@ -582,7 +583,7 @@ static int run(const glue_decoder_args* args, int mode, float* out, cudaStream_t
     }
     if (nbf) {
         auto k = dec_rowstats_kernel<KP>;
-        GLUE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GLUE_SMEM_ONCE(k, smem);
         k<<<p.ncta, TF, smem, st>>>(p);
         GLUE_CHECK_LAUNCH();
         dec_lse_kernel<<<(a.B * 32 + 255) / 256, 256, 0, st>>>(p.ws, p.ncta, a.B);
@@ -603,11 +604,11 @@ static int run(const glue_decoder_args* args, int mode, float* out, cudaStream_t
     if (mode == MODE_GRAD) {
         if (nbf) {
             auto k = dec_softmax_bwd_kernel<KP>;
-            GLUE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GLUE_SMEM_ONCE(k, smem);
             k<<<p.ncta, TF, smem, st>>>(p);
             GLUE_CHECK_LAUNCH();
         }
-        if (!a.wmat && a.reduce == 0) {
+        if (!a.wmat && !a.row_weight && a.reduce == 0) {
             dec_rescale_kernel<<<sm_count(), 256, 0, st>>>(p);
             GLUE_CHECK_LAUNCH();
         }

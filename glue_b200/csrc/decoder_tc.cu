@@ -80,7 +80,7 @@ struct __align__(1024) SmemMain {
     uint8_t v_hi[2][OP_BYTES], v_lo[2][OP_BYTES];
     uint8_t x_hi[2 * OP_BYTES], x_lo[2 * OP_BYTES];  // [cell block of 64][128 feature rows][128 B]
     long long xoff[128];
-    float lse[128], l[128], c[128];
+    float lse[128], l[128], c[128], wrow[128];
     int bidx[128];
     float cw[2][4][128];
     float c_acc[128];
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         S.lse[t] = (ok && NBF) ? P.p.ws.lse[pos] * LOG2EF : 0.f;  // base 2
         S.c[t] = (ok && PHASE == 1) ? P.p.ws.c[pos] : 0.f;
         S.c_acc[t] = 0.f;
+        S.wrow[t] = ok ? (a.row_weight ? -a.row_weight[orig] : P.p.w0) : 0.f;  // weight of log_prob
     }
     if (GRAD) {  // cells beyond ncell must read as exact zeros in the coefficient tile
         uint4* xz = reinterpret_cast<uint4*>(S.x_hi);
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         const int g_begin = h == 0 ? 0 : (ngrp + 1) / 2;
         const int g_end = h == 0 ? (ngrp + 1) / 2 : ngrp;
         const bool add_v = (PHASE == 1) || P.acc;
+        const bool skip_nan = a.reduce == 0 && !a.row_weight;  // nanmean semantics
         float loss_acc = 0.f;
         int bad_acc = 0;
 
@@ -515,8 +517,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 uint32_t d[8];
                 tmem_ld8(tmem_base + lane_addr + COL_ACC + s * 128 + c0, d);
                 // per-cell scalars of the group (vector shared-memory loads)
-                float lsev[8], auxv[8];  // aux = library size (pass B) or c_i (pass C)
+                float lsev[8], auxv[8], wv[8];  // aux = library size (pass B) or c_i (pass C)
                 int bv[8];
+                if (PHASE == 0) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&S.wrow[c0]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&S.wrow[c0 + 4]);
+                    wv[0] = w0.x, wv[1] = w0.y, wv[2] = w0.z, wv[3] = w0.w;
+                    wv[4] = w1.x, wv[5] = w1.y, wv[6] = w1.z, wv[7] = w1.w;
+                }
                 {
                     const float4 l0 = *reinterpret_cast<const float4*>(&S.lse[c0]);
                     const float4 l1 = *reinterpret_cast<const float4*>(&S.lse[c0 + 4]);
@@ -566,12 +574,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                         const float x = xv[e8];
                         const bool isnan_x = x != x;
                         bool valid = jok && (c0 + e8 < ncell);
-                        if (a.reduce == 0 && isnan_x) {
+                        if (skip_nan && isnan_x) {
                             bad_acc += valid ? 1 : 0;
                             valid = false;
                         }
-                        xs[e8] = isnan_x ? 0.f : x;
-                        Wv[e8] = valid ? P.p.w0 : 0.f;
+                        xs[e8] = (skip_nan && isnan_x) ? 0.f : x;
+                        Wv[e8] = valid ? wv[e8] : 0.f;
                         const float pr = ex2f(fmaf(s2, dot, b2) - lsev[e8]);
                         const float mu = pr * auxv[e8];
                         const float m = mu + GLUE_EPS, mt = m + fp.th;
@@ -640,11 +648,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                                 const float lse_nat = NBF ? lsev[e8] * LN2F : 0.f;
                                 const ElemOut e = element<FAM, true>(fp, av, x, lse_nat, auxv[e8]);
                                 bool valid = jok && cok;
-                                if (a.reduce == 0 && x != x) {
+                                if (skip_nan && x != x) {
                                     bad_acc += valid ? 1 : 0;
                                     valid = false;
                                 }
-                                const float W = valid ? P.p.w0 : 0.f;
+                                const float W = valid ? wv[e8] : 0.f;
                                 loss_acc += valid ? W * e.lp : 0.f;
                                 if (GRAD) {
                                     G = valid ? W * e.g : 0.f;
@@ -846,7 +854,7 @@ int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t
 #define GLUE_TC_LAUNCH(PH, GR)                                                                      \
     {                                                                                               \
         auto k = tc_main_kernel<FAM, PH, GR, NB1>;                                                  \
-        GLUE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GLUE_SMEM_ONCE(k, smem); \
         k<<<ncta, NTHREADS, smem, st>>>(P);                                                         \
     }
     if (phase == 1) GLUE_TC_LAUNCH(1, true)
@@ -911,7 +919,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     }
     if (nbf) {
         const size_t smem = sizeof(SmemStats);
-        GLUE_CUDA(cudaFuncSetAttribute(tc_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
         tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
         GLUE_CHECK_LAUNCH();
         dec_lse_kernel<<<(a.B * 32 + 255) / 256, 256, 0, st>>>(p.ws, 2 * ncta, a.B);
@@ -931,7 +939,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         }
         tc_grad_u_kernel<<<a.B, 256, 0, st>>>(p, ncta);
         GLUE_CHECK_LAUNCH();
-        if (a.reduce == 0) {
+        if (a.reduce == 0 && !a.row_weight) {
             dec_rescale_kernel<<<sm_count(), 256, 0, st>>>(p);
             GLUE_CHECK_LAUNCH();
         }

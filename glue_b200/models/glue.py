@@ -133,8 +133,11 @@ class GLUETrainer(Trainer):
         return [net.g2v, net.v2g, net.x2u, net.u2x]
 
     def _make_optim(self, modules) -> torch.optim.Optimizer:
-        params = itertools.chain(*(m.parameters() for m in modules))
-        return getattr(torch.optim, self.optim_name)(params, lr=self.lr, **self.optim_kwargs)
+        params = list(itertools.chain(*(m.parameters() for m in modules)))
+        kwargs = dict(self.optim_kwargs)
+        if self.net.device.type == "cuda" and self.optim_name in ("RMSprop", "Adam", "AdamW"):
+            kwargs.setdefault("capturable", True)  # same arithmetic, no host reads: graph-safe
+        return getattr(torch.optim, self.optim_name)(params, lr=self.lr, **kwargs)
 
     # -- data-parallel gradient exchange -------------------------------------------------
     def _sync_grads(self, which: str) -> None:
@@ -267,3 +270,6 @@ class GLUETrainer(Trainer):
         self.vae_optim.load_state_dict(state_dict.pop("vae_optim"))
         self.dsc_optim.load_state_dict(state_dict.pop("dsc_optim"))
         super().load_state_dict(state_dict)
+        graphs = getattr(self, "graphs", None)
+        if graphs is not None:  # captured steps reference the replaced optimizer state
+            graphs.invalidate()

@@ -1,0 +1,128 @@
+r"""
+CUDA-graph capture / replay of whole training steps.
+
+One SCGLUE ``train_step`` is ~700 small launches (two forward/backward passes, two RMSprop
+updates) around a handful of fused kernels; eagerly it is bound by the host launch path, not
+by the GPU.  After a couple of eager steps with a given input signature the step is captured
+once -- discriminator update, generator update, both optimizers, the gradient all-reduce when
+data parallel -- and afterwards every step is: copy the minibatch into the static input
+buffers, one graph launch.  Nothing about the arithmetic changes: the captured kernels are the
+ones the eager step launches, in the same order, on the same parameters and optimizer state.
+
+What makes the step capturable (no host synchronisation, static shapes):
+
+* the graph-reconstruction loss balances positive / negative edges on the device
+  (``ops.graph_nll``; the reference reads the positive count with ``.item()``,
+  ``scglue.py:333``);
+* the paired-cell losses use per-cell weights instead of compacted row subsets
+  (``PairedSCGLUETrainer._extra_losses``);
+* RMSprop runs with ``capturable=True``; the learning rate is part of the graph key, so a
+  ``ReduceLROnPlateau`` step simply leads to a re-capture;
+* the burn-in noise coefficient is a device scalar refreshed before every replay.
+"""
+
+from collections import OrderedDict
+from typing import Any, Dict, List, Mapping, Optional
+
+import torch
+
+from .. import ops
+from ..utils import config, logged
+
+
+@logged
+class StepGraphs:
+    r"""Per-trainer cache of captured training steps, keyed by everything that is baked into a
+    capture: input shapes / dtypes, the ``freeze_u`` / burn-in switches and the learning rates."""
+
+    WARMUP_STEPS = 2   # eager steps with a new key before it is captured
+    MAX_GRAPHS = 4
+
+    def __init__(self, trainer) -> None:
+        self.trainer = trainer
+        self.entries: "OrderedDict[tuple, Dict[str, Any]]" = OrderedDict()
+        self.pool = None
+        self.disabled_reason: Optional[str] = None
+        self.replays = 0
+
+    # ------------------------------------------------------------------------------ helpers
+    def usable(self) -> bool:
+        tr = self.trainer
+        return (self.disabled_reason is None and config.USE_CUDA_GRAPHS
+                and tr.net.device.type == "cuda" and not ops.TIMER.enabled)
+
+    def invalidate(self) -> None:
+        r"""Drop every capture (optimizer state or parameters were replaced, e.g. by
+        ``load_state_dict``)."""
+        self.entries.clear()
+
+    def _key(self, data: List[torch.Tensor], anneal: float) -> tuple:
+        tr = self.trainer
+        lrs = tuple(float(g["lr"]) for opt in (tr.vae_optim, tr.dsc_optim) for g in opt.param_groups)
+        return (tuple((tuple(t.shape), t.dtype) for t in data), bool(anneal), bool(tr.freeze_u),
+                lrs, tr.dsc_steps)
+
+    def info(self) -> Mapping[str, Any]:
+        r"""``{"graphs", "replays", "kernels_per_step"}`` (native kernels inside the most
+        recently used capture)."""
+        last = next(reversed(self.entries.values()), None) if self.entries else None
+        return {"graphs": sum(1 for e in self.entries.values() if e["graph"] is not None),
+                "replays": self.replays,
+                "kernels_per_step": None if last is None else last.get("native_kernels"),
+                "disabled": self.disabled_reason}
+
+    # ------------------------------------------------------------------------------ stepping
+    def step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        tr = self.trainer
+        anneal = tr.burnin_anneal(engine.state.epoch)
+        key = self._key(data, anneal)
+        entry = self.entries.get(key)
+        if entry is None:
+            entry = {"seen": 0, "graph": None}
+            self.entries[key] = entry
+            while len(self.entries) > self.MAX_GRAPHS:
+                self.entries.popitem(last=False)
+        else:
+            self.entries.move_to_end(key)
+        if entry["graph"] is None:
+            entry["seen"] += 1
+            if entry["seen"] <= self.WARMUP_STEPS:
+                return tr.eager_train_step(engine, data)
+            self._capture(entry, engine, data)
+            if entry["graph"] is None:
+                return tr.eager_train_step(engine, data)
+        for static, fresh in zip(entry["inputs"], data):
+            static.copy_(fresh, non_blocking=True)
+        tr.anneal_buffer.fill_(anneal)
+        entry["graph"].replay()
+        self.replays += 1
+        return entry["outputs"]
+
+    def _capture(self, entry: Dict[str, Any], engine, data: List[torch.Tensor]) -> None:
+        tr = self.trainer
+        device = tr.net.device
+        try:
+            inputs = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in data]
+            for static, fresh in zip(inputs, data):
+                static.copy_(fresh, non_blocking=True)
+            torch.cuda.synchronize(device)
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
+            graph = torch.cuda.CUDAGraph()
+            launches0 = ops.kernel_launches()
+            tr.capturing = True
+            try:
+                with torch.cuda.graph(graph, pool=self.pool, capture_error_mode="thread_local"):
+                    outputs = tr.eager_train_step(engine, inputs)
+            finally:
+                tr.capturing = False
+            entry.update(graph=graph, inputs=inputs, outputs=dict(outputs),
+                         native_kernels=ops.kernel_launches() - launches0)
+            self.logger.debug("captured a training step (%d native kernels)",
+                              entry["native_kernels"])
+        except Exception as e:  # capture is an optimisation: fall back to eager launches
+            torch.cuda.synchronize(device)
+            self.disabled_reason = f"{type(e).__name__}: {e}"
+            self.logger.warning("CUDA-graph capture of the training step failed (%s); "
+                                "continuing with eager launches", self.disabled_reason)
+            entry["graph"] = None

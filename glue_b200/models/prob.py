@@ -94,11 +94,11 @@ class FusedDataDistribution:
     def _params(self):
         return self.scale_lin, self.bias, self.disp, self.zi_logits
 
-    def nll(self, value: torch.Tensor, reduce: str = "nanmean",
-            unit_upstream: bool = False) -> torch.Tensor:
+    def nll(self, value: torch.Tensor, reduce: str = "nanmean", unit_upstream: bool = False,
+            row_weight: torch.Tensor = None) -> torch.Tensor:
         return ops.decoder_nll(self.family, self.u, self.v, *self._params(), b=self.b, l=self.l,
                                x=value, vidx=self.vidx, reduce=reduce,
-                               unit_upstream=unit_upstream)
+                               unit_upstream=unit_upstream, row_weight=row_weight)
 
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
         return ops.decoder_log_prob(self.family, self.u, self.v, *self._params(), b=self.b,

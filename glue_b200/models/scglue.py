@@ -29,6 +29,7 @@ from . import sc
 from .base import Model
 from .data import AnnDataset, ArrayDataset, DataLoader, GraphDataset
 from .glue import GLUE, GLUETrainer
+from .graphs import StepGraphs
 from .nn import freeze_running_stats
 
 # ---------------------------------------------------------- prob-model registry
@@ -101,6 +102,10 @@ class SCGLUETrainer(GLUETrainer):
         # `noise(shape_like, tag)` supplies standard-normal draws; tests inject host noise
         self.noise: Callable[[torch.Tensor, str], torch.Tensor] = \
             lambda like, tag: torch.randn_like(like)
+        # whole-step CUDA graphs (see models/graphs.py)
+        self.graphs = StepGraphs(self)
+        self.capturing = False
+        self.anneal_buffer = torch.zeros((), dtype=torch.float32, device=net.device)
 
     @property
     def freeze_u(self) -> bool:
@@ -148,17 +153,27 @@ class SCGLUETrainer(GLUETrainer):
             usamp = {k: F.normalize(usamp[k], dim=1) for k in net.keys}
         return u, l, usamp
 
+    def burnin_anneal(self, epoch: int) -> float:
+        r"""Burn-in noise coefficient of the alignment term (``scglue.py:318-324``)."""
+        return max(1 - (epoch - 1) / self.align_burnin, 0) if self.align_burnin else 0
+
     def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int):
         net = self.net
         u_cat = torch.cat([u[k].mean for k in net.keys])
         xbch_cat = torch.cat([xbch[k] for k in net.keys])
         xdwt_cat = torch.cat([xdwt[k] for k in net.keys])
         xflag_cat = torch.cat([xflag[k] for k in net.keys])
-        anneal = max(1 - (epoch - 1) / self.align_burnin, 0) if self.align_burnin else 0
+        anneal = self.burnin_anneal(epoch)
         if anneal:
             with torch.no_grad():  # D.Normal(0, std).sample(): not differentiated through
                 jitter = self.noise(u_cat, "burnin") * u_cat.std(dim=0)
-            u_cat = u_cat + (anneal * self.BURNIN_NOISE_EXAG) * jitter
+            # inside a captured step the coefficient is read from a device scalar
+            # (fp32 product in both cases, so replayed and eager steps agree bit for bit)
+            if self.capturing:
+                coeff = self.anneal_buffer * self.BURNIN_NOISE_EXAG
+            else:
+                coeff = float(np.float32(anneal) * np.float32(self.BURNIN_NOISE_EXAG))
+            u_cat = u_cat + coeff * jitter
         dsc_loss = F.cross_entropy(net.du(u_cat, xbch_cat), xflag_cat, reduction="none")
         dsc_loss = (dsc_loss * xdwt_cat).sum() / xdwt_cat.numel()
         return u_cat, dsc_loss
@@ -180,14 +195,19 @@ class SCGLUETrainer(GLUETrainer):
         g_kl = _kl_to_prior(v, prior) / vsamp.shape[0]
         return vsamp, g_nll, g_kl
 
-    def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str) -> torch.Tensor:
+    def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str,
+                  row_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
         r"""``-u2x[k](usamp, vsamp[idx_k], xbch, l).log_prob(x).<reduce>()``; kernel-backed
-        decoders take the whole vertex table and gather ``idx_k`` rows themselves."""
+        decoders take the whole vertex table and gather ``idx_k`` rows themselves.  With
+        ``row_weight`` ``[B]`` the result is ``-sum_i row_weight[i] sum_j log_prob[i, j]``."""
         net = self.net
         decoder, idx = net.u2x[k], getattr(net, f"{k}_idx")
         if isinstance(decoder, sc._FusedDecoder):
-            return decoder(usamp, vsamp, xbch, l, vidx=idx).nll(x, reduce=reduce)
+            return decoder(usamp, vsamp, xbch, l, vidx=idx).nll(x, reduce=reduce,
+                                                                row_weight=row_weight)
         log_prob = decoder(usamp, vsamp[idx], xbch, l).log_prob(x)
+        if row_weight is not None:
+            return -(log_prob * row_weight.unsqueeze(1)).sum()
         return -(log_prob.nanmean() if reduce == "nanmean" else log_prob.mean())
 
     DATA_REDUCE = "nanmean"  # scglue.py:345
@@ -230,6 +250,13 @@ class SCGLUETrainer(GLUETrainer):
 
     # -- steps -------------------------------------------------------------------------------
     def train_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        r"""One discriminator + one generator update.  On CUDA, steps whose input signature
+        has been seen before are replayed from a captured graph (:class:`StepGraphs`)."""
+        if self.graphs.usable():
+            return self.graphs.step(engine, data)
+        return self.eager_train_step(engine, data)
+
+    def eager_train_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
         self.net.train()
         data = self.format_data(data)
         epoch = engine.state.epoch
@@ -248,7 +275,9 @@ class SCGLUETrainer(GLUETrainer):
         losses["gen_loss"].backward()
         self._sync_grads("vae")
         self.vae_optim.step()
-        return losses
+        # detached: the returned values feed metrics only, and a live autograd graph would keep
+        # this step's AccumulateGrad nodes (bound to this stream) alive into a later capture
+        return {name: value.detach() for name, value in losses.items()}
 
     @torch.no_grad()
     def val_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
@@ -266,10 +295,10 @@ class SCGLUETrainer(GLUETrainer):
 class PairedSCGLUETrainer(SCGLUETrainer):
     r"""
     Trainer for partially paired data (``scglue.py:423-701``): adds joint-cross,
-    real-cross and cosine losses over the cells observed in several modalities.  Subsets are
-    taken by compacting row indices on the device (``nonzero``), which needs one host read
-    of the subset sizes per step -- as in the reference, whose boolean-mask indexing does the
-    same implicitly.
+    real-cross and cosine losses over the cells observed in several modalities.  The
+    reference takes the subsets with boolean-mask indexing (dynamic shapes, an implicit host
+    synchronisation per subset); here they are per-cell weights of the fused decoder, so the
+    step has static shapes and can be captured in a CUDA graph.
     """
 
     PAIRED = True
@@ -312,38 +341,33 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         if self.normalize_u:
             umean = F.normalize(umean, dim=1)
 
-        # row subsets: observed in modality k, and observed in both of an ordered pair
-        pair_masks = {(i, j): pmsk[i] & pmsk[j]
-                      for i in range(len(keys)) for j in range(len(keys)) if i != j}
-        all_masks = list(pmsk) + list(pair_masks.values())
-        counts = torch.stack([m.sum() for m in all_masks]).tolist()  # the one host read
-        single_n = counts[:len(keys)]
-        pair_n = dict(zip(pair_masks, counts[len(keys):]))
-        rows_of = lambda m: m.nonzero(as_tuple=True)[0]
+        # Row subsets (observed in modality k; observed in both modalities of an ordered pair)
+        # enter as per-cell weights  mask / (n_masked * n_features):  the mean over the subset
+        # without compacting rows -- static shapes, no host read of the subset sizes.
+        pf = pmsk.to(torch.float32)
 
-        def subset_nll(k, usrc, rows):
-            lk = None if l[k] is None else l[k][rows]
-            return self._data_nll(k, usrc[rows], vsamp, xbch[k][rows], lk, x[k][rows], "mean")
+        def subset_nll(k, usrc, maskf):
+            w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
+            return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w)
 
         joint = zero
         if self.lam_joint_cross:
             for i, k in enumerate(keys):
-                if single_n[i]:
-                    joint = joint + self.modality_weight[k] * subset_nll(k, umean, rows_of(pmsk[i]))
+                joint = joint + self.modality_weight[k] * subset_nll(k, umean, pf[i])
         real = zero
         if self.lam_real_cross:
             for i, kt in enumerate(keys):
                 acc = zero
                 for j, ks in enumerate(keys):
-                    if i != j and pair_n[(j, i)]:
-                        acc = acc + subset_nll(kt, usamp[ks], rows_of(pair_masks[(j, i)]))
+                    if i != j:
+                        acc = acc + subset_nll(kt, usamp[ks], pf[i] * pf[j])
                 real = real + self.modality_weight[kt] * acc
         cos = zero
         if self.lam_cos:
             for i, k in enumerate(keys):
-                if single_n[i]:
-                    rows = rows_of(pmsk[i])
-                    cos = cos + (1 - F.cosine_similarity(ustack[i][rows], umean[rows]).mean())
+                n = pf[i].sum()
+                sim = (F.cosine_similarity(ustack[i], umean) * pf[i]).sum() / n.clamp(min=1.0)
+                cos = cos + torch.where(n > 0, 1 - sim, zero)
         return {"joint_cross_loss": (self.lam_joint_cross, joint),
                 "real_cross_loss": (self.lam_real_cross, real),
                 "cos_loss": (self.lam_cos, cos)}

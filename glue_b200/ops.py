@@ -271,8 +271,8 @@ class DecoderCall:
     r"""Argument marshalling for one ``glue_decoder_*`` call (keeps tensors alive)."""
 
     def __init__(self, family: str, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits,
-                 reduce: str = "nanmean"):
-        dev = require_cuda(u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits)
+                 reduce: str = "nanmean", row_weight=None):
+        dev = require_cuda(u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, row_weight)
         if family not in FAMILY:
             raise ValueError(f"unknown decoder family {family!r}")
         self.family, self.device = family, dev
@@ -287,6 +287,9 @@ class DecoderCall:
         self.B, self.K = self.u.shape
         self.n_batches, self.F = self.scale_lin.shape
         self.reduce = {"nanmean": 0, "mean": 1}[reduce]
+        self.row_weight = None if row_weight is None else _f32(row_weight, "row_weight").reshape(-1)
+        if self.row_weight is not None and self.row_weight.numel() != self.B:
+            raise ValueError("`row_weight` must have one entry per cell")
         if self.v.dim() != 2 or self.v.shape[1] != self.K:
             raise ValueError("`u` and `v` must share the latent dimension")
         if self.K > 64:
@@ -320,6 +323,7 @@ class DecoderCall:
         a.row_order, a.l, a.x = ptr(self.row_order), ptr(self.l), ptr(self.x)
         a.scale_lin, a.bias, a.disp = ptr(self.scale_lin), ptr(self.bias), ptr(self.disp)
         a.zi_logits = ptr(self.zi)
+        a.row_weight = ptr(self.row_weight)
         a.workspace, a.workspace_bytes = ptr(self.ws), self.ws.numel()
         for key, t in out.items():
             setattr(a, key, ptr(t))
@@ -344,8 +348,9 @@ class _DecoderNllFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family, reduce,
-                unit_upstream):
-        call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce)
+                unit_upstream, row_weight):
+        call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce,
+                           row_weight)
         loss = torch.empty((), dtype=torch.float32, device=call.device)
         need_grad = any(t is not None and t.requires_grad
                         for t in (u, v, scale_lin, bias, disp, zi_logits))
@@ -374,11 +379,12 @@ class _DecoderNllFn(torch.autograd.Function):
         if not ctx.unit_upstream:
             live = [g for g in grads if g is not None]
             torch._foreach_mul_(live, grad_out)
-        return (*grads, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None)
 
 
 def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
-                x=None, vidx=None, reduce: str = "nanmean", unit_upstream: bool = False):
+                x=None, vidx=None, reduce: str = "nanmean", unit_upstream: bool = False,
+                row_weight=None):
     r"""Fused data decoder + negative log-likelihood.
 
     Replaces ``-u2x(u, v, b, l).log_prob(x).nanmean()`` (``scglue/models/scglue.py:342-347``;
@@ -386,11 +392,14 @@ def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=N
     ``vidx`` given, ``v`` is the full vertex table and ``v[vidx]`` is gathered inside the
     kernel (saves the ``[F, K]`` gather and its ``index_put_`` backward).
     ``unit_upstream=True`` promises that this loss enters the final objective with
-    coefficient exactly 1, so backward hands the gradients over without rescaling."""
+    coefficient exactly 1, so backward hands the gradients over without rescaling.
+    ``row_weight`` (``[B]``, not differentiated) replaces the mean by
+    ``-sum_i row_weight[i] sum_j log_prob[i, j]``: weighted / masked row subsets with static
+    shapes (the paired-cell losses of ``scglue.py:603-640`` use ``mask / (n_masked * F)``)."""
     if x is None:
         raise ValueError("`x` is required")
     return _DecoderNllFn.apply(u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family,
-                               reduce, unit_upstream)
+                               reduce, unit_upstream, row_weight)
 
 
 class _DecoderLogProbFn(torch.autograd.Function):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLUE_B200_ABI_VERSION 1
+#define GLUE_B200_ABI_VERSION 2
 
 #define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
 #define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */
@@ -138,6 +138,12 @@ typedef struct glue_decoder_args {
     const float *wmat;        /* optional [B, F] upstream d L / d log_prob; when
                                  non-NULL the objective is L = sum wmat*log_prob and
                                  `reduce`/`loss` are ignored                         */
+    const float *row_weight;  /* optional [B] per-cell weights w_i >= 0: the objective
+                                 becomes loss = -sum_i w_i sum_j log_prob_ij (masked /
+                                 weighted row subsets with static shapes, e.g.
+                                 w_i = mask_i / (n_masked * F) for the paired-cell losses,
+                                 scglue/models/scglue.py:603-640); NaN observations are
+                                 not skipped in this mode                            */
     /* outputs (any may be NULL when its gradient is not wanted) */
     float *loss;           /* [1]  -mean(log_prob)                                   */
     float *grad_u;         /* [B, K]                                                 */

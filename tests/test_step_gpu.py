@@ -130,3 +130,64 @@ def test_short_fit_runs_and_learns(native_lib):
         model.save(f"{tmp}/m.dill")
         loaded = models.load_model(f"{tmp}/m.dill")
         assert np.allclose(loaded.encode_data("rna", adatas["rna"]), emb, atol=1e-5)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_graph_replayed_steps_equal_eager_steps(native_lib, golden, paired):
+    """Six train steps from the same state and inputs, once launched eagerly and once through
+    StepGraphs (2 eager warm-up steps, capture, replays): identical kernels on identical data,
+    so losses and final parameters must agree bit for bit."""
+    from glue_b200.utils import config
+
+    g = golden("step_paired" if paired else "step_scglue")
+    graph = golden("graph")
+    keys = ["rna", "atac"]
+    B = g["x__rna"].shape[0]
+    t = lambda a: torch.as_tensor(a).to(DEV)
+    data = ([t(g[f"x__{k}"]) for k in keys] + [t(g[f"xrep__{k}"]) for k in keys]
+            + [t(g[f"xbch__{k}"]) for k in keys]
+            + [torch.full((B,), -1, dtype=torch.int64, device=DEV) for _ in keys]
+            + [t(g[f"xdwt__{k}"]) for k in keys]
+            + [t(g["pmsk"]), t(g["eidx"]), t(g["ewt"]), t(g["esgn"])])
+
+    class Eng:
+        class state:
+            epoch = int(g["epoch"])
+
+    def run(use_graphs):
+        config.USE_CUDA_GRAPHS = use_graphs
+        net, trainer, _ = build(g, paired)
+        trainer.eidx, trainer.enorm, trainer.esgn = (t(graph["eidx"]), t(graph["enorm_keepvar"]),
+                                                      t(graph["esgn"]))
+        trainer.align_burnin = int(g["align_burnin"])
+        cache = {}
+
+        def noise(like, tag):  # fixed device-resident draws: the same in every step and run
+            key = (tag, tuple(like.shape))
+            if key not in cache:
+                gen = torch.Generator().manual_seed(abs(hash(key)) % (2 ** 31))
+                cache[key] = torch.randn(like.shape, generator=gen).to(like.device)
+            return cache[key]
+
+        with torch.random.fork_rng(devices=[0]):
+            torch.manual_seed(0)
+            trainer.noise = noise
+            out = None
+            for _ in range(6):
+                out = trainer.train_step(Eng, data)
+            out = {k: v.detach().clone() for k, v in out.items()}
+        torch.cuda.synchronize()
+        return net, trainer, out
+
+    try:
+        net_e, _, loss_e = run(False)
+        net_g, tr_g, loss_g = run(True)
+    finally:
+        config.USE_CUDA_GRAPHS = True
+    info = tr_g.graphs.info()
+    assert info["graphs"] == 1 and info["replays"] == 4, info
+    assert info["kernels_per_step"] and info["kernels_per_step"] > 10, info
+    for name in loss_e:
+        assert torch.equal(loss_e[name], loss_g[name]), name
+    for (name, a), (_, b) in zip(net_e.state_dict().items(), net_g.state_dict().items()):
+        assert torch.equal(a, b), name
