@@ -519,7 +519,7 @@ static size_t ws_layout(const glue_decoder_args& a, int ncta, int KP, char* base
     float* losspart = (float*)take((size_t)ncta * 4);
     int* badpart = (int*)take((size_t)ncta * 4);
     float* rescale = (float*)take(4);
-    if (ws) *ws = DecWs{pmax, psum, lse, cpart, c, apart, losspart, badpart, rescale};
+    if (ws) *ws = DecWs{pmax, psum, lse, cpart, c, apart, losspart, badpart, rescale, nullptr};
     return off;
 }
 

@@ -18,6 +18,7 @@ struct DecWs {  // workspace carve-up (device pointers)
     float* losspart; // [ncta]
     int* badpart;    // [ncta]  number of NaN observations skipped
     float* rescale;  // [1]  (B*F)/count when NaNs were skipped, else 1
+    unsigned int* counters;  // [4] arrival tickets of the "last CTA reduces" tails (tensor-core path)
 };
 
 struct DecParams {

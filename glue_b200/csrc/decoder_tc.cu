@@ -84,10 +84,13 @@ struct __align__(1024) SmemMain {
     int bidx[128];
     float cw[2][4][128];
     float c_acc[128];
+    float stage[128][65];  // d/dv tile on its way from TMEM (thread <-> row) to coalesced stores
     float red_l[EPI_WARPS];
     int red_b[EPI_WARPS];
+    float cpart3[3][128];
     Bars bars;
     uint32_t tmem_base;
+    uint32_t ticket;
 };
 
 struct __align__(1024) SmemStats {
@@ -95,8 +98,10 @@ struct __align__(1024) SmemStats {
     uint8_t v_hi[2][OP_BYTES], v_lo[2][OP_BYTES];
     float2 ptab[2][NB_MAX][130];  // (softplus(scale_lin), bias) per (stage, batch, feature-in-tile)
     int bidx[128];
+    float red[2][3][128];
     Bars bars;
     uint32_t tmem_base;
+    uint32_t ticket;
 };
 
 struct TcParams {
@@ -265,10 +270,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
             P.p.ws.psum[slot] = ssum;
         }
     }
+    // ---- the last CTA to arrive turns the partials into lse_i (fixed summation order) --------
+    __threadfence();
     tc_fence_before();
     __syncthreads();
-    if (t == 0) TC_TRACE(0, 7, 1);
+    if (t == 0) S.ticket = atomicAdd(P.p.ws.counters + 0, 1u);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
+    __syncthreads();
+    if (S.ticket == gridDim.x - 1) {
+        __threadfence();
+        // thread <-> (cell, one of three strided sub-ranges of the partials): consecutive threads
+        // read consecutive addresses
+        const int nparts = 2 * (int)gridDim.x;
+        const int cell = t & 127, sub = t >> 7;
+        const bool act = t < 384 && cell < P.ncell;
+        const int row = P.cell0 + cell;
+        float mx = -INFINITY;
+        if (act) {
+#pragma unroll 8
+            for (int c = sub; c < nparts; c += 3) mx = fmaxf(mx, __ldcg(P.p.ws.pmax + (int64_t)c * a.B + row));
+            S.red[0][sub][cell] = mx;
+        }
+        __syncthreads();
+        float sum = 0.f;
+        if (act) {
+            mx = fmaxf(fmaxf(S.red[0][0][cell], S.red[0][1][cell]), S.red[0][2][cell]);
+#pragma unroll 8
+            for (int c = sub; c < nparts; c += 3) {
+                const float pm = __ldcg(P.p.ws.pmax + (int64_t)c * a.B + row);
+                const float ps = __ldcg(P.p.ws.psum + (int64_t)c * a.B + row);
+                sum += pm > -INFINITY ? ps * expf(pm - mx) : 0.f;
+            }
+            S.red[1][sub][cell] = sum;
+        }
+        __syncthreads();
+        if (act && sub == 0)
+            P.p.ws.lse[row] = mx + logf((S.red[1][0][cell] + S.red[1][1][cell]) + S.red[1][2][cell]);
+    }
+    if (t == 0) TC_TRACE(0, 7, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,21 +467,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.bars.d1_empty[s]);
-            if (j < a.F && a.grad_v) {
-                const int64_t vr = a.vidx ? a.vidx[j] : (int64_t)j;
-                float2* dst = reinterpret_cast<float2*>(a.grad_v + vr * a.K + 32 * h);
-                float2 old[16];
+            // transpose through shared memory: thread <-> feature row in TMEM, but a row of d/dv
+            // (K contiguous floats) should leave with consecutive lanes on consecutive addresses
+            (void)j;
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {  // every load before the first store
-                    old[k2] = make_float2(0.f, 0.f);
-                    if (add_v && 32 * h + 2 * k2 < a.K) old[k2] = dst[k2];
+            for (int k = 0; k < 32; ++k) S.stage[frow][32 * h + k] = __uint_as_float(r[k]);
+            named_bar_sync(3, EPI_THREADS);
+            if (a.grad_v) {
+                const int f0p = (cta + itp * ncta) * 128;
+                const int k2 = lane;  // float2 index inside the row
+                const bool kok = 2 * k2 < a.K;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float2 old[8];
+                    float2* dst[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {  // every load before the first store
+                        const int row = warp + 8 * (rr + 8 * half);
+                        const int jj = f0p + row;
+                        dst[rr] = nullptr;
+                        old[rr] = make_float2(0.f, 0.f);
+                        if (jj < a.F && kok) {
+                            const int64_t vr = a.vidx ? a.vidx[jj] : (int64_t)jj;
+                            dst[rr] = reinterpret_cast<float2*>(a.grad_v + vr * a.K) + k2;
+                            if (add_v) old[rr] = *dst[rr];
+                        }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int row = warp + 8 * (rr + 8 * half);
+                        if (dst[rr] != nullptr)
+                            *dst[rr] = make_float2(S.stage[row][2 * k2] + old[rr].x,
+                                                   S.stage[row][2 * k2 + 1] + old[rr].y);
+                    }
                 }
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2)
-                    if (32 * h + 2 * k2 < a.K)
-                        dst[k2] = make_float2(__uint_as_float(r[2 * k2]) + old[k2].x,
-                                              __uint_as_float(r[2 * k2 + 1]) + old[k2].y);
             }
+            named_bar_sync(3, EPI_THREADS);  // the staging tile is free again
         };
 
         for (int it = 0; it < ntl; ++it) {
@@ -764,48 +824,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         }
     }
     tc_fence_before();
+    if (PHASE == 0) __threadfence();
     __syncthreads();
-    if (t == 0) TC_TRACE(1 + PHASE, 7, 1);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// c_i = sum over CTAs of the partials (8 strided sub-sums per cell, combined in a fixed order);
-// loss and the nanmean rescale factor.  One block of 1024 threads.
-__global__ void __launch_bounds__(1024) tc_finish_main_kernel(DecParams p, int ncta, int nbf, int grad) {
-    const glue_decoder_args& a = p.a;
-    const int t = threadIdx.x;
-    __shared__ float part[8][128];
-    __shared__ double lpart[32];
-    __shared__ long long bpart[32];
-    if (grad && nbf) {
-        const int i = t & 127, sub = t >> 7;
-        float c = 0.f;
-        if (i < a.B)
-            for (int q = sub; q < ncta; q += 8) c += p.ws.cpart[(int64_t)q * a.B + i];
-        part[sub][i] = c;
-    }
-    if (t < 32) {
-        double loss = 0.0;
-        long long bad = 0;
-        for (int q = t; q < ncta; q += 32) {
-            loss += (double)p.ws.losspart[q];
-            bad += p.ws.badpart[q];
+    if (PHASE == 0) {
+        // ---- the last CTA to arrive reduces the per-CTA partials: c_i, loss, nanmean factor -----
+        if (t == 0) S.ticket = atomicAdd(P.p.ws.counters + 1, 1u);
+        __syncthreads();
+        if (S.ticket == gridDim.x - 1) {
+            __threadfence();
+            const int nc = (int)gridDim.x;
+            if (GRAD && NBF && t < 384) {  // three strided sub-sums per cell, combined in a fixed order
+                const int cell = t & 127, sub = t >> 7;
+                float c = 0.f;
+                if (cell < ncell) {
+#pragma unroll 10
+                    for (int q = sub; q < nc; q += 3) c += __ldcg(P.p.ws.cpart + (int64_t)q * a.B + P.cell0 + cell);
+                }
+                S.cpart3[sub][cell] = c;
+            }
+            if (warp == MMA_WARP) {
+                double loss = 0.0;
+                long long bad = 0;
+                for (int q = lane; q < nc; q += 32) {
+                    loss += (double)__ldcg(P.p.ws.losspart + q);
+                    bad += __ldcg(P.p.ws.badpart + q);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    loss += __shfl_xor_sync(FULL, loss, o);
+                    bad += __shfl_xor_sync(FULL, bad, o);
+                }
+                if (lane == 0) {
+                    const double total = (double)a.B * (double)a.F;
+                    const double ratio = bad > 0 ? total / (total - (double)bad) : 1.0;
+                    P.p.ws.rescale[0] = (float)ratio;
+                    if (a.loss) a.loss[0] = (float)(loss * ratio);
+                }
+            }
+            __syncthreads();
+            if (GRAD && NBF && t < ncell)
+                P.p.ws.c[P.cell0 + t] = (S.cpart3[0][t] + S.cpart3[1][t]) + S.cpart3[2][t];
         }
-        lpart[t] = loss, bpart[t] = bad;
     }
-    __syncthreads();
-    if (grad && nbf && t < a.B && t < 128)
-        p.ws.c[t] = ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) +
-                    ((part[4][t] + part[5][t]) + (part[6][t] + part[7][t]));
-    if (t == 0) {
-        double loss = 0.0;
-        long long bad = 0;
-        for (int q = 0; q < 32; ++q) loss += lpart[q], bad += bpart[q];
-        const double total = (double)a.B * (double)a.F;
-        const double ratio = bad > 0 ? total / (total - (double)bad) : 1.0;
-        p.ws.rescale[0] = (float)ratio;
-        if (a.loss) a.loss[0] = (float)(loss * ratio);
-    }
+    if (t == 0) TC_TRACE(1 + PHASE, 7, 1);
 }
 
 // d/du = sum over CTAs of the D2 partials; grid = B blocks (sorted position), 256 threads =
@@ -839,7 +901,8 @@ size_t tc_ws_layout(const glue_decoder_args& a, int ncta, char* base, DecWs* ws)
     float* losspart = (float*)take((size_t)ncta * 4);
     int* badpart = (int*)take((size_t)ncta * 4);
     float* rescale = (float*)take(4);
-    if (ws) *ws = DecWs{pmax, psum, lse, cpart, c, apart, losspart, badpart, rescale};
+    unsigned int* counters = (unsigned int*)take(16);
+    if (ws) *ws = DecWs{pmax, psum, lse, cpart, c, apart, losspart, badpart, rescale, counters};
     return off;
 }
 
@@ -910,6 +973,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
 
+    GLUE_CUDA(cudaMemsetAsync(p.ws.counters, 0, 16, st));
     if (grad && a.n_batches > 1) {
         const size_t tab = (size_t)a.n_batches * a.F * sizeof(float);
         if (a.grad_scale_lin) GLUE_CUDA(cudaMemsetAsync(a.grad_scale_lin, 0, tab, st));
@@ -922,15 +986,11 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
         tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
         GLUE_CHECK_LAUNCH();
-        dec_lse_kernel<<<(a.B * 32 + 255) / 256, 256, 0, st>>>(p.ws, 2 * ncta, a.B);
-        GLUE_CHECK_LAUNCH();
     }
     const bool nb1 = a.n_batches == 1;
     int rc = nb1 ? launch_family<true>(a.family, 0, grad, P, ncta, st)
                  : launch_family<false>(a.family, 0, grad, P, ncta, st);
     if (rc) return rc;
-    tc_finish_main_kernel<<<1, 1024, 0, st>>>(p, ncta, nbf ? 1 : 0, grad ? 1 : 0);
-    GLUE_CHECK_LAUNCH();
     if (grad) {
         if (nbf) {
             rc = nb1 ? launch_family<true>(a.family, 1, true, P, ncta, st)
