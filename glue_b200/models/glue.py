@@ -13,7 +13,8 @@ from .. import dist as gdist
 from ..num import normalize_edges
 from ..utils import config, logged
 from .base import Trainer, TrainingPlugin
-from .data import AnnDataset, ArrayDataset, DataLoader, GraphDataset, ParallelDataLoader
+from .data import (AnnDataset, ArrayDataset, DataLoader, DevicePrefetcher, GraphDataset,
+                   ParallelDataLoader)
 from .nn import autodevice
 from .plugins import EarlyStopping, LRScheduler, Tensorboard
 
@@ -221,6 +222,9 @@ class GLUETrainer(Trainer):
         train_loader = self._loaders(data_train, graph, fetches, fetches, random_seed,
                                      len(data_train) > fetches, len(graph) > fetches, shard=True)
         val_loader = self._loaders(data_val, graph, fetches, fetches, random_seed, False, False)
+        if self.net.device.type == "cuda" and getattr(data, "device", None) is None:
+            # host-resident datasets: upload minibatch i + 1 while step i runs
+            train_loader = DevicePrefetcher(train_loader, self.net.device)
         self.align_burnin = align_burnin
 
         default_plugins: List[TrainingPlugin] = [Tensorboard()]

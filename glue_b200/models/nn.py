@@ -9,6 +9,7 @@ import numpy as np
 import torch
 from torch.nn.modules.batchnorm import _NormBase
 
+from .. import dist as gdist
 from .. import ops
 from ..utils import config, logged
 
@@ -26,6 +27,10 @@ class GraphConv(torch.nn.Module):
     def forward(self, input: torch.Tensor, eidx: torch.Tensor, enorm: torch.Tensor,
                 esgn: torch.Tensor) -> torch.Tensor:
         csr = ops.csr_for(eidx, enorm, esgn, input.shape[0])
+        if config.PARTITION_GRAPH and gdist.is_distributed():
+            # atlas scale: each rank aggregates a block of target rows, blocks are all-gathered
+            part = ops.partition_for(csr, gdist.rank(), gdist.world_size())
+            return ops.graph_conv_partitioned(input, part)
         return ops.graph_conv(input, csr)
 
 

@@ -44,6 +44,10 @@ class _Settings:
         DEVICE_DATA_BUDGET_BYTES=120 << 30,
         # replay training steps from captured CUDA graphs once their input signature repeats
         USE_CUDA_GRAPHS=True,
+        # data parallel only: split the guidance graph's edges over ranks by target-row blocks
+        # (GraphConv forward = local block + all-gather); for graphs too large to be worth
+        # aggregating redundantly on every rank
+        PARTITION_GRAPH=False,
     )
 
     def __init__(self) -> None:

@@ -52,3 +52,60 @@ def test_grad_bucket_all_reduce_mean_gloo():
     assert torch.allclose(w0b, torch.full((3, 5), 3.0)) and torch.equal(w0b, w1b)
     assert torch.allclose(b0, torch.full((3,), 2.0)) and torch.equal(b0, b1)
     assert torch.allclose(e0, torch.zeros(4)) and torch.equal(e0, e1)  # second step: no grads
+
+
+def _cpu_spmm(csr_part, inp, n_rows=None, out=None):
+    """CPU stand-in for the CSR GraphConv kernel (tests of the host-side partition logic)."""
+    indptr, col, val = csr_part
+    n = indptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n), (indptr[1:] - indptr[:-1]).long())
+    res = torch.zeros(n, inp.shape[1], dtype=inp.dtype)
+    res.index_add_(0, rows, inp[col.long()] * val.unsqueeze(1))
+    if out is None:
+        return res
+    out[:n] = res
+    return out
+
+
+def _partition_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import numpy as np
+    import torch.distributed as td
+    from glue_b200 import dist as gdist
+    from glue_b200 import ops
+    from oracle import sampling
+    from tests.util import random_graph
+    gdist.init_from_env(backend="gloo")
+    V, E, K = 101, 700, 6   # V not divisible by the world size: the last block is short
+    rs = np.random.RandomState(5)
+    eidx, ewt, esgn = random_graph(rs, V, E)
+    enorm = sampling.normalize_edges(eidx, ewt)
+    csr = ops.GraphCSR.__new__(ops.GraphCSR)  # host-built CSR (the device builder needs a GPU)
+    csr.vnum, csr.n_edges, csr.device = V, eidx.shape[1], torch.device("cpu")
+    csr.fwd = tuple(torch.as_tensor(a) for a in sampling.csr_forward(eidx, enorm, esgn, V))
+    csr.bwd = tuple(torch.as_tensor(a) for a in sampling.csr_transposed(eidx, enorm, esgn, V))
+    ops._spmm = lambda part, inp: _cpu_spmm(part, inp)
+    ops._spmm_rows = lambda part, inp, n_rows, o: _cpu_spmm(part, inp, n_rows, o)
+    part = ops.PartitionedGraphCSR(csr, rank, world)
+    torch.manual_seed(0)
+    inp = torch.randn(V, K, requires_grad=True)
+    res = ops.graph_conv_partitioned(inp, part)
+    gout = torch.randn(V, K, generator=torch.Generator().manual_seed(10 + rank))  # rank-specific
+    (gin,) = torch.autograd.grad(res, inp, gout)
+    want = _cpu_spmm(csr.fwd, inp.detach())
+    want_gin = _cpu_spmm(csr.bwd, gout)
+    out[rank] = (torch.equal(res.detach(), want), torch.allclose(gin, want_gin, atol=1e-6),
+                 part.n_rows, part.row0)
+    td.barrier()
+    td.destroy_process_group()
+
+
+def test_partitioned_graphconv_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_partition_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0][0] and out[1][0], "all-gathered row blocks must equal the unpartitioned result"
+    assert out[0][1] and out[1][1], "backward must apply the whole transposed graph locally"
+    assert (out[0][2], out[0][3]) == (51, 0) and (out[1][2], out[1][3]) == (50, 51)
