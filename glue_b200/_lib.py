@@ -23,6 +23,9 @@ EXPORTED_SYMBOLS = (
     "glue_graphconv_csr",
     "glue_csr_build_workspace_bytes",
     "glue_csr_build",
+    "glue_graphenc_workspace_bytes",
+    "glue_graphenc_head_fwd",
+    "glue_graphenc_head_bwd",
     "glue_graphdec_workspace_bytes",
     "glue_graphdec_bce_fwd",
     "glue_graphdec_bwd",
@@ -96,6 +99,15 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_csr_build.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
         c_void_p, c_size_t, c_void_p]
+
+    lib.glue_graphenc_workspace_bytes.restype = c_size_t
+    lib.glue_graphenc_workspace_bytes.argtypes = [c_int64, c_int32]
+    lib.glue_graphenc_head_fwd.restype = c_int32
+    lib.glue_graphenc_head_fwd.argtypes = [c_void_p] * 6 + [c_int64, c_int32] + [c_void_p] * 5 + [
+        c_size_t, c_void_p]
+    lib.glue_graphenc_head_bwd.restype = c_int32
+    lib.glue_graphenc_head_bwd.argtypes = [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 6 + [
+        c_size_t, c_void_p]
 
     lib.glue_graphdec_workspace_bytes.restype = c_size_t
     lib.glue_graphdec_workspace_bytes.argtypes = [c_int64, c_int64]

@@ -1,0 +1,408 @@
+// GraphEncoder head, fused (sm_100a).
+//
+// Replaces, for the whole vertex table in one forward and one backward launch sequence,
+//   loc / std_lin Linear layers + softplus        scglue/models/sc.py:44-46
+//   the reparameterised sample  v = mu + eps*sigma scglue/models/scglue.py:329
+//   KL(N(mu, sigma) || N(0, 1)) summed             scglue/models/scglue.py:339-340
+// i.e. ~30 ATen kernels over [V, K] tensors, among them two weight-gradient GEMMs with a
+// K x K output and a V-long reduction that cuBLAS runs on a single CTA (154 us each at
+// V = 52 000, profiles/r01c_launches_summary.md).
+//
+//   mu = ptr W_loc^T + b_loc        s = ptr W_std^T + b_std       sigma = softplus(s) + 1e-7
+//   v  = mu + noise * sigma         kl = sum_ik ( -log sigma + (sigma^2 + mu^2)/2 - 1/2 )
+//
+// Tiles of 64 vertices per CTA iteration, 256 threads; thread (row r = t >> 2, lane group
+// ig = t & 3) owns the float4 column blocks b = ig, ig + 4, ... of its row.  Weight matrices
+// live in shared memory ([out][in], row stride chosen so that the 8 rows of a warp hit
+// distinct banks).  Weight gradients are accumulated in registers over all tiles of a CTA
+// (thread <-> (out = t >> 2, in = ig + 4 ii)), written as per-CTA partials and reduced in a fixed
+// order => bit-reproducible.  Bound: FFMA / shared-memory issue (10 000 FMA per vertex fwd + bwd
+// against 1 KB of HBM traffic per vertex).
+#include "common.cuh"
+
+namespace glue {
+namespace {
+
+constexpr int TR = 64;          // vertex rows per tile
+constexpr int ENC_THREADS = 256;
+
+template <int KP>
+struct EncCfg {
+    static constexpr int NB4 = KP / 4;                   // float4 blocks per row
+    static constexpr int KS = (KP % 32 == 20) ? KP : KP + 4;  // row stride (words): 4-bank skew per row
+    static constexpr int NJ = (NB4 + 3) / 4;             // blocks per thread
+};
+
+template <int KP>
+struct EncSmem {
+    float x[TR][EncCfg<KP>::KS];
+    float wl[KP][EncCfg<KP>::KS];
+    float ws[KP][EncCfg<KP>::KS];
+    float d1[TR][EncCfg<KP>::KS];  // backward: d L / d mu
+    float d2[TR][EncCfg<KP>::KS];  // backward: d L / d s
+    float bl[KP], bs[KP];
+    double red[ENC_THREADS / 32];
+    unsigned int ticket;
+};
+
+struct EncArgs {
+    const float *ptr, *w_loc, *b_loc, *w_std, *b_std, *noise;
+    float *mu, *sigma, *vsamp, *kl_sum;
+    // backward
+    const float *grad_vsamp, *kl_coef;
+    float *grad_ptr, *grad_w_loc, *grad_b_loc, *grad_w_std, *grad_b_std;
+    // workspace
+    double* klpart;         // [ncta]
+    float* gwpart;          // [ncta][2][KP][KP + 1]  (last column: bias gradient)
+    unsigned int* counter;  // [1]
+    int64_t V;
+    int K;
+};
+
+template <int KP>
+__device__ __forceinline__ void load_weights(EncSmem<KP>& S, const EncArgs& a) {
+    constexpr int KS = EncCfg<KP>::KS;
+    for (int idx = threadIdx.x; idx < KP * KS; idx += ENC_THREADS) {
+        const int o = idx / KS, i = idx - o * KS;
+        const bool ok = o < a.K && i < a.K;
+        S.wl[o][i] = ok ? a.w_loc[o * a.K + i] : 0.f;
+        S.ws[o][i] = ok ? a.w_std[o * a.K + i] : 0.f;
+    }
+    for (int o = threadIdx.x; o < KP; o += ENC_THREADS) {
+        S.bl[o] = o < a.K ? a.b_loc[o] : 0.f;
+        S.bs[o] = o < a.K ? a.b_std[o] : 0.f;
+    }
+}
+
+template <int KP>
+__device__ __forceinline__ void load_x_tile(EncSmem<KP>& S, const EncArgs& a, int64_t row0) {
+    constexpr int KS = EncCfg<KP>::KS;
+    const int K = a.K;
+    for (int idx = threadIdx.x; idx < TR * K; idx += ENC_THREADS) {
+        const int r = idx / K, k = idx - r * K;
+        const int64_t row = row0 + r;
+        S.x[r][k] = row < a.V ? __ldg(a.ptr + row * K + k) : 0.f;
+    }
+    if (K < KS)
+        for (int idx = threadIdx.x; idx < TR * (KS - K); idx += ENC_THREADS) {
+            const int r = idx / (KS - K), k = K + idx % (KS - K);
+            S.x[r][k] = 0.f;
+        }
+}
+
+__device__ __forceinline__ float dot4(const float4& x, const float4& w, float acc) {
+    acc = fmaf(x.x, w.x, acc);
+    acc = fmaf(x.y, w.y, acc);
+    acc = fmaf(x.z, w.z, acc);
+    return fmaf(x.w, w.w, acc);
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int KP>
+__global__ void __launch_bounds__(ENC_THREADS) graphenc_fwd_kernel(EncArgs a) {
+    extern __shared__ float4 enc_smem_raw[];
+    EncSmem<KP>& S = *reinterpret_cast<EncSmem<KP>*>(enc_smem_raw);
+    constexpr int NB4 = EncCfg<KP>::NB4, NJ = EncCfg<KP>::NJ;
+    const int t = threadIdx.x, r = t >> 2, ig = t & 3;
+    const int K = a.K;
+    load_weights<KP>(S, a);
+    double kl_acc = 0.0;
+    const int64_t ntiles = (a.V + TR - 1) / TR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        load_x_tile<KP>(S, a, tile * TR);
+        __syncthreads();
+        const int64_t row = tile * TR + r;
+        const bool rowok = row < a.V;
+        float4 xr[NB4];
+#pragma unroll
+        for (int i4 = 0; i4 < NB4; ++i4) xr[i4] = *reinterpret_cast<const float4*>(&S.x[r][4 * i4]);
+        float kl_row = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const int b = ig + 4 * jj;
+            if (b >= NB4) continue;
+            float mu4[4], s4[4];
+#pragma unroll
+            for (int oo = 0; oo < 4; ++oo) {
+                const int o = 4 * b + oo;
+                float accl = S.bl[o], accs = S.bs[o];
+#pragma unroll
+                for (int i4 = 0; i4 < NB4; ++i4) {
+                    accl = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.wl[o][4 * i4]), accl);
+                    accs = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.ws[o][4 * i4]), accs);
+                }
+                mu4[oo] = accl, s4[oo] = accs;
+            }
+#pragma unroll
+            for (int o2 = 0; o2 < 2; ++o2) {  // float2 granularity: rows are 8-byte aligned for even K
+                const int o = 4 * b + 2 * o2;
+                if (!rowok || o >= K) continue;
+                const int64_t off = row * K + o;
+                float2 nz = make_float2(0.f, 0.f);
+                if (a.noise) nz = __ldg(reinterpret_cast<const float2*>(a.noise + off));
+                const float m0 = mu4[2 * o2], m1 = mu4[2 * o2 + 1];
+                const float g0 = softplusf(s4[2 * o2]) + GLUE_EPS, g1 = softplusf(s4[2 * o2 + 1]) + GLUE_EPS;
+                *reinterpret_cast<float2*>(a.mu + off) = make_float2(m0, m1);
+                *reinterpret_cast<float2*>(a.sigma + off) = make_float2(g0, g1);
+                *reinterpret_cast<float2*>(a.vsamp + off) = make_float2(fmaf(nz.x, g0, m0), fmaf(nz.y, g1, m1));
+                kl_row += (-logf(g0) + 0.5f * (g0 * g0 + m0 * m0) - 0.5f) +
+                          (-logf(g1) + 0.5f * (g1 * g1 + m1 * m1) - 0.5f);
+            }
+        }
+        kl_acc += (double)kl_row;
+    }
+    // KL: deterministic block reduction, per-CTA partial, last CTA sums the partials in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kl_acc += __shfl_xor_sync(FULL, kl_acc, o);
+    if ((t & 31) == 0) S.red[t >> 5] = kl_acc;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < ENC_THREADS / 32; ++w) s += S.red[w];
+        a.klpart[blockIdx.x] = s;
+        __threadfence();
+        S.ticket = atomicAdd(a.counter, 1u);
+    }
+    __syncthreads();
+    if (S.ticket == gridDim.x - 1 && t == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned q = 0; q < gridDim.x; ++q) s += __ldcg(a.klpart + q);
+        a.kl_sum[0] = (float)s;
+        *a.counter = 0u;  // ready for the next call on this workspace
+    }
+}
+
+// ----------------------------------------------------------------------------------- backward
+template <int KP>
+__global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_kernel(EncArgs a) {
+    extern __shared__ float4 enc_smem_raw[];
+    EncSmem<KP>& S = *reinterpret_cast<EncSmem<KP>*>(enc_smem_raw);
+    constexpr int NB4 = EncCfg<KP>::NB4, NJ = EncCfg<KP>::NJ, KS = EncCfg<KP>::KS;
+    constexpr int NI = KP / 4;  // inputs per thread in the weight-gradient mapping (i = ig + 4 ii)
+    const int t = threadIdx.x, r = t >> 2, ig = t & 3;
+    const int K = a.K;
+    load_weights<KP>(S, a);
+    const float ckl = a.kl_coef ? __ldg(a.kl_coef) : 0.f;
+    float gwl[NI], gws[NI], gbl = 0.f, gbs = 0.f;
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) gwl[ii] = gws[ii] = 0.f;
+    const int wo = t >> 2;  // output feature owned in the weight-gradient mapping (TR == 64 == max KP)
+    const int64_t ntiles = (a.V + TR - 1) / TR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        load_x_tile<KP>(S, a, tile * TR);
+        const int64_t row = tile * TR + r;
+        const bool rowok = row < a.V;
+        // d L / d mu, d L / d s of this thread's column blocks
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const int b = ig + 4 * jj;
+            if (b >= NB4) continue;
+            float dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int o2 = 0; o2 < 2; ++o2) {
+                const int o = 4 * b + 2 * o2;
+                if (!rowok || o >= K) continue;
+                const int64_t off = row * K + o;
+                const float2 gv = a.grad_vsamp ? __ldg(reinterpret_cast<const float2*>(a.grad_vsamp + off))
+                                               : make_float2(0.f, 0.f);
+                const float2 nz = a.noise ? __ldg(reinterpret_cast<const float2*>(a.noise + off))
+                                          : make_float2(0.f, 0.f);
+                const float2 m = __ldg(reinterpret_cast<const float2*>(a.mu + off));
+                const float2 g = __ldg(reinterpret_cast<const float2*>(a.sigma + off));
+                dm[2 * o2] = fmaf(ckl, m.x, gv.x);
+                dm[2 * o2 + 1] = fmaf(ckl, m.y, gv.y);
+                // d sigma / d s = sigmoid(s) = 1 - exp(-softplus(s)),  softplus(s) = sigma - 1e-7
+                const float dsg0 = fmaf(gv.x, nz.x, ckl * (g.x - 1.f / g.x));
+                const float dsg1 = fmaf(gv.y, nz.y, ckl * (g.y - 1.f / g.y));
+                ds[2 * o2] = dsg0 * (1.f - expf(-(g.x - GLUE_EPS)));
+                ds[2 * o2 + 1] = dsg1 * (1.f - expf(-(g.y - GLUE_EPS)));
+            }
+            *reinterpret_cast<float4*>(&S.d1[r][4 * b]) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+            *reinterpret_cast<float4*>(&S.d2[r][4 * b]) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+        }
+        __syncthreads();
+        // (1) d L / d ptr[r, i] = sum_o dmu[r, o] W_loc[o, i] + ds[r, o] W_std[o, i]
+        {
+            float4 acc[NJ];
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int o = 0; o < K; ++o) {
+                const float d1 = S.d1[r][o], d2 = S.d2[r][o];
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    const int b = ig + 4 * jj;
+                    if (b >= NB4) continue;
+                    const float4 wl = *reinterpret_cast<const float4*>(&S.wl[o][4 * b]);
+                    const float4 ws = *reinterpret_cast<const float4*>(&S.ws[o][4 * b]);
+                    acc[jj].x = fmaf(d1, wl.x, fmaf(d2, ws.x, acc[jj].x));
+                    acc[jj].y = fmaf(d1, wl.y, fmaf(d2, ws.y, acc[jj].y));
+                    acc[jj].z = fmaf(d1, wl.z, fmaf(d2, ws.z, acc[jj].z));
+                    acc[jj].w = fmaf(d1, wl.w, fmaf(d2, ws.w, acc[jj].w));
+                }
+            }
+            if (rowok && a.grad_ptr) {
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    const int b = ig + 4 * jj;
+                    if (b >= NB4) continue;
+                    float* dst = a.grad_ptr + row * K + 4 * b;
+                    if (4 * b < K) *reinterpret_cast<float2*>(dst) = make_float2(acc[jj].x, acc[jj].y);
+                    if (4 * b + 2 < K) *reinterpret_cast<float2*>(dst + 2) = make_float2(acc[jj].z, acc[jj].w);
+                }
+            }
+        }
+        // (2) weight gradients: thread <-> (out = wo, in = ig + 4 ii), summed over the tile's rows
+        if (wo < K) {
+            for (int rr = 0; rr < TR; ++rr) {
+                const float d1 = S.d1[rr][wo], d2 = S.d2[rr][wo];
+#pragma unroll
+                for (int ii = 0; ii < NI; ++ii) {
+                    const float xi = S.x[rr][ig + 4 * ii];
+                    gwl[ii] = fmaf(d1, xi, gwl[ii]);
+                    gws[ii] = fmaf(d2, xi, gws[ii]);
+                }
+                if (ig == 0) gbl += d1, gbs += d2;
+            }
+        }
+        (void)KS;
+    }
+    // per-CTA partials [2][KP][KP + 1]
+    if (wo < K) {
+        float* base = a.gwpart + (size_t)blockIdx.x * 2 * KP * (KP + 1);
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii) {
+            const int i = ig + 4 * ii;
+            if (i < K) {
+                base[wo * (KP + 1) + i] = gwl[ii];
+                base[(KP + wo) * (KP + 1) + i] = gws[ii];
+            }
+        }
+        if (ig == 0) {
+            base[wo * (KP + 1) + KP] = gbl;
+            base[(KP + wo) * (KP + 1) + KP] = gbs;
+        }
+    }
+}
+
+// fixed-order sum of the per-CTA weight-gradient partials; one thread per (matrix, out, in | bias)
+template <int KP>
+__global__ void graphenc_wgrad_reduce_kernel(EncArgs a, int ncta) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = KP * (KP + 1);
+    if (idx >= 2 * per) return;
+    const int mat = idx / per, rem = idx - mat * per;
+    const int o = rem / (KP + 1), i = rem - o * (KP + 1);
+    if (o >= a.K || (i >= a.K && i != KP)) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < ncta; ++q) s += a.gwpart[(size_t)q * 2 * per + idx];
+    if (i == KP) {
+        float* gb = mat == 0 ? a.grad_b_loc : a.grad_b_std;
+        if (gb) gb[o] = s;
+    } else {
+        float* gw = mat == 0 ? a.grad_w_loc : a.grad_w_std;
+        if (gw) gw[o * a.K + i] = s;
+    }
+}
+
+int pick_kp(int K) { return K <= 52 ? 52 : (K <= 64 ? 64 : 0); }
+
+int enc_grid(int64_t V) {
+    const int64_t ntiles = (V + TR - 1) / TR;
+    const int cap = 2 * sm_count();
+    return (int)(ntiles < cap ? ntiles : cap);
+}
+
+size_t enc_ws_layout(int64_t V, int KP, char* base, EncArgs* a) {
+    const int ncta = enc_grid(V);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    unsigned int* counter = (unsigned int*)take(16);
+    double* klpart = (double*)take((size_t)ncta * 8);
+    float* gwpart = (float*)take((size_t)ncta * 2 * KP * (KP + 1) * 4);
+    if (a) a->counter = counter, a->klpart = klpart, a->gwpart = gwpart;
+    return off;
+}
+
+template <int KP>
+int run_fwd(EncArgs a, cudaStream_t st) {
+    const size_t smem = sizeof(EncSmem<KP>);
+    auto k = graphenc_fwd_kernel<KP>;
+    GLUE_SMEM_ONCE(k, smem);
+    k<<<enc_grid(a.V), ENC_THREADS, smem, st>>>(a);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int KP>
+int run_bwd(EncArgs a, cudaStream_t st) {
+    const size_t smem = sizeof(EncSmem<KP>);
+    auto k = graphenc_bwd_kernel<KP>;
+    GLUE_SMEM_ONCE(k, smem);
+    const int ncta = enc_grid(a.V);
+    k<<<ncta, ENC_THREADS, smem, st>>>(a);
+    GLUE_CHECK_LAUNCH();
+    const int total = 2 * KP * (KP + 1);
+    graphenc_wgrad_reduce_kernel<KP><<<(total + 255) / 256, 256, 0, st>>>(a, ncta);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+}  // namespace glue
+
+extern "C" size_t glue_graphenc_workspace_bytes(int64_t V, int32_t K) {
+    const int KP = glue::pick_kp(K);
+    if (V <= 0 || KP == 0) return 0;
+    return glue::enc_ws_layout(V, KP, nullptr, nullptr);
+}
+
+extern "C" int glue_graphenc_head_fwd(const float* ptr, const float* w_loc, const float* b_loc, const float* w_std,
+                                      const float* b_std, const float* noise, int64_t V, int32_t K, float* mu,
+                                      float* sigma, float* vsamp, float* kl_sum, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    using namespace glue;
+    if (!ptr || !w_loc || !b_loc || !w_std || !b_std || !mu || !sigma || !vsamp || !kl_sum || !workspace)
+        return GLUE_E_BADARG;
+    if (V <= 0 || K <= 0) return GLUE_E_BADARG;
+    const int KP = pick_kp(K);
+    if (KP == 0 || (K & 1)) return GLUE_E_UNSUPPORTED;
+    EncArgs a = {};
+    a.ptr = ptr, a.w_loc = w_loc, a.b_loc = b_loc, a.w_std = w_std, a.b_std = b_std, a.noise = noise;
+    a.mu = mu, a.sigma = sigma, a.vsamp = vsamp, a.kl_sum = kl_sum, a.V = V, a.K = K;
+    if (workspace_bytes < enc_ws_layout(V, KP, nullptr, nullptr)) return GLUE_E_WORKSPACE;
+    enc_ws_layout(V, KP, (char*)workspace, &a);
+    cudaStream_t st = (cudaStream_t)stream;
+    GLUE_CUDA(cudaMemsetAsync(a.counter, 0, 16, st));
+    return KP == 52 ? run_fwd<52>(a, st) : run_fwd<64>(a, st);
+}
+
+extern "C" int glue_graphenc_head_bwd(const float* ptr, const float* w_loc, const float* w_std, const float* noise,
+                                      const float* mu, const float* sigma, const float* grad_vsamp,
+                                      const float* kl_coef, int64_t V, int32_t K, float* grad_ptr,
+                                      float* grad_w_loc, float* grad_b_loc, float* grad_w_std, float* grad_b_std,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace glue;
+    if (!ptr || !w_loc || !w_std || !mu || !sigma || !workspace) return GLUE_E_BADARG;
+    if (V <= 0 || K <= 0) return GLUE_E_BADARG;
+    const int KP = pick_kp(K);
+    if (KP == 0 || (K & 1)) return GLUE_E_UNSUPPORTED;
+    EncArgs a = {};
+    a.ptr = ptr, a.w_loc = w_loc, a.w_std = w_std, a.noise = noise, a.mu = const_cast<float*>(mu);
+    a.sigma = const_cast<float*>(sigma), a.grad_vsamp = grad_vsamp, a.kl_coef = kl_coef;
+    // biases are not read by the backward pass; point them at the weights to keep load_weights simple
+    a.b_loc = w_loc, a.b_std = w_std;
+    a.grad_ptr = grad_ptr, a.grad_w_loc = grad_w_loc, a.grad_b_loc = grad_b_loc;
+    a.grad_w_std = grad_w_std, a.grad_b_std = grad_b_std, a.V = V, a.K = K;
+    if (workspace_bytes < enc_ws_layout(V, KP, nullptr, nullptr)) return GLUE_E_WORKSPACE;
+    enc_ws_layout(V, KP, (char*)workspace, &a);
+    cudaStream_t st = (cudaStream_t)stream;
+    return KP == 52 ? run_bwd<52>(a, st) : run_bwd<64>(a, st);
+}

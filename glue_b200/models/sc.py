@@ -16,6 +16,7 @@ import torch
 import torch.distributions as D
 import torch.nn.functional as F
 
+from .. import ops
 from ..num import EPS
 from . import glue
 from .nn import GraphConv
@@ -42,6 +43,16 @@ class GraphEncoder(glue.GraphEncoder):
     def forward(self, eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor) -> D.Normal:
         ptr = self.conv(self.vrepr, eidx, enorm, esgn)
         return D.Normal(self.loc(ptr), F.softplus(self.std_lin(ptr)) + EPS, validate_args=False)
+
+    def sample_with_kl(self, eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor,
+                       noise: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        r"""Training-path entry point: ``(v.mean + noise * v.stddev, kl(v || N(0, 1)).sum())`` for
+        ``v = self(eidx, enorm, esgn)``, computed by the fused head kernel right after the
+        propagation (same values as the two-step formulation of ``scglue.py:328-340``)."""
+        ptr = self.conv(self.vrepr, eidx, enorm, esgn)
+        vsamp, kl_sum, _, _ = ops.graph_encoder_head(ptr, self.loc.weight, self.loc.bias,
+                                                     self.std_lin.weight, self.std_lin.bias, noise)
+        return vsamp, kl_sum
 
 
 class GraphDecoder(glue.GraphDecoder):

@@ -189,10 +189,22 @@ class SCGLUETrainer(GLUETrainer):
 
     def _graph_terms(self, eidx, ewt, esgn, prior):
         net = self.net
-        v = net.g2v(self.eidx, self.enorm, self.esgn)
-        vsamp = v.mean + self.noise(v.mean, "v") * v.stddev
+        g2v = net.g2v
+        latent = g2v.vrepr.shape[1] if hasattr(g2v, "vrepr") else 0
+        if getattr(self, "_unit_prior", None) is None:  # one host read, at the first step
+            self._unit_prior = (float(net.prior.loc) == 0.0 and float(net.prior.std) == 1.0
+                                if hasattr(net.prior, "loc") else False)
+        if (hasattr(g2v, "sample_with_kl") and g2v.vrepr.is_cuda and latent <= 64
+                and latent % 2 == 0 and self._unit_prior):
+            # fused Gaussian head: sample and KL in one launch (prior is N(0, 1), sc.py:640-660)
+            vsamp, kl_sum = g2v.sample_with_kl(self.eidx, self.enorm, self.esgn,
+                                               self.noise(g2v.vrepr, "v"))
+            g_kl = kl_sum / (vsamp.shape[0] * vsamp.shape[0])
+        else:
+            v = g2v(self.eidx, self.enorm, self.esgn)
+            vsamp = v.mean + self.noise(v.mean, "v") * v.stddev
+            g_kl = _kl_to_prior(v, prior) / vsamp.shape[0]
         g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
-        g_kl = _kl_to_prior(v, prior) / vsamp.shape[0]
         return vsamp, g_nll, g_kl
 
     def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str,

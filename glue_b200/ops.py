@@ -175,6 +175,68 @@ def graph_conv(inp: torch.Tensor, csr: GraphCSR) -> torch.Tensor:
     return _GraphConvFn.apply(inp, csr)
 
 
+# --------------------------------------------------------------- graph encoder head
+
+
+class _GraphEncHeadFn(torch.autograd.Function):
+    r"""``(vsamp, kl_sum, mu, sigma)`` of the graph encoder's Gaussian head in one launch; the
+    backward pass produces every gradient from ``d L / d vsamp`` and ``d L / d kl_sum``."""
+
+    @staticmethod
+    def forward(ctx, ptr_, w_loc, b_loc, w_std, b_std, noise):
+        dev = ptr_.device
+        V, K = ptr_.shape
+        L = _lib.lib()
+        mu, sigma, vsamp = (torch.empty_like(ptr_) for _ in range(3))
+        kl = torch.empty((), dtype=torch.float32, device=dev)
+        ws = _workspace(L.glue_graphenc_workspace_bytes(V, K), dev)
+        ev = TIMER.start("graphenc_head_fwd", dev)
+        check(L.glue_graphenc_head_fwd(ptr(ptr_), ptr(w_loc), ptr(b_loc), ptr(w_std), ptr(b_std),
+                                       ptr(noise), V, K, ptr(mu), ptr(sigma), ptr(vsamp), ptr(kl),
+                                       ptr(ws), ws.numel(), current_stream(dev)), "graphenc_head_fwd")
+        TIMER.stop(ev, dev)
+        ctx.save_for_backward(ptr_, w_loc, w_std, noise, mu, sigma)
+        ctx.mark_non_differentiable(mu, sigma)
+        return vsamp, kl, mu, sigma
+
+    @staticmethod
+    def backward(ctx, g_vsamp, g_kl, _g_mu, _g_sigma):
+        ptr_, w_loc, w_std, noise, mu, sigma = ctx.saved_tensors
+        dev = ptr_.device
+        V, K = ptr_.shape
+        L = _lib.lib()
+        g_ptr = torch.empty_like(ptr_)
+        g_wl, g_ws = torch.empty_like(w_loc), torch.empty_like(w_std)
+        g_bl = torch.empty(K, dtype=torch.float32, device=dev)
+        g_bs = torch.empty(K, dtype=torch.float32, device=dev)
+        ws = _workspace(L.glue_graphenc_workspace_bytes(V, K), dev)
+        g_vsamp = None if g_vsamp is None else _f32(g_vsamp, "grad_vsamp")
+        g_kl = None if g_kl is None else _f32(g_kl, "grad_kl")
+        check(L.glue_graphenc_head_bwd(ptr(ptr_), ptr(w_loc), ptr(w_std), ptr(noise), ptr(mu),
+                                       ptr(sigma), ptr(g_vsamp), ptr(g_kl), V, K, ptr(g_ptr),
+                                       ptr(g_wl), ptr(g_bl), ptr(g_ws), ptr(g_bs), ptr(ws), ws.numel(),
+                                       current_stream(dev)), "graphenc_head_bwd")
+        return g_ptr, g_wl, g_bl, g_ws, g_bs, None
+
+
+def graph_encoder_head(ptr_, w_loc, b_loc, w_std, b_std, noise=None):
+    r"""Gaussian head of the graph encoder (``scglue/models/sc.py:44-46``) fused with the
+    reparameterised sample and the KL term against ``N(0, 1)``:
+    returns ``(vsamp, kl_sum, mu, sigma)`` with ``vsamp = mu + noise * sigma`` and
+    ``kl_sum = kl_divergence(N(mu, sigma), N(0, 1)).sum()``; ``mu`` / ``sigma`` are detached."""
+    require_cuda(ptr_, w_loc, b_loc, w_std, b_std, noise)
+    args = [_f32(t, n) for t, n in ((ptr_, "ptr"), (w_loc, "w_loc"), (b_loc, "b_loc"),
+                                    (w_std, "w_std"), (b_std, "b_std"))]
+    V, K = args[0].shape
+    if K > 64 or K % 2:
+        raise ValueError("glue_b200 graph encoder head supports even latent_dim <= 64")
+    if noise is not None:
+        noise = _f32(noise, "noise")
+        if noise.shape != args[0].shape:
+            raise ValueError("`noise` must have the shape of the vertex table")
+    return _GraphEncHeadFn.apply(*args, noise)
+
+
 # ------------------------------------------------- edge-partitioned GraphConv (atlas scale)
 
 

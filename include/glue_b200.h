@@ -68,6 +68,34 @@ int glue_csr_build(const int64_t *key, const int64_t *other, const float *val, i
                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * GraphEncoder head -- replaces, for the whole vertex table, the two Linear layers +
+ * softplus of scglue/models/sc.py:44-46, the reparameterised sample
+ * (scglue/models/scglue.py:329) and the KL term against N(0, 1)
+ * (scglue/models/scglue.py:339-340), forward and backward:
+ *
+ *   mu = ptr W_loc^T + b_loc,  sigma = softplus(ptr W_std^T + b_std) + 1e-7
+ *   vsamp = mu + noise * sigma               (noise == NULL: vsamp = mu)
+ *   kl_sum[0] = sum_ik ( -log sigma + (sigma^2 + mu^2) / 2 - 1/2 )
+ *
+ * ptr / noise / mu / sigma / vsamp: [V, K]; W_*: [K, K] ([out, in] as torch.nn.Linear);
+ * K even, <= 64.  Backward takes d L / d vsamp (NULL = zeros) and the DEVICE scalar
+ * kl_coef[0] = d L / d kl_sum (NULL = 0) and writes every gradient; weight gradients
+ * are reduced in a fixed order (bit-reproducible).
+ * workspace: glue_graphenc_workspace_bytes(V, K), shared by forward and backward.
+ * ------------------------------------------------------------------------- */
+size_t glue_graphenc_workspace_bytes(int64_t V, int32_t K);
+int glue_graphenc_head_fwd(const float *ptr, const float *w_loc, const float *b_loc,
+                           const float *w_std, const float *b_std, const float *noise, int64_t V,
+                           int32_t K, float *mu, float *sigma, float *vsamp, float *kl_sum,
+                           void *workspace, size_t workspace_bytes, void *stream);
+int glue_graphenc_head_bwd(const float *ptr, const float *w_loc, const float *w_std,
+                           const float *noise, const float *mu, const float *sigma,
+                           const float *grad_vsamp, const float *kl_coef, int64_t V, int32_t K,
+                           float *grad_ptr, float *grad_w_loc, float *grad_b_loc,
+                           float *grad_w_std, float *grad_b_std, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * GraphDecoder + Bernoulli log-prob + pos/neg balanced mean -- replaces
  * scglue/models/sc.py:54-59 and scglue/models/scglue.py:331-338.
  *

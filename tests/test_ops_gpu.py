@@ -291,3 +291,42 @@ def test_decoder_rejects_cpu_tensors(ops):
     p = torch.zeros(1, 6)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.decoder_nll("NB", u, v, p, p, p, l=torch.ones(4, 1), x=torch.ones(4, 6))
+
+
+# ------------------------------------------------------------------ graph encoder head
+@pytest.mark.parametrize("V,K,with_noise", [(37, 50, True), (5000, 50, True), (52000, 50, True),
+                                            (1000, 16, False), (777, 64, True), (300, 2, True)])
+def test_graph_encoder_head_vs_torch(ops, V, K, with_noise):
+    """Fused Gaussian head (Linear x2 + softplus + sample + KL) against the ATen formulation of
+    scglue/models/sc.py:44-46 and scglue/models/scglue.py:329-340, values and every gradient."""
+    import torch.distributions as D
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(V + K)
+    ptr_ = torch.randn(V, K, generator=gen) * 0.7
+    wl, ws = torch.randn(K, K, generator=gen) * 0.2, torch.randn(K, K, generator=gen) * 0.2
+    bl, bs = torch.randn(K, generator=gen) * 0.1, torch.randn(K, generator=gen) * 0.1
+    noise = torch.randn(V, K, generator=gen) if with_noise else None
+    gv = torch.randn(V, K, generator=gen)
+    ckl = 0.37
+
+    def run(dev, fused):
+        args = [t.to(dev).requires_grad_(True) for t in (ptr_, wl, bl, ws, bs)]
+        nz = None if noise is None else noise.to(dev)
+        if fused:
+            vsamp, kl, mu, sigma = ops.graph_encoder_head(*args, nz)
+        else:
+            p, a, b, c, d = args
+            q = D.Normal(F.linear(p, a, b), F.softplus(F.linear(p, c, d)) + 1e-7, validate_args=False)
+            mu, sigma = q.mean, q.stddev
+            vsamp = mu if nz is None else mu + nz * sigma
+            kl = D.kl_divergence(q, D.Normal(torch.zeros((), device=dev), torch.ones((), device=dev))).sum()
+        loss = (vsamp * gv.to(dev)).sum() + ckl * kl
+        grads = torch.autograd.grad(loss, args)
+        return [vsamp, kl, mu, sigma] + list(grads)
+
+    got, want = run(DEV, True), run("cpu", False)
+    for name, g, w in zip(["vsamp", "kl", "mu", "sigma", "d/dptr", "d/dW_loc", "d/db_loc", "d/dW_std",
+                           "d/db_std"], got, want):
+        assert_close(g, w, 2e-5, name)
+    again = run(DEV, True)
+    assert all(torch.equal(a, b) for a, b in zip(got, again)), "graph encoder head must be deterministic"
