@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_nll_fwd",
     "glue_decoder_log_prob",
     "glue_decoder_mean",
+    "glue_rmsprop_flat",
     "glue_tc_selftest",
     "glue_tc_set_trace",
 )
@@ -143,6 +144,9 @@ def _declare(lib: ctypes.CDLL) -> None:
         ctypes.c_uint32, c_void_p, c_void_p]
 
 
+    lib.glue_rmsprop_flat.restype = c_int32
+    lib.glue_rmsprop_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                      c_float, c_void_p]
     lib.glue_tc_set_trace.restype = None
     lib.glue_tc_set_trace.argtypes = [c_void_p]
 

@@ -136,13 +136,23 @@ class GLUETrainer(Trainer):
     def _make_optim(self, modules) -> torch.optim.Optimizer:
         params = list(itertools.chain(*(m.parameters() for m in modules)))
         kwargs = dict(self.optim_kwargs)
-        if self.net.device.type == "cuda" and self.optim_name in ("RMSprop", "Adam", "AdamW"):
+        on_gpu = self.net.device.type == "cuda"
+        if (on_gpu and self.optim_name == "RMSprop" and config.USE_FUSED_OPTIMIZER
+                and set(kwargs) <= {"alpha", "eps"}):
+            # the reference's optimizer (scglue.py:889-942) as one fused kernel per step
+            from ..optim import FlatRMSprop
+            return FlatRMSprop(params, lr=self.lr, **kwargs)
+        if on_gpu and self.optim_name in ("RMSprop", "Adam", "AdamW"):
             kwargs.setdefault("capturable", True)  # same arithmetic, no host reads: graph-safe
         return getattr(torch.optim, self.optim_name)(params, lr=self.lr, **kwargs)
 
     # -- data-parallel gradient exchange -------------------------------------------------
     def _sync_grads(self, which: str) -> None:
         if not gdist.is_distributed():
+            return
+        optim = self.vae_optim if which == "vae" else self.dsc_optim
+        if hasattr(optim, "all_reduce_mean"):  # FlatRMSprop: gradients already live in one buffer
+            optim.all_reduce_mean()
             return
         attr = f"_{which}_bucket"
         if getattr(self, attr) is None:

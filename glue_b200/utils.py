@@ -48,6 +48,8 @@ class _Settings:
         # (GraphConv forward = local block + all-gather); for graphs too large to be worth
         # aggregating redundantly on every rank
         PARTITION_GRAPH=False,
+        # RMSprop as one fused kernel over flat parameter / gradient buffers
+        USE_FUSED_OPTIMIZER=True,
     )
 
     def __init__(self) -> None:

@@ -196,6 +196,17 @@ int glue_decoder_log_prob(const glue_decoder_args *args, float *out, void *strea
 int glue_decoder_mean(const glue_decoder_args *args, float *out, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Fused RMSprop over a flat range -- replaces the multi-tensor launch sequence of
+ * torch.optim.RMSprop(momentum=0, centered=False, weight_decay=0), the optimizer
+ * scglue compiles its trainers with (scglue/models/scglue.py:889-942):
+ *   square_avg = alpha * square_avg + (1 - alpha) * grad^2
+ *   param     -= lr * grad / (sqrt(square_avg) + eps)
+ * param / grad / square_avg: [n] fp32 (16-byte aligned ranges take the vector path).
+ * ------------------------------------------------------------------------- */
+int glue_rmsprop_flat(float *param, const float *grad, float *square_avg, int64_t n, float lr,
+                      float alpha, float eps, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
  * M = 128) steps on caller-built shared-memory operand images and return the
  * accumulator tile out[128][N].  a_img / b_img are device buffers copied

@@ -330,3 +330,41 @@ def test_graph_encoder_head_vs_torch(ops, V, K, with_noise):
         assert_close(g, w, 2e-5, name)
     again = run(DEV, True)
     assert all(torch.equal(a, b) for a, b in zip(got, again)), "graph encoder head must be deterministic"
+
+
+# ------------------------------------------------------------------ fused optimizer
+def test_flat_rmsprop_matches_torch_rmsprop(native_lib):
+    """FlatRMSprop (one fused kernel over flat buffers) against torch.optim.RMSprop over several
+    steps: a parameter without gradient is skipped, the learning rate changes mid-way, and the
+    state survives a state_dict round trip."""
+    from glue_b200.optim import FlatRMSprop
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(52000, 50), (50, 50), (50,), (3, 7), (1, 50001), (5,)]
+    init = [torch.randn(s, generator=gen) for s in shapes]
+    ref_p = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    our_p = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    ref = torch.optim.RMSprop(ref_p, lr=2e-3)
+    ours = FlatRMSprop(our_p, lr=2e-3)
+    for step in range(6):
+        grads = [torch.randn(s, generator=gen).to(DEV) * (10.0 ** (step - 3)) for s in shapes]
+        for ps in (ref_p, our_p):
+            for i, (p, g) in enumerate(zip(ps, grads)):
+                p.grad = None if (i == 3 and step % 2) else g.clone()
+        if step == 3:
+            for opt in (ref, ours):
+                opt.param_groups[0]["lr"] = 5e-4
+        if step == 4:  # checkpoint round trip (EarlyStopping restores optimizer state this way)
+            ours.load_state_dict(ours.state_dict())
+        ref.step()
+        ours.step()
+        ours.zero_grad()
+        for a, b in zip(our_p, ref_p):
+            assert_close(a, b, 1e-6, f"parameters after step {step}")
+    for a, b in zip(our_p, ref_p):
+        assert_close(ours.state[a]["square_avg"], ref.state[b]["square_avg"], 1e-6, "square_avg")
+    # parameters are views of one flat buffer, and survive being re-allocated by .to()
+    assert all(p.data_ptr() == v.data_ptr() for p, v in zip(our_p, ours._pviews))
+    our_p[1].data = our_p[1].data.clone()
+    our_p[1].grad = torch.ones_like(our_p[1])
+    ours.step()
+    assert our_p[1].data_ptr() == ours._pviews[1].data_ptr()
