@@ -320,16 +320,22 @@ def main():
     # i + 1 on a side stream while step i runs) -> trainer.train_step -> D2H read of the loss
     from glue_b200.models.data import DevicePrefetcher
 
-    def run_e2e(n):
-        feed = DevicePrefetcher((host_pool[i % pool_n] for i in range(n)), device)
+    def run_e2e(n, prefetch):
+        feed = (host_pool[i % pool_n] for i in range(n))
+        if prefetch:
+            feed = DevicePrefetcher(feed, device)
         last = 0.0
         for batch in feed:
             losses = trainer.train_step(_Engine, batch)
             last = float(losses["vae_loss"])  # D2H read of the step's result
         return last
 
-    run_e2e(4)
-    ms_e2e = timed(lambda i: run_e2e(args.steps) if i == 0 else None, 1)
+    e2e_runs = {}
+    for mode, prefetch in (("direct", False), ("prefetch", True)):
+        run_e2e(4, prefetch)
+        e2e_runs[mode] = timed(lambda i, p=prefetch: run_e2e(args.steps, p) if i == 0 else None, 1)
+    e2e_feed = min(e2e_runs, key=e2e_runs.get)
+    ms_e2e = e2e_runs[e2e_feed]
     e2e_value = cells / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -424,7 +430,8 @@ def main():
                    "parallelism": f"dp{world}" + ("+graph-partition" if args.partition_graph else ""),
                    "l2": f"inputs cycle through {pool_n} minibatches (8 x 27 MB > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "feed": e2e_feed,
+                "ms_per_step_by_feed": {k: v / args.steps for k, v in e2e_runs.items()}},
         "gpu_launches": int(launches),
         "cuda_graph": {k: ginfo[k] for k in ("graphs", "kernels_per_step", "disabled")},
         "clocks": clocks.summary(),

@@ -219,25 +219,32 @@ __global__ void __launch_bounds__(1024)
 graphdec_finalize_kernel(const float* __restrict__ partial, int nblocks,
                          const float* __restrict__ ewt, int64_t E, float* __restrict__ out_loss,
                          float* __restrict__ out_coef) {
-    __shared__ double acc[4];
+    // every block reduces the (few KB of) per-block partials itself, in a fixed order:
+    // thread <-> (component c = t & 3, one of 256 strided sub-sums), then a shuffle tree per
+    // component and a fixed-order sum over the 8 warps that hold it.
+    __shared__ double wsum[32][4];
     __shared__ float scale[2];
-    if (threadIdx.x < 4) {
-        double a = 0.0;
-        for (int b = 0; b < nblocks; ++b) a += (double)partial[(int64_t)b * 4 + threadIdx.x];
-        acc[threadIdx.x] = a;
-    }
+    const int t = threadIdx.x, c = t & 3, sub = t >> 2;
+    double a = 0.0;
+    for (int b = sub; b < nblocks; b += 256) a += (double)partial[(int64_t)b * 4 + c];
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) a += __shfl_xor_sync(FULL, a, o);  // lanes with equal (t & 3)
+    if ((t & 31) < 4) wsum[t >> 5][c] = a;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 32; ++w)
+            for (int q = 0; q < 4; ++q) acc[q] += wsum[w][q];
         const double n_neg = acc[2], n_pos = acc[3];
         const double avgc = (n_pos > 0) + (n_neg > 0);
         const double inv_neg = 1.0 / (fmax(n_neg, 1.0) * avgc), inv_pos = 1.0 / (fmax(n_pos, 1.0) * avgc);
-        if (out_loss) out_loss[0] = (float)(acc[0] * inv_neg + acc[1] * inv_pos);
+        if (out_loss && blockIdx.x == 0) out_loss[0] = (float)(acc[0] * inv_neg + acc[1] * inv_pos);
         scale[0] = (float)inv_neg;
         scale[1] = (float)inv_pos;
     }
     __syncthreads();
     if (out_coef)
-        for (int64_t e = threadIdx.x; e < E; e += blockDim.x)
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + t; e < E; e += (int64_t)gridDim.x * blockDim.x)
             out_coef[e] *= scale[ewt[e] != 0.f ? 1 : 0];
 }
 
@@ -378,7 +385,9 @@ extern "C" int glue_graphdec_bce_fwd(const float* v, const int64_t* eidx, const 
     graphdec_fwd_kernel<<<grid, GD_THREADS, 0, st>>>(v, eidx, esgn, ewt, E, K, vec2, out_logits,
                                                      out_nll, out_coef, partial);
     GLUE_CHECK_LAUNCH();
-    graphdec_finalize_kernel<<<1, 1024, 0, st>>>(partial, grid, ewt, E, out_loss, out_coef);
+    const int fin_blocks = out_coef ? (int)((E + 4095) / 4096 < 64 ? (E + 4095) / 4096 : 64) : 1;
+    graphdec_finalize_kernel<<<fin_blocks < 1 ? 1 : fin_blocks, 1024, 0, st>>>(partial, grid, ewt, E, out_loss,
+                                                                             out_coef);
     GLUE_CHECK_LAUNCH();
     return 0;
 }

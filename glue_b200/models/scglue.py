@@ -104,6 +104,7 @@ class SCGLUETrainer(GLUETrainer):
             lambda like, tag: torch.randn_like(like)
         # whole-step CUDA graphs (see models/graphs.py)
         self.graphs = StepGraphs(self)
+        self._side_streams: List[torch.cuda.Stream] = []
         self.capturing = False
         self.anneal_buffer = torch.zeros((), dtype=torch.float32, device=net.device)
 
@@ -143,14 +144,50 @@ class SCGLUETrainer(GLUETrainer):
         return x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn
 
     # -- shared pieces of the objective ----------------------------------------------------
-    def _encode(self, x, xrep, dsc_only: bool):
-        net = self.net
-        u, l = {}, {}
-        for k in net.keys:
-            u[k], l[k] = net.x2u[k](x[k], xrep[k], lazy_normalizer=dsc_only)
-        usamp = {k: u[k].mean + self.noise(u[k].mean, f"u_{k}") * u[k].stddev for k in net.keys}
+    def _parallel(self, thunks):
+        r"""Run independent branches of the step on forked CUDA streams (branch 0 stays on the
+        current stream) and join them.  A step is hundreds of tiny kernels; inside the captured
+        graph the forks become parallel branches, so the per-kernel launch latencies of e.g.
+        the two data encoders and the graph encoder overlap instead of adding up.  Autograd
+        replays every backward node on its forward stream, so the backward pass forks the
+        same way.  Pure scheduling: the arithmetic of each branch is unchanged."""
+        device = self.net.device
+        if device.type != "cuda" or not config.MULTI_STREAM or len(thunks) < 2:
+            return [f() for f in thunks]
+        main = torch.cuda.current_stream(device)
+        while len(self._side_streams) < len(thunks) - 1:
+            self._side_streams.append(torch.cuda.Stream(device))
+        sides = self._side_streams[:len(thunks) - 1]
+        for side in sides:
+            side.wait_stream(main)
+        results = [thunks[0]()]
+        for side, f in zip(sides, thunks[1:]):
+            with torch.cuda.stream(side):
+                results.append(f())
+        for side in sides:
+            main.wait_stream(side)
+        return results
+
+    def _encode_one(self, k: str, x, xrep, dsc_only: bool):
+        u, l = self.net.x2u[k](x[k], xrep[k], lazy_normalizer=dsc_only)
+        usamp = u.mean + self.noise(u.mean, f"u_{k}") * u.stddev
         if self.normalize_u:
-            usamp = {k: F.normalize(usamp[k], dim=1) for k in net.keys}
+            usamp = F.normalize(usamp, dim=1)
+        return u, l, usamp
+
+    def _encode(self, x, xrep, dsc_only: bool, extra=None):
+        r"""Per-modality encoders (and optionally one more independent branch, ``extra``) side
+        by side; returns ``(u, l, usamp[, extra_result])``."""
+        keys = self.net.keys
+        thunks = [lambda k=k: self._encode_one(k, x, xrep, dsc_only) for k in keys]
+        if extra is not None:
+            thunks.append(extra)
+        out = self._parallel(thunks)
+        u = {k: o[0] for k, o in zip(keys, out)}
+        l = {k: o[1] for k, o in zip(keys, out)}
+        usamp = {k: o[2] for k, o in zip(keys, out)}
+        if extra is not None:
+            return u, l, usamp, out[len(keys)]
         return u, l, usamp
 
     def burnin_anneal(self, epoch: int) -> float:
@@ -228,13 +265,17 @@ class SCGLUETrainer(GLUETrainer):
                        ) -> Mapping[str, torch.Tensor]:
         net = self.net
         x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
-        u, l, usamp = self._encode(x, xrep, dsc_only)
         prior = net.prior()
-        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
         if dsc_only:
+            u, l, usamp = self._encode(x, xrep, dsc_only)
+            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
             return {"dsc_loss": self.lam_align * dsc_loss}
+        # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
+        # the data encoders: it runs beside them
+        u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
+            x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
+        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
         sup_loss = self._supervision(u_cat, xlbl)
-        vsamp, g_nll, g_kl = self._graph_terms(eidx, ewt, esgn, prior)
         g_elbo = g_nll + self.lam_kl * g_kl
         x_nll = {k: self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE)
                  for k in net.keys}

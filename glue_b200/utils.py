@@ -50,6 +50,8 @@ class _Settings:
         PARTITION_GRAPH=False,
         # RMSprop as one fused kernel over flat parameter / gradient buffers
         USE_FUSED_OPTIMIZER=True,
+        # run independent branches of a step (data encoders, graph branch) on forked streams
+        MULTI_STREAM=True,
     )
 
     def __init__(self) -> None:
