@@ -98,7 +98,6 @@ struct __align__(1024) SmemStats {
     uint8_t v_hi[2][OP_BYTES], v_lo[2][OP_BYTES];
     float2 ptab[2][NB_MAX][130];  // (softplus(scale_lin), bias) per (stage, batch, feature-in-tile)
     int bidx[128];
-    float red[2][3][128];
     Bars bars;
     uint32_t tmem_base;
     uint32_t ticket;
@@ -270,43 +269,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
             P.p.ws.psum[slot] = ssum;
         }
     }
-    // ---- the last CTA to arrive turns the partials into lse_i (fixed summation order) --------
-    __threadfence();
     tc_fence_before();
     __syncthreads();
-    if (t == 0) S.ticket = atomicAdd(P.p.ws.counters + 0, 1u);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
-    __syncthreads();
-    if (S.ticket == gridDim.x - 1) {
-        __threadfence();
-        // thread <-> (cell, one of three strided sub-ranges of the partials): consecutive threads
-        // read consecutive addresses
-        const int nparts = 2 * (int)gridDim.x;
-        const int cell = t & 127, sub = t >> 7;
-        const bool act = t < 384 && cell < P.ncell;
-        const int row = P.cell0 + cell;
-        float mx = -INFINITY;
-        if (act) {
-#pragma unroll 8
-            for (int c = sub; c < nparts; c += 3) mx = fmaxf(mx, __ldcg(P.p.ws.pmax + (int64_t)c * a.B + row));
-            S.red[0][sub][cell] = mx;
-        }
-        __syncthreads();
-        float sum = 0.f;
-        if (act) {
-            mx = fmaxf(fmaxf(S.red[0][0][cell], S.red[0][1][cell]), S.red[0][2][cell]);
-#pragma unroll 8
-            for (int c = sub; c < nparts; c += 3) {
-                const float pm = __ldcg(P.p.ws.pmax + (int64_t)c * a.B + row);
-                const float ps = __ldcg(P.p.ws.psum + (int64_t)c * a.B + row);
-                sum += pm > -INFINITY ? ps * expf(pm - mx) : 0.f;
-            }
-            S.red[1][sub][cell] = sum;
-        }
-        __syncthreads();
-        if (act && sub == 0)
-            P.p.ws.lse[row] = mx + logf((S.red[1][0][cell] + S.red[1][1][cell]) + S.red[1][2][cell]);
-    }
     if (t == 0) TC_TRACE(0, 7, 1);
 }
 
@@ -870,6 +835,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     if (t == 0) TC_TRACE(1 + PHASE, 7, 1);
 }
 
+// lse_i from the per-(CTA, column half) partials.  Block = 32 cells x 8 strided sub-ranges of the
+// partials (consecutive lanes read consecutive cells); sub-results meet in a fixed order.
+__global__ void __launch_bounds__(256) tc_lse_kernel(DecWs ws, int nparts, int B) {
+    __shared__ float red[2][8][32];
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    const bool act = row < B;
+    float mx = -INFINITY;
+    if (act) {
+#pragma unroll 8
+        for (int c = sub; c < nparts; c += 8) mx = fmaxf(mx, ws.pmax[(int64_t)c * B + row]);
+    }
+    red[0][sub][lane] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx = fmaxf(mx, red[0][q][lane]);
+    float sum = 0.f;
+    if (act) {
+#pragma unroll 8
+        for (int c = sub; c < nparts; c += 8) {
+            const float pm = ws.pmax[(int64_t)c * B + row];
+            sum += pm > -INFINITY ? ws.psum[(int64_t)c * B + row] * expf(pm - mx) : 0.f;
+        }
+    }
+    red[1][sub][lane] = sum;
+    __syncthreads();
+    if (act && sub == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += red[1][q][lane];
+        ws.lse[row] = mx + logf(tot);
+    }
+}
+
 // d/du = sum over CTAs of the D2 partials; grid = B blocks (sorted position), 256 threads =
 // 64 latent columns x 4 strided sub-sums combined in a fixed order
 __global__ void __launch_bounds__(256) tc_grad_u_kernel(DecParams p, int ncta) {
@@ -985,6 +984,8 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         const size_t smem = sizeof(SmemStats);
         GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
         tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
+        GLUE_CHECK_LAUNCH();
+        tc_lse_kernel<<<(a.B + 31) / 32, 256, 0, st>>>(p.ws, 2 * ncta, a.B);
         GLUE_CHECK_LAUNCH();
     }
     const bool nb1 = a.n_batches == 1;

@@ -604,24 +604,43 @@ class DevicePrefetcher:
     reference copies synchronously inside ``format_data``, ``scglue.py:276-289``).
 
     Host tensors should be pinned (``DataLoader(pin_memory=True)``) for the copies to be
-    asynchronous.  Tensors that already live on ``device`` pass through.  Every yielded batch
-    is safe to use on the current stream: the consumer stream waits on the copy event, and the
-    device buffers of a batch are recycled only after the consumer stream has passed the point
-    where the following batch was requested.
+    asynchronous.  Tensors that already live on ``device`` pass through.  Copies land in a ring
+    of ``depth + 1`` pre-allocated device buffer sets.  Every yielded batch is safe to use on
+    the current stream (it waits on the copy event) until the next ``depth`` batches have been
+    requested: before a slot is overwritten the copy stream waits for everything the consumer
+    stream had queued when the overwrite was requested.
     """
 
     def __init__(self, loader, device: torch.device, depth: int = 2) -> None:
         self.loader, self.device, self.depth = loader, torch.device(device), max(1, depth)
         self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._rings, self._next_slot = {}, 0
 
     def __len__(self) -> int:
         return len(self.loader)
 
+    def _buffers(self, batch, slot: int):
+        r"""Device staging buffers of ring slot ``slot`` (allocated once per input signature: no
+        allocator traffic, and no cross-stream frees, in the steady state)."""
+        sig = tuple((tuple(t.shape), t.dtype) for t in batch)
+        ring = self._rings.setdefault(sig, {})
+        if slot not in ring:
+            ring[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch]
+        return ring[slot]
+
     def _upload(self, batch):
         if self.stream is None:
             return list(batch), None
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % (self.depth + 1)
         with torch.cuda.stream(self.stream):
-            moved = [t.to(self.device, non_blocking=True) for t in batch]
+            moved = []
+            for buf, t in zip(self._buffers(batch, slot), batch):
+                if t.device == self.device:
+                    moved.append(t)
+                else:
+                    buf.copy_(t, non_blocking=True)
+                    moved.append(buf)
             event = torch.cuda.Event()
             event.record(self.stream)
         return moved, event
@@ -637,10 +656,7 @@ class DevicePrefetcher:
         while queue:
             moved, event = queue.pop(0)
             if event is not None:
-                current = torch.cuda.current_stream(self.device)
-                current.wait_event(event)
-                for t in moved:  # the caching allocator must not recycle them under the consumer
-                    t.record_stream(current)
+                torch.cuda.current_stream(self.device).wait_event(event)
             try:
                 if self.stream is not None:  # do not run ahead of the consumer by more than `depth`
                     self.stream.wait_stream(torch.cuda.current_stream(self.device))

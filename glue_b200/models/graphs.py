@@ -122,7 +122,10 @@ class StepGraphs:
                               entry["native_kernels"])
         except Exception as e:  # capture is an optimisation: fall back to eager launches
             torch.cuda.synchronize(device)
+            import traceback
             self.disabled_reason = f"{type(e).__name__}: {e}"
+            self.logger.debug("capture traceback:\n%s", traceback.format_exc())
+            self.last_traceback = traceback.format_exc()
             self.logger.warning("CUDA-graph capture of the training step failed (%s); "
                                 "continuing with eager launches", self.disabled_reason)
             entry["graph"] = None

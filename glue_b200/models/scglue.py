@@ -267,7 +267,12 @@ class SCGLUETrainer(GLUETrainer):
         x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
         prior = net.prior()
         if dsc_only:
-            u, l, usamp = self._encode(x, xrep, dsc_only)
+            # only the discriminator is updated in this pass: the encoders run forward (BatchNorm
+            # statistics and dropout streams advance as in the reference) but are not
+            # differentiated -- the reference computes and then discards those gradients
+            # (``scglue.py:386-390``: zero_grad before the generator pass)
+            with torch.no_grad():
+                u, l, usamp = self._encode(x, xrep, dsc_only)
             u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
             return {"dsc_loss": self.lam_align * dsc_loss}
         # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
@@ -277,14 +282,24 @@ class SCGLUETrainer(GLUETrainer):
         u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
         sup_loss = self._supervision(u_cat, xlbl)
         g_elbo = g_nll + self.lam_kl * g_kl
-        x_nll = {k: self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE)
-                 for k in net.keys}
+        # one stream per modality: the decoder calls of a small modality (16 CTAs for 2 000
+        # genes) fill the SMs that the tail of a large one (50 000 peaks) leaves idle
+        self._prepare_extra(usamp)
+        per_mod = self._parallel([
+            lambda k=k: (self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE),
+                         self._extra_losses_for(k, data, usamp, vsamp, l))
+            for k in net.keys])
+        x_nll = {k: out[0] for k, out in zip(net.keys, per_mod)}
+        self._extra_parts = {k: out[1] for k, out in zip(net.keys, per_mod)}
         x_kl = {k: _kl_to_prior(u[k], prior) / x[k].shape[1] for k in net.keys}
         x_elbo = {k: x_nll[k] + self.lam_kl * x_kl[k] for k in net.keys}
         x_elbo_sum = sum(self.modality_weight[k] * x_elbo[k] for k in net.keys)
         vae_loss = (self.lam_data * x_elbo_sum + self.lam_graph * len(net.keys) * g_elbo
                     + self.lam_sup * sup_loss)
         extra = self._extra_losses(data, usamp, vsamp, l)
+        # nothing that carries an autograd graph may outlive the step on `self`: it would keep
+        # this step's AccumulateGrad nodes (bound to the current streams) alive into a capture
+        self._extra_parts = self._shared_extra = None
         for weight, term in extra.values():
             vae_loss = vae_loss + weight * term
         gen_loss = vae_loss - self.lam_align * dsc_loss
@@ -297,6 +312,14 @@ class SCGLUETrainer(GLUETrainer):
         if net.u2c:
             losses["sup_loss"] = sup_loss
         return losses
+
+    def _prepare_extra(self, usamp) -> None:
+        r"""Quantities shared by the per-modality extra terms (computed before the fork)."""
+
+    def _extra_losses_for(self, k: str, data, usamp, vsamp, l):
+        r"""Extra decoder-based loss terms whose *target* modality is ``k`` (evaluated on the
+        stream of that modality's decoder); combined by :meth:`_extra_losses`."""
+        return None
 
     def _extra_losses(self, data, usamp, vsamp, l) -> Mapping[str, Tuple[float, torch.Tensor]]:
         return {}
@@ -381,40 +404,55 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         return super().compute_losses((x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn),
                                       epoch, dsc_only=dsc_only)
 
-    def _extra_losses(self, data, usamp, vsamp, l):
-        net = self.net
-        x, xrep, xbch, *_ = data
-        keys = net.keys
-        device = net.device
+    def _prepare_extra(self, usamp) -> None:
+        self._shared_extra = self._umean(usamp)
+
+    def _umean(self, usamp):
+        r"""Mean embedding of each cell over the modalities it is observed in
+        (``scglue.py:618-622``); computed once per step, on the main stream."""
+        keys = self.net.keys
         pmsk = self._pmsk.T  # [n_modalities, B]
-        zero = torch.zeros((), device=device)
         ustack = torch.stack([usamp[k] for k in keys])
         pstack = pmsk.unsqueeze(2).expand_as(ustack)
         umean = (ustack * pstack).sum(dim=0) / pstack.sum(dim=0)
         if self.normalize_u:
             umean = F.normalize(umean, dim=1)
+        return ustack, umean, pmsk.to(torch.float32)
 
-        # Row subsets (observed in modality k; observed in both modalities of an ordered pair)
-        # enter as per-cell weights  mask / (n_masked * n_features):  the mean over the subset
-        # without compacting rows -- static shapes, no host read of the subset sizes.
-        pf = pmsk.to(torch.float32)
+    def _extra_losses_for(self, k: str, data, usamp, vsamp, l):
+        r"""Joint-cross and real-cross reconstruction of modality ``k`` (``scglue.py:624-652``).
+        Row subsets (observed in ``k``; observed in both modalities of an ordered pair) enter as
+        per-cell weights ``mask / (n_masked * n_features)``: the mean over the subset without
+        compacting rows -- static shapes, no host read of the subset sizes."""
+        net = self.net
+        x, xrep, xbch, *_ = data
+        keys = net.keys
+        i = keys.index(k)
+        _, umean, pf = self._shared_extra
+        zero = torch.zeros((), device=net.device)
 
-        def subset_nll(k, usrc, maskf):
+        def subset_nll(usrc, maskf):
             w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
             return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w)
 
-        joint = zero
-        if self.lam_joint_cross:
-            for i, k in enumerate(keys):
-                joint = joint + self.modality_weight[k] * subset_nll(k, umean, pf[i])
+        joint = subset_nll(umean, pf[i]) if self.lam_joint_cross else zero
         real = zero
         if self.lam_real_cross:
-            for i, kt in enumerate(keys):
-                acc = zero
-                for j, ks in enumerate(keys):
-                    if i != j:
-                        acc = acc + subset_nll(kt, usamp[ks], pf[i] * pf[j])
-                real = real + self.modality_weight[kt] * acc
+            for j, ks in enumerate(keys):
+                if i != j:
+                    real = real + subset_nll(usamp[ks], pf[i] * pf[j])
+        return joint, real
+
+    def _extra_losses(self, data, usamp, vsamp, l):
+        net = self.net
+        keys = net.keys
+        zero = torch.zeros((), device=net.device)
+        ustack, umean, pf = self._shared_extra
+        joint, real = zero, zero
+        for k in keys:
+            j_k, r_k = self._extra_parts[k]
+            joint = joint + self.modality_weight[k] * j_k
+            real = real + self.modality_weight[k] * r_k
         cos = zero
         if self.lam_cos:
             for i, k in enumerate(keys):
