@@ -320,15 +320,28 @@ def main():
     # i + 1 on a side stream while step i runs) -> trainer.train_step -> D2H read of the loss
     from glue_b200.models.data import DevicePrefetcher
 
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+
     def run_e2e(n, prefetch):
+        """Every step's loss is read back to the host (pinned, asynchronous D2H): the value of
+        step i is consumed while step i + 1 is already queued, as a training loop that logs
+        metrics does."""
         feed = (host_pool[i % pool_n] for i in range(n))
         if prefetch:
             feed = DevicePrefetcher(feed, device)
-        last = 0.0
-        for batch in feed:
+        seen = []
+        for i, batch in enumerate(feed):
             losses = trainer.train_step(_Engine, batch)
-            last = float(losses["vae_loss"])  # D2H read of the step's result
-        return last
+            loss_host[i & 1].copy_(losses["vae_loss"].reshape(1), non_blocking=True)
+            loss_done[i & 1].record()
+            if i:
+                loss_done[(i - 1) & 1].synchronize()
+                seen.append(float(loss_host[(i - 1) & 1]))
+        loss_done[(n - 1) & 1].synchronize()
+        seen.append(float(loss_host[(n - 1) & 1]))
+        assert len(seen) == n and all(v == v for v in seen), "every step's loss must reach the host"
+        return seen[-1]
 
     e2e_runs = {}
     for mode, prefetch in (("direct", False), ("prefetch", True)):

@@ -53,6 +53,7 @@ class DecoderArgs(ctypes.Structure):
         ("K", c_int32),
         ("n_batches", c_int32),
         ("reduce", c_int32),
+        ("grad_scale", c_float),
         ("u", c_void_p),
         ("v", c_void_p),
         ("vidx", c_void_p),

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TF, 1) dec_main_kernel(DecParams p) {
                         continue;
                     }
                     float W = a.wmat ? (jok ? a.wmat[(int64_t)S.row[rr] * a.F + j] : 0.f)
-                                     : (a.row_weight ? -a.row_weight[S.row[rr]] : p.w0);
+                                     : (a.row_weight ? -a.row_weight[S.row[rr]] * p.gscale : p.w0);
                     bool valid = jok;
                     if (a.reduce == 0 && !a.row_weight && xv != xv) {  // nanmean: NaN observations carry no weight
                         valid = false;
@@ -412,7 +412,7 @@ __global__ void dec_reduce_kernel(DecParams p, int nbf, int grad) {
         const double total = (double)a.B * (double)a.F;
         const double ratio = (bad > 0 && !a.wmat) ? total / (total - (double)bad) : 1.0;
         p.ws.rescale[0] = (float)ratio;
-        if (a.loss) a.loss[0] = (float)(loss * ratio);
+        if (a.loss) a.loss[0] = (float)(loss * ratio / (double)p.gscale);
     }
 }
 
@@ -566,7 +566,9 @@ static int run(const glue_decoder_args* args, int mode, float* out, cudaStream_t
     const size_t need = ws_layout(a, p.ncta, KP, nullptr, nullptr);
     if (a.workspace_bytes < need) return GLUE_E_WORKSPACE;
     ws_layout(a, p.ncta, KP, (char*)a.workspace, &p.ws);
-    p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F));
+    const float gscale = (a.grad_scale != 0.f && !a.wmat) ? a.grad_scale : 1.f;
+    p.gscale = gscale;
+    p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F)) * gscale;
     p.out = out;
     const bool nbf = is_nb_family(a.family);
     const size_t smem = sizeof(DecSmem<KP>);

@@ -26,7 +26,8 @@ struct DecParams {
     DecWs ws;
     int ncta;
     int feat_per_cta;
-    float w0;  // uniform weight -1/(B*F) when wmat == NULL
+    float w0;      // uniform weight -grad_scale/(B*F) when wmat == NULL
+    float gscale;  // grad_scale (1 when unset): folded into the weights, divided out of the loss
     float* out;  // MODE_LOGP / MODE_MEAN
 };
 

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         S.lse[t] = (ok && NBF) ? P.p.ws.lse[pos] * LOG2EF : 0.f;  // base 2
         S.c[t] = (ok && PHASE == 1) ? P.p.ws.c[pos] : 0.f;
         S.c_acc[t] = 0.f;
-        S.wrow[t] = ok ? (a.row_weight ? -a.row_weight[orig] : P.p.w0) : 0.f;  // weight of log_prob
+        S.wrow[t] = ok ? (a.row_weight ? -a.row_weight[orig] * P.p.gscale : P.p.w0) : 0.f;  // weight of log_prob
     }
     if (GRAD) {  // cells beyond ncell must read as exact zeros in the coefficient tile
         uint4* xz = reinterpret_cast<uint4*>(S.x_hi);
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                     const double total = (double)a.B * (double)a.F;
                     const double ratio = bad > 0 ? total / (total - (double)bad) : 1.0;
                     P.p.ws.rescale[0] = (float)ratio;
-                    if (a.loss) a.loss[0] = (float)(loss * ratio);
+                    if (a.loss) a.loss[0] = (float)(loss * ratio / (double)P.p.gscale);
                 }
             }
             __syncthreads();
@@ -835,36 +835,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     if (t == 0) TC_TRACE(1 + PHASE, 7, 1);
 }
 
-// lse_i from the per-(CTA, column half) partials.  Block = 32 cells x 8 strided sub-ranges of the
-// partials (consecutive lanes read consecutive cells); sub-results meet in a fixed order.
-__global__ void __launch_bounds__(256) tc_lse_kernel(DecWs ws, int nparts, int B) {
-    __shared__ float red[2][8][32];
+// lse_i from the per-(CTA, column half) partials.  Block = 32 cells x 32 strided sub-ranges of
+// the partials (consecutive lanes read consecutive cells, <= 10 loads in flight per thread);
+// sub-results meet in a fixed order.
+__global__ void __launch_bounds__(1024) tc_lse_kernel(DecWs ws, int nparts, int B) {
+    __shared__ float red[2][32][33];
     const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     const int row = blockIdx.x * 32 + lane;
     const bool act = row < B;
-    float mx = -INFINITY;
-    if (act) {
-#pragma unroll 8
-        for (int c = sub; c < nparts; c += 8) mx = fmaxf(mx, ws.pmax[(int64_t)c * B + row]);
+    float pm[10], ps[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int c = sub + 32 * i;
+        const bool ok = act && c < nparts;
+        pm[i] = ok ? ws.pmax[(int64_t)c * B + row] : -INFINITY;
+        ps[i] = ok ? ws.psum[(int64_t)c * B + row] : 0.f;
     }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) mx = fmaxf(mx, pm[i]);
     red[0][sub][lane] = mx;
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) mx = fmaxf(mx, red[0][q][lane]);
-    float sum = 0.f;
-    if (act) {
 #pragma unroll 8
-        for (int c = sub; c < nparts; c += 8) {
-            const float pm = ws.pmax[(int64_t)c * B + row];
-            sum += pm > -INFINITY ? ws.psum[(int64_t)c * B + row] * expf(pm - mx) : 0.f;
-        }
-    }
+    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, red[0][q][lane]);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) sum += pm[i] > -INFINITY ? ps[i] * expf(pm[i] - mx) : 0.f;
     red[1][sub][lane] = sum;
     __syncthreads();
     if (act && sub == 0) {
         float tot = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tot += red[1][q][lane];
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) tot += red[1][q][lane];
         ws.lse[row] = mx + logf(tot);
     }
 }
@@ -967,7 +969,8 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     if (a.workspace_bytes < need) return GLUE_E_WORKSPACE;
     tc_ws_layout(a, ncta, (char*)a.workspace, &p.ws);
     p.ncta = ncta;
-    p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F));
+    p.gscale = a.grad_scale != 0.f ? a.grad_scale : 1.f;
+    p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F)) * p.gscale;
     P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
@@ -985,7 +988,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
         tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
         GLUE_CHECK_LAUNCH();
-        tc_lse_kernel<<<(a.B + 31) / 32, 256, 0, st>>>(p.ws, 2 * ncta, a.B);
+        tc_lse_kernel<<<(a.B + 31) / 32, 1024, 0, st>>>(p.ws, 2 * ncta, a.B);  // 2 * ncta <= 320 partials
         GLUE_CHECK_LAUNCH();
     }
     const bool nb1 = a.n_batches == 1;

@@ -31,13 +31,18 @@ struct EncCfg {
     static constexpr int NB4 = KP / 4;                   // float4 blocks per row
     static constexpr int KS = (KP % 32 == 20) ? KP : KP + 4;  // row stride (words): 4-bank skew per row
     static constexpr int NJ = (NB4 + 3) / 4;             // blocks per thread
+    // weight rows: stride a multiple of 32 words plus a skew of 4 ((o >> 2) & 3) words, so that
+    // the four lane groups of a warp (output rows o, o + 4, o + 8, o + 12) read distinct banks
+    static constexpr int WS = (KP + 12 + 31) / 32 * 32;
 };
+
+__device__ __forceinline__ int wskew(int o) { return 4 * ((o >> 2) & 3); }
 
 template <int KP>
 struct EncSmem {
     float x[TR][EncCfg<KP>::KS];
-    float wl[KP][EncCfg<KP>::KS];
-    float ws[KP][EncCfg<KP>::KS];
+    float wl[KP][EncCfg<KP>::WS];
+    float ws[KP][EncCfg<KP>::WS];
     float d1[TR][EncCfg<KP>::KS];  // backward: d L / d mu
     float d2[TR][EncCfg<KP>::KS];  // backward: d L / d s
     float bl[KP], bs[KP];
@@ -61,12 +66,11 @@ struct EncArgs {
 
 template <int KP>
 __device__ __forceinline__ void load_weights(EncSmem<KP>& S, const EncArgs& a) {
-    constexpr int KS = EncCfg<KP>::KS;
-    for (int idx = threadIdx.x; idx < KP * KS; idx += ENC_THREADS) {
-        const int o = idx / KS, i = idx - o * KS;
+    for (int idx = threadIdx.x; idx < KP * KP; idx += ENC_THREADS) {
+        const int o = idx / KP, i = idx - o * KP;
         const bool ok = o < a.K && i < a.K;
-        S.wl[o][i] = ok ? a.w_loc[o * a.K + i] : 0.f;
-        S.ws[o][i] = ok ? a.w_std[o * a.K + i] : 0.f;
+        S.wl[o][wskew(o) + i] = ok ? a.w_loc[o * a.K + i] : 0.f;
+        S.ws[o][wskew(o) + i] = ok ? a.w_std[o * a.K + i] : 0.f;
     }
     for (int o = threadIdx.x; o < KP; o += ENC_THREADS) {
         S.bl[o] = o < a.K ? a.b_loc[o] : 0.f;
@@ -129,8 +133,8 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_fwd_kernel(EncArgs a) {
                 float accl = S.bl[o], accs = S.bs[o];
 #pragma unroll
                 for (int i4 = 0; i4 < NB4; ++i4) {
-                    accl = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.wl[o][4 * i4]), accl);
-                    accs = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.ws[o][4 * i4]), accs);
+                    accl = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.wl[o][4 * ig + 4 * i4]), accl);
+                    accs = dot4(xr[i4], *reinterpret_cast<const float4*>(&S.ws[o][4 * ig + 4 * i4]), accs);
                 }
                 mu4[oo] = accl, s4[oo] = accs;
             }
@@ -231,12 +235,13 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_kernel(EncArgs a) {
             for (int jj = 0; jj < NJ; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int o = 0; o < K; ++o) {
                 const float d1 = S.d1[r][o], d2 = S.d2[r][o];
+                const int sk = wskew(o);
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
                     const int b = ig + 4 * jj;
                     if (b >= NB4) continue;
-                    const float4 wl = *reinterpret_cast<const float4*>(&S.wl[o][4 * b]);
-                    const float4 ws = *reinterpret_cast<const float4*>(&S.ws[o][4 * b]);
+                    const float4 wl = *reinterpret_cast<const float4*>(&S.wl[o][sk + 4 * b]);
+                    const float4 ws = *reinterpret_cast<const float4*>(&S.ws[o][sk + 4 * b]);
                     acc[jj].x = fmaf(d1, wl.x, fmaf(d2, ws.x, acc[jj].x));
                     acc[jj].y = fmaf(d1, wl.y, fmaf(d2, ws.y, acc[jj].y));
                     acc[jj].z = fmaf(d1, wl.z, fmaf(d2, ws.z, acc[jj].z));

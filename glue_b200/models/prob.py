@@ -95,10 +95,11 @@ class FusedDataDistribution:
         return self.scale_lin, self.bias, self.disp, self.zi_logits
 
     def nll(self, value: torch.Tensor, reduce: str = "nanmean", unit_upstream: bool = False,
-            row_weight: torch.Tensor = None) -> torch.Tensor:
+            row_weight: torch.Tensor = None, upstream: float = None) -> torch.Tensor:
         return ops.decoder_nll(self.family, self.u, self.v, *self._params(), b=self.b, l=self.l,
                                x=value, vidx=self.vidx, reduce=reduce,
-                               unit_upstream=unit_upstream, row_weight=row_weight)
+                               unit_upstream=unit_upstream, row_weight=row_weight,
+                               upstream=upstream)
 
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
         return ops.decoder_log_prob(self.family, self.u, self.v, *self._params(), b=self.b,

@@ -245,15 +245,19 @@ class SCGLUETrainer(GLUETrainer):
         return vsamp, g_nll, g_kl
 
     def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str,
-                  row_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  row_weight: Optional[torch.Tensor] = None,
+                  upstream: Optional[float] = None) -> torch.Tensor:
         r"""``-u2x[k](usamp, vsamp[idx_k], xbch, l).log_prob(x).<reduce>()``; kernel-backed
         decoders take the whole vertex table and gather ``idx_k`` rows themselves.  With
         ``row_weight`` ``[B]`` the result is ``-sum_i row_weight[i] sum_j log_prob[i, j]``."""
         net = self.net
         decoder, idx = net.u2x[k], getattr(net, f"{k}_idx")
         if isinstance(decoder, sc._FusedDecoder):
+            # `upstream`: the coefficient of this term in the objective that is differentiated
+            # (gen_loss), folded into the kernel's weights instead of a pass over the gradients
             return decoder(usamp, vsamp, xbch, l, vidx=idx).nll(x, reduce=reduce,
-                                                                row_weight=row_weight)
+                                                                row_weight=row_weight,
+                                                                upstream=upstream)
         log_prob = decoder(usamp, vsamp[idx], xbch, l).log_prob(x)
         if row_weight is not None:
             return -(log_prob * row_weight.unsqueeze(1)).sum()
@@ -286,7 +290,8 @@ class SCGLUETrainer(GLUETrainer):
         # genes) fill the SMs that the tail of a large one (50 000 peaks) leaves idle
         self._prepare_extra(usamp)
         per_mod = self._parallel([
-            lambda k=k: (self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE),
+            lambda k=k: (self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE,
+                                        upstream=self.lam_data * self.modality_weight[k]),
                          self._extra_losses_for(k, data, usamp, vsamp, l))
             for k in net.keys])
         x_nll = {k: out[0] for k, out in zip(net.keys, per_mod)}
@@ -431,16 +436,17 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         _, umean, pf = self._shared_extra
         zero = torch.zeros((), device=net.device)
 
-        def subset_nll(usrc, maskf):
+        def subset_nll(usrc, maskf, lam):
             w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
-            return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w)
+            return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w,
+                                  upstream=lam * self.modality_weight[k])
 
-        joint = subset_nll(umean, pf[i]) if self.lam_joint_cross else zero
+        joint = subset_nll(umean, pf[i], self.lam_joint_cross) if self.lam_joint_cross else zero
         real = zero
         if self.lam_real_cross:
             for j, ks in enumerate(keys):
                 if i != j:
-                    real = real + subset_nll(usamp[ks], pf[i] * pf[j])
+                    real = real + subset_nll(usamp[ks], pf[i] * pf[j], self.lam_real_cross)
         return joint, real
 
     def _extra_losses(self, data, usamp, vsamp, l):

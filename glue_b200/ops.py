@@ -413,7 +413,7 @@ class DecoderCall:
     r"""Argument marshalling for one ``glue_decoder_*`` call (keeps tensors alive)."""
 
     def __init__(self, family: str, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits,
-                 reduce: str = "nanmean", row_weight=None):
+                 reduce: str = "nanmean", row_weight=None, grad_scale: float = 0.0):
         dev = require_cuda(u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, row_weight)
         if family not in FAMILY:
             raise ValueError(f"unknown decoder family {family!r}")
@@ -429,6 +429,7 @@ class DecoderCall:
         self.B, self.K = self.u.shape
         self.n_batches, self.F = self.scale_lin.shape
         self.reduce = {"nanmean": 0, "mean": 1}[reduce]
+        self.grad_scale = float(grad_scale or 0.0)
         self.row_weight = None if row_weight is None else _f32(row_weight, "row_weight").reshape(-1)
         if self.row_weight is not None and self.row_weight.numel() != self.B:
             raise ValueError("`row_weight` must have one entry per cell")
@@ -461,6 +462,7 @@ class DecoderCall:
         a = DecoderArgs()
         a.family, a.B, a.F, a.K = FAMILY[self.family], self.B, self.F, self.K
         a.n_batches, a.reduce = self.n_batches, self.reduce
+        a.grad_scale = self.grad_scale
         a.u, a.v, a.vidx, a.b = ptr(self.u), ptr(self.v), ptr(self.vidx), ptr(self.b)
         a.row_order, a.l, a.x = ptr(self.row_order), ptr(self.l), ptr(self.x)
         a.scale_lin, a.bias, a.disp = ptr(self.scale_lin), ptr(self.bias), ptr(self.disp)
@@ -490,9 +492,10 @@ class _DecoderNllFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family, reduce,
-                unit_upstream, row_weight):
+                unit_upstream, row_weight, upstream):
         call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce,
-                           row_weight)
+                           row_weight, grad_scale=upstream)
+        unit_upstream = unit_upstream or bool(upstream)
         loss = torch.empty((), dtype=torch.float32, device=call.device)
         need_grad = any(t is not None and t.requires_grad
                         for t in (u, v, scale_lin, bias, disp, zi_logits))
@@ -521,12 +524,12 @@ class _DecoderNllFn(torch.autograd.Function):
         if not ctx.unit_upstream:
             live = [g for g in grads if g is not None]
             torch._foreach_mul_(live, grad_out)
-        return (*grads, None, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None, None)
 
 
 def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
                 x=None, vidx=None, reduce: str = "nanmean", unit_upstream: bool = False,
-                row_weight=None):
+                row_weight=None, upstream: float = None):
     r"""Fused data decoder + negative log-likelihood.
 
     Replaces ``-u2x(u, v, b, l).log_prob(x).nanmean()`` (``scglue/models/scglue.py:342-347``;
@@ -534,14 +537,16 @@ def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=N
     ``vidx`` given, ``v`` is the full vertex table and ``v[vidx]`` is gathered inside the
     kernel (saves the ``[F, K]`` gather and its ``index_put_`` backward).
     ``unit_upstream=True`` promises that this loss enters the final objective with
-    coefficient exactly 1, so backward hands the gradients over without rescaling.
+    coefficient exactly 1, so backward hands the gradients over without rescaling;
+    ``upstream=c`` promises coefficient exactly ``c`` (a non-zero Python number): the kernels
+    fold it into their weights, the returned loss stays unscaled.
     ``row_weight`` (``[B]``, not differentiated) replaces the mean by
     ``-sum_i row_weight[i] sum_j log_prob[i, j]``: weighted / masked row subsets with static
     shapes (the paired-cell losses of ``scglue.py:603-640`` use ``mask / (n_masked * F)``)."""
     if x is None:
         raise ValueError("`x` is required")
     return _DecoderNllFn.apply(u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family,
-                               reduce, unit_upstream, row_weight)
+                               reduce, unit_upstream, row_weight, upstream)
 
 
 class _DecoderLogProbFn(torch.autograd.Function):

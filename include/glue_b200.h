@@ -150,6 +150,9 @@ typedef struct glue_decoder_args {
     int32_t K;         /* latent dimension, 1..64                                    */
     int32_t n_batches; /* rows of the per-feature parameter tables                   */
     int32_t reduce;    /* 0: mean over non-NaN x (nanmean)  1: plain mean            */
+    float grad_scale;  /* gradients are those of grad_scale * loss (the coefficient with
+                          which the caller adds `loss` to its objective), `loss` itself is
+                          reported unscaled; 0 is read as 1                             */
     /* inputs */
     const float *u;           /* [B, K]                                              */
     const float *v;           /* [n_vrows, K] feature-latent table                   */
