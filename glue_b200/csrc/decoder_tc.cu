@@ -20,8 +20,10 @@
 //
 // Warp roles (416 threads, 1 CTA / SM): warps 0-7 epilogue (warp w owns TMEM lanes
 // 32 (w & 3) .. +31 and one half of the cell columns), warps 8-11 stage the v tiles (double
-// buffered, one thread per row) and prefetch the step's observations into L2, warp 12 issues
+// buffered) and prefetch the step's observations into L2, warp 12 issues
 // tcgen05.mma (one lane).  Pipelines are mbarrier based.
+#include <stdlib.h>
+
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
 
@@ -71,6 +73,34 @@ __device__ __forceinline__ float rcpf(float x) {
     return y;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) --------
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up(f2 x, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
 struct Bars {
     uint64_t v_full[2], v_empty[2], acc_full[2], acc_empty[2], x_full, x_empty, d1_full[2], d1_empty[2], d2_full;
 };
@@ -109,6 +139,7 @@ struct TcParams {
     int cell0, ncell;  // cell block [cell0, cell0 + ncell) of the (sorted) minibatch, ncell <= 128
     int acc;           // outputs accumulate (a previous cell block already wrote them)
     long long* trace;  // optional: clock64 stamps of CTA 0, [kernel 0..2][tile < 8][event < 16]
+    int dbg;           // timing experiments only (GLUE_TC_DBG): 1 = no x loads, 2 = no X stores / c_i reduce
 };
 
 #define TC_TRACE(kern, it, ev)                                                              \
@@ -316,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         S.bidx[t] = (ok && a.b) ? (int)a.b[orig] : 0;
         S.xoff[t] = (long long)orig * a.F;
         S.l[t] = (ok && a.l) ? a.l[orig] : 1.f;
-        S.lse[t] = (ok && NBF) ? P.p.ws.lse[pos] * LOG2EF : 0.f;  // base 2
+        S.lse[t] = (ok && NBF) ? -(P.p.ws.lse[pos] * LOG2EF) : 0.f;  // -lse in base 2
         S.c[t] = (ok && PHASE == 1) ? P.p.ws.c[pos] : 0.f;
         S.c_acc[t] = 0.f;
         S.wrow[t] = ok ? (a.row_weight ? -a.row_weight[orig] * P.p.gscale : P.p.w0) : 0.f;  // weight of log_prob
@@ -337,11 +368,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         const int pt = t - PROD_T0;
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1, f0 = (cta + it * ncta) * 128;
-            if (PHASE == 0 && pt < ncell) {
-                const float* px = a.x + S.xoff[pt] + f0;
+            if (PHASE == 0) {
                 const int nvalid = min(128, a.F - f0);
-                for (int o = 0; o < nvalid; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(px + nvalid - 1));
+                for (int cell = pt; cell < ncell; cell += PROD_THREADS) {
+                    const float* px = a.x + S.xoff[cell] + f0;
+                    for (int o = 0; o < nvalid; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(px + nvalid - 1));
+                }
             }
             mbar_wait(&S.bars.v_empty[s], ((it >> 1) & 1) ^ 1);
             if (pt == 0) TC_TRACE(1 + PHASE, it, 0);
@@ -510,10 +543,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 gb = gs = gd = gz = 0.f;
             };
             float s2 = 0.f, b2 = 0.f, lg1 = 0.f, dg1 = 0.f, lg2 = 0.f, dg2 = 0.f;
+            f2 ngb2 = pk(0.f, 0.f), ngs2 = pk(0.f, 0.f), gd2 = pk(0.f, 0.f), loss2 = pk(0.f, 0.f);
             if (NB1) {
                 fp = load_params<FAM>(a, 0, j, jok);
                 cur_b = 0;
                 s2 = fp.s * LOG2EF, b2 = fp.bias * LOG2EF;  // logits in base 2
+                if (PHASE == 1 && !jok) b2 = -INFINITY;     // features beyond F: p = 0
                 if (NBF && PHASE == 0) {  // log-gamma / digamma differences for counts 1 and 2
                     const float ti = 1.f / fp.th;
                     lg1 = fp.disp, dg1 = ti;
@@ -528,9 +563,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 #pragma unroll
                 for (int e8 = 0; e8 < 8; ++e8) {
                     const int cell = 8 * g + e8;
-                    xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell) ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
+                    xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell && !(P.dbg & 1))
+                                 ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
                 }
             };
+            const f2 S2 = pk(s2, s2), B2 = pk(b2, b2), NS2 = pk(-fp.s, -fp.s), TH2 = pk(fp.th, fp.th);
+            const f2 EPS2 = pk(GLUE_EPS, GLUE_EPS), M1 = pk(-1.f, -1.f), LN2_2 = pk(LN2F, LN2F);
+            const f2 NLN2 = pk(-LN2F, -LN2F), DISP2 = pk(fp.disp, fp.disp);
             load_x(g_begin);
             if (t == 0) TC_TRACE(1 + PHASE, it, 5);
             mbar_wait(&S.bars.acc_full[s], (it >> 1) & 1);
@@ -578,17 +617,90 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 }
                 float coef[8], gch[8];
                 if constexpr (NB1 && PHASE == 1) {
-                    // ---- pass C, straight-line over the 8 cells --------------------------------
+                    // ---- pass C: packed pairs of cells, -G = p c accumulated (signs fixed at the flush)
 #pragma unroll
-                    for (int e8 = 0; e8 < 8; ++e8) {
-                        const float dot = __uint_as_float(d[e8]);
-                        const float pr = ex2f(fmaf(s2, dot, b2) - lsev[e8]);
-                        float G = -(pr * auxv[e8]);
-                        G = (jok && c0 + e8 < ncell) ? G : 0.f;
-                        gb += G;
-                        gs = fmaf(G, dot, gs);
-                        coef[e8] = G * fp.s;
-                        gch[e8] = G;
+                    for (int pr_ = 0; pr_ < 4; ++pr_) {
+                        const int e0 = 2 * pr_, e1 = e0 + 1;
+                        const f2 dot2 = pk(__uint_as_float(d[e0]), __uint_as_float(d[e1]));
+                        const f2 t2 = add2(fma2(S2, dot2, B2), pk(lsev[e0], lsev[e1]));  // b2 = -inf kills !jok
+                        float t0, t1;
+                        up(t2, t0, t1);
+                        const f2 nG2 = mul2(pk(ex2f(t0), ex2f(t1)), pk(auxv[e0], auxv[e1]));  // c_i = 0 beyond ncell
+                        ngb2 = add2(ngb2, nG2);
+                        ngs2 = fma2(nG2, dot2, ngs2);
+                        up(mul2(nG2, NS2), coef[e0], coef[e1]);
+                        gch[e0] = gch[e1] = 0.f;
+                    }
+                } else if constexpr (NB1 && FAM == GLUE_NB) {
+                    // ---- pass B, NB: packed pairs of cells in three stages ---------------------------
+                    // (-G accumulated: nG = W (-(x - (x + theta) sig)) ratio; signs fixed at the flush)
+                    f2 dot2[4], xs2[4], dlt2[4], xl2[4], ndd2[4], rat2[4], W2[4];
+                    float lgv[8], dgv[8], xsc[8];
+#pragma unroll
+                    for (int pr_ = 0; pr_ < 4; ++pr_) {
+                        const int e0 = 2 * pr_, e1 = e0 + 1;
+                        float w01[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int e8 = e0 + q;
+                            const float x = xv[e8];
+                            const bool isnan_x = x != x;
+                            bool valid = jok;  // cells beyond ncell carry weight 0 already
+                            if (skip_nan && isnan_x) {
+                                bad_acc += (valid && c0 + e8 < ncell) ? 1 : 0;
+                                valid = false;
+                            }
+                            xsc[e8] = (skip_nan && isnan_x) ? 0.f : x;
+                            w01[q] = valid ? wv[e8] : 0.f;
+                            lgv[e8] = xsc[e8] == 1.f ? lg1 : (xsc[e8] == 2.f ? lg2 : 0.f);
+                            dgv[e8] = xsc[e8] == 1.f ? dg1 : (xsc[e8] == 2.f ? dg2 : 0.f);
+                        }
+                        W2[pr_] = pk(w01[0], w01[1]);
+                        xs2[pr_] = pk(xsc[e0], xsc[e1]);
+                        dot2[pr_] = pk(__uint_as_float(d[e0]), __uint_as_float(d[e1]));
+                        const f2 t2 = add2(fma2(S2, dot2[pr_], B2), pk(lsev[e0], lsev[e1]));
+                        float t0, t1;
+                        up(t2, t0, t1);
+                        const f2 mu2 = mul2(pk(ex2f(t0), ex2f(t1)), pk(auxv[e0], auxv[e1]));
+                        const f2 m2 = add2(mu2, EPS2), mt2 = add2(m2, TH2);
+                        float m0, m1, mt0, mt1, mm0, mm1;
+                        up(m2, m0, m1);
+                        up(mt2, mt0, mt1);
+                        const f2 l2m = pk(lg2f(m0), lg2f(m1)), l2t = pk(lg2f(mt0), lg2f(mt1));
+                        up(mul2(m2, mt2), mm0, mm1);
+                        const f2 r2 = pk(rcpf(mm0), rcpf(mm1));  // 1/m = r mt, 1/(m + theta) = r m
+                        const f2 sig2 = mul2(mul2(m2, m2), r2);
+                        rat2[pr_] = mul2(mu2, mul2(r2, mt2));
+                        dlt2[pr_] = fma2(l2t, NLN2, DISP2);               // log theta - log(m + theta)
+                        xl2[pr_] = mul2(fma2(l2t, M1, l2m), LN2_2);       // log m - log(m + theta)
+                        ndd2[pr_] = fma2(add2(xs2[pr_], TH2), sig2, mul2(xs2[pr_], M1));  // -(x - (x+theta) sig)
+                    }
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8)  // counts other than 0, 1, 2: rare
+                        if (!(xsc[e8] == 0.f || xsc[e8] == 1.f || xsc[e8] == 2.f)) {
+                            float lg_t, dg_t;  // (locals: the out-of-line slow path takes addresses)
+                            nb_gamma_terms_t<true>(xsc[e8], fp.th, lg_t, dg_t);
+                            lgv[e8] = lg_t, dgv[e8] = dg_t;
+                        }
+#pragma unroll
+                    for (int pr_ = 0; pr_ < 4; ++pr_) {
+                        const int e0 = 2 * pr_, e1 = e0 + 1;
+                        const f2 lp2 = fma2(TH2, dlt2[pr_], fma2(xs2[pr_], xl2[pr_], pk(lgv[e0], lgv[e1])));
+                        const f2 tl2 = fma2(TH2, add2(dlt2[pr_], pk(dgv[e0], dgv[e1])), ndd2[pr_]);
+                        loss2 = fma2(W2[pr_], lp2, loss2);
+                        if (GRAD) {
+                            const f2 nG2 = mul2(W2[pr_], mul2(ndd2[pr_], rat2[pr_]));
+                            ngb2 = add2(ngb2, nG2);
+                            ngs2 = fma2(nG2, dot2[pr_], ngs2);
+                            gd2 = fma2(W2[pr_], tl2, gd2);
+                            up(mul2(nG2, NS2), coef[e0], coef[e1]);
+                            float g0, g1;
+                            up(nG2, g0, g1);
+                            gch[e0] = -g0, gch[e1] = -g1;
+                        } else {
+                            coef[e0] = coef[e1] = 0.f;
+                            gch[e0] = gch[e1] = 0.f;
+                        }
                     }
                 } else if constexpr (NB1 && NBF) {
                     // ---- pass B, NB / ZINB, straight-line in three stages -------------------------
@@ -605,7 +717,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                         }
                         xs[e8] = (skip_nan && isnan_x) ? 0.f : x;
                         Wv[e8] = valid ? wv[e8] : 0.f;
-                        const float pr = ex2f(fmaf(s2, dot, b2) - lsev[e8]);
+                        const float pr = ex2f(fmaf(s2, dot, b2) + lsev[e8]);
                         const float mu = pr * auxv[e8];
                         const float m = mu + GLUE_EPS, mt = m + fp.th;
                         const float Lm = lg2f(m) * LN2F, Lt = lg2f(mt) * LN2F;
@@ -670,7 +782,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                             const float av = fmaf(fp.s, dot, fp.bias);
                             if (PHASE == 0) {
                                 const float x = xv[e8];
-                                const float lse_nat = NBF ? lsev[e8] * LN2F : 0.f;
+                                const float lse_nat = NBF ? -(lsev[e8] * LN2F) : 0.f;
                                 const ElemOut e = element<FAM, true>(fp, av, x, lse_nat, auxv[e8]);
                                 bool valid = jok && cok;
                                 if (skip_nan && x != x) {
@@ -688,7 +800,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                                     gz += valid ? W * e.gz : 0.f;
                                 }
                             } else {
-                                const float pr = (jok && cok) ? ex2f(av * LOG2EF - lsev[e8]) : 0.f;
+                                const float pr = (jok && cok) ? ex2f(fmaf(av, LOG2EF, lsev[e8])) : 0.f;
                                 G = -(pr * auxv[e8]);
                                 cf = G * fp.s;
                                 gb += G;
@@ -699,7 +811,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                         gch[e8] = G;
                     }
                 }
-                if (GRAD) {
+                if (GRAD && !(P.dbg & 2)) {
                     // coefficient tile -> shared memory (bf16 hi / lo): rows = features, 128 B = 64 cells
                     uint32_t hh[4], ll[4];
 #pragma unroll
@@ -726,6 +838,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                         if ((lane & 3) == 0) S.cw[it & 1][q][c0 + (lane >> 2)] = tot;
                     }
                 }
+            }
+            if (NB1) {  // packed accumulators of the fast paths (they hold -G sums)
+                float a0, a1;
+                up(ngb2, a0, a1);
+                gb -= a0 + a1;
+                up(ngs2, a0, a1);
+                gs -= a0 + a1;
+                up(gd2, a0, a1);
+                gd += a0 + a1;
+                up(loss2, a0, a1);
+                loss_acc += a0 + a1;
             }
             flush();
             if (t == 0) TC_TRACE(1 + PHASE, it, 8);
@@ -972,6 +1095,10 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     p.gscale = a.grad_scale != 0.f ? a.grad_scale : 1.f;
     p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F)) * p.gscale;
     P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
+    {
+        const char* e = getenv("GLUE_TC_DBG");
+        P.dbg = e ? atoi(e) : 0;
+    }
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
 
