@@ -39,6 +39,7 @@ constexpr int PROD_T0 = 256;  // warps 8-11: one producer thread per operand row
 constexpr int PROD_THREADS = 128;
 constexpr int MMA_WARP = 12;
 constexpr int NB_MAX = 24;  // parameter rows the row-statistics table holds per v stage
+constexpr int TC_MAX_CHUNKS = 32;  // cell blocks of 128 per call (B <= 4096)
 
 constexpr uint32_t COL_ACC = 0;    // logits accumulators: 2 x 128 columns
 constexpr uint32_t COL_D1 = 256;   // d/dv tile accumulators: 2 x 64 columns
@@ -138,6 +139,7 @@ struct TcParams {
     int ntiles;
     int cell0, ncell;  // cell block [cell0, cell0 + ncell) of the (sorted) minibatch, ncell <= 128
     int acc;           // outputs accumulate (a previous cell block already wrote them)
+    int chunk, nchunks;  // this launch handles cell block `chunk` of `nchunks`
     long long* trace;  // optional: clock64 stamps of CTA 0, [kernel 0..2][tile < 8][event < 16]
     int dbg;           // timing experiments only (GLUE_TC_DBG): 1 = no x loads, 2 = no X stores / c_i reduce
 };
@@ -906,8 +908,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 float sl = 0.f;
                 int sb = 0;
                 for (int w = 0; w < EPI_WARPS; ++w) sl += S.red_l[w], sb += S.red_b[w];
-                P.p.ws.losspart[cta] = sl;
-                P.p.ws.badpart[cta] = sb;
+                P.p.ws.losspart[P.chunk * (int)gridDim.x + cta] = sl;
+                P.p.ws.badpart[P.chunk * (int)gridDim.x + cta] = sb;
             }
         }
     }
@@ -919,7 +921,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         // ---- the last CTA to arrive reduces the per-CTA partials: c_i, loss, nanmean factor -----
         if (t == 0) S.ticket = atomicAdd(P.p.ws.counters + 1, 1u);
         __syncthreads();
-        if (S.ticket == gridDim.x - 1) {
+        if (S.ticket == (unsigned)(P.chunk + 1) * gridDim.x - 1) {  // tickets keep counting across cell blocks
             __threadfence();
             const int nc = (int)gridDim.x;
             if (GRAD && NBF && t < 384) {  // three strided sub-sums per cell, combined in a fixed order
@@ -931,10 +933,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 }
                 S.cpart3[sub][cell] = c;
             }
-            if (warp == MMA_WARP) {
+            if (warp == MMA_WARP && P.chunk == P.nchunks - 1) {  // loss of the whole call: all cell blocks
                 double loss = 0.0;
                 long long bad = 0;
-                for (int q = lane; q < nc; q += 32) {
+                for (int q = lane; q < nc * P.nchunks; q += 32) {
                     loss += (double)__ldcg(P.p.ws.losspart + q);
                     bad += __ldcg(P.p.ws.badpart + q);
                 }
@@ -996,16 +998,17 @@ __global__ void __launch_bounds__(1024) tc_lse_kernel(DecWs ws, int nparts, int 
 
 // d/du = sum over CTAs of the D2 partials; grid = B blocks (sorted position), 256 threads =
 // 64 latent columns x 4 strided sub-sums combined in a fixed order
-__global__ void __launch_bounds__(256) tc_grad_u_kernel(DecParams p, int ncta) {
+__global__ void __launch_bounds__(256) tc_grad_u_kernel(DecParams p, int ncta, int cell0) {
     const glue_decoder_args& a = p.a;
-    const int pos = blockIdx.x, k = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    const int pos = blockIdx.x, k = threadIdx.x & 63, sub = threadIdx.x >> 6;  // pos: cell within the block
     __shared__ float part[4][64];
     float acc = 0.f;
     for (int q = sub; q < ncta; q += 4) acc += p.ws.apart[((int64_t)q * 128 + pos) * 64 + k];
     part[sub][k] = acc;
     __syncthreads();
     if (sub == 0 && k < a.K && a.grad_u)
-        a.grad_u[(int64_t)orig_row(a, pos) * a.K + k] = (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
+        a.grad_u[(int64_t)orig_row(a, cell0 + pos) * a.K + k] =
+            (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
 }
 
 size_t tc_ws_layout(const glue_decoder_args& a, int ncta, char* base, DecWs* ws) {
@@ -1022,8 +1025,9 @@ size_t tc_ws_layout(const glue_decoder_args& a, int ncta, char* base, DecWs* ws)
     float* cpart = (float*)take(nb * 4);
     float* c = (float*)take((size_t)a.B * 4);
     float* apart = (float*)take((size_t)ncta * 128 * 64 * 4);
-    float* losspart = (float*)take((size_t)ncta * 4);
-    int* badpart = (int*)take((size_t)ncta * 4);
+    const size_t nchunks = ((size_t)a.B + 127) / 128;
+    float* losspart = (float*)take(nchunks * ncta * 4);
+    int* badpart = (int*)take(nchunks * ncta * 4);
     float* rescale = (float*)take(4);
     unsigned int* counters = (unsigned int*)take(16);
     if (ws) *ws = DecWs{pmax, psum, lse, cpart, c, apart, losspart, badpart, rescale, counters};
@@ -1076,7 +1080,7 @@ size_t tc_workspace_bytes(const glue_decoder_args& a) {
 bool tc_eligible(const glue_decoder_args& a, int mode) {
     if (mode != MODE_LOSS && mode != MODE_GRAD) return false;
     if (a.wmat) return false;
-    if (a.B > 128 || a.K > 64 || (a.K & 1) || a.n_batches > NB_MAX) return false;
+    if (a.B > 128 * TC_MAX_CHUNKS || a.K > 64 || (a.K & 1) || a.n_batches > NB_MAX) return false;
     if (a.n_batches > 1 && a.b && !a.row_order) return false;
     auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
     if (!al8(a.u) || !al8(a.v) || !al8(a.grad_v)) return false;
@@ -1094,13 +1098,22 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     p.ncta = ncta;
     p.gscale = a.grad_scale != 0.f ? a.grad_scale : 1.f;
     p.w0 = (float)(-1.0 / ((double)a.B * (double)a.F)) * p.gscale;
+    const int nchunks = (a.B + 127) / 128;
     P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
+    P.chunk = 0, P.nchunks = nchunks;
     {
         const char* e = getenv("GLUE_TC_DBG");
         P.dbg = e ? atoi(e) : 0;
     }
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
+    const bool nb1 = a.n_batches == 1;
+    // Cells are handled in blocks of <= 128 (soft-max rows are independent); feature-side outputs
+    // (d/dv, parameter tables) accumulate from the second block on, in launch order.
+    auto block = [&](int c) {
+        P.chunk = c, P.cell0 = 128 * c, P.ncell = a.B - 128 * c < 128 ? a.B - 128 * c : 128;
+        P.acc = c > 0 ? 1 : 0;
+    };
 
     GLUE_CUDA(cudaMemsetAsync(p.ws.counters, 0, 16, st));
     if (grad && a.n_batches > 1) {
@@ -1113,27 +1126,32 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     if (nbf) {
         const size_t smem = sizeof(SmemStats);
         GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
-        tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
-        GLUE_CHECK_LAUNCH();
+        for (int c = 0; c < nchunks; ++c) {
+            block(c);
+            tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
+            GLUE_CHECK_LAUNCH();
+        }
         tc_lse_kernel<<<(a.B + 31) / 32, 1024, 0, st>>>(p.ws, 2 * ncta, a.B);  // 2 * ncta <= 320 partials
         GLUE_CHECK_LAUNCH();
     }
-    const bool nb1 = a.n_batches == 1;
-    int rc = nb1 ? launch_family<true>(a.family, 0, grad, P, ncta, st)
-                 : launch_family<false>(a.family, 0, grad, P, ncta, st);
-    if (rc) return rc;
-    if (grad) {
-        if (nbf) {
-            rc = nb1 ? launch_family<true>(a.family, 1, true, P, ncta, st)
-                     : launch_family<false>(a.family, 1, true, P, ncta, st);
-            if (rc) return rc;
-        }
-        tc_grad_u_kernel<<<a.B, 256, 0, st>>>(p, ncta);
-        GLUE_CHECK_LAUNCH();
-        if (a.reduce == 0 && !a.row_weight) {
-            dec_rescale_kernel<<<sm_count(), 256, 0, st>>>(p);
+    for (int c = 0; c < nchunks; ++c) {
+        block(c);
+        int rc = nb1 ? launch_family<true>(a.family, 0, grad, P, ncta, st)
+                     : launch_family<false>(a.family, 0, grad, P, ncta, st);
+        if (rc) return rc;
+        if (grad) {
+            if (nbf) {
+                rc = nb1 ? launch_family<true>(a.family, 1, true, P, ncta, st)
+                         : launch_family<false>(a.family, 1, true, P, ncta, st);
+                if (rc) return rc;
+            }
+            tc_grad_u_kernel<<<P.ncell, 256, 0, st>>>(p, ncta, P.cell0);
             GLUE_CHECK_LAUNCH();
         }
+    }
+    if (grad && a.reduce == 0 && !a.row_weight) {
+        dec_rescale_kernel<<<sm_count(), 256, 0, st>>>(p);
+        GLUE_CHECK_LAUNCH();
     }
     return 0;
 }

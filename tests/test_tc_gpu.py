@@ -102,6 +102,8 @@ def _run_decoder(ops, family, case, reduce):
     ("NB", 128, 2000, 50, 1), ("NB", 128, 50000, 50, 1), ("NB", 77, 1300, 50, 1), ("NB", 20, 140, 8, 1),
     ("ZINB", 128, 3000, 50, 20), ("NB", 100, 5000, 50, 5), ("Normal", 128, 4000, 50, 3),
     ("ZILN", 96, 2500, 50, 1), ("NB", 128, 150000, 50, 1),
+    # more than 128 cells: cell blocks of 128, feature-side outputs accumulate over the blocks
+    ("NB", 512, 4000, 50, 1), ("NB", 300, 1000, 50, 3), ("ZINB", 257, 700, 50, 1), ("Normal", 130, 900, 16, 1),
 ])
 def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F, K, nb):
     from glue_b200 import ops
