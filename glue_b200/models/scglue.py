@@ -105,6 +105,7 @@ class SCGLUETrainer(GLUETrainer):
         # whole-step CUDA graphs (see models/graphs.py)
         self.graphs = StepGraphs(self)
         self._side_streams: List[torch.cuda.Stream] = []
+        self._dsc_stream: Optional[torch.cuda.Stream] = None
         self.capturing = False
         self.anneal_buffer = torch.zeros((), dtype=torch.float32, device=net.device)
 
@@ -265,11 +266,35 @@ class SCGLUETrainer(GLUETrainer):
 
     DATA_REDUCE = "nanmean"  # scglue.py:345
 
-    def compute_losses(self, data, epoch: int, dsc_only: bool = False
+    def compute_losses(self, data, epoch: int, dsc_only: bool = False,
+                       dsc_update: Optional[Callable[[torch.Tensor], None]] = None
                        ) -> Mapping[str, torch.Tensor]:
+        r"""Objective of one pass (``scglue.py:292-376``).  With ``dsc_update`` given, this call
+        is a whole training step: the discriminator pass (encoders forward, discriminator loss,
+        ``dsc_update(dsc_loss)`` = backward + optimizer step) runs first *in program order* but
+        on its own stream, beside the part of the generator pass that does not read the
+        discriminator (data encoders, graph branch, decoders); the generator's alignment term
+        waits for the updated discriminator."""
         net = self.net
         x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
         prior = net.prior()
+        dsc_stream = None
+        if dsc_update is not None:
+            # encoders, discriminator pass first: BatchNorm statistics and dropout streams advance
+            # in the reference's order because each modality keeps its stream for both passes
+            with torch.no_grad():
+                u_d, _, _ = self._encode(x, xrep, True)
+            main = torch.cuda.current_stream(net.device)
+            if self._dsc_stream is None:
+                self._dsc_stream = torch.cuda.Stream(net.device)
+            dsc_stream = self._dsc_stream
+            dsc_stream.wait_stream(main)
+            with torch.cuda.stream(dsc_stream):
+                for k in net.keys:  # allocated on other streams, consumed here
+                    u_d[k].mean.record_stream(dsc_stream)
+                _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch)
+                dsc_update(self.lam_align * dsc_loss_d)
+            del u_d, dsc_loss_d
         if dsc_only:
             # only the discriminator is updated in this pass: the encoders run forward (BatchNorm
             # statistics and dropout streams advance as in the reference) but are not
@@ -283,8 +308,6 @@ class SCGLUETrainer(GLUETrainer):
         # the data encoders: it runs beside them
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
             x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
-        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
-        sup_loss = self._supervision(u_cat, xlbl)
         g_elbo = g_nll + self.lam_kl * g_kl
         # one stream per modality: the decoder calls of a small modality (16 CTAs for 2 000
         # genes) fill the SMs that the tail of a large one (50 000 peaks) leaves idle
@@ -296,6 +319,10 @@ class SCGLUETrainer(GLUETrainer):
             for k in net.keys])
         x_nll = {k: out[0] for k, out in zip(net.keys, per_mod)}
         self._extra_parts = {k: out[1] for k, out in zip(net.keys, per_mod)}
+        if dsc_stream is not None:  # the alignment term needs the updated discriminator
+            torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
+        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
+        sup_loss = self._supervision(u_cat, xlbl)
         x_kl = {k: _kl_to_prior(u[k], prior) / x[k].shape[1] for k in net.keys}
         x_elbo = {k: x_nll[k] + self.lam_kl * x_kl[k] for k in net.keys}
         x_elbo_sum = sum(self.modality_weight[k] * x_elbo[k] for k in net.keys)
@@ -341,9 +368,17 @@ class SCGLUETrainer(GLUETrainer):
         self.net.train()
         data = self.format_data(data)
         epoch = engine.state.epoch
+        dsc_update = None
         if self.freeze_u:
             self.net.x2u.apply(freeze_running_stats)
             self.net.du.apply(freeze_running_stats)
+        elif (self.dsc_steps == 1 and config.MULTI_STREAM and config.OVERLAP_DISCRIMINATOR
+              and self.net.device.type == "cuda"):
+            def dsc_update(scaled_dsc_loss):  # runs on the discriminator stream
+                self.net.zero_grad(set_to_none=True)
+                scaled_dsc_loss.backward()
+                self._sync_grads("dsc")
+                self.dsc_optim.step()
         else:  # discriminator step
             for _ in range(self.dsc_steps):
                 losses = self.compute_losses(data, epoch, dsc_only=True)
@@ -351,7 +386,7 @@ class SCGLUETrainer(GLUETrainer):
                 losses["dsc_loss"].backward()  # already scaled by lam_align
                 self._sync_grads("dsc")
                 self.dsc_optim.step()
-        losses = self.compute_losses(data, epoch)  # generator step
+        losses = self.compute_losses(data, epoch, dsc_update=dsc_update)  # generator step
         self.net.zero_grad(set_to_none=True)
         losses["gen_loss"].backward()
         self._sync_grads("vae")
@@ -403,11 +438,11 @@ class PairedSCGLUETrainer(SCGLUETrainer):
             lam_joint_cross, lam_real_cross, lam_cos)
         self.required_losses += ["joint_cross_loss", "real_cross_loss", "cos_loss"]
 
-    def compute_losses(self, data, epoch: int, dsc_only: bool = False):
+    def compute_losses(self, data, epoch: int, dsc_only: bool = False, dsc_update=None):
         x, xrep, xbch, xlbl, xdwt, xflag, pmsk, eidx, ewt, esgn = data
         self._pmsk = pmsk
         return super().compute_losses((x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn),
-                                      epoch, dsc_only=dsc_only)
+                                      epoch, dsc_only=dsc_only, dsc_update=dsc_update)
 
     def _prepare_extra(self, usamp) -> None:
         self._shared_extra = self._umean(usamp)

@@ -52,6 +52,8 @@ class _Settings:
         USE_FUSED_OPTIMIZER=True,
         # run independent branches of a step (data encoders, graph branch) on forked streams
         MULTI_STREAM=True,
+        # run the discriminator update beside the generator pass's encoders / decoders
+        OVERLAP_DISCRIMINATOR=True,
     )
 
     def __init__(self) -> None:
