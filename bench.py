@@ -385,8 +385,10 @@ def main():
         ls = [x.sum(1, keepdim=True) for x in x_of[k]]
 
         def dec_call(i, dec=dec, idx=idx, u=u, ls=ls, k=k):
-            return ops.decoder_nll("NB", u, vtab, dec.scale_lin, dec.bias, dec.log_theta, None, b=bz,
-                                   l=ls[i % pool_n], x=x_of[k][i % pool_n], vidx=idx, reduce="mean")
+            xb = x_of[k][i % pool_n]
+            n = xb.shape[0]  # the block-shuffled loader can yield a short minibatch
+            return ops.decoder_nll("NB", u[:n], vtab, dec.scale_lin, dec.bias, dec.log_theta, None,
+                                   b=bz[:n], l=ls[i % pool_n], x=xb, vidx=idx, reduce="mean")
 
         ktimes[f"decoder_fwd_bwd_NB_F{x_of[k][0].shape[1]}_B{B}"] = (time_calls(dec_call), 3)
     csr = ops.csr_for(trainer.eidx, trainer.enorm, trainer.esgn, len(model.vertices))
@@ -485,5 +487,33 @@ def run_reference(args, cfg):
     }))
 
 
+def _only_json_on_stdout(fn):
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there)
+    get stderr as their fd 1 for the whole run, the result line goes to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    captured = []
+    import builtins
+    orig_print = builtins.print
+
+    def tee(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            captured.append(" ".join(str(x) for x in a))
+        else:
+            orig_print(*a, **k)
+
+    builtins.print = tee
+    try:
+        fn()
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        for line in captured:
+            out.write(line + "\n")
+        out.flush()
+
+
 if __name__ == "__main__":
-    main()
+    _only_json_on_stdout(main)
