@@ -300,7 +300,10 @@ def main():
     # (after two eager steps the trainer replays the step from a captured CUDA graph)
     step_dev = lambda i: trainer.train_step(_Engine, dev_pool[i % pool_n])
     with ClockSampler(local_rank) as clocks:  # sampled from warm-up on (the timed region is short)
-        for i in range(max(warmup, 4)):
+        # every distinct minibatch signature of the pool (the block-shuffled loader can yield a
+        # short minibatch) is stepped until its graph exists; at least `warmup` steps in any case
+        n_sig = len({tuple(tuple(t.shape) for t in b) for b in dev_pool})
+        for i in range(max(warmup, 4, 3 * pool_n if n_sig > 1 else 0)):
             step_dev(i)
         launches0, replays0 = ops.kernel_launches(), trainer.graphs.replays
         ms = timed(step_dev, args.steps)

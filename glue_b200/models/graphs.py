@@ -35,7 +35,8 @@ class StepGraphs:
     r"""Per-trainer cache of captured training steps, keyed by everything that is baked into a
     capture: input shapes / dtypes, the ``freeze_u`` / burn-in switches and the learning rates."""
 
-    WARMUP_STEPS = 2   # eager steps with a new key before it is captured
+    WARMUP_STEPS = 2        # eager steps before the first capture (optimizer state, workspaces)
+    WARMUP_STEPS_LATER = 1  # eager steps with a further key (e.g. the short last minibatch)
     MAX_GRAPHS = 4
 
     def __init__(self, trainer) -> None:
@@ -86,7 +87,8 @@ class StepGraphs:
             self.entries.move_to_end(key)
         if entry["graph"] is None:
             entry["seen"] += 1
-            if entry["seen"] <= self.WARMUP_STEPS:
+            have_graph = any(e["graph"] is not None for e in self.entries.values())
+            if entry["seen"] <= (self.WARMUP_STEPS_LATER if have_graph else self.WARMUP_STEPS):
                 return tr.eager_train_step(engine, data)
             self._capture(entry, engine, data)
             if entry["graph"] is None:
