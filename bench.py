@@ -303,7 +303,12 @@ def main():
         # every distinct minibatch signature of the pool (the block-shuffled loader can yield a
         # short minibatch) is stepped until its graph exists; at least `warmup` steps in any case
         n_sig = len({tuple(tuple(t.shape) for t in b) for b in dev_pool})
-        for i in range(max(warmup, 4, 3 * pool_n if n_sig > 1 else 0)):
+        if world > 1:  # every rank must take the same number of steps (gradient all-reduce)
+            t_sig = torch.tensor([n_sig], device=device)
+            torch.distributed.all_reduce(t_sig, op=torch.distributed.ReduceOp.MAX)
+            n_sig = int(t_sig.item())
+        warmup = max(warmup, 4, 3 * pool_n if n_sig > 1 else 0)
+        for i in range(warmup):
             step_dev(i)
         launches0, replays0 = ops.kernel_launches(), trainer.graphs.replays
         ms = timed(step_dev, args.steps)
