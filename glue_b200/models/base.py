@@ -229,6 +229,9 @@ class Model:
         finally:
             self.net.device = device_backup
             self._trainer = trainer_backup
+            graphs = getattr(trainer_backup, "graphs", None)
+            if graphs is not None:  # the round trip through the CPU re-allocated every parameter
+                graphs.invalidate()
 
     @staticmethod
     def load(fname: os.PathLike) -> "Model":

@@ -56,12 +56,24 @@ class StepGraphs:
         r"""Drop every capture (optimizer state or parameters were replaced, e.g. by
         ``load_state_dict``)."""
         self.entries.clear()
+        self.pool = None  # the memory pool dies with its last graph: later captures get a new one
 
     def _key(self, data: List[torch.Tensor], anneal: float) -> tuple:
         tr = self.trainer
         lrs = tuple(float(g["lr"]) for opt in (tr.vae_optim, tr.dsc_optim) for g in opt.param_groups)
         return (tuple((tuple(t.shape), t.dtype) for t in data), bool(anneal), bool(tr.freeze_u),
                 lrs, tr.dsc_steps)
+
+    def _storage_fingerprint(self) -> tuple:
+        r"""Addresses of the first and last parameter of every optimizer: a capture is only valid
+        while the parameters live where they lived when it was taken (``net.to(...)``, as done by
+        ``Model.save``, re-allocates them)."""
+        tr = self.trainer
+        out = []
+        for opt in (tr.vae_optim, tr.dsc_optim):
+            params = opt.param_groups[0]["params"]
+            out += [params[0].data_ptr(), params[-1].data_ptr()]
+        return tuple(out)
 
     def info(self) -> Mapping[str, Any]:
         r"""``{"graphs", "replays", "kernels_per_step"}`` (native kernels inside the most
@@ -75,6 +87,11 @@ class StepGraphs:
     # ------------------------------------------------------------------------------ stepping
     def step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
         tr = self.trainer
+        fingerprint = self._storage_fingerprint()
+        if fingerprint != getattr(self, "_fingerprint", fingerprint):
+            self.logger.info("parameters were re-allocated: dropping captured training steps")
+            self.invalidate()
+        self._fingerprint = fingerprint
         anneal = tr.burnin_anneal(engine.state.epoch)
         key = self._key(data, anneal)
         entry = self.entries.get(key)
@@ -89,7 +106,9 @@ class StepGraphs:
             entry["seen"] += 1
             have_graph = any(e["graph"] is not None for e in self.entries.values())
             if entry["seen"] <= (self.WARMUP_STEPS_LATER if have_graph else self.WARMUP_STEPS):
-                return tr.eager_train_step(engine, data)
+                out = tr.eager_train_step(engine, data)
+                self._fingerprint = self._storage_fingerprint()  # the optimizer may re-adopt storage
+                return out
             self._capture(entry, engine, data)
             if entry["graph"] is None:
                 return tr.eager_train_step(engine, data)

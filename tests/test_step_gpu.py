@@ -244,3 +244,33 @@ def test_partially_paired_fit_runs(native_lib):
     for key in ("joint_cross_loss", "real_cross_loss", "cos_loss"):
         assert key in losses
     assert model.trainer.graphs.info()["disabled"] is None
+
+
+def test_training_continues_correctly_after_save(native_lib):
+    """Model.save moves the network to the CPU and back, which re-allocates every parameter:
+    captured steps must be dropped and the fused optimizer must re-adopt the new storage, so
+    that a second fit keeps training the network's own parameters."""
+    import tempfile
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+
+    adatas, graph = make_synthetic(n_cells=(260, 240), n_feat=(40, 70), n_pairs=120, seed=11, rep_dim=12)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep")
+    model = models.SCGLUEModel(adatas, sorted(graph.nodes), latent_dim=16, h_dim=32, random_seed=4)
+    model.compile()
+    kw = dict(data_batch_size=32, graph_batch_size=64, max_epochs=3, align_burnin=1, patience=None,
+              reduce_lr_patience=None)
+    with tempfile.TemporaryDirectory() as tmp:
+        model.fit(adatas, graph, directory=tmp, **kw)
+        assert model.trainer.graphs.info()["replays"] > 0
+        model.save(f"{tmp}/m.dill")
+        before = {k: v.detach().clone() for k, v in model.net.state_dict().items()}
+        replays = model.trainer.graphs.replays
+        model.fit(adatas, graph, directory=tmp, **kw)
+    after = model.net.state_dict()
+    moved = [k for k in before if before[k].dtype.is_floating_point and not torch.equal(before[k], after[k])]
+    assert "g2v.vrepr" in moved and "du.pred.weight" in moved, "second fit must update the parameters"
+    assert model.trainer.graphs.replays > replays
+    opt = model.trainer.vae_optim
+    assert all(p.data_ptr() == v.data_ptr() for p, v in zip(opt._plist, opt._pviews))
