@@ -6,6 +6,8 @@
 // (pos/neg balanced Bernoulli NLL).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace glue {
@@ -88,6 +90,61 @@ graphconv_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restri
                 for (int q = 0; q < VEC; ++q) rs[q] = acc[q];
                 reinterpret_cast<V*>(out + row * K)[c] = r;
             }
+        }
+    }
+}
+
+// Sub-warp variant for rows of <= 32 float2 (K <= 64, even): 8 lanes per row, 4 rows per warp.
+// The row-at-a-time kernel keeps one row's gathers in flight per warp and is bound by the
+// pointer -> column -> source-row load latencies; here every warp has 4 independent rows (and two
+// edges per row, up to four) in flight.  Each row is still summed by its own lanes in edge order with the
+// products rounded before the add, so results are bit-identical to the warp-per-row kernel.
+__global__ void __launch_bounds__(256)
+graphconv_csr_sub8_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
+                          const float* __restrict__ val, const float* __restrict__ in,
+                          float* __restrict__ out, int64_t n_rows, int K) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nvec = K >> 1;  // float2 per row, <= 32
+    bool act[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) act[q] = sub + 8 * q < nvec;
+    for (int64_t row4 = warp0 * 4; row4 < n_rows; row4 += nwarps * 4) {
+        const int64_t row = row4 + grp;
+        const bool rok = row < n_rows;
+        const int beg = rok ? __ldg(indptr + row) : 0, end = rok ? __ldg(indptr + row + 1) : 0;
+        float2 acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+        for (int e = beg; e < end; e += 2) {  // two edges (8 gathers per lane) in flight: 4 was slower
+            const bool two = e + 1 < end;
+            const int c0 = __ldg(col + e), c1 = two ? __ldg(col + e + 1) : 0;
+            const float w0 = __ldg(val + e), w1 = two ? __ldg(val + e + 1) : 0.f;
+            const float2* s0 = reinterpret_cast<const float2*>(in + (int64_t)c0 * K);
+            const float2* s1 = reinterpret_cast<const float2*>(in + (int64_t)c1 * K);
+            float2 x0[4], x1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (act[q]) x0[q] = __ldg(s0 + sub + 8 * q);
+                if (act[q] && two) x1[q] = __ldg(s1 + sub + 8 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (act[q]) {
+                    acc[q].x = __fadd_rn(acc[q].x, __fmul_rn(x0[q].x, w0));
+                    acc[q].y = __fadd_rn(acc[q].y, __fmul_rn(x0[q].y, w0));
+                    if (two) {
+                        acc[q].x = __fadd_rn(acc[q].x, __fmul_rn(x1[q].x, w1));
+                        acc[q].y = __fadd_rn(acc[q].y, __fmul_rn(x1[q].y, w1));
+                    }
+                }
+        }
+        if (rok) {
+            float2* dst = reinterpret_cast<float2*>(out + row * K);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (act[q]) dst[sub + 8 * q] = acc[q];
         }
     }
 }
@@ -311,6 +368,17 @@ extern "C" int glue_graphconv_csr(const int32_t* indptr, const int32_t* col, con
     const int64_t want = (n_rows + 7) / 8;
     const int grid = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
     const uintptr_t bits = (uintptr_t)in | (uintptr_t)out;
+    static const bool use_sub8 = [] {
+        const char* e = getenv("GLUE_GC_SUB8");
+        return !(e && e[0] == '0');
+    }();
+    if (use_sub8 && K % 2 == 0 && K <= 64 && bits % 8 == 0) {
+        const int64_t want4 = ((n_rows + 3) / 4 + 7) / 8;  // 4 rows per warp, 8 warps per block
+        const int grid4 = (int)(want4 < 1 ? 1 : (want4 < (int64_t)sm_count() * 32 ? want4 : (int64_t)sm_count() * 32));
+        graphconv_csr_sub8_kernel<<<grid4, threads, 0, st>>>(indptr, col, val, in, out, n_rows, K);
+        GLUE_CHECK_LAUNCH();
+        return 0;
+    }
     if (K % 4 == 0 && bits % 16 == 0)
         graphconv_csr_kernel<4><<<grid, threads, 0, st>>>(indptr, col, val, in, out, n_rows, K);
     else if (K % 2 == 0 && bits % 8 == 0)
