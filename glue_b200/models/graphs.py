@@ -61,8 +61,13 @@ class StepGraphs:
     def _key(self, data: List[torch.Tensor], anneal: float) -> tuple:
         tr = self.trainer
         lrs = tuple(float(g["lr"]) for opt in (tr.vae_optim, tr.dsc_optim) for g in opt.param_groups)
+        # loss weights are Python numbers baked into the captured kernels' arguments
+        weights = tuple(float(getattr(tr, name)) for name in (
+            "lam_data", "lam_kl", "lam_graph", "lam_align", "lam_sup", "lam_joint_cross",
+            "lam_real_cross", "lam_cos") if hasattr(tr, name))
+        weights += tuple(float(v) for v in tr.modality_weight.values())
         return (tuple((tuple(t.shape), t.dtype) for t in data), bool(anneal), bool(tr.freeze_u),
-                lrs, tr.dsc_steps)
+                lrs, tr.dsc_steps, weights, bool(tr.normalize_u), tr.align_burnin)
 
     def _storage_fingerprint(self) -> tuple:
         r"""Addresses of the first and last parameter of every optimizer: a capture is only valid
