@@ -272,6 +272,13 @@ def main():
     _, host_loader, _ = make_loaders(model, adatas, graph, cfg, device_resident=False)
     it = iter(host_loader)
     host_pool = [[t.pin_memory() for t in next(it)] for _ in range(pool_n)]
+    if os.environ.get("GLUE_BENCH_SHORT_RANK") == str(rank):
+        # test knob: give this rank alone a short minibatch (as the block-shuffled loader can),
+        # to exercise the rank-uniform warm-up below
+        n_short = cfg["batch"] - 16
+        cut = lambda batch, pin: [(t[:n_short].contiguous().pin_memory() if pin else t[:n_short].contiguous())
+                                  if t.dim() and t.shape[0] == cfg["batch"] else t for t in batch]
+        dev_pool[3], host_pool[5] = cut(dev_pool[3], False), cut(host_pool[5], True)
     h2d = sum(t.numel() * t.element_size() for t in host_pool[0])
     e_mb = int(dev_pool[0][-1].numel())
 
@@ -302,7 +309,7 @@ def main():
     with ClockSampler(local_rank) as clocks:  # sampled from warm-up on (the timed region is short)
         # every distinct minibatch signature of the pool (the block-shuffled loader can yield a
         # short minibatch) is stepped until its graph exists; at least `warmup` steps in any case
-        n_sig = len({tuple(tuple(t.shape) for t in b) for b in dev_pool})
+        n_sig = len({tuple(tuple(t.shape) for t in b) for b in dev_pool + host_pool})
         if world > 1:  # every rank must take the same number of steps (gradient all-reduce)
             t_sig = torch.tensor([n_sig], device=device)
             torch.distributed.all_reduce(t_sig, op=torch.distributed.ReduceOp.MAX)
@@ -353,7 +360,7 @@ def main():
 
     e2e_runs = {}
     for mode, prefetch in (("direct", False), ("prefetch", True)):
-        run_e2e(4, prefetch)
+        run_e2e(2 * pool_n if n_sig > 1 else 4, prefetch)  # (every signature of the host pool has its graph)
         e2e_runs[mode] = timed(lambda i, p=prefetch: run_e2e(args.steps, p) if i == 0 else None, 1)
     e2e_feed = min(e2e_runs, key=e2e_runs.get)
     ms_e2e = e2e_runs[e2e_feed]

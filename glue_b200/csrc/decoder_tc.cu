@@ -22,6 +22,7 @@
 // 32 (w & 3) .. +31 and one half of the cell columns), warps 8-11 stage the v tiles (double
 // buffered) and prefetch the step's observations into L2, warp 12 issues
 // tcgen05.mma (one lane).  Pipelines are mbarrier based.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "decoder_common.cuh"
@@ -32,12 +33,14 @@ using namespace tc;
 
 namespace {
 
+// row-statistics kernel (and the default shape of the main kernel): 8 epilogue warps
 constexpr int NTHREADS = 416;
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_WARPS = 8;
 constexpr int PROD_T0 = 256;  // warps 8-11: one producer thread per operand row
 constexpr int PROD_THREADS = 128;
 constexpr int MMA_WARP = 12;
+constexpr int MAX_EPI_WARPS = 16;  // main kernel, EW = 16: four epilogue warps per TMEM lane quarter
 constexpr int NB_MAX = 24;  // parameter rows the row-statistics table holds per v stage
 constexpr int TC_MAX_CHUNKS = 32;  // cell blocks of 128 per call (B <= 4096)
 
@@ -116,9 +119,12 @@ struct __align__(1024) SmemMain {
     float cw[2][4][128];
     float c_acc[128];
     float stage[128][65];  // d/dv tile on its way from TMEM (thread <-> row) to coalesced stores
-    float red_l[EPI_WARPS];
-    int red_b[EPI_WARPS];
+    float red_l[MAX_EPI_WARPS];
+    int red_b[MAX_EPI_WARPS];
     float cpart3[3][128];
+    alignas(16) uint32_t xoff32[136];  // element offset of every cell's row of x (streamlined path); 8 pad entries
+    alignas(16) float zeros[128];      // weights seen by feature rows beyond F
+    float gpart[2][3][4][128];     // 16 epilogue warps: parameter-gradient partials of the upper cell quarters
     Bars bars;
     uint32_t tmem_base;
     uint32_t ticket;
@@ -133,6 +139,11 @@ struct __align__(1024) SmemStats {
     uint32_t tmem_base;
     uint32_t ticket;
 };
+
+static_assert(offsetof(SmemMain, wrow) % 16 == 0 && offsetof(SmemMain, lse) % 16 == 0 &&
+                  offsetof(SmemMain, xoff32) % 16 == 0 && offsetof(SmemMain, zeros) % 16 == 0,
+              "vector loads of the per-cell tables");
+static_assert(sizeof(SmemMain) <= 227 * 1024, "shared memory per CTA");
 
 struct TcParams {
     DecParams p;
@@ -154,16 +165,32 @@ __device__ __forceinline__ int orig_row(const glue_decoder_args& a, int pos) {
     return a.row_order ? a.row_order[pos] : pos;
 }
 
-// v tile producer: one thread per feature row
+// v tile producer: one thread per feature row.  CINV (streamlined pass B, single parameter row,
+// K <= 62): operand column K carries 1 / softplus(scale_lin_j).  The logits and the d/dv product
+// never see it (u has zeros there); in the d/du product  D2[cell, k] = sum_j X[j, cell] V[j, k]
+// with X = G softplus(scale) it makes column K the soft-max correction  c_i = sum_j G_ij.
+template <bool CINV = false, int NPROD = PROD_THREADS>
 __device__ __forceinline__ void produce_v_rows(const glue_decoder_args& a, uint8_t* hi, uint8_t* lo, int f0, int pt) {
-    for (int r = pt; r < 128; r += PROD_THREADS) {
+    for (int r = pt; r < 128; r += NPROD) {
         const int j = f0 + r;
         const float* src = nullptr;
+        float rs = 0.f;
         if (j < a.F) {
             const int64_t vr = a.vidx ? a.vidx[j] : (int64_t)j;
             src = a.v + vr * a.K;
+            if (CINV) {
+                const float sp = softplusf(a.scale_lin[j]);
+                rs = sp > 1e-18f ? 1.f / sp : 0.f;
+            }
         }
         stage_row(smem_u32(hi), smem_u32(lo), (uint32_t)r, src, a.K);
+        if (CINV) {  // (same thread: ordered after the zero fill of the chunk above)
+            uint32_t h2, l2;
+            split2(rs, 0.f, h2, l2);
+            const uint32_t off = swz((uint32_t)r, (uint32_t)a.K >> 3) + (((uint32_t)a.K & 7u) << 1);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(hi) + off), "r"(h2) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(lo) + off), "r"(l2) : "memory");
+        }
     }
 }
 
@@ -311,9 +338,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
 // ---------------------------------------------------------------------------------------------
 // pass B (PHASE 0: likelihood + all G terms) and pass C (PHASE 1: the -p_ij c_i soft-max terms).
 // D[feature, cell] = V U^T; thread <-> feature.  NB1: a single parameter row (n_batches == 1).
+// EW: epilogue warps (8, or 16 = four warps per TMEM lane quarter, each owning a quarter of the
+// cell columns; NB1 only).  FAST: streamlined NB pass B (NB1, K <= 62, B F < 2^31) -- 32-bit
+// unpredicated observation loads, gamma terms of the counts 0 / 1 / 2 as a quadratic, everything
+// else (larger counts, NaN) handled per thread ahead of the packed arithmetic, c_i taken from
+// the tensor cores (produce_v_rows<CINV>).
 // ---------------------------------------------------------------------------------------------
-template <int FAM, int PHASE, bool GRAD, bool NB1>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
+template <int FAM, int PHASE, bool GRAD, bool NB1, int EW, bool FAST>
+__global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcParams P) {
+    static_assert(EW == 8 || EW == 16, "epilogue warps");
+    static_assert(EW == 8 || NB1, "16 epilogue warps: single parameter row only");
+    static_assert(!FAST || (FAM == GLUE_NB && NB1 && PHASE == 0), "streamlined path: NB pass B");
+    // epilogue warps, producer warps, 1 MMA warp.  EW = 16 runs 3 producer warps: 20 warps = 5 per
+    // scheduler keep 96 registers per thread (21 warps would cap them at 80)
+    constexpr int PW = EW == 16 ? 3 : 4;
+    constexpr int NPROD = PW * 32;
+    constexpr int NT = (EW + PW + 1) * 32;
+    constexpr int EPI_T = EW * 32;
+    constexpr int PROD0 = EW * 32;
+    constexpr int MMAW = EW + PW;
+    constexpr int NH = EW / 4;    // threads sharing a feature row (splits of the cell columns)
+    constexpr int DC = 64 / NH;   // columns of the 64-wide gradient accumulators per thread
+    constexpr bool CINV = FAST && GRAD;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemMain& S = *reinterpret_cast<SmemMain*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzled operand tiles need 1024 B alignment
@@ -328,19 +374,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 
     if (t == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&S.bars.v_full[s], PROD_THREADS);
+            mbar_init(&S.bars.v_full[s], NPROD);
             mbar_init(&S.bars.v_empty[s], 1);
             mbar_init(&S.bars.acc_full[s], 1);
-            mbar_init(&S.bars.acc_empty[s], EPI_WARPS);
+            mbar_init(&S.bars.acc_empty[s], EW);
             mbar_init(&S.bars.d1_full[s], 1);
-            mbar_init(&S.bars.d1_empty[s], EPI_WARPS);
+            mbar_init(&S.bars.d1_empty[s], EW);
         }
-        mbar_init(&S.bars.x_full, EPI_WARPS);
+        mbar_init(&S.bars.x_full, EW);
         mbar_init(&S.bars.x_empty, 1);
         mbar_init(&S.bars.d2_full, 1);
         mbar_fence_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
+    if (warp == MMAW) tmem_alloc(&S.tmem_base, TMEM_COLS);
     if (t < 128) {
         const bool ok = t < ncell;
         const int pos = P.cell0 + t;
@@ -348,6 +394,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
         stage_row(smem_u32(S.u_hi), smem_u32(S.u_lo), (uint32_t)t, ok ? a.u + (int64_t)orig * a.K : nullptr, a.K);
         S.bidx[t] = (ok && a.b) ? (int)a.b[orig] : 0;
         S.xoff[t] = (long long)orig * a.F;
+        S.xoff32[t] = (uint32_t)((long long)orig * a.F);  // (FAST: B F < 2^31 checked by the host)
+        S.zeros[t] = 0.f;
+        if (t < 8) S.xoff32[128 + t] = 0u;
         S.l[t] = (ok && a.l) ? a.l[orig] : 1.f;
         S.lse[t] = (ok && NBF) ? -(P.p.ws.lse[pos] * LOG2EF) : 0.f;  // -lse in base 2
         S.c[t] = (ok && PHASE == 1) ? P.p.ws.c[pos] : 0.f;
@@ -356,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     }
     if (GRAD) {  // cells beyond ncell must read as exact zeros in the coefficient tile
         uint4* xz = reinterpret_cast<uint4*>(S.x_hi);
-        for (int i = t; i < (int)(4 * OP_BYTES / 16); i += NTHREADS) xz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = t; i < (int)(4 * OP_BYTES / 16); i += NT) xz[i] = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -365,14 +414,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     const uint32_t tmem_base = S.tmem_base;
     if (t == 0) TC_TRACE(1 + PHASE, 7, 0);
 
-    if (warp >= PROD_T0 / 32 && warp < MMA_WARP) {
+    if (warp >= PROD0 / 32 && warp < MMAW) {
         // ===== v tile producers (one thread per row); x tile of the same step -> L2 =====
-        const int pt = t - PROD_T0;
+        const int pt = t - PROD0;
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1, f0 = (cta + it * ncta) * 128;
             if (PHASE == 0) {
                 const int nvalid = min(128, a.F - f0);
-                for (int cell = pt; cell < ncell; cell += PROD_THREADS) {
+                for (int cell = pt; cell < ncell; cell += NPROD) {
                     const float* px = a.x + S.xoff[cell] + f0;
                     for (int o = 0; o < nvalid; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(px + nvalid - 1));
@@ -380,12 +429,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             }
             mbar_wait(&S.bars.v_empty[s], ((it >> 1) & 1) ^ 1);
             if (pt == 0) TC_TRACE(1 + PHASE, it, 0);
-            produce_v_rows(a, S.v_hi[s], S.v_lo[s], f0, pt);
+            produce_v_rows<CINV, NPROD>(a, S.v_hi[s], S.v_lo[s], f0, pt);
             fence_proxy_async();
             mbar_arrive(&S.bars.v_full[s]);
             if (pt == 0) TC_TRACE(1 + PHASE, it, 1);
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == MMAW) {
         // ===== MMA issuer =====
         if (lane == 0) {
             auto issue_fwd = [&](int it) {
@@ -441,16 +490,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             }
             if (GRAD) umma_commit(&S.bars.d2_full);
         }
-    } else if (warp < EPI_WARPS) {
+    } else if (warp < EW) {
         // ===== epilogue =====
         const int q = warp & 3, h = warp >> 2;
         const int frow = 32 * q + lane;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        // groups of 8 cells (= one 16-byte chunk of a coefficient-tile row); the two threads that
-        // share a feature split the groups in two contiguous halves
+        // groups of 8 cells (= one 16-byte chunk of a coefficient-tile row); the NH threads that
+        // share a feature split the groups in contiguous runs
         const int ngrp = (ncell + 7) >> 3;
-        const int g_begin = h == 0 ? 0 : (ngrp + 1) / 2;
-        const int g_end = h == 0 ? (ngrp + 1) / 2 : ngrp;
+        const int g_begin = (ngrp * h + NH - 1) / NH;
+        const int g_end = (ngrp * (h + 1) + NH - 1) / NH;
         const bool add_v = (PHASE == 1) || P.acc;
         const bool skip_nan = a.reduce == 0 && !a.row_weight;  // nanmean semantics
         float loss_acc = 0.f;
@@ -461,8 +510,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             const int j = (cta + itp * ncta) * 128 + frow;
             mbar_wait(&S.bars.d1_full[s], (itp >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + COL_D1 + s * 64 + 32 * h, r);
+            uint32_t r[DC];
+            if constexpr (NH == 2) tmem_ld32(tmem_base + lane_addr + COL_D1 + s * 64 + DC * h, r);
+            else tmem_ld16(tmem_base + lane_addr + COL_D1 + s * 64 + DC * h, r);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -471,19 +521,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             // (K contiguous floats) should leave with consecutive lanes on consecutive addresses
             (void)j;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) S.stage[frow][32 * h + k] = __uint_as_float(r[k]);
-            named_bar_sync(3, EPI_THREADS);
+            for (int k = 0; k < DC; ++k) S.stage[frow][DC * h + k] = __uint_as_float(r[k]);
+            named_bar_sync(3, EPI_T);
             if (a.grad_v) {
                 const int f0p = (cta + itp * ncta) * 128;
                 const int k2 = lane;  // float2 index inside the row
                 const bool kok = 2 * k2 < a.K;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 16 / EW; ++half) {
                     float2 old[8];
                     float2* dst[8];
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {  // every load before the first store
-                        const int row = warp + 8 * (rr + 8 * half);
+                        const int row = warp + EW * (rr + 8 * half);
                         const int jj = f0p + row;
                         dst[rr] = nullptr;
                         old[rr] = make_float2(0.f, 0.f);
@@ -495,14 +545,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                     }
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
-                        const int row = warp + 8 * (rr + 8 * half);
+                        const int row = warp + EW * (rr + 8 * half);
                         if (dst[rr] != nullptr)
                             *dst[rr] = make_float2(S.stage[row][2 * k2] + old[rr].x,
                                                    S.stage[row][2 * k2 + 1] + old[rr].y);
                     }
                 }
             }
-            named_bar_sync(3, EPI_THREADS);  // the staging tile is free again
+            named_bar_sync(3, EPI_T);  // the staging tile is free again
         };
 
         for (int it = 0; it < ntl; ++it) {
@@ -536,7 +586,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 if (GRAD && cur_b >= 0 && jok) {
                     const int64_t off = (int64_t)cur_b * a.F + j;
                     const float vs = gs * fp.sg;
-                    if (h == 1 && !pend) {
+                    if constexpr (NH == 4) {
+                        // one flush per tile (NB1): the upper quarters hand their sums to the h == 0
+                        // thread through shared memory; it adds them in a fixed order after the barrier
+                        if (h > 0) {
+                            float(*gp)[128] = S.gpart[it & 1][h - 1];
+                            gp[0][frow] = gb, gp[1][frow] = vs, gp[2][frow] = gd, gp[3][frow] = gz;
+                        } else {
+                            pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
+                        }
+                    } else if (h == 1 && !pend) {
                         pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
                     } else {
                         write_param(off, gb, vs, gd, gz, (PHASE == 1) || P.acc || !NB1 || h == 1);
@@ -561,22 +620,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 
             // observations of the first group are requested before the logits are waited for
             float xn[8];
+            // FAST: every load is in bounds without predicates -- feature column clamped to F - 1,
+            // cells beyond ncell (and the group after the last one) read row offset 0; what they
+            // compute carries weight 0
+            const float* xj = a.x + (jok ? j : a.F - 1);
+            if (FAST) asm volatile("" : "+l"(xj));  // keep the column base in a register pair (IMAD.WIDE per load)
             auto load_x = [&](int g) {
+                if constexpr (FAST) {
+                    const uint4 o0 = *reinterpret_cast<const uint4*>(&S.xoff32[8 * g]);
+                    const uint4 o1 = *reinterpret_cast<const uint4*>(&S.xoff32[8 * g + 4]);
+                    xn[0] = __ldg(xj + o0.x), xn[1] = __ldg(xj + o0.y), xn[2] = __ldg(xj + o0.z), xn[3] = __ldg(xj + o0.w);
+                    xn[4] = __ldg(xj + o1.x), xn[5] = __ldg(xj + o1.y), xn[6] = __ldg(xj + o1.z), xn[7] = __ldg(xj + o1.w);
+                } else {
 #pragma unroll
-                for (int e8 = 0; e8 < 8; ++e8) {
-                    const int cell = 8 * g + e8;
-                    xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell && !(P.dbg & 1))
-                                 ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int cell = 8 * g + e8;
+                        xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell && !(P.dbg & 1))
+                                     ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
+                    }
                 }
             };
             const f2 S2 = pk(s2, s2), B2 = pk(b2, b2), NS2 = pk(-fp.s, -fp.s), TH2 = pk(fp.th, fp.th);
             const f2 EPS2 = pk(GLUE_EPS, GLUE_EPS), M1 = pk(-1.f, -1.f), LN2_2 = pk(LN2F, LN2F);
             const f2 NLN2 = pk(-LN2F, -LN2F), DISP2 = pk(fp.disp, fp.disp);
+            // FAST: log-gamma / digamma differences of the counts 0, 1, 2 as x (c1 + c2 x)
+            const float lq_c2 = 0.5f * lg2 - lg1, lq_c1 = lg1 - lq_c2;
+            const float dq_c2 = 0.5f * dg2 - dg1, dq_c1 = dg1 - dq_c2;
+            const f2 LQ1 = pk(lq_c1, lq_c1), LQ2 = pk(lq_c2, lq_c2), DQ1 = pk(dq_c1, dq_c1), DQ2 = pk(dq_c2, dq_c2);
+            const f2 M2 = pk(-2.f, -2.f);
+            const float* wsrc = (FAST && !jok) ? S.zeros : S.wrow;
             load_x(g_begin);
             if (t == 0) TC_TRACE(1 + PHASE, it, 5);
             mbar_wait(&S.bars.acc_full[s], (it >> 1) & 1);
             tc_fence_after();
             if (t == 0) TC_TRACE(1 + PHASE, it, 6);
+            if (FAST && GRAD && g_begin < g_end) {  // the coefficient tile of the previous step was consumed
+                mbar_wait(&S.bars.x_empty, (it & 1) ^ 1);
+                if (t == 0) TC_TRACE(1 + PHASE, it, 7);
+            }
 #pragma unroll 1
             for (int g = g_begin; g < g_end; ++g) {
                 const int c0 = g * 8;
@@ -586,8 +667,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 float lsev[8], auxv[8], wv[8];  // aux = library size (pass B) or c_i (pass C)
                 int bv[8];
                 if (PHASE == 0) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(&S.wrow[c0]);
-                    const float4 w1 = *reinterpret_cast<const float4*>(&S.wrow[c0 + 4]);
+                    const float4 w0 = *reinterpret_cast<const float4*>(&wsrc[c0]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&wsrc[c0 + 4]);
                     wv[0] = w0.x, wv[1] = w0.y, wv[2] = w0.z, wv[3] = w0.w;
                     wv[4] = w1.x, wv[5] = w1.y, wv[6] = w1.z, wv[7] = w1.w;
                 }
@@ -613,12 +694,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 for (int e8 = 0; e8 < 8; ++e8) xv[e8] = xn[e8];
                 load_x(g + 1);
                 tmem_ld_wait();
-                if (GRAD && g == g_begin) {
+                if (!FAST && GRAD && g == g_begin) {
                     mbar_wait(&S.bars.x_empty, (it & 1) ^ 1);
                     if (t == 0) TC_TRACE(1 + PHASE, it, 7);
                 }
                 float coef[8], gch[8];
-                if constexpr (NB1 && PHASE == 1) {
+                if constexpr (FAST) {
+                    // ---- pass B, NB, streamlined: counts outside {0, 1, 2} and NaN are dealt with per
+                    // thread first (their gamma terms go straight to the accumulators, their quadratic
+                    // argument becomes 0), then packed pairs of cells without any selects
+                    float xq[8];
+                    uint32_t rb = 0u;
+#pragma unroll
+                    for (int pr_ = 0; pr_ < 4; ++pr_) {
+                        const f2 x2 = pk(xv[2 * pr_], xv[2 * pr_ + 1]);
+                        float p0, p1;
+                        up(mul2(mul2(x2, add2(x2, M1)), add2(x2, M2)), p0, p1);  // x (x - 1) (x - 2)
+                        rb |= __float_as_uint(p0) | __float_as_uint(p1);
+                        xq[2 * pr_] = xv[2 * pr_], xq[2 * pr_ + 1] = xv[2 * pr_ + 1];
+                    }
+                    if ((rb & 0x7fffffffu) != 0u) {
+#pragma unroll
+                        for (int e8 = 0; e8 < 8; ++e8) {
+                            const float x = xv[e8];
+                            if (skip_nan && x != x) {
+                                bad_acc += (jok && c0 + e8 < ncell) ? 1 : 0;
+                                xv[e8] = 0.f, xq[e8] = 0.f, wv[e8] = 0.f;
+                            } else if (!(x == 0.f || x == 1.f || x == 2.f)) {
+                                float lg_t, dg_t;  // (locals: the out-of-line slow path takes addresses)
+                                nb_gamma_terms_t<true>(x, fp.th, lg_t, dg_t);
+                                xq[e8] = 0.f;
+                                loss_acc = fmaf(wv[e8], lg_t, loss_acc);
+                                if (GRAD) gd = fmaf(wv[e8] * fp.th, dg_t, gd);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int pr_ = 0; pr_ < 4; ++pr_) {
+                        const int e0 = 2 * pr_, e1 = e0 + 1;
+                        const f2 x2 = pk(xv[e0], xv[e1]), xq2 = pk(xq[e0], xq[e1]), W2 = pk(wv[e0], wv[e1]);
+                        const f2 dot2 = pk(__uint_as_float(d[e0]), __uint_as_float(d[e1]));
+                        const f2 t2 = add2(fma2(S2, dot2, B2), pk(lsev[e0], lsev[e1]));
+                        float t0, t1;
+                        up(t2, t0, t1);
+                        const f2 mu2 = mul2(pk(ex2f(t0), ex2f(t1)), pk(auxv[e0], auxv[e1]));
+                        const f2 m2 = add2(mu2, EPS2), mt2 = add2(m2, TH2);
+                        float m0, m1, mt0, mt1, mm0, mm1;
+                        up(m2, m0, m1);
+                        up(mt2, mt0, mt1);
+                        const f2 l2m = pk(lg2f(m0), lg2f(m1)), l2t = pk(lg2f(mt0), lg2f(mt1));
+                        up(mul2(m2, mt2), mm0, mm1);
+                        const f2 r2 = pk(rcpf(mm0), rcpf(mm1));  // 1/m = r mt, 1/(m + theta) = r m
+                        const f2 sig2 = mul2(mul2(m2, m2), r2);
+                        const f2 dlt2 = fma2(l2t, NLN2, DISP2);                        // log theta - log(m + theta)
+                        const f2 xl2 = mul2(fma2(l2t, M1, l2m), LN2_2);                // log m - log(m + theta)
+                        const f2 ndd2 = fma2(add2(x2, TH2), sig2, mul2(x2, M1));       // -(x - (x + theta) sig)
+                        const f2 lgq2 = mul2(xq2, fma2(LQ2, xq2, LQ1));
+                        const f2 lp2 = fma2(TH2, dlt2, fma2(x2, xl2, lgq2));
+                        loss2 = fma2(W2, lp2, loss2);
+                        if (GRAD) {
+                            const f2 rat2 = mul2(mu2, mul2(r2, mt2));
+                            const f2 dgq2 = mul2(xq2, fma2(DQ2, xq2, DQ1));
+                            const f2 tl2 = fma2(TH2, add2(dlt2, dgq2), ndd2);
+                            const f2 nG2 = mul2(W2, mul2(ndd2, rat2));
+                            ngb2 = add2(ngb2, nG2);
+                            ngs2 = fma2(nG2, dot2, ngs2);
+                            gd2 = fma2(W2, tl2, gd2);
+                            up(mul2(nG2, NS2), coef[e0], coef[e1]);
+                        } else {
+                            coef[e0] = coef[e1] = 0.f;
+                        }
+                        gch[e0] = gch[e1] = 0.f;
+                    }
+                } else if constexpr (NB1 && PHASE == 1) {
                     // ---- pass C: packed pairs of cells, -G = p c accumulated (signs fixed at the flush)
 #pragma unroll
                     for (int pr_ = 0; pr_ < 4; ++pr_) {
@@ -821,7 +969,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                     const uint32_t off = (uint32_t)(c0 >> 6) * OP_BYTES + swz((uint32_t)frow, (uint32_t)((c0 & 63) >> 3));
                     st_shared_v4(smem_u32(S.x_hi) + off, hh[0], hh[1], hh[2], hh[3]);
                     st_shared_v4(smem_u32(S.x_lo) + off, ll[0], ll[1], ll[2], ll[3]);
-                    if (NBF && PHASE == 0) {
+                    if (NBF && PHASE == 0 && !FAST) {
                         // c_i partial: transpose-reduce the (32 feature lanes x 8 cells) block over lanes;
                         // afterwards lane L holds the warp total of cell c0 + 4 bit4(L) + 2 bit3(L) + bit2(L)
 #pragma unroll
@@ -863,10 +1011,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 if (GRAD) mbar_arrive(&S.bars.x_full);
             }
             if (GRAD) {
-                named_bar_sync(1, EPI_THREADS);
+                named_bar_sync(1, EPI_T);
                 if (t == 0) TC_TRACE(1 + PHASE, it, 10);
-                if (pend) write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
-                if (NBF && PHASE == 0 && t < ncell)
+                if (pend) {
+                    if constexpr (NH == 4) {
+#pragma unroll
+                        for (int hh = 0; hh < 3; ++hh) {
+                            const float(*gp)[128] = S.gpart[it & 1][hh];
+                            pend_b += gp[0][frow], pend_s += gp[1][frow], pend_d += gp[2][frow], pend_z += gp[3][frow];
+                        }
+                        write_param(pend_off, pend_b, pend_s, pend_d, pend_z, (PHASE == 1) || P.acc);
+                    } else {
+                        write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
+                    }
+                }
+                if (NBF && PHASE == 0 && !FAST && t < ncell)
                     S.c_acc[t] += (S.cw[it & 1][0][t] + S.cw[it & 1][1][t]) + (S.cw[it & 1][2][t] + S.cw[it & 1][3][t]);
                 if (it > 0) readout_d1(it - 1);
                 if (t == 0) TC_TRACE(1 + PHASE, it, 11);
@@ -879,22 +1038,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
             mbar_wait(&S.bars.d2_full, 0);
             tc_fence_after();
             if (t == 0) TC_TRACE(1 + PHASE, 6, 14);
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + COL_D2 + 32 * h, r);
+            uint32_t r[DC];
+            if constexpr (NH == 2) tmem_ld32(tmem_base + lane_addr + COL_D2 + DC * h, r);
+            else tmem_ld16(tmem_base + lane_addr + COL_D2 + DC * h, r);
             tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(P.p.ws.apart + ((int64_t)cta * 128 + frow) * 64 + 32 * h);
-            float4 old[8];
+            float4* dst = reinterpret_cast<float4*>(P.p.ws.apart + ((int64_t)cta * 128 + frow) * 64 + DC * h);
+            float4 old[DC / 4];
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) old[k4] = PHASE == 1 ? dst[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k4 = 0; k4 < DC / 4; ++k4) old[k4] = PHASE == 1 ? dst[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4)
+            for (int k4 = 0; k4 < DC / 4; ++k4)
                 dst[k4] = make_float4(__uint_as_float(r[4 * k4]) + old[k4].x, __uint_as_float(r[4 * k4 + 1]) + old[k4].y,
                                       __uint_as_float(r[4 * k4 + 2]) + old[k4].z,
                                       __uint_as_float(r[4 * k4 + 3]) + old[k4].w);
             if (t == 0) TC_TRACE(1 + PHASE, 6, 15);
             if (NBF && PHASE == 0) {
-                named_bar_sync(1, EPI_THREADS);
-                if (t < ncell) P.p.ws.cpart[(int64_t)cta * a.B + P.cell0 + t] = S.c_acc[t];
+                if constexpr (FAST) {
+                    // c_i partial of this CTA = column K of the d/du accumulator (produce_v_rows<CINV>);
+                    // rows of D2 are cells, so the thread that holds column K of cell `frow` writes it
+                    float cval = 0.f;
+#pragma unroll
+                    for (int k = 0; k < DC; ++k)
+                        if (DC * h + k == a.K) cval = __uint_as_float(r[k]);
+                    if (a.K / DC == h && frow < ncell) P.p.ws.cpart[(int64_t)cta * a.B + P.cell0 + frow] = cval;
+                } else {
+                    named_bar_sync(1, EPI_T);
+                    if (t < ncell) P.p.ws.cpart[(int64_t)cta * a.B + P.cell0 + t] = S.c_acc[t];
+                }
             }
         }
         if (PHASE == 0) {
@@ -903,11 +1073,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) wb += __shfl_xor_sync(FULL, wb, o);
             if (lane == 0) S.red_l[warp] = wl, S.red_b[warp] = wb;
-            named_bar_sync(2, EPI_THREADS);
+            named_bar_sync(2, EPI_T);
             if (t == 0) {
                 float sl = 0.f;
                 int sb = 0;
-                for (int w = 0; w < EPI_WARPS; ++w) sl += S.red_l[w], sb += S.red_b[w];
+                for (int w = 0; w < EW; ++w) sl += S.red_l[w], sb += S.red_b[w];
                 P.p.ws.losspart[P.chunk * (int)gridDim.x + cta] = sl;
                 P.p.ws.badpart[P.chunk * (int)gridDim.x + cta] = sb;
             }
@@ -916,7 +1086,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     tc_fence_before();
     if (PHASE == 0) __threadfence();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == MMAW) tmem_dealloc(tmem_base, TMEM_COLS);
     if (PHASE == 0) {
         // ---- the last CTA to arrive reduces the per-CTA partials: c_i, loss, nanmean factor -----
         if (t == 0) S.ticket = atomicAdd(P.p.ws.counters + 1, 1u);
@@ -933,7 +1103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                 }
                 S.cpart3[sub][cell] = c;
             }
-            if (warp == MMA_WARP && P.chunk == P.nchunks - 1) {  // loss of the whole call: all cell blocks
+            if (warp == MMAW && P.chunk == P.nchunks - 1) {  // loss of the whole call: all cell blocks
                 double loss = 0.0;
                 long long bad = 0;
                 for (int q = lane; q < nc * P.nchunks; q += 32) {
@@ -1039,31 +1209,45 @@ int tc_grid(const glue_decoder_args& a, int& ntiles) {
     return ntiles < sm_count() ? ntiles : sm_count();
 }
 
-template <int FAM, bool NB1>
-int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
+template <int FAM, int PHASE, bool GRAD, bool NB1, int EW, bool FAST>
+int launch_kernel(const TcParams& P, int ncta, cudaStream_t st) {
     const size_t smem = sizeof(SmemMain);
-#define GLUE_TC_LAUNCH(PH, GR)                                                                      \
-    {                                                                                               \
-        auto k = tc_main_kernel<FAM, PH, GR, NB1>;                                                  \
-        GLUE_SMEM_ONCE(k, smem); \
-        k<<<ncta, NTHREADS, smem, st>>>(P);                                                         \
-    }
-    if (phase == 1) GLUE_TC_LAUNCH(1, true)
-    else if (grad) GLUE_TC_LAUNCH(0, true)
-    else GLUE_TC_LAUNCH(0, false)
-#undef GLUE_TC_LAUNCH
+    auto k = tc_main_kernel<FAM, PHASE, GRAD, NB1, EW, FAST>;
+    GLUE_SMEM_ONCE(k, smem);
+    k<<<ncta, EW == 16 ? 640 : 416, smem, st>>>(P);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
 
+template <int FAM, bool NB1, int EW, bool FAST>
+int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
+    if (phase == 1) return launch_kernel<FAM, 1, true, NB1, EW, false>(P, ncta, st);
+    if (grad) return launch_kernel<FAM, 0, true, NB1, EW, FAST>(P, ncta, st);
+    return launch_kernel<FAM, 0, false, NB1, EW, FAST>(P, ncta, st);
+}
+
+// variant bits (VARIANT_*): only the NB family with a single parameter row has the wide / streamlined forms
+constexpr int VARIANT_FAST = 1, VARIANT_EW16 = 2;
+constexpr int TC_DEFAULT_VARIANT = 0;
+
 template <bool NB1>
-int launch_family(int family, int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
-    if (phase == 1) return launch_phase<GLUE_NB, NB1>(1, true, P, ncta, st);  // pass C is family independent
+int launch_family(int family, int phase, bool grad, int variant, const TcParams& P, int ncta, cudaStream_t st) {
+    if constexpr (NB1) {
+        if (family == GLUE_NB || phase == 1) {  // pass C is family independent
+            switch (variant) {
+                case VARIANT_FAST: return launch_phase<GLUE_NB, true, 8, true>(phase, grad, P, ncta, st);
+                case VARIANT_EW16: return launch_phase<GLUE_NB, true, 16, false>(phase, grad, P, ncta, st);
+                case VARIANT_FAST | VARIANT_EW16: return launch_phase<GLUE_NB, true, 16, true>(phase, grad, P, ncta, st);
+                default: return launch_phase<GLUE_NB, true, 8, false>(phase, grad, P, ncta, st);
+            }
+        }
+    }
+    if (phase == 1) return launch_phase<GLUE_NB, NB1, 8, false>(1, true, P, ncta, st);  // pass C is family independent
     switch (family) {
-        case GLUE_NB: return launch_phase<GLUE_NB, NB1>(0, grad, P, ncta, st);
-        case GLUE_ZINB: return launch_phase<GLUE_ZINB, NB1>(0, grad, P, ncta, st);
-        case GLUE_NORMAL: return launch_phase<GLUE_NORMAL, NB1>(0, grad, P, ncta, st);
-        default: return launch_phase<GLUE_ZILN, NB1>(0, grad, P, ncta, st);
+        case GLUE_NB: return launch_phase<GLUE_NB, NB1, 8, false>(0, grad, P, ncta, st);
+        case GLUE_ZINB: return launch_phase<GLUE_ZINB, NB1, 8, false>(0, grad, P, ncta, st);
+        case GLUE_NORMAL: return launch_phase<GLUE_NORMAL, NB1, 8, false>(0, grad, P, ncta, st);
+        default: return launch_phase<GLUE_ZILN, NB1, 8, false>(0, grad, P, ncta, st);
     }
 }
 
@@ -1108,6 +1292,14 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
     const bool nb1 = a.n_batches == 1;
+    // kernel variant: GLUE_TC_VARIANT = bit 0 streamlined NB pass B, bit 1 sixteen epilogue warps
+    int variant = TC_DEFAULT_VARIANT;
+    {
+        const char* e = getenv("GLUE_TC_VARIANT");
+        if (e) variant = atoi(e) & (VARIANT_FAST | VARIANT_EW16);
+    }
+    if (!(a.family == GLUE_NB && nb1 && a.K <= 62 && (long long)a.B * (long long)a.F < (1ll << 31)))
+        variant &= ~VARIANT_FAST;
     // Cells are handled in blocks of <= 128 (soft-max rows are independent); feature-side outputs
     // (d/dv, parameter tables) accumulate from the second block on, in launch order.
     auto block = [&](int c) {
@@ -1136,13 +1328,13 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     }
     for (int c = 0; c < nchunks; ++c) {
         block(c);
-        int rc = nb1 ? launch_family<true>(a.family, 0, grad, P, ncta, st)
-                     : launch_family<false>(a.family, 0, grad, P, ncta, st);
+        int rc = nb1 ? launch_family<true>(a.family, 0, grad, variant, P, ncta, st)
+                     : launch_family<false>(a.family, 0, grad, variant, P, ncta, st);
         if (rc) return rc;
         if (grad) {
             if (nbf) {
-                rc = nb1 ? launch_family<true>(a.family, 1, true, P, ncta, st)
-                         : launch_family<false>(a.family, 1, true, P, ncta, st);
+                rc = nb1 ? launch_family<true>(a.family, 1, true, variant, P, ncta, st)
+                         : launch_family<false>(a.family, 1, true, variant, P, ncta, st);
                 if (rc) return rc;
             }
             tc_grad_u_kernel<<<P.ncell, 256, 0, st>>>(p, ncta, P.cell0);

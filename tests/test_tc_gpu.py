@@ -120,3 +120,108 @@ def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F,
         assert_close(a, b, 1e-4, f"{family} d/d{n} (v2 vs v1)")
     l3, g3 = _run_decoder(ops, family, case, "nanmean")
     assert torch.equal(l2, l3) and all(torch.equal(a, b) for a, b in zip(g2, g3)), "v2 must be deterministic"
+
+
+# ------------------------------------------------------------------ kernel variants of the main pass
+# GLUE_TC_VARIANT: bit 0 = streamlined NB pass B (32-bit unpredicated x loads, quadratic gamma terms
+# for the counts 0 / 1 / 2, c_i from the tensor cores), bit 1 = sixteen epilogue warps.  Every
+# combination must agree with the base kernel, which the tests above / test_ops_gpu.py tie to the
+# CUDA-core decoder and to the oracle.
+def _variant_case(B, F, K, seed, sparse, nan_frac, extra_rows):
+    from tests.test_ops_gpu import _decoder_case
+    u, v, b, l, x, params, vidx = _decoder_case("NB", B, F, K, 1, seed=seed, extra_rows=extra_rows)
+    gen = torch.Generator().manual_seed(seed + 1)
+    if sparse:  # ATAC-like: mostly 0, some 1 / 2, a few larger counts
+        x = torch.poisson(torch.full((B, F), 0.08), generator=gen)
+        x[torch.rand(B, F, generator=gen) < 0.002] = 5.0
+        l = x.sum(dim=1, keepdim=True) + 1.0
+    if nan_frac:
+        x[torch.rand(B, F, generator=gen) < nan_frac] = float("nan")
+    return u, v, b, l, x, params, vidx
+
+
+def _run_variant(ops, variant, case, reduce, row_weight=None):
+    u, v, b, l, x, params, vidx = case
+    d = lambda t: None if t is None else t.to(DEV)
+    du, dv = d(u).requires_grad_(True), d(v).requires_grad_(True)
+    dp = [d(params[n]).requires_grad_(True) for n in ("scale_lin", "bias", "log_theta")]
+    os.environ["GLUE_TC_VARIANT"] = str(variant)
+    try:
+        loss = ops.decoder_nll("NB", du, dv, dp[0], dp[1], dp[2], None, b=d(b), l=d(l), x=d(x), vidx=d(vidx),
+                               reduce=reduce, row_weight=d(row_weight))
+        grads = torch.autograd.grad(loss, [du, dv] + dp)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("GLUE_TC_VARIANT")
+    return loss, grads
+
+
+VARIANT_CASES = [
+    # B, F, K, sparse, nan_frac, extra_rows, reduce, weighted
+    (128, 2000, 50, False, 0.0, 0, "nanmean", False),
+    (128, 50000, 50, True, 0.0, 0, "nanmean", False),
+    (128, 6000, 50, True, 0.01, 0, "nanmean", False),
+    (128, 3000, 50, False, 0.01, 0, "nanmean", False),
+    (77, 1300, 50, True, 0.0, 0, "mean", False),
+    (100, 5000, 50, True, 0.0, 300, "nanmean", False),
+    (20, 140, 8, False, 0.0, 0, "nanmean", False),
+    (5, 130, 62, True, 0.0, 0, "nanmean", False),
+    (64, 400, 64, True, 0.0, 0, "nanmean", False),     # K = 64: no spare operand column, bit 0 is ignored
+    (1, 5, 50, False, 0.0, 0, "nanmean", False),
+    (512, 4000, 50, True, 0.0, 0, "nanmean", False),   # four cell blocks
+    (300, 1000, 50, False, 0.0, 40, "mean", False),
+    (128, 2500, 50, True, 0.0, 0, "mean", True),       # per-cell weights (paired losses)
+    (200, 1500, 50, True, 0.01, 0, "mean", True),
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("B,F,K,sparse,nan_frac,extra,reduce,weighted", VARIANT_CASES)
+def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, sparse, nan_frac, extra, reduce, weighted):
+    from glue_b200 import ops
+    case = _variant_case(B, F, K, seed=7 * B + F, sparse=sparse, nan_frac=nan_frac, extra_rows=extra)
+    if nan_frac and reduce == "mean":
+        case[4].nan_to_num_(nan=3.0)  # (NaN only has a meaning under nanmean)
+    rw = None
+    if weighted:
+        rw = torch.rand(B, generator=torch.Generator().manual_seed(B)) * (torch.arange(B) % 3 != 0)
+        if nan_frac:
+            case[4].nan_to_num_(nan=1.0)
+    l0, g0 = _run_variant(ops, 0, case, reduce, rw)
+    l1, g1 = _run_variant(ops, variant, case, reduce, rw)
+    assert torch.isfinite(l0).all() and torch.isfinite(l1).all()
+    assert_close(l1, l0, 2e-5, f"loss (variant {variant})")
+    for n, a, b in zip(["u", "v", "scale_lin", "bias", "log_theta"], g1, g0):
+        assert_close(a, b, 1e-4, f"d/d{n} (variant {variant} vs base)")
+    l2, g2 = _run_variant(ops, variant, case, reduce, rw)
+    assert torch.equal(l1, l2) and all(torch.equal(a, b) for a, b in zip(g1, g2)), "variants must be deterministic"
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_main_pass_variants_vs_oracle(native_lib, variant):
+    from glue_b200 import ops
+    from tests.test_ops_gpu import TOL, _oracle_nll
+    case = _variant_case(128, 1500, 50, seed=11, sparse=True, nan_frac=0.005, extra_rows=0)
+    ref_loss, _, ref_grads = _oracle_nll("NB", *case, "nanmean")
+    loss, grads = _run_variant(ops, variant, case, "nanmean")
+    assert_close(loss, ref_loss, TOL, "nll vs oracle")
+    for n, g, rg in zip(["u", "v", "scale_lin", "bias", "log_theta"], grads, ref_grads):
+        assert_close(g, rg, TOL, f"d/d{n} vs oracle (variant {variant})")
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_wide_epilogue_softmax_pass_with_zinb(native_lib, variant):
+    """ZINB keeps the 8-warp pass B; with bit 1 its soft-max pass (family independent) runs wide."""
+    from glue_b200 import ops
+    from tests.test_ops_gpu import PARAM_NAMES, _decoder_case
+    case = _decoder_case("ZINB", 128, 1800, 50, 1, seed=5)
+    l0, g0 = _run_decoder(ops, "ZINB", case, "nanmean")
+    os.environ["GLUE_TC_VARIANT"] = str(variant)
+    try:
+        l1, g1 = _run_decoder(ops, "ZINB", case, "nanmean")
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("GLUE_TC_VARIANT")
+    assert_close(l1, l0, 2e-5, "loss")
+    for n, a, b in zip(["u", "v"] + list(PARAM_NAMES["ZINB"]), g1, g0):
+        assert_close(a, b, 1e-4, f"ZINB d/d{n} (variant {variant} vs base)")

@@ -32,7 +32,9 @@ for name, F, rate in (("atac", 50000, 0.05), ("rna", 2000, 0.3), ("atac150k", 15
             return ops.decoder_nll("NB", u.detach(), v.detach(), ps[0].detach(), ps[1].detach(),
                                    ps[2].detach(), None, l=ls[i % 8], x=xs[i % 8])
 
-    for grad in (True, False):
+    for variant, grad in [(vv, gg) for vv in os.environ.get("VARIANTS", "").split(",") for gg in (True, False)]:
+        if variant:
+            os.environ["GLUE_TC_VARIANT"] = variant  # read by the library at every call
         for i in range(3):
             call(i, grad)
         torch.cuda.synchronize()
@@ -46,6 +48,6 @@ for name, F, rate in (("atac", 50000, 0.05), ("rna", 2000, 0.3), ("atac150k", 15
         torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / ITERS
         alg = B * F * 4 + (2 if grad else 1) * (F * K * 4 + 3 * F * 4 + B * K * 4) + 16 * B
-        out[f"{name}_{'fwd_bwd' if grad else 'fwd'}"] = {"us": us, "GBps": alg / us / 1e3,
+        out[f"{name}_{'fwd_bwd' if grad else 'fwd'}" + (f"_variant{variant}" if variant else "")] = {"us": us, "GBps": alg / us / 1e3,
                                                          "frac_of_6554.9": alg / us / 1e3 / 6554.9}
 print(json.dumps(out, indent=1))
