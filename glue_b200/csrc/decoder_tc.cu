@@ -1228,7 +1228,7 @@ int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t
 
 // variant bits (VARIANT_*): only the NB family with a single parameter row has the wide / streamlined forms
 constexpr int VARIANT_FAST = 1, VARIANT_EW16 = 2;
-constexpr int TC_DEFAULT_VARIANT = 0;
+constexpr int TC_DEFAULT_VARIANT = VARIANT_FAST;  // measured: 117.7 -> 99.1 us (ATAC fwd+bwd); 16 warps add nothing on top
 
 template <bool NB1>
 int launch_family(int family, int phase, bool grad, int variant, const TcParams& P, int ncta, cudaStream_t st) {
