@@ -31,6 +31,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # (see glue_b200/__init__.py)
+
 import numpy as np
 import torch
 

@@ -309,16 +309,24 @@ class SCGLUETrainer(GLUETrainer):
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
             x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
         g_elbo = g_nll + self.lam_kl * g_kl
-        # one stream per modality: the decoder calls of a small modality (16 CTAs for 2 000
-        # genes) fill the SMs that the tail of a large one (50 000 peaks) leaves idle
+        # one stream per decoder call (per modality: the reconstruction term and, for paired data,
+        # the joint-cross / real-cross terms): each call is a short sequence of one-CTA-per-SM
+        # kernels, so the calls of a small modality (16 CTAs for 2 000 genes) and the prologue of
+        # the next large kernel fill the SMs that the tail of a large one (50 000 peaks) leaves idle
         self._prepare_extra(usamp)
-        per_mod = self._parallel([
-            lambda k=k: (self._data_nll(k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE,
-                                        upstream=self.lam_data * self.modality_weight[k]),
-                         self._extra_losses_for(k, data, usamp, vsamp, l))
-            for k in net.keys])
-        x_nll = {k: out[0] for k, out in zip(net.keys, per_mod)}
-        self._extra_parts = {k: out[1] for k, out in zip(net.keys, per_mod)}
+        jobs = []
+        for k in net.keys:
+            jobs.append((k, "nll", lambda k=k: self._data_nll(
+                k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE,
+                upstream=self.lam_data * self.modality_weight[k])))
+            jobs.extend((k, kind, thunk) for kind, thunk in self._extra_thunks_for(k, data, usamp, vsamp, l))
+        results = self._parallel([thunk for _, _, thunk in jobs])
+        x_nll = {k: res for (k, kind, _), res in zip(jobs, results) if kind == "nll"}
+        self._extra_parts = {k: {} for k in net.keys}
+        for (k, kind, _), res in zip(jobs, results):  # (several real-cross terms add up in job order)
+            if kind != "nll":
+                self._extra_parts[k][kind] = res if kind not in self._extra_parts[k] \
+                    else self._extra_parts[k][kind] + res
         if dsc_stream is not None:  # the alignment term needs the updated discriminator
             torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
         u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
@@ -348,10 +356,11 @@ class SCGLUETrainer(GLUETrainer):
     def _prepare_extra(self, usamp) -> None:
         r"""Quantities shared by the per-modality extra terms (computed before the fork)."""
 
-    def _extra_losses_for(self, k: str, data, usamp, vsamp, l):
-        r"""Extra decoder-based loss terms whose *target* modality is ``k`` (evaluated on the
-        stream of that modality's decoder); combined by :meth:`_extra_losses`."""
-        return None
+    def _extra_thunks_for(self, k: str, data, usamp, vsamp, l):
+        r"""Extra decoder-based loss terms whose *target* modality is ``k``, as
+        ``[(kind, thunk), ...]`` (each evaluated on its own stream beside the reconstruction
+        term); combined by :meth:`_extra_losses`."""
+        return []
 
     def _extra_losses(self, data, usamp, vsamp, l) -> Mapping[str, Tuple[float, torch.Tensor]]:
         return {}
@@ -459,30 +468,32 @@ class PairedSCGLUETrainer(SCGLUETrainer):
             umean = F.normalize(umean, dim=1)
         return ustack, umean, pmsk.to(torch.float32)
 
-    def _extra_losses_for(self, k: str, data, usamp, vsamp, l):
-        r"""Joint-cross and real-cross reconstruction of modality ``k`` (``scglue.py:624-652``).
-        Row subsets (observed in ``k``; observed in both modalities of an ordered pair) enter as
-        per-cell weights ``mask / (n_masked * n_features)``: the mean over the subset without
-        compacting rows -- static shapes, no host read of the subset sizes."""
+    def _extra_thunks_for(self, k: str, data, usamp, vsamp, l):
+        r"""Joint-cross and real-cross reconstruction of modality ``k`` (``scglue.py:624-652``) as
+        independent decoder calls ``[("joint" | "real", thunk), ...]``.  Row subsets (observed in
+        ``k``; observed in both modalities of an ordered pair) enter as per-cell weights
+        ``mask / (n_masked * n_features)``: the mean over the subset without compacting rows --
+        static shapes, no host read of the subset sizes."""
         net = self.net
         x, xrep, xbch, *_ = data
         keys = net.keys
         i = keys.index(k)
         _, umean, pf = self._shared_extra
-        zero = torch.zeros((), device=net.device)
 
         def subset_nll(usrc, maskf, lam):
             w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
             return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w,
                                   upstream=lam * self.modality_weight[k])
 
-        joint = subset_nll(umean, pf[i], self.lam_joint_cross) if self.lam_joint_cross else zero
-        real = zero
+        thunks = []
+        if self.lam_joint_cross:
+            thunks.append(("joint", lambda: subset_nll(umean, pf[i], self.lam_joint_cross)))
         if self.lam_real_cross:
             for j, ks in enumerate(keys):
                 if i != j:
-                    real = real + subset_nll(usamp[ks], pf[i] * pf[j], self.lam_real_cross)
-        return joint, real
+                    thunks.append(("real", lambda j=j, ks=ks: subset_nll(usamp[ks], pf[i] * pf[j],
+                                                                          self.lam_real_cross)))
+        return thunks
 
     def _extra_losses(self, data, usamp, vsamp, l):
         net = self.net
@@ -491,9 +502,9 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         ustack, umean, pf = self._shared_extra
         joint, real = zero, zero
         for k in keys:
-            j_k, r_k = self._extra_parts[k]
-            joint = joint + self.modality_weight[k] * j_k
-            real = real + self.modality_weight[k] * r_k
+            parts = self._extra_parts[k]
+            joint = joint + self.modality_weight[k] * parts.get("joint", zero)
+            real = real + self.modality_weight[k] * parts.get("real", zero)
         cos = zero
         if self.lam_cos:
             for i, k in enumerate(keys):
