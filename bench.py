@@ -345,11 +345,15 @@ def main():
         step i is consumed while step i + 1 is already queued, as a training loop that logs
         metrics does."""
         feed = (host_pool[i % pool_n] for i in range(n))
-        if prefetch:
-            feed = DevicePrefetcher(feed, device)
+        if prefetch:  # (the loader object lives as long as the training loop: built once, like its stream)
+            prefetcher.loader = feed
+            feed = prefetcher
         seen = []
+        marks = e2e_marks[prefetch][:n]  # where the GPU time of the region goes: inside the steps / between them
         for i, batch in enumerate(feed):
+            marks[i][0].record()
             losses = trainer.train_step(_Engine, batch)
+            marks[i][1].record()
             loss_host[i & 1].copy_(losses["vae_loss"].reshape(1), non_blocking=True)
             loss_done[i & 1].record()
             if i:
@@ -360,12 +364,19 @@ def main():
         assert len(seen) == n and all(v == v for v in seen), "every step's loss must reach the host"
         return seen[-1]
 
+    prefetcher = DevicePrefetcher(None, device)
+    n_marks = max(args.steps, 2 * pool_n)
     e2e_runs = {}
+    e2e_marks = {p: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(n_marks)] for p in (False, True)}
     for mode, prefetch in (("direct", False), ("prefetch", True)):
         run_e2e(2 * pool_n if n_sig > 1 else 4, prefetch)  # (every signature of the host pool has its graph)
         e2e_runs[mode] = timed(lambda i, p=prefetch: run_e2e(args.steps, p) if i == 0 else None, 1)
     e2e_feed = min(e2e_runs, key=e2e_runs.get)
     ms_e2e = e2e_runs[e2e_feed]
+    marks = e2e_marks[e2e_feed == "prefetch"][:args.steps]
+    e2e_step_gpu_ms = sum(a.elapsed_time(b) for a, b in marks) / len(marks)
+    e2e_gap_ms = sum(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1)) / max(1, len(marks) - 1)
     e2e_value = cells / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -463,7 +474,8 @@ def main():
                    "l2": f"inputs cycle through {pool_n} minibatches (8 x 27 MB > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "feed": e2e_feed,
-                "ms_per_step_by_feed": {k: v / args.steps for k, v in e2e_runs.items()}},
+                "ms_per_step_by_feed": {k: v / args.steps for k, v in e2e_runs.items()},
+                "gpu_ms_inside_steps": e2e_step_gpu_ms, "gpu_ms_between_steps": e2e_gap_ms},
         "gpu_launches": int(launches),
         "cuda_graph": {k: ginfo[k] for k in ("graphs", "kernels_per_step", "disabled")},
         "clocks": clocks.summary(),
