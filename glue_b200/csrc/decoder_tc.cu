@@ -33,14 +33,12 @@ using namespace tc;
 
 namespace {
 
-// row-statistics kernel (and the default shape of the main kernel): 8 epilogue warps
 constexpr int NTHREADS = 416;
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_WARPS = 8;
 constexpr int PROD_T0 = 256;  // warps 8-11: one producer thread per operand row
 constexpr int PROD_THREADS = 128;
 constexpr int MMA_WARP = 12;
-constexpr int MAX_EPI_WARPS = 16;  // main kernel, EW = 16: four epilogue warps per TMEM lane quarter
 constexpr int NB_MAX = 24;  // parameter rows the row-statistics table holds per v stage
 constexpr int TC_MAX_CHUNKS = 32;  // cell blocks of 128 per call (B <= 4096)
 
@@ -119,12 +117,12 @@ struct __align__(1024) SmemMain {
     float cw[2][4][128];
     float c_acc[128];
     float stage[128][65];  // d/dv tile on its way from TMEM (thread <-> row) to coalesced stores
-    float red_l[MAX_EPI_WARPS];
-    int red_b[MAX_EPI_WARPS];
+    float red_l[EPI_WARPS];
+    int red_b[EPI_WARPS];
     float cpart3[3][128];
+    long long gvrow[3][128];           // d/dv element offset of every feature row of the tiles in flight (-1 beyond F)
     alignas(16) uint32_t xoff32[136];  // element offset of every cell's row of x (streamlined path); 8 pad entries
     alignas(16) float zeros[128];      // weights seen by feature rows beyond F
-    float gpart[2][3][4][128];     // 16 epilogue warps: parameter-gradient partials of the upper cell quarters
     Bars bars;
     uint32_t tmem_base;
     uint32_t ticket;
@@ -170,14 +168,17 @@ __device__ __forceinline__ int orig_row(const glue_decoder_args& a, int pos) {
 // never see it (u has zeros there); in the d/du product  D2[cell, k] = sum_j X[j, cell] V[j, k]
 // with X = G softplus(scale) it makes column K the soft-max correction  c_i = sum_j G_ij.
 template <bool CINV = false, int NPROD = PROD_THREADS>
-__device__ __forceinline__ void produce_v_rows(const glue_decoder_args& a, uint8_t* hi, uint8_t* lo, int f0, int pt) {
+__device__ __forceinline__ void produce_v_rows(const glue_decoder_args& a, uint8_t* hi, uint8_t* lo, int f0, int pt,
+                                               long long* gvrow = nullptr) {
     for (int r = pt; r < 128; r += NPROD) {
         const int j = f0 + r;
         const float* src = nullptr;
         float rs = 0.f;
+        if (gvrow) gvrow[r] = -1;
         if (j < a.F) {
             const int64_t vr = a.vidx ? a.vidx[j] : (int64_t)j;
             src = a.v + vr * a.K;
+            if (gvrow && a.grad_v) gvrow[r] = vr * a.K;
             if (CINV) {
                 const float sp = softplusf(a.scale_lin[j]);
                 rs = sp > 1e-18f ? 1.f / sp : 0.f;
@@ -338,27 +339,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
 // ---------------------------------------------------------------------------------------------
 // pass B (PHASE 0: likelihood + all G terms) and pass C (PHASE 1: the -p_ij c_i soft-max terms).
 // D[feature, cell] = V U^T; thread <-> feature.  NB1: a single parameter row (n_batches == 1).
-// EW: epilogue warps (8, or 16 = four warps per TMEM lane quarter, each owning a quarter of the
-// cell columns; NB1 only).  FAST: streamlined NB pass B (NB1, K <= 62, B F < 2^31) -- 32-bit
-// unpredicated observation loads, gamma terms of the counts 0 / 1 / 2 as a quadratic, everything
-// else (larger counts, NaN) handled per thread ahead of the packed arithmetic, c_i taken from
-// the tensor cores (produce_v_rows<CINV>).
+// FAST: streamlined NB pass B (NB1, K <= 62, B F < 2^31) -- 32-bit unpredicated observation
+// loads, gamma terms of the counts 0 / 1 / 2 as a quadratic, everything else (larger counts, NaN)
+// handled per thread ahead of the packed arithmetic, c_i taken from the tensor cores
+// (produce_v_rows<CINV>).
+// (A variant with 16 epilogue warps -- four per TMEM lane quarter -- was parity-green and no
+// faster: with the streamlined arithmetic the loop is bound by the FP32 pipe, not by latency.)
 // ---------------------------------------------------------------------------------------------
-template <int FAM, int PHASE, bool GRAD, bool NB1, int EW, bool FAST>
-__global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcParams P) {
-    static_assert(EW == 8 || EW == 16, "epilogue warps");
-    static_assert(EW == 8 || NB1, "16 epilogue warps: single parameter row only");
+template <int FAM, int PHASE, bool GRAD, bool NB1, bool FAST>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     static_assert(!FAST || (FAM == GLUE_NB && NB1 && PHASE == 0), "streamlined path: NB pass B");
-    // epilogue warps, producer warps, 1 MMA warp.  EW = 16 runs 3 producer warps: 20 warps = 5 per
-    // scheduler keep 96 registers per thread (21 warps would cap them at 80)
-    constexpr int PW = EW == 16 ? 3 : 4;
-    constexpr int NPROD = PW * 32;
-    constexpr int NT = (EW + PW + 1) * 32;
-    constexpr int EPI_T = EW * 32;
-    constexpr int PROD0 = EW * 32;
-    constexpr int MMAW = EW + PW;
-    constexpr int NH = EW / 4;    // threads sharing a feature row (splits of the cell columns)
-    constexpr int DC = 64 / NH;   // columns of the 64-wide gradient accumulators per thread
+    constexpr int EW = EPI_WARPS, NPROD = PROD_THREADS, NT = NTHREADS, EPI_T = EPI_THREADS;
+    constexpr int PROD0 = PROD_T0, MMAW = MMA_WARP;
+    constexpr int NH = 2;    // threads sharing a feature row (splits of the cell columns)
+    constexpr int DC = 32;   // columns of the 64-wide d/du accumulator per epilogue thread
     constexpr bool CINV = FAST && GRAD;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemMain& S = *reinterpret_cast<SmemMain*>(smem_raw);
@@ -379,7 +373,7 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
             mbar_init(&S.bars.acc_full[s], 1);
             mbar_init(&S.bars.acc_empty[s], EW);
             mbar_init(&S.bars.d1_full[s], 1);
-            mbar_init(&S.bars.d1_empty[s], EW);
+            mbar_init(&S.bars.d1_empty[s], NPROD / 32);
         }
         mbar_init(&S.bars.x_full, EW);
         mbar_init(&S.bars.x_empty, 1);
@@ -415,8 +409,61 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
     if (t == 0) TC_TRACE(1 + PHASE, 7, 0);
 
     if (warp >= PROD0 / 32 && warp < MMAW) {
-        // ===== v tile producers (one thread per row); x tile of the same step -> L2 =====
-        const int pt = t - PROD0;
+        // ===== v tile producers (one thread per row); x tile of the same step -> L2; these four
+        // warps (one per TMEM lane quarter) also move the finished d/dv tiles out, two tiles behind
+        // the one they stage, so the write-out is off the epilogue's critical path =====
+        const int pt = t - PROD0;        // operand row = TMEM lane = feature row of the tile
+        const int pw = warp - PROD0 / 32;
+        const bool add_v = (PHASE == 1) || P.acc;
+        auto readout_d1 = [&](int itp) {
+            const int s = itp & 1;
+            mbar_wait(&S.bars.d1_full[s], (itp >> 1) & 1);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * pw) << 16) + COL_D1 + s * 64;
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.bars.d1_empty[s]);
+            // transpose through shared memory: thread <-> feature row in TMEM, but a row of d/dv
+            // (K contiguous floats) should leave with consecutive lanes on consecutive addresses
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                S.stage[pt][k] = __uint_as_float(r0[k]);
+                S.stage[pt][32 + k] = __uint_as_float(r1[k]);
+            }
+            named_bar_sync(3, NPROD);
+            {
+                // warp pw writes rows pw, pw + 4, ...: lane <-> float2 of the row; row pointers were
+                // resolved (vidx) when the tile was staged
+                const long long* rows = S.gvrow[itp % 3];
+                const int k2 = lane;
+                const bool kok = 2 * k2 < a.K;
+                float* const gbase = a.grad_v + 2 * k2;
+#pragma unroll 1
+                for (int batch = 0; batch < 2; ++batch) {
+                    float2 old[16];
+                    long long off[16];
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {  // every load before the first store
+                        off[rr] = kok ? rows[pw + 4 * (rr + 16 * batch)] : -1;
+                        old[rr] = (add_v && off[rr] >= 0) ? *reinterpret_cast<const float2*>(gbase + off[rr])
+                                                          : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int row = pw + 4 * (rr + 16 * batch);
+                        const float v0 = S.stage[row][2 * k2], v1 = S.stage[row][2 * k2 + 1];
+                        if (off[rr] >= 0)
+                            *reinterpret_cast<float2*>(gbase + off[rr]) = make_float2(v0 + old[rr].x, v1 + old[rr].y);
+                    }
+                }
+            }
+            named_bar_sync(3, NPROD);  // the staging tile is free again
+            if (pt == 0) TC_TRACE(1 + PHASE, itp, 11);
+        };
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1, f0 = (cta + it * ncta) * 128;
             if (PHASE == 0) {
@@ -429,10 +476,16 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
             }
             mbar_wait(&S.bars.v_empty[s], ((it >> 1) & 1) ^ 1);
             if (pt == 0) TC_TRACE(1 + PHASE, it, 0);
-            produce_v_rows<CINV, NPROD>(a, S.v_hi[s], S.v_lo[s], f0, pt);
+            produce_v_rows<CINV, NPROD>(a, S.v_hi[s], S.v_lo[s], f0, pt, GRAD ? S.gvrow[it % 3] : nullptr);
             fence_proxy_async();
             mbar_arrive(&S.bars.v_full[s]);
             if (pt == 0) TC_TRACE(1 + PHASE, it, 1);
+            if (GRAD && it >= 2) readout_d1(it - 2);  // (its MMAs completed before v_empty[s] was released)
+        }
+        if (GRAD) {
+            if (ntl >= 2) readout_d1(ntl - 2);
+            readout_d1(ntl - 1);
+            if (pt == 0) TC_TRACE(1 + PHASE, 6, 13);
         }
     } else if (warp == MMAW) {
         // ===== MMA issuer =====
@@ -500,60 +553,9 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
         const int ngrp = (ncell + 7) >> 3;
         const int g_begin = (ngrp * h + NH - 1) / NH;
         const int g_end = (ngrp * (h + 1) + NH - 1) / NH;
-        const bool add_v = (PHASE == 1) || P.acc;
         const bool skip_nan = a.reduce == 0 && !a.row_weight;  // nanmean semantics
         float loss_acc = 0.f;
         int bad_acc = 0;
-
-        auto readout_d1 = [&](int itp) {
-            const int s = itp & 1;
-            const int j = (cta + itp * ncta) * 128 + frow;
-            mbar_wait(&S.bars.d1_full[s], (itp >> 1) & 1);
-            tc_fence_after();
-            uint32_t r[DC];
-            if constexpr (NH == 2) tmem_ld32(tmem_base + lane_addr + COL_D1 + s * 64 + DC * h, r);
-            else tmem_ld16(tmem_base + lane_addr + COL_D1 + s * 64 + DC * h, r);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.bars.d1_empty[s]);
-            // transpose through shared memory: thread <-> feature row in TMEM, but a row of d/dv
-            // (K contiguous floats) should leave with consecutive lanes on consecutive addresses
-            (void)j;
-#pragma unroll
-            for (int k = 0; k < DC; ++k) S.stage[frow][DC * h + k] = __uint_as_float(r[k]);
-            named_bar_sync(3, EPI_T);
-            if (a.grad_v) {
-                const int f0p = (cta + itp * ncta) * 128;
-                const int k2 = lane;  // float2 index inside the row
-                const bool kok = 2 * k2 < a.K;
-#pragma unroll
-                for (int half = 0; half < 16 / EW; ++half) {
-                    float2 old[8];
-                    float2* dst[8];
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {  // every load before the first store
-                        const int row = warp + EW * (rr + 8 * half);
-                        const int jj = f0p + row;
-                        dst[rr] = nullptr;
-                        old[rr] = make_float2(0.f, 0.f);
-                        if (jj < a.F && kok) {
-                            const int64_t vr = a.vidx ? a.vidx[jj] : (int64_t)jj;
-                            dst[rr] = reinterpret_cast<float2*>(a.grad_v + vr * a.K) + k2;
-                            if (add_v) old[rr] = *dst[rr];
-                        }
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int row = warp + EW * (rr + 8 * half);
-                        if (dst[rr] != nullptr)
-                            *dst[rr] = make_float2(S.stage[row][2 * k2] + old[rr].x,
-                                                   S.stage[row][2 * k2 + 1] + old[rr].y);
-                    }
-                }
-            }
-            named_bar_sync(3, EPI_T);  // the staging tile is free again
-        };
 
         for (int it = 0; it < ntl; ++it) {
             const int s = it & 1;
@@ -586,16 +588,7 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
                 if (GRAD && cur_b >= 0 && jok) {
                     const int64_t off = (int64_t)cur_b * a.F + j;
                     const float vs = gs * fp.sg;
-                    if constexpr (NH == 4) {
-                        // one flush per tile (NB1): the upper quarters hand their sums to the h == 0
-                        // thread through shared memory; it adds them in a fixed order after the barrier
-                        if (h > 0) {
-                            float(*gp)[128] = S.gpart[it & 1][h - 1];
-                            gp[0][frow] = gb, gp[1][frow] = vs, gp[2][frow] = gd, gp[3][frow] = gz;
-                        } else {
-                            pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
-                        }
-                    } else if (h == 1 && !pend) {
+                    if (h == 1 && !pend) {
                         pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
                     } else {
                         write_param(off, gb, vs, gd, gz, (PHASE == 1) || P.acc || !NB1 || h == 1);
@@ -1013,34 +1006,18 @@ __global__ void __launch_bounds__(EW == 16 ? 640 : 416, 1) tc_main_kernel(TcPara
             if (GRAD) {
                 named_bar_sync(1, EPI_T);
                 if (t == 0) TC_TRACE(1 + PHASE, it, 10);
-                if (pend) {
-                    if constexpr (NH == 4) {
-#pragma unroll
-                        for (int hh = 0; hh < 3; ++hh) {
-                            const float(*gp)[128] = S.gpart[it & 1][hh];
-                            pend_b += gp[0][frow], pend_s += gp[1][frow], pend_d += gp[2][frow], pend_z += gp[3][frow];
-                        }
-                        write_param(pend_off, pend_b, pend_s, pend_d, pend_z, (PHASE == 1) || P.acc);
-                    } else {
-                        write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
-                    }
-                }
+                if (pend) write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
                 if (NBF && PHASE == 0 && !FAST && t < ncell)
                     S.c_acc[t] += (S.cw[it & 1][0][t] + S.cw[it & 1][1][t]) + (S.cw[it & 1][2][t] + S.cw[it & 1][3][t]);
-                if (it > 0) readout_d1(it - 1);
-                if (t == 0) TC_TRACE(1 + PHASE, it, 11);
             }
         }
         if (GRAD) {
-            readout_d1(ntl - 1);
-            if (t == 0) TC_TRACE(1 + PHASE, 6, 13);
             // d/du partial of this CTA: rows = cells
             mbar_wait(&S.bars.d2_full, 0);
             tc_fence_after();
             if (t == 0) TC_TRACE(1 + PHASE, 6, 14);
             uint32_t r[DC];
-            if constexpr (NH == 2) tmem_ld32(tmem_base + lane_addr + COL_D2 + DC * h, r);
-            else tmem_ld16(tmem_base + lane_addr + COL_D2 + DC * h, r);
+            tmem_ld32(tmem_base + lane_addr + COL_D2 + DC * h, r);
             tmem_ld_wait();
             float4* dst = reinterpret_cast<float4*>(P.p.ws.apart + ((int64_t)cta * 128 + frow) * 64 + DC * h);
             float4 old[DC / 4];
@@ -1209,45 +1186,38 @@ int tc_grid(const glue_decoder_args& a, int& ntiles) {
     return ntiles < sm_count() ? ntiles : sm_count();
 }
 
-template <int FAM, int PHASE, bool GRAD, bool NB1, int EW, bool FAST>
+template <int FAM, int PHASE, bool GRAD, bool NB1, bool FAST>
 int launch_kernel(const TcParams& P, int ncta, cudaStream_t st) {
     const size_t smem = sizeof(SmemMain);
-    auto k = tc_main_kernel<FAM, PHASE, GRAD, NB1, EW, FAST>;
+    auto k = tc_main_kernel<FAM, PHASE, GRAD, NB1, FAST>;
     GLUE_SMEM_ONCE(k, smem);
-    k<<<ncta, EW == 16 ? 640 : 416, smem, st>>>(P);
+    k<<<ncta, NTHREADS, smem, st>>>(P);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
 
-template <int FAM, bool NB1, int EW, bool FAST>
+template <int FAM, bool NB1, bool FAST>
 int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t st) {
-    if (phase == 1) return launch_kernel<FAM, 1, true, NB1, EW, false>(P, ncta, st);
-    if (grad) return launch_kernel<FAM, 0, true, NB1, EW, FAST>(P, ncta, st);
-    return launch_kernel<FAM, 0, false, NB1, EW, FAST>(P, ncta, st);
+    if (phase == 1) return launch_kernel<FAM, 1, true, NB1, false>(P, ncta, st);
+    if (grad) return launch_kernel<FAM, 0, true, NB1, FAST>(P, ncta, st);
+    return launch_kernel<FAM, 0, false, NB1, FAST>(P, ncta, st);
 }
 
-// variant bits (VARIANT_*): only the NB family with a single parameter row has the wide / streamlined forms
-constexpr int VARIANT_FAST = 1, VARIANT_EW16 = 2;
-constexpr int TC_DEFAULT_VARIANT = VARIANT_FAST;  // measured: 117.7 -> 99.1 us (ATAC fwd+bwd); 16 warps add nothing on top
+// variant bits (GLUE_TC_VARIANT): bit 0 = streamlined NB pass B (single parameter row)
+constexpr int VARIANT_FAST = 1;
+constexpr int TC_DEFAULT_VARIANT = VARIANT_FAST;  // measured: 117.7 -> 99.1 us per ATAC fwd+bwd call
 
 template <bool NB1>
 int launch_family(int family, int phase, bool grad, int variant, const TcParams& P, int ncta, cudaStream_t st) {
+    if (phase == 1) return launch_phase<GLUE_NB, NB1, false>(1, true, P, ncta, st);  // pass C is family independent
     if constexpr (NB1) {
-        if (family == GLUE_NB || phase == 1) {  // pass C is family independent
-            switch (variant) {
-                case VARIANT_FAST: return launch_phase<GLUE_NB, true, 8, true>(phase, grad, P, ncta, st);
-                case VARIANT_EW16: return launch_phase<GLUE_NB, true, 16, false>(phase, grad, P, ncta, st);
-                case VARIANT_FAST | VARIANT_EW16: return launch_phase<GLUE_NB, true, 16, true>(phase, grad, P, ncta, st);
-                default: return launch_phase<GLUE_NB, true, 8, false>(phase, grad, P, ncta, st);
-            }
-        }
+        if (family == GLUE_NB && (variant & VARIANT_FAST)) return launch_phase<GLUE_NB, true, true>(0, grad, P, ncta, st);
     }
-    if (phase == 1) return launch_phase<GLUE_NB, NB1, 8, false>(1, true, P, ncta, st);  // pass C is family independent
     switch (family) {
-        case GLUE_NB: return launch_phase<GLUE_NB, NB1, 8, false>(0, grad, P, ncta, st);
-        case GLUE_ZINB: return launch_phase<GLUE_ZINB, NB1, 8, false>(0, grad, P, ncta, st);
-        case GLUE_NORMAL: return launch_phase<GLUE_NORMAL, NB1, 8, false>(0, grad, P, ncta, st);
-        default: return launch_phase<GLUE_ZILN, NB1, 8, false>(0, grad, P, ncta, st);
+        case GLUE_NB: return launch_phase<GLUE_NB, NB1, false>(0, grad, P, ncta, st);
+        case GLUE_ZINB: return launch_phase<GLUE_ZINB, NB1, false>(0, grad, P, ncta, st);
+        case GLUE_NORMAL: return launch_phase<GLUE_NORMAL, NB1, false>(0, grad, P, ncta, st);
+        default: return launch_phase<GLUE_ZILN, NB1, false>(0, grad, P, ncta, st);
     }
 }
 
@@ -1292,11 +1262,11 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
     const bool nb1 = a.n_batches == 1;
-    // kernel variant: GLUE_TC_VARIANT = bit 0 streamlined NB pass B, bit 1 sixteen epilogue warps
+    // kernel variant: GLUE_TC_VARIANT = 0 switches the streamlined NB pass B off (A/B runs, tests)
     int variant = TC_DEFAULT_VARIANT;
     {
         const char* e = getenv("GLUE_TC_VARIANT");
-        if (e) variant = atoi(e) & (VARIANT_FAST | VARIANT_EW16);
+        if (e) variant = atoi(e) & VARIANT_FAST;
     }
     if (!(a.family == GLUE_NB && nb1 && a.K <= 62 && (long long)a.B * (long long)a.F < (1ll << 31)))
         variant &= ~VARIANT_FAST;

@@ -124,9 +124,9 @@ def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F,
 
 # ------------------------------------------------------------------ kernel variants of the main pass
 # GLUE_TC_VARIANT: bit 0 = streamlined NB pass B (32-bit unpredicated x loads, quadratic gamma terms
-# for the counts 0 / 1 / 2, c_i from the tensor cores), bit 1 = sixteen epilogue warps.  Every
-# combination must agree with the base kernel, which the tests above / test_ops_gpu.py tie to the
-# CUDA-core decoder and to the oracle.
+# for the counts 0 / 1 / 2, c_i from the tensor cores; the default for NB with one parameter row).
+# It must agree with the base kernel (GLUE_TC_VARIANT=0), which the tests above / test_ops_gpu.py
+# tie to the CUDA-core decoder and to the oracle.
 def _variant_case(B, F, K, seed, sparse, nan_frac, extra_rows):
     from tests.test_ops_gpu import _decoder_case
     u, v, b, l, x, params, vidx = _decoder_case("NB", B, F, K, 1, seed=seed, extra_rows=extra_rows)
@@ -175,7 +175,7 @@ VARIANT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1])
 @pytest.mark.parametrize("B,F,K,sparse,nan_frac,extra,reduce,weighted", VARIANT_CASES)
 def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, sparse, nan_frac, extra, reduce, weighted):
     from glue_b200 import ops
@@ -197,7 +197,7 @@ def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, spar
     assert torch.equal(l1, l2) and all(torch.equal(a, b) for a, b in zip(g1, g2)), "variants must be deterministic"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_main_pass_variants_vs_oracle(native_lib, variant):
     from glue_b200 import ops
     from tests.test_ops_gpu import TOL, _oracle_nll
@@ -207,21 +207,3 @@ def test_main_pass_variants_vs_oracle(native_lib, variant):
     assert_close(loss, ref_loss, TOL, "nll vs oracle")
     for n, g, rg in zip(["u", "v", "scale_lin", "bias", "log_theta"], grads, ref_grads):
         assert_close(g, rg, TOL, f"d/d{n} vs oracle (variant {variant})")
-
-
-@pytest.mark.parametrize("variant", [2, 3])
-def test_wide_epilogue_softmax_pass_with_zinb(native_lib, variant):
-    """ZINB keeps the 8-warp pass B; with bit 1 its soft-max pass (family independent) runs wide."""
-    from glue_b200 import ops
-    from tests.test_ops_gpu import PARAM_NAMES, _decoder_case
-    case = _decoder_case("ZINB", 128, 1800, 50, 1, seed=5)
-    l0, g0 = _run_decoder(ops, "ZINB", case, "nanmean")
-    os.environ["GLUE_TC_VARIANT"] = str(variant)
-    try:
-        l1, g1 = _run_decoder(ops, "ZINB", case, "nanmean")
-        torch.cuda.synchronize()
-    finally:
-        os.environ.pop("GLUE_TC_VARIANT")
-    assert_close(l1, l0, 2e-5, "loss")
-    for n, a, b in zip(["u", "v"] + list(PARAM_NAMES["ZINB"]), g1, g0):
-        assert_close(a, b, 1e-4, f"ZINB d/d{n} (variant {variant} vs base)")
