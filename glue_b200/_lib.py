@@ -36,6 +36,8 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_log_prob",
     "glue_decoder_mean",
     "glue_rmsprop_flat",
+    "glue_kl_unit_normal_fwd",
+    "glue_kl_unit_normal_bwd",
     "glue_tc_selftest",
     "glue_tc_set_trace",
 )
@@ -148,6 +150,11 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_rmsprop_flat.restype = c_int32
     lib.glue_rmsprop_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                       c_float, c_void_p]
+    lib.glue_kl_unit_normal_fwd.restype = c_int32
+    lib.glue_kl_unit_normal_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]
+    lib.glue_kl_unit_normal_bwd.restype = c_int32
+    lib.glue_kl_unit_normal_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]
     lib.glue_tc_set_trace.restype = None
     lib.glue_tc_set_trace.argtypes = [c_void_p]
 

@@ -40,6 +40,27 @@ namespace glue {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A kernel launched with launch_pdl may start (barrier set-up, staging of its own inputs) while the
+// kernel in front of it on the stream is still draining; griddep_wait() blocks until that kernel
+// has completed and its writes are visible, and has to precede the first access to anything the
+// earlier kernel wrote or read.  griddep_launch() lets the kernel behind start early.  Both are
+// no-ops without a programmatic dependency.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool enable, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = enable ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);

@@ -151,6 +151,7 @@ struct TcParams {
     int chunk, nchunks;  // this launch handles cell block `chunk` of `nchunks`
     long long* trace;  // optional: clock64 stamps of CTA 0, [kernel 0..2][tile < 8][event < 16]
     int dbg;           // timing experiments only (GLUE_TC_DBG): 1 = no x loads, 2 = no X stores / c_i reduce
+    int pdl;           // launches carry the programmatic-dependent-launch attribute (GLUE_TC_PDL=0 switches it off)
 };
 
 #define TC_TRACE(kern, it, ev)                                                              \
@@ -220,6 +221,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_rowstats_kernel(TcParams P) {
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int ntl = (P.ntiles - cta + ncta - 1) / ncta;
     if (t == 0) TC_TRACE(0, 7, 2);
+    griddep_launch();
+    griddep_wait();
 
     if (t == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -365,6 +368,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
     const int ntl = (P.ntiles - cta + ncta - 1) / ncta;
     const int ncell = P.ncell;
     if (t == 0) TC_TRACE(1 + PHASE, 7, 2);
+    griddep_launch();
+    griddep_wait();
 
     if (t == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -1112,6 +1117,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 // sub-results meet in a fixed order.
 __global__ void __launch_bounds__(1024) tc_lse_kernel(DecWs ws, int nparts, int B) {
     __shared__ float red[2][32][33];
+    griddep_launch();
+    griddep_wait();
     const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
     const int row = blockIdx.x * 32 + lane;
     const bool act = row < B;
@@ -1149,6 +1156,8 @@ __global__ void __launch_bounds__(256) tc_grad_u_kernel(DecParams p, int ncta, i
     const glue_decoder_args& a = p.a;
     const int pos = blockIdx.x, k = threadIdx.x & 63, sub = threadIdx.x >> 6;  // pos: cell within the block
     __shared__ float part[4][64];
+    griddep_launch();
+    griddep_wait();
     float acc = 0.f;
     for (int q = sub; q < ncta; q += 4) acc += p.ws.apart[((int64_t)q * 128 + pos) * 64 + k];
     part[sub][k] = acc;
@@ -1191,7 +1200,7 @@ int launch_kernel(const TcParams& P, int ncta, cudaStream_t st) {
     const size_t smem = sizeof(SmemMain);
     auto k = tc_main_kernel<FAM, PHASE, GRAD, NB1, FAST>;
     GLUE_SMEM_ONCE(k, smem);
-    k<<<ncta, NTHREADS, smem, st>>>(P);
+    GLUE_CUDA(launch_pdl(P.pdl != 0, k, dim3(ncta), dim3(NTHREADS), smem, st, P));
     GLUE_CHECK_LAUNCH();
     return 0;
 }
@@ -1205,6 +1214,7 @@ int launch_phase(int phase, bool grad, const TcParams& P, int ncta, cudaStream_t
 
 // variant bits (GLUE_TC_VARIANT): bit 0 = streamlined NB pass B (single parameter row)
 constexpr int VARIANT_FAST = 1;
+constexpr int TC_DEFAULT_PDL = 0;
 constexpr int TC_DEFAULT_VARIANT = VARIANT_FAST;  // measured: 117.7 -> 99.1 us per ATAC fwd+bwd call
 
 template <bool NB1>
@@ -1258,6 +1268,8 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     {
         const char* e = getenv("GLUE_TC_DBG");
         P.dbg = e ? atoi(e) : 0;
+        e = getenv("GLUE_TC_PDL");
+        P.pdl = e ? atoi(e) : TC_DEFAULT_PDL;
     }
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
@@ -1290,10 +1302,12 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
         GLUE_SMEM_ONCE(tc_rowstats_kernel, smem);
         for (int c = 0; c < nchunks; ++c) {
             block(c);
-            tc_rowstats_kernel<<<ncta, NTHREADS, smem, st>>>(P);
+            // (the first launch follows a memset node: plain stream order)
+            GLUE_CUDA(launch_pdl(P.pdl != 0 && c > 0, tc_rowstats_kernel, dim3(ncta), dim3(NTHREADS), smem, st, P));
             GLUE_CHECK_LAUNCH();
         }
-        tc_lse_kernel<<<(a.B + 31) / 32, 1024, 0, st>>>(p.ws, 2 * ncta, a.B);  // 2 * ncta <= 320 partials
+        GLUE_CUDA(launch_pdl(P.pdl != 0, tc_lse_kernel, dim3((a.B + 31) / 32), dim3(1024), 0, st, p.ws, 2 * ncta,
+                             a.B));  // 2 * ncta <= 320 partials
         GLUE_CHECK_LAUNCH();
     }
     for (int c = 0; c < nchunks; ++c) {
@@ -1307,7 +1321,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
                          : launch_family<false>(a.family, 1, true, variant, P, ncta, st);
                 if (rc) return rc;
             }
-            tc_grad_u_kernel<<<P.ncell, 256, 0, st>>>(p, ncta, P.cell0);
+            GLUE_CUDA(launch_pdl(P.pdl != 0, tc_grad_u_kernel, dim3(P.ncell), dim3(256), 0, st, p, ncta, P.cell0));
             GLUE_CHECK_LAUNCH();
         }
     }

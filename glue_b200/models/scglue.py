@@ -308,7 +308,6 @@ class SCGLUETrainer(GLUETrainer):
         # the data encoders: it runs beside them
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
             x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
-        g_elbo = g_nll + self.lam_kl * g_kl
         # one stream per decoder call (per modality: the reconstruction term and, for paired data,
         # the joint-cross / real-cross terms): each call is a short sequence of one-CTA-per-SM
         # kernels, so the calls of a small modality (16 CTAs for 2 000 genes) and the prologue of
@@ -331,27 +330,66 @@ class SCGLUETrainer(GLUETrainer):
             torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
         u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
         sup_loss = self._supervision(u_cat, xlbl)
-        x_kl = {k: _kl_to_prior(u[k], prior) / x[k].shape[1] for k in net.keys}
-        x_elbo = {k: x_nll[k] + self.lam_kl * x_kl[k] for k in net.keys}
-        x_elbo_sum = sum(self.modality_weight[k] * x_elbo[k] for k in net.keys)
-        vae_loss = (self.lam_data * x_elbo_sum + self.lam_graph * len(net.keys) * g_elbo
-                    + self.lam_sup * sup_loss)
-        extra = self._extra_losses(data, usamp, vsamp, l)
+        x_kl = {k: self._data_kl(u[k], prior, x[k].shape[1]) for k in net.keys}
+        extra_comps, extra_terms = self._extra_losses(data, usamp, vsamp, l)
         # nothing that carries an autograd graph may outlive the step on `self`: it would keep
         # this step's AccumulateGrad nodes (bound to the current streams) alive into a capture
         self._extra_parts = self._shared_extra = None
-        for weight, term in extra.values():
-            vae_loss = vae_loss + weight * term
-        gen_loss = vae_loss - self.lam_align * dsc_loss
-        losses = {"dsc_loss": dsc_loss, "vae_loss": vae_loss, "gen_loss": gen_loss,
-                  "g_nll": g_nll, "g_kl": g_kl, "g_elbo": g_elbo}
-        losses.update({name: term for name, (_, term) in extra.items()})
+
+        # The objective and every reported term are fixed linear combinations of a dozen scalar
+        # components (``scglue.py:349-376``; paired terms ``scglue.py:654-672``).  Evaluated one
+        # scalar op at a time that is ~60 tiny launches forward + backward on the serial tail of
+        # the step; here: one stack, one matrix-vector product each way.
+        comps = {"dsc": dsc_loss, "g_nll": g_nll, "g_kl": g_kl, "sup": sup_loss}
         for k in net.keys:
-            losses.update({f"x_{k}_nll": x_nll[k], f"x_{k}_kl": x_kl[k],
-                           f"x_{k}_elbo": x_elbo[k]})
+            comps[f"x_{k}_nll"], comps[f"x_{k}_kl"] = x_nll[k], x_kl[k]
+        comps.update(extra_comps)
+        n_mod = len(net.keys)
+        rows = {"dsc_loss": {"dsc": 1.0}, "vae_loss": None, "gen_loss": None,  # (filled in below)
+                "g_nll": {"g_nll": 1.0}, "g_kl": {"g_kl": 1.0},
+                "g_elbo": {"g_nll": 1.0, "g_kl": self.lam_kl}}
+        vae = {"g_nll": self.lam_graph * n_mod, "g_kl": self.lam_graph * n_mod * self.lam_kl,
+               "sup": self.lam_sup}
+        for k in net.keys:
+            w = self.lam_data * self.modality_weight[k]
+            rows[f"x_{k}_nll"] = {f"x_{k}_nll": 1.0}
+            rows[f"x_{k}_kl"] = {f"x_{k}_kl": 1.0}
+            rows[f"x_{k}_elbo"] = {f"x_{k}_nll": 1.0, f"x_{k}_kl": self.lam_kl}
+            vae[f"x_{k}_nll"], vae[f"x_{k}_kl"] = w, w * self.lam_kl
+        for name, (weight, row) in extra_terms.items():
+            rows[name] = row
+            for comp, coeff in row.items():
+                vae[comp] = vae.get(comp, 0.0) + weight * coeff
+        rows["vae_loss"] = vae
+        rows["gen_loss"] = dict(vae, dsc=-self.lam_align)
         if net.u2c:
-            losses["sup_loss"] = sup_loss
-        return losses
+            rows["sup_loss"] = {"sup": 1.0}
+        return self._combine(comps, rows)
+
+    def _data_kl(self, u: D.Normal, prior: D.Normal, n_features: int) -> torch.Tensor:
+        r"""``kl_divergence(u, prior).sum(dim=1).mean() / n_features`` (``scglue.py:349-353``);
+        one fused launch each way for the standard-normal prior."""
+        if getattr(self, "_unit_prior", None) and u.mean.is_cuda:
+            from .. import ops
+            return ops.kl_unit_normal(u.mean, u.stddev, 1.0 / (u.mean.shape[0] * n_features))
+        return _kl_to_prior(u, prior) / n_features
+
+    def _combine(self, comps: Mapping[str, torch.Tensor],
+                 rows: Mapping[str, Mapping[str, float]]) -> Mapping[str, torch.Tensor]:
+        r"""``{name: sum_c rows[name][c] * comps[c]}`` as one matrix-vector product; the coefficient
+        matrix lives on the device, cached per set of loss weights (a change of weights is a new
+        step-graph key, so the matrix is always built outside a capture)."""
+        names, keys = list(rows), list(comps)
+        flat = tuple(tuple(float(rows[n].get(c, 0.0)) for c in keys) for n in names)
+        cache = self.__dict__.setdefault("_combine_cache", {})
+        cache_key = (tuple(names), tuple(keys), flat)
+        mat = cache.get(cache_key)
+        if mat is None:
+            if len(cache) > 8:
+                cache.clear()
+            mat = cache[cache_key] = torch.tensor(flat, dtype=torch.float32, device=self.net.device)
+        out = mat @ torch.stack([comps[c].reshape(()) for c in keys])
+        return {n: out[i] for i, n in enumerate(names)}
 
     def _prepare_extra(self, usamp) -> None:
         r"""Quantities shared by the per-modality extra terms (computed before the fork)."""
@@ -362,8 +400,10 @@ class SCGLUETrainer(GLUETrainer):
         term); combined by :meth:`_extra_losses`."""
         return []
 
-    def _extra_losses(self, data, usamp, vsamp, l) -> Mapping[str, Tuple[float, torch.Tensor]]:
-        return {}
+    def _extra_losses(self, data, usamp, vsamp, l):
+        r"""``(components, terms)``: extra scalar components ``{name: tensor}`` and the reported /
+        weighted terms built from them ``{term: (weight in vae_loss, {component: coefficient})}``."""
+        return {}, {}
 
     # -- steps -------------------------------------------------------------------------------
     def train_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
@@ -500,20 +540,23 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         keys = net.keys
         zero = torch.zeros((), device=net.device)
         ustack, umean, pf = self._shared_extra
-        joint, real = zero, zero
+        comps, joint_row, real_row = {}, {}, {}
         for k in keys:
             parts = self._extra_parts[k]
-            joint = joint + self.modality_weight[k] * parts.get("joint", zero)
-            real = real + self.modality_weight[k] * parts.get("real", zero)
+            if "joint" in parts:
+                comps[f"joint_{k}"], joint_row[f"joint_{k}"] = parts["joint"], self.modality_weight[k]
+            if "real" in parts:
+                comps[f"real_{k}"], real_row[f"real_{k}"] = parts["real"], self.modality_weight[k]
         cos = zero
         if self.lam_cos:
             for i, k in enumerate(keys):
                 n = pf[i].sum()
                 sim = (F.cosine_similarity(ustack[i], umean) * pf[i]).sum() / n.clamp(min=1.0)
                 cos = cos + torch.where(n > 0, 1 - sim, zero)
-        return {"joint_cross_loss": (self.lam_joint_cross, joint),
-                "real_cross_loss": (self.lam_real_cross, real),
-                "cos_loss": (self.lam_cos, cos)}
+        comps["cos"] = cos
+        return comps, {"joint_cross_loss": (self.lam_joint_cross, joint_row),
+                       "real_cross_loss": (self.lam_real_cross, real_row),
+                       "cos_loss": (self.lam_cos, {"cos": 1.0})}
 
 
 # ------------------------------------------------------------------- public API

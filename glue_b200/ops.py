@@ -237,6 +237,43 @@ def graph_encoder_head(ptr_, w_loc, b_loc, w_std, b_std, noise=None):
     return _GraphEncHeadFn.apply(*args, noise)
 
 
+# ------------------------------------------------------------- KL of the data encoders
+
+
+class _KlUnitNormalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, std, scale):
+        dev = mean.device
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        check(_lib.lib().glue_kl_unit_normal_fwd(ptr(mean), ptr(std), mean.numel(), scale, ptr(out),
+                                                 current_stream(dev)), "kl_unit_normal_fwd")
+        ctx.save_for_backward(mean, std)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mean, std = ctx.saved_tensors
+        dev = mean.device
+        g = _f32(g, "grad_kl")
+        g_mean, g_std = torch.empty_like(mean), torch.empty_like(std)
+        check(_lib.lib().glue_kl_unit_normal_bwd(ptr(mean), ptr(std), mean.numel(), ctx.scale, ptr(g),
+                                                 ptr(g_mean), ptr(g_std), current_stream(dev)),
+              "kl_unit_normal_bwd")
+        return g_mean, g_std, None
+
+
+def kl_unit_normal(mean: torch.Tensor, std: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    r"""``scale * kl_divergence(Normal(mean, std), Normal(0, 1)).sum()`` in one launch each way
+    (``scglue/models/scglue.py:349-353`` with the standard-normal prior of ``sc.py:640-660``;
+    ``scale = 1 / (batch * n_features)`` turns it into ``.sum(dim=1).mean() / n_features``)."""
+    require_cuda(mean, std)
+    mean, std = _f32(mean, "mean"), _f32(std, "std")
+    if mean.shape != std.shape:
+        raise ValueError("`mean` and `std` must have the same shape")
+    return _KlUnitNormalFn.apply(mean, std, float(scale))
+
+
 # ------------------------------------------------- edge-partitioned GraphConv (atlas scale)
 
 

@@ -210,6 +210,21 @@ int glue_rmsprop_flat(float *param, const float *grad, float *square_avg, int64_
                       float alpha, float eps, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * KL( N(mean, std) || N(0, 1) ) of a data encoder's posterior.
+ * Replaces  D.kl_divergence(u, prior).sum(dim=1).mean() / n_features
+ * (scglue/models/scglue.py:349-353) for the standard-normal prior of
+ * scglue/models/sc.py:640-660:
+ *   out[0] = scale * sum_i ( 0.5 (std_i^2 + mean_i^2 - 1) - log std_i )
+ *   grad_mean = upstream[0] * scale * mean,  grad_std = upstream[0] * scale * (std - 1 / std)
+ * mean / std / grads: [n] fp32; out, upstream: device scalars.  One block forward
+ * (fixed summation order).
+ * ------------------------------------------------------------------------- */
+int glue_kl_unit_normal_fwd(const float *mean, const float *std_, int64_t n, float scale, float *out,
+                            void *stream);
+int glue_kl_unit_normal_bwd(const float *mean, const float *std_, int64_t n, float scale,
+                            const float *upstream, float *grad_mean, float *grad_std, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
  * M = 128) steps on caller-built shared-memory operand images and return the
  * accumulator tile out[128][N].  a_img / b_img are device buffers copied

@@ -368,3 +368,24 @@ def test_flat_rmsprop_matches_torch_rmsprop(native_lib):
     our_p[1].grad = torch.ones_like(our_p[1])
     ours.step()
     assert our_p[1].data_ptr() == ours._pviews[1].data_ptr()
+
+
+# ------------------------------------------------------------------ KL of the data encoders
+@pytest.mark.parametrize("B,K", [(128, 50), (1, 2), (37, 64), (1000, 50)])
+def test_kl_unit_normal_vs_torch_distributions(ops, B, K):
+    import torch.distributions as D
+    gen = torch.Generator().manual_seed(B + K)
+    mean = torch.randn(B, K, generator=gen).requires_grad_(True)
+    std = (torch.rand(B, K, generator=gen) * 2 + 1e-3).requires_grad_(True)
+    n_features = 2000
+    ref = D.kl_divergence(D.Normal(mean, std), D.Normal(torch.tensor(0.0), torch.tensor(1.0))) \
+        .sum(dim=1).mean() / n_features
+    rg = torch.autograd.grad(3.0 * ref, [mean, std])
+    dm, ds = mean.detach().to(DEV).requires_grad_(True), std.detach().to(DEV).requires_grad_(True)
+    out = ops.kl_unit_normal(dm, ds, 1.0 / (B * n_features))
+    g = torch.autograd.grad(3.0 * out, [dm, ds])
+    assert_close(out, ref, TOL, "kl")
+    assert_close(g[0], rg[0], TOL, "d kl / d mean")
+    assert_close(g[1], rg[1], TOL, "d kl / d std")
+    out2 = ops.kl_unit_normal(dm, ds, 1.0 / (B * n_features))
+    assert torch.equal(out, out2), "fixed summation order"

@@ -33,7 +33,9 @@ for name, F, rate in (("atac", 50000, 0.05), ("rna", 2000, 0.3), ("atac150k", 15
                                    ps[2].detach(), None, l=ls[i % 8], x=xs[i % 8])
 
     for variant, grad in [(vv, gg) for vv in os.environ.get("VARIANTS", "").split(",") for gg in (True, False)]:
-        if variant:
+        if "=" in variant:  # e.g. VARIANTS=GLUE_TC_PDL=0,GLUE_TC_PDL=1
+            os.environ[variant.split("=")[0]] = variant.split("=")[1]
+        elif variant:
             os.environ["GLUE_TC_VARIANT"] = variant  # read by the library at every call
         for i in range(3):
             call(i, grad)

@@ -52,4 +52,35 @@ for e in ev:
     agg[k] = (n + 1, d + e["dur"])
 for k, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{d / 3:8.1f} us/step  {n / 3:6.1f} x {d / n:7.2f} us  {k}")
+# timeline of the last step: every activity of at least 5 us, and how many streams are busy over time
+starts = [e for e in ev if "Memcpy DtoD" in e["name"] or "memcpy" in e["name"].lower()]
+last0 = ev[len(ev) * 2 // 3]["ts"]
+lastev = [e for e in ev if e["ts"] >= last0]
+base = lastev[0]["ts"]
+print("\nlast step, activities >= 5 us (start us, dur us, stream, name):")
+for e in lastev:
+    if e["dur"] >= 5:
+        print(f"{e['ts'] - base:8.0f} {e['dur']:7.1f}  s{e['args'].get('stream')}  {e['name'][:70]}")
+span = max(e["ts"] + e["dur"] for e in lastev) - base
+print("\nbusy streams per 50 us bucket:")
+for b in range(0, int(span) + 1, 50):
+    act = set()
+    tot = 0.0
+    for e in lastev:
+        s0, s1 = e["ts"] - base, e["ts"] - base + e["dur"]
+        ov = min(s1, b + 50) - max(s0, b)
+        if ov > 0:
+            act.add(e["args"].get("stream"))
+            tot += ov
+    print(f"{b:6d} us: {len(act)} streams, {tot / 50:.2f} average concurrency")
+if os.environ.get("WINDOW"):
+    w0, w1 = (float(v) for v in os.environ["WINDOW"].split(","))
+    print(f"\nall activities of the last step starting in [{w0:.0f}, {w1:.0f}) us, in order:")
+    prev_end = None
+    for e in lastev:
+        s0 = e["ts"] - base
+        if w0 <= s0 < w1:
+            gap = "" if prev_end is None else f"(+{s0 - prev_end:4.1f})"
+            print(f"{s0:8.1f} {gap:8s} {e['dur']:6.1f}  s{e['args'].get('stream')}  {e['name'][:110]}")
+            prev_end = s0 + e["dur"]
 os.remove(path)
