@@ -38,6 +38,8 @@ EXPORTED_SYMBOLS = (
     "glue_rmsprop_flat",
     "glue_kl_unit_normal_fwd",
     "glue_kl_unit_normal_bwd",
+    "glue_paired_mean_cos_fwd",
+    "glue_paired_mean_cos_bwd",
     "glue_tc_selftest",
     "glue_tc_set_trace",
 )
@@ -155,6 +157,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_kl_unit_normal_bwd.restype = c_int32
     lib.glue_kl_unit_normal_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p,
                                             c_void_p, c_void_p]
+    lib.glue_paired_mean_cos_fwd.restype = c_int32
+    lib.glue_paired_mean_cos_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]
+    lib.glue_paired_mean_cos_bwd.restype = c_int32
+    lib.glue_paired_mean_cos_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
+                                             c_void_p, c_void_p, c_void_p, c_void_p]
     lib.glue_tc_set_trace.restype = None
     lib.glue_tc_set_trace.argtypes = [c_void_p]
 

@@ -45,6 +45,134 @@ __global__ void __launch_bounds__(256) kl_unit_normal_bwd_kernel(const float* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Paired cells (scglue/models/scglue.py:618-622, 654-660): mean embedding of every cell over the
+// modalities it is observed in, and the cosine term
+//   cos_loss = sum_k [n_k > 0] (1 - sum_i p_ki cos(u_ki, m_i) / max(n_k, 1)),   n_k = sum_i p_ki,
+//   m_i = sum_k p_ki u_ki / sum_k p_ki,   cos(x, y) = x.y / (max(|x|, eps) max(|y|, eps)), eps = 1e-8
+// (F.cosine_similarity).  Through torch ops that is ~30 launches forward and ~80 backward on the
+// serial tail of the step.  One block each way, one warp per cell, fixed summation order.
+// ---------------------------------------------------------------------------------------------
+constexpr int PM_MAX_MOD = 8;
+constexpr int PM_THREADS = 1024;
+constexpr float PM_EPS = 1e-8f;
+
+struct PmRow {
+    float m[2];   // this lane's two latent columns of m_i
+    float nm;     // |m_i|
+    float cnt;    // sum_k p_ki
+};
+
+// lane handles latent columns lane and lane + 32 (K <= 64)
+__device__ __forceinline__ PmRow pm_mean(const float* __restrict__ u, const float* __restrict__ pf, int M, int B, int K,
+                                         int i, int lane) {
+    PmRow r;
+    r.m[0] = r.m[1] = 0.f, r.cnt = 0.f;
+    for (int k = 0; k < M; ++k) {
+        const float p = pf[(int64_t)k * B + i];
+        const float* row = u + ((int64_t)k * B + i) * K;
+        r.cnt += p;
+        if (lane < K) r.m[0] = fmaf(p, row[lane], r.m[0]);
+        if (lane + 32 < K) r.m[1] = fmaf(p, row[lane + 32], r.m[1]);
+    }
+    r.m[0] /= r.cnt, r.m[1] /= r.cnt;
+    r.nm = sqrtf(warp_sum(fmaf(r.m[0], r.m[0], r.m[1] * r.m[1])));
+    return r;
+}
+
+__global__ void __launch_bounds__(PM_THREADS) paired_mean_cos_fwd_kernel(const float* __restrict__ u,
+                                                                         const float* __restrict__ pf, int M, int B,
+                                                                         int K, float* __restrict__ umean,
+                                                                         float* __restrict__ cos_out,
+                                                                         float* __restrict__ nk_out) {
+    __shared__ float part_s[PM_THREADS / 32][PM_MAX_MOD], part_n[PM_THREADS / 32][PM_MAX_MOD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc_s[PM_MAX_MOD], acc_n[PM_MAX_MOD];
+#pragma unroll
+    for (int k = 0; k < PM_MAX_MOD; ++k) acc_s[k] = acc_n[k] = 0.f;
+    for (int i = warp; i < B; i += PM_THREADS / 32) {
+        const PmRow r = pm_mean(u, pf, M, B, K, i, lane);
+        if (lane < K) umean[(int64_t)i * K + lane] = r.m[0];
+        if (lane + 32 < K) umean[(int64_t)i * K + lane + 32] = r.m[1];
+#pragma unroll
+        for (int k = 0; k < PM_MAX_MOD; ++k) {
+            if (k < M) {
+                const float p = pf[(int64_t)k * B + i];
+                const float* row = u + ((int64_t)k * B + i) * K;
+                const float x0 = lane < K ? row[lane] : 0.f, x1 = lane + 32 < K ? row[lane + 32] : 0.f;
+                const float dot = warp_sum(fmaf(x0, r.m[0], x1 * r.m[1]));
+                const float nu = sqrtf(warp_sum(fmaf(x0, x0, x1 * x1)));
+                const float sim = dot / (fmaxf(nu, PM_EPS) * fmaxf(r.nm, PM_EPS));
+                acc_s[k] = fmaf(p, sim, acc_s[k]);
+                acc_n[k] += p;
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < PM_MAX_MOD; ++k) part_s[warp][k] = acc_s[k], part_n[warp][k] = acc_n[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float cosv = 0.f;
+        for (int k = 0; k < M; ++k) {
+            float s = 0.f, n = 0.f;
+            for (int w = 0; w < PM_THREADS / 32; ++w) s += part_s[w][k], n += part_n[w][k];
+            nk_out[k] = n;
+            if (n > 0.f) cosv += 1.f - s / fmaxf(n, 1.f);
+        }
+        cos_out[0] = cosv;
+    }
+}
+
+__global__ void __launch_bounds__(PM_THREADS) paired_mean_cos_bwd_kernel(const float* __restrict__ u,
+                                                                         const float* __restrict__ pf,
+                                                                         const float* __restrict__ nk, int M, int B,
+                                                                         int K, const float* __restrict__ g_umean,
+                                                                         const float* __restrict__ g_cos,
+                                                                         float* __restrict__ g_u) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float gc = g_cos ? g_cos[0] : 0.f;
+    for (int i = warp; i < B; i += PM_THREADS / 32) {
+        const PmRow r = pm_mean(u, pf, M, B, K, i, lane);
+        const float dm = fmaxf(r.nm, PM_EPS);
+        // gradient reaching m_i: from the consumers of umean and from every cosine it takes part in
+        float gm0 = (g_umean && lane < K) ? g_umean[(int64_t)i * K + lane] : 0.f;
+        float gm1 = (g_umean && lane + 32 < K) ? g_umean[(int64_t)i * K + lane + 32] : 0.f;
+        float du0[PM_MAX_MOD], du1[PM_MAX_MOD];  // direct d cos_loss / d u_ki
+#pragma unroll
+        for (int k = 0; k < PM_MAX_MOD; ++k) {
+            du0[k] = du1[k] = 0.f;
+            if (k < M) {
+                const float p = pf[(int64_t)k * B + i];
+                const float n = nk[k];
+                const float a = (n > 0.f) ? -gc * p / fmaxf(n, 1.f) : 0.f;  // d loss / d sim_ki
+                const float* row = u + ((int64_t)k * B + i) * K;
+                const float x0 = lane < K ? row[lane] : 0.f, x1 = lane + 32 < K ? row[lane + 32] : 0.f;
+                const float dot = warp_sum(fmaf(x0, r.m[0], x1 * r.m[1]));
+                const float nu = sqrtf(warp_sum(fmaf(x0, x0, x1 * x1)));
+                const float du = fmaxf(nu, PM_EPS);
+                const float inv = 1.f / (du * dm);
+                const float sim = dot * inv;
+                // d sim / d x = m inv - sim x / |x|^2  (the second term only where the norm is not clamped)
+                const float cu = nu > PM_EPS ? sim / (nu * nu) : 0.f;
+                const float cm = r.nm > PM_EPS ? sim / (r.nm * r.nm) : 0.f;
+                du0[k] = a * (r.m[0] * inv - cu * x0), du1[k] = a * (r.m[1] * inv - cu * x1);
+                gm0 += a * (x0 * inv - cm * r.m[0]), gm1 += a * (x1 * inv - cm * r.m[1]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PM_MAX_MOD; ++k) {
+            if (k < M) {
+                const float w = pf[(int64_t)k * B + i] / r.cnt;  // d m_i / d u_ki
+                float* out = g_u + ((int64_t)k * B + i) * K;
+                if (lane < K) out[lane] = fmaf(w, gm0, du0[k]);
+                if (lane + 32 < K) out[lane + 32] = fmaf(w, gm1, du1[k]);
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace glue
 
@@ -64,6 +192,27 @@ extern "C" int glue_kl_unit_normal_bwd(const float* mean, const float* std_, int
     const int grid = (int)(want > cap ? cap : want);
     glue::kl_unit_normal_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mean, std_, n, scale, upstream, grad_mean,
                                                                             grad_std);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glue_paired_mean_cos_fwd(const float* ustack, const float* pmask, int32_t n_modalities, int64_t B,
+                                        int32_t K, float* umean, float* cos_loss, float* n_k, void* stream) {
+    if (!ustack || !pmask || !umean || !cos_loss || !n_k || B <= 0) return GLUE_E_BADARG;
+    if (n_modalities < 1 || n_modalities > glue::PM_MAX_MOD || K < 1 || K > 64) return GLUE_E_UNSUPPORTED;
+    glue::paired_mean_cos_fwd_kernel<<<1, glue::PM_THREADS, 0, (cudaStream_t)stream>>>(
+        ustack, pmask, n_modalities, (int)B, K, umean, cos_loss, n_k);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glue_paired_mean_cos_bwd(const float* ustack, const float* pmask, const float* n_k,
+                                        int32_t n_modalities, int64_t B, int32_t K, const float* grad_umean,
+                                        const float* grad_cos, float* grad_ustack, void* stream) {
+    if (!ustack || !pmask || !n_k || !grad_ustack || B <= 0) return GLUE_E_BADARG;
+    if (n_modalities < 1 || n_modalities > glue::PM_MAX_MOD || K < 1 || K > 64) return GLUE_E_UNSUPPORTED;
+    glue::paired_mean_cos_bwd_kernel<<<1, glue::PM_THREADS, 0, (cudaStream_t)stream>>>(
+        ustack, pmask, n_k, n_modalities, (int)B, K, grad_umean, grad_cos, grad_ustack);
     GLUE_CHECK_LAUNCH();
     return 0;
 }

@@ -195,12 +195,17 @@ class SCGLUETrainer(GLUETrainer):
         r"""Burn-in noise coefficient of the alignment term (``scglue.py:318-324``)."""
         return max(1 - (epoch - 1) / self.align_burnin, 0) if self.align_burnin else 0
 
-    def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int):
+    def _alignment_inputs(self, xbch, xdwt, xflag):
+        r"""Per-cell covariates of the discriminator, concatenated over the modalities (the same
+        for the discriminator pass and the generator pass of a step: built once)."""
+        keys = self.net.keys
+        return (torch.cat([xbch[k] for k in keys]), torch.cat([xdwt[k] for k in keys]),
+                torch.cat([xflag[k] for k in keys]))
+
+    def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int, cat_inputs=None):
         net = self.net
         u_cat = torch.cat([u[k].mean for k in net.keys])
-        xbch_cat = torch.cat([xbch[k] for k in net.keys])
-        xdwt_cat = torch.cat([xdwt[k] for k in net.keys])
-        xflag_cat = torch.cat([xflag[k] for k in net.keys])
+        xbch_cat, xdwt_cat, xflag_cat = cat_inputs or self._alignment_inputs(xbch, xdwt, xflag)
         anneal = self.burnin_anneal(epoch)
         if anneal:
             with torch.no_grad():  # D.Normal(0, std).sample(): not differentiated through
@@ -278,6 +283,7 @@ class SCGLUETrainer(GLUETrainer):
         net = self.net
         x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
         prior = net.prior()
+        cat_inputs = self._alignment_inputs(xbch, xdwt, xflag)
         dsc_stream = None
         if dsc_update is not None:
             # encoders, discriminator pass first: BatchNorm statistics and dropout streams advance
@@ -292,7 +298,9 @@ class SCGLUETrainer(GLUETrainer):
             with torch.cuda.stream(dsc_stream):
                 for k in net.keys:  # allocated on other streams, consumed here
                     u_d[k].mean.record_stream(dsc_stream)
-                _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch)
+                for t in cat_inputs:
+                    t.record_stream(dsc_stream)
+                _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
                 dsc_update(self.lam_align * dsc_loss_d)
             del u_d, dsc_loss_d
         if dsc_only:
@@ -302,7 +310,7 @@ class SCGLUETrainer(GLUETrainer):
             # (``scglue.py:386-390``: zero_grad before the generator pass)
             with torch.no_grad():
                 u, l, usamp = self._encode(x, xrep, dsc_only)
-            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
+            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
             return {"dsc_loss": self.lam_align * dsc_loss}
         # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
         # the data encoders: it runs beside them
@@ -328,7 +336,7 @@ class SCGLUETrainer(GLUETrainer):
                     else self._extra_parts[k][kind] + res
         if dsc_stream is not None:  # the alignment term needs the updated discriminator
             torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
-        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch)
+        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
         sup_loss = self._supervision(u_cat, xlbl)
         x_kl = {k: self._data_kl(u[k], prior, x[k].shape[1]) for k in net.keys}
         extra_comps, extra_terms = self._extra_losses(data, usamp, vsamp, l)
@@ -369,7 +377,7 @@ class SCGLUETrainer(GLUETrainer):
     def _data_kl(self, u: D.Normal, prior: D.Normal, n_features: int) -> torch.Tensor:
         r"""``kl_divergence(u, prior).sum(dim=1).mean() / n_features`` (``scglue.py:349-353``);
         one fused launch each way for the standard-normal prior."""
-        if getattr(self, "_unit_prior", None) and u.mean.is_cuda:
+        if getattr(self, "_unit_prior", None) and u.mean.is_cuda and config.USE_FUSED_OBJECTIVE:
             from .. import ops
             return ops.kl_unit_normal(u.mean, u.stddev, 1.0 / (u.mean.shape[0] * n_features))
         return _kl_to_prior(u, prior) / n_features
@@ -498,15 +506,30 @@ class PairedSCGLUETrainer(SCGLUETrainer):
 
     def _umean(self, usamp):
         r"""Mean embedding of each cell over the modalities it is observed in
-        (``scglue.py:618-622``); computed once per step, on the main stream."""
+        (``scglue.py:618-622``) and the cosine term between every modality's embedding and that
+        mean (``scglue.py:654-660``); computed once per step, on the main stream.  On CUDA both come
+        out of one fused launch (and one for their backward)."""
         keys = self.net.keys
         pmsk = self._pmsk.T  # [n_modalities, B]
+        pf = pmsk.to(torch.float32)
         ustack = torch.stack([usamp[k] for k in keys])
+        if (ustack.is_cuda and not self.normalize_u and len(keys) <= 8 and ustack.shape[2] <= 64
+                and config.USE_FUSED_OBJECTIVE):
+            from .. import ops
+            umean, cos = ops.paired_mean_cos(ustack, pf.contiguous())
+            return ustack, umean, pf, cos
         pstack = pmsk.unsqueeze(2).expand_as(ustack)
         umean = (ustack * pstack).sum(dim=0) / pstack.sum(dim=0)
         if self.normalize_u:
             umean = F.normalize(umean, dim=1)
-        return ustack, umean, pmsk.to(torch.float32)
+        zero = torch.zeros((), device=ustack.device)
+        cos = zero
+        if self.lam_cos:
+            for i in range(len(keys)):
+                n = pf[i].sum()
+                sim = (F.cosine_similarity(ustack[i], umean) * pf[i]).sum() / n.clamp(min=1.0)
+                cos = cos + torch.where(n > 0, 1 - sim, zero)
+        return ustack, umean, pf, cos
 
     def _extra_thunks_for(self, k: str, data, usamp, vsamp, l):
         r"""Joint-cross and real-cross reconstruction of modality ``k`` (``scglue.py:624-652``) as
@@ -518,7 +541,7 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         x, xrep, xbch, *_ = data
         keys = net.keys
         i = keys.index(k)
-        _, umean, pf = self._shared_extra
+        _, umean, pf, _ = self._shared_extra
 
         def subset_nll(usrc, maskf, lam):
             w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
@@ -536,10 +559,8 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         return thunks
 
     def _extra_losses(self, data, usamp, vsamp, l):
-        net = self.net
-        keys = net.keys
-        zero = torch.zeros((), device=net.device)
-        ustack, umean, pf = self._shared_extra
+        keys = self.net.keys
+        ustack, umean, pf, cos = self._shared_extra
         comps, joint_row, real_row = {}, {}, {}
         for k in keys:
             parts = self._extra_parts[k]
@@ -547,12 +568,6 @@ class PairedSCGLUETrainer(SCGLUETrainer):
                 comps[f"joint_{k}"], joint_row[f"joint_{k}"] = parts["joint"], self.modality_weight[k]
             if "real" in parts:
                 comps[f"real_{k}"], real_row[f"real_{k}"] = parts["real"], self.modality_weight[k]
-        cos = zero
-        if self.lam_cos:
-            for i, k in enumerate(keys):
-                n = pf[i].sum()
-                sim = (F.cosine_similarity(ustack[i], umean) * pf[i]).sum() / n.clamp(min=1.0)
-                cos = cos + torch.where(n > 0, 1 - sim, zero)
         comps["cos"] = cos
         return comps, {"joint_cross_loss": (self.lam_joint_cross, joint_row),
                        "real_cross_loss": (self.lam_real_cross, real_row),

@@ -274,6 +274,47 @@ def kl_unit_normal(mean: torch.Tensor, std: torch.Tensor, scale: float = 1.0) ->
     return _KlUnitNormalFn.apply(mean, std, float(scale))
 
 
+class _PairedMeanCosFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ustack, pmask):
+        dev = ustack.device
+        M, B, K = ustack.shape
+        umean = torch.empty(B, K, dtype=torch.float32, device=dev)
+        cos = torch.empty((), dtype=torch.float32, device=dev)
+        n_k = torch.empty(M, dtype=torch.float32, device=dev)
+        check(_lib.lib().glue_paired_mean_cos_fwd(ptr(ustack), ptr(pmask), M, B, K, ptr(umean), ptr(cos),
+                                                  ptr(n_k), current_stream(dev)), "paired_mean_cos_fwd")
+        ctx.save_for_backward(ustack, pmask, n_k)
+        return umean, cos
+
+    @staticmethod
+    def backward(ctx, g_umean, g_cos):
+        ustack, pmask, n_k = ctx.saved_tensors
+        dev = ustack.device
+        M, B, K = ustack.shape
+        g_umean = None if g_umean is None else _f32(g_umean, "grad_umean")
+        g_cos = None if g_cos is None else _f32(g_cos, "grad_cos")
+        g_u = torch.empty_like(ustack)
+        check(_lib.lib().glue_paired_mean_cos_bwd(ptr(ustack), ptr(pmask), ptr(n_k), M, B, K, ptr(g_umean),
+                                                  ptr(g_cos), ptr(g_u), current_stream(dev)),
+              "paired_mean_cos_bwd")
+        return g_u, None
+
+
+def paired_mean_cos(ustack: torch.Tensor, pmask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    r"""``(umean, cos_loss)`` of paired cells (``scglue/models/scglue.py:618-622, 654-660``):
+    ``umean = (ustack * pmask).sum(0) / pmask.sum(0)`` and
+    ``cos_loss = sum_k [n_k > 0] (1 - (cosine_similarity(ustack[k], umean) * pmask[k]).sum() / n_k)``
+    in one launch each way.  ``ustack``: ``[M, B, K]``, ``pmask``: ``[M, B]`` fp32 0 / 1."""
+    require_cuda(ustack, pmask)
+    ustack, pmask = _f32(ustack, "ustack"), _f32(pmask, "pmask")
+    if ustack.dim() != 3 or pmask.shape != ustack.shape[:2]:
+        raise ValueError("`ustack` must be [M, B, K] and `pmask` [M, B]")
+    if ustack.shape[0] > 8 or ustack.shape[2] > 64:
+        raise ValueError("glue_b200 paired mean supports <= 8 modalities and latent_dim <= 64")
+    return _PairedMeanCosFn.apply(ustack, pmask)
+
+
 # ------------------------------------------------- edge-partitioned GraphConv (atlas scale)
 
 

@@ -54,6 +54,8 @@ class _Settings:
         MULTI_STREAM=True,
         # run the discriminator update beside the generator pass's encoders / decoders
         OVERLAP_DISCRIMINATOR=True,
+        # fused kernels for the scalar tail of the objective (data-encoder KL, paired mean + cosine term)
+        USE_FUSED_OBJECTIVE=True,
     )
 
     def __init__(self) -> None:

@@ -225,6 +225,22 @@ int glue_kl_unit_normal_bwd(const float *mean, const float *std_, int64_t n, flo
                             const float *upstream, float *grad_mean, float *grad_std, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Paired cells: mean embedding over the modalities a cell is observed in and the
+ * cosine term of PairedSCGLUETrainer (scglue/models/scglue.py:618-622, 654-660):
+ *   umean_i  = sum_k p_ki u_ki / sum_k p_ki
+ *   cos_loss = sum_k [n_k > 0] (1 - sum_i p_ki cos(u_ki, umean_i) / max(n_k, 1)),  n_k = sum_i p_ki
+ * with cos as F.cosine_similarity (eps = 1e-8).  ustack: [M, B, K], pmask: [M, B]
+ * (0 / 1 as fp32), umean: [B, K], cos_loss: [1], n_k: [M]; M <= 8, K <= 64.
+ * bwd: grad_ustack [M, B, K] from grad_umean [B, K] (may be NULL) and the device
+ * scalar grad_cos (may be NULL).  One block each way, fixed summation order.
+ * ------------------------------------------------------------------------- */
+int glue_paired_mean_cos_fwd(const float *ustack, const float *pmask, int32_t n_modalities, int64_t B,
+                             int32_t K, float *umean, float *cos_loss, float *n_k, void *stream);
+int glue_paired_mean_cos_bwd(const float *ustack, const float *pmask, const float *n_k,
+                             int32_t n_modalities, int64_t B, int32_t K, const float *grad_umean,
+                             const float *grad_cos, float *grad_ustack, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
  * M = 128) steps on caller-built shared-memory operand images and return the
  * accumulator tile out[128][N].  a_img / b_img are device buffers copied

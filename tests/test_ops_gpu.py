@@ -389,3 +389,41 @@ def test_kl_unit_normal_vs_torch_distributions(ops, B, K):
     assert_close(g[1], rg[1], TOL, "d kl / d std")
     out2 = ops.kl_unit_normal(dm, ds, 1.0 / (B * n_features))
     assert torch.equal(out, out2), "fixed summation order"
+
+
+# ------------------------------------------------------------------ paired cells: mean + cosine term
+@pytest.mark.parametrize("M,B,K,empty_mod", [(2, 128, 50, False), (3, 37, 64, False), (2, 16, 8, True),
+                                             (2, 1000, 50, False)])
+def test_paired_mean_cos_vs_torch(ops, M, B, K, empty_mod):
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(M * 1000 + B)
+    ustack = torch.randn(M, B, K, generator=gen).requires_grad_(True)
+    pf = (torch.rand(M, B, generator=gen) < 0.7).float()
+    pf[0, pf.sum(0) == 0] = 1.0  # every cell is observed somewhere
+    if empty_mod:
+        pf[1] = 0.0              # a modality without cells in this minibatch: its term is skipped
+        pf[0] = 1.0
+    w = torch.randn(B, K, generator=gen)  # a consumer of umean (the joint-cross decoder call)
+
+    def reference(us):
+        pstack = pf.unsqueeze(2).expand_as(us)
+        umean = (us * pstack).sum(dim=0) / pstack.sum(dim=0)
+        cos = torch.zeros(())
+        for i in range(M):
+            n = pf[i].sum()
+            sim = (F.cosine_similarity(us[i], umean) * pf[i]).sum() / n.clamp(min=1.0)
+            cos = cos + torch.where(n > 0, 1 - sim, torch.zeros(()))
+        return umean, cos
+
+    umean_r, cos_r = reference(ustack)
+    (g_r,) = torch.autograd.grad((umean_r * w).sum() + 0.7 * cos_r, [ustack])
+    du = ustack.detach().to(DEV).requires_grad_(True)
+    umean, cos = ops.paired_mean_cos(du, pf.to(DEV))
+    (g,) = torch.autograd.grad((umean * w.to(DEV)).sum() + 0.7 * cos, [du])
+    assert_close(umean, umean_r, TOL, "umean")
+    assert_close(cos, cos_r, TOL, "cos_loss")
+    assert_close(g, g_r, TOL, "d / d ustack")
+    # only one of the two outputs used downstream
+    (g_only_cos,) = torch.autograd.grad(ops.paired_mean_cos(du, pf.to(DEV))[1], [du])
+    (g_only_cos_r,) = torch.autograd.grad(reference(ustack)[1], [ustack])
+    assert_close(g_only_cos, g_only_cos_r, TOL, "d cos / d ustack")
