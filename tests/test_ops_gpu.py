@@ -426,4 +426,7 @@ def test_paired_mean_cos_vs_torch(ops, M, B, K, empty_mod):
     # only one of the two outputs used downstream
     (g_only_cos,) = torch.autograd.grad(ops.paired_mean_cos(du, pf.to(DEV))[1], [du])
     (g_only_cos_r,) = torch.autograd.grad(reference(ustack)[1], [ustack])
-    assert_close(g_only_cos, g_only_cos_r, TOL, "d cos / d ustack")
+    if empty_mod:  # umean == ustack[0]: the cosine is 1 and its gradient vanishes (rounding noise only)
+        assert g_only_cos.abs().max().item() < 1e-5 and g_only_cos_r.abs().max().item() < 1e-5
+    else:
+        assert_close(g_only_cos, g_only_cos_r, TOL, "d cos / d ustack")
