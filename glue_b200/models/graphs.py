@@ -117,22 +117,12 @@ class StepGraphs:
             self._capture(entry, engine, data)
             if entry["graph"] is None:
                 return tr.eager_train_step(engine, data)
-        self._stage_inputs(entry["inputs"], data)
+        for static, fresh in zip(entry["inputs"], data):
+            static.copy_(fresh, non_blocking=True)
         tr.anneal_buffer.fill_(anneal)
         entry["graph"].replay()
         self.replays += 1
         return entry["outputs"]
-
-    @staticmethod
-    def _stage_inputs(statics: List[torch.Tensor], data: List[torch.Tensor]) -> None:
-        r"""Minibatch -> the capture's static input buffers.  Device-resident minibatches go through
-        one multi-tensor copy (a few launches) instead of one memcpy node per tensor: fourteen
-        serialized copies cost ~65 us in front of a 1.1 ms step."""
-        if all(t.is_cuda and t.device == s.device and t.dtype == s.dtype for s, t in zip(statics, data)):
-            torch._foreach_copy_(statics, list(data))
-        else:
-            for static, fresh in zip(statics, data):
-                static.copy_(fresh, non_blocking=True)
 
     def _capture(self, entry: Dict[str, Any], engine, data: List[torch.Tensor]) -> None:
         tr = self.trainer
