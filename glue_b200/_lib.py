@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "glue_graphdec_bce_fwd",
     "glue_graphdec_bwd",
     "glue_graphdec_bwd_scaled",
+    "glue_graphdec_sort_incidence",
+    "glue_graphdec_bwd_sorted",
     "glue_decoder_workspace_bytes",
     "glue_decoder_nll_fwd_bwd",
     "glue_decoder_nll_fwd",
@@ -129,6 +131,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_graphdec_bwd_scaled.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
         c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.glue_graphdec_sort_incidence.restype = c_int32
+    lib.glue_graphdec_sort_incidence.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]
+    lib.glue_graphdec_bwd_sorted.restype = c_int32
+    lib.glue_graphdec_bwd_sorted.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_size_t, c_void_p]
 
     lib.glue_decoder_workspace_bytes.restype = c_size_t
     lib.glue_decoder_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
@@ -159,7 +167,7 @@ def _declare(lib: ctypes.CDLL) -> None:
                                             c_void_p, c_void_p]
     lib.glue_paired_mean_cos_fwd.restype = c_int32
     lib.glue_paired_mean_cos_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p,
-                                             c_void_p, c_void_p, c_void_p]
+                                             c_void_p, c_void_p, c_void_p, c_void_p]
     lib.glue_paired_mean_cos_bwd.restype = c_int32
     lib.glue_paired_mean_cos_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
                                              c_void_p, c_void_p, c_void_p, c_void_p]

@@ -464,38 +464,74 @@ extern "C" int glue_graphdec_bwd(const float* v, const int64_t* eidx, const floa
                                  const float* coef, int64_t E, int64_t V, int32_t K, float* grad_v,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+namespace {
+struct GdSortBufs {
+    int32_t *k_in, *k_out, *p_in, *p_out;
+    void* temp;
+    size_t temp_bytes;
+};
+GdSortBufs gd_sort_bufs(void* workspace, int64_t E) {
+    char* ws = (char*)workspace + align_up((size_t)148 * 16 * 4 * sizeof(float), 256);
+    const size_t seg = align_up((size_t)E * 8, 256);
+    GdSortBufs b;
+    b.k_in = (int32_t*)ws, b.k_out = (int32_t*)(ws + seg);
+    b.p_in = (int32_t*)(ws + 2 * seg), b.p_out = (int32_t*)(ws + 3 * seg);
+    b.temp = ws + 4 * seg, b.temp_bytes = sort_temp_bytes(2 * E);
+    return b;
+}
+}  // namespace
+
+// The backward pass sums, per vertex, over its incident edges of the minibatch: (vertex, edge)
+// incidences sorted by vertex.  That order depends on `eidx` only, so it can be prepared right after
+// the forward kernel (off the critical path of the backward pass) in the same workspace, which then
+// has to stay alive until glue_graphdec_bwd_sorted has run.
+extern "C" int glue_graphdec_sort_incidence(const int64_t* eidx, int64_t E, int64_t V, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    if (!eidx || E <= 0 || V <= 0 || !workspace) return GLUE_E_BADARG;
+    if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
+    if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const GdSortBufs b = gd_sort_bufs(workspace, E);
+    const int threads = 256;
+    graphdec_incidence_kernel<<<(unsigned)((2 * E + threads - 1) / threads), threads, 0, st>>>(eidx, E, b.k_in,
+                                                                                               b.p_in);
+    GLUE_CHECK_LAUNCH();
+    size_t temp_bytes = b.temp_bytes;
+    GLUE_CUDA(cub::DeviceRadixSort::SortPairs(b.temp, temp_bytes, b.k_in, b.k_out, b.p_in, b.p_out, (int)(2 * E), 0,
+                                              bits_for(V), st));
+    return 0;
+}
+
 // `upstream` (device scalar, may be NULL) multiplies every coefficient: lets
 // autograd hand over d L / d loss without an extra pass over grad_v.
+extern "C" int glue_graphdec_bwd_sorted(const float* v, const int64_t* eidx, const float* esgn, const float* coef,
+                                        const float* upstream, int64_t E, int64_t V, int32_t K, float* grad_v,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!v || !eidx || !esgn || !coef || !grad_v || E <= 0 || V <= 0 || K <= 0 || !workspace)
+        return GLUE_E_BADARG;
+    if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
+    if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const GdSortBufs b = gd_sort_bufs(workspace, E);
+    GLUE_CUDA(cudaMemsetAsync(grad_v, 0, (size_t)V * K * sizeof(float), st));
+    const int64_t groups = 2 * E;
+    const int64_t blocks = (groups * GD_LPE + GD_THREADS - 1) / GD_THREADS;
+    graphdec_bwd_kernel<<<(unsigned)blocks, GD_THREADS, 0, st>>>(v, eidx, esgn, coef, upstream, b.k_out, b.p_out, E,
+                                                                 K, grad_v);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int glue_graphdec_bwd_scaled(const float* v, const int64_t* eidx, const float* esgn,
                                         const float* coef, const float* upstream, int64_t E,
                                         int64_t V, int32_t K, float* grad_v, void* workspace,
                                         size_t workspace_bytes, void* stream) {
     if (!v || !eidx || !esgn || !coef || !grad_v || E <= 0 || V <= 0 || K <= 0 || !workspace)
         return GLUE_E_BADARG;
-    if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
-    if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    char* ws = (char*)workspace + align_up((size_t)148 * 16 * 4 * sizeof(float), 256);
-    const size_t seg = align_up((size_t)E * 8, 256);
-    int32_t* k_in = (int32_t*)ws;
-    int32_t* k_out = (int32_t*)(ws + seg);
-    int32_t* p_in = (int32_t*)(ws + 2 * seg);
-    int32_t* p_out = (int32_t*)(ws + 3 * seg);
-    void* temp = ws + 4 * seg;
-    size_t temp_bytes = sort_temp_bytes(2 * E);
-    const int threads = 256;
-    graphdec_incidence_kernel<<<(unsigned)((2 * E + threads - 1) / threads), threads, 0, st>>>(
-        eidx, E, k_in, p_in);
-    GLUE_CHECK_LAUNCH();
-    GLUE_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, p_in, p_out,
-                                              (int)(2 * E), 0, bits_for(V), st));
-    GLUE_CUDA(cudaMemsetAsync(grad_v, 0, (size_t)V * K * sizeof(float), st));
-    const int64_t groups = 2 * E;
-    const int64_t blocks = (groups * GD_LPE + GD_THREADS - 1) / GD_THREADS;
-    graphdec_bwd_kernel<<<(unsigned)blocks, GD_THREADS, 0, st>>>(v, eidx, esgn, coef, upstream,
-                                                                 k_out, p_out, E, K, grad_v);
-    GLUE_CHECK_LAUNCH();
-    return 0;
+    const int rc = glue_graphdec_sort_incidence(eidx, E, V, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return glue_graphdec_bwd_sorted(v, eidx, esgn, coef, upstream, E, V, K, grad_v, workspace, workspace_bytes,
+                                    stream);
 }
 
 extern "C" int glue_graphdec_bwd(const float* v, const int64_t* eidx, const float* esgn,

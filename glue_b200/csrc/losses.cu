@@ -51,10 +51,11 @@ __global__ void __launch_bounds__(256) kl_unit_normal_bwd_kernel(const float* __
 //   cos_loss = sum_k [n_k > 0] (1 - sum_i p_ki cos(u_ki, m_i) / max(n_k, 1)),   n_k = sum_i p_ki,
 //   m_i = sum_k p_ki u_ki / sum_k p_ki,   cos(x, y) = x.y / (max(|x|, eps) max(|y|, eps)), eps = 1e-8
 // (F.cosine_similarity).  Through torch ops that is ~30 launches forward and ~80 backward on the
-// serial tail of the step.  One block each way, one warp per cell, fixed summation order.
+// serial tail of the step.  One warp per cell; the sums over cells are taken by one block in a
+// fixed order.
 // ---------------------------------------------------------------------------------------------
 constexpr int PM_MAX_MOD = 8;
-constexpr int PM_THREADS = 1024;
+constexpr int PM_ROWS = 8;  // cells (warps) per block
 constexpr float PM_EPS = 1e-8f;
 
 struct PmRow {
@@ -80,52 +81,54 @@ __device__ __forceinline__ PmRow pm_mean(const float* __restrict__ u, const floa
     return r;
 }
 
-__global__ void __launch_bounds__(PM_THREADS) paired_mean_cos_fwd_kernel(const float* __restrict__ u,
-                                                                         const float* __restrict__ pf, int M, int B,
-                                                                         int K, float* __restrict__ umean,
-                                                                         float* __restrict__ cos_out,
-                                                                         float* __restrict__ nk_out) {
-    __shared__ float part_s[PM_THREADS / 32][PM_MAX_MOD], part_n[PM_THREADS / 32][PM_MAX_MOD];
+// rows: one warp per cell, PM_ROWS cells per block; writes umean and p_ki cos(u_ki, m_i)
+__global__ void __launch_bounds__(PM_ROWS * 32) paired_mean_cos_rows_kernel(const float* __restrict__ u,
+                                                                            const float* __restrict__ pf, int M, int B,
+                                                                            int K, float* __restrict__ umean,
+                                                                            float* __restrict__ psim) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc_s[PM_MAX_MOD], acc_n[PM_MAX_MOD];
-#pragma unroll
-    for (int k = 0; k < PM_MAX_MOD; ++k) acc_s[k] = acc_n[k] = 0.f;
-    for (int i = warp; i < B; i += PM_THREADS / 32) {
+    for (int i = blockIdx.x * PM_ROWS + warp; i < B; i += gridDim.x * PM_ROWS) {
         const PmRow r = pm_mean(u, pf, M, B, K, i, lane);
         if (lane < K) umean[(int64_t)i * K + lane] = r.m[0];
         if (lane + 32 < K) umean[(int64_t)i * K + lane + 32] = r.m[1];
-#pragma unroll
-        for (int k = 0; k < PM_MAX_MOD; ++k) {
-            if (k < M) {
-                const float p = pf[(int64_t)k * B + i];
-                const float* row = u + ((int64_t)k * B + i) * K;
-                const float x0 = lane < K ? row[lane] : 0.f, x1 = lane + 32 < K ? row[lane + 32] : 0.f;
-                const float dot = warp_sum(fmaf(x0, r.m[0], x1 * r.m[1]));
-                const float nu = sqrtf(warp_sum(fmaf(x0, x0, x1 * x1)));
-                const float sim = dot / (fmaxf(nu, PM_EPS) * fmaxf(r.nm, PM_EPS));
-                acc_s[k] = fmaf(p, sim, acc_s[k]);
-                acc_n[k] += p;
-            }
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < PM_MAX_MOD; ++k) part_s[warp][k] = acc_s[k], part_n[warp][k] = acc_n[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float cosv = 0.f;
         for (int k = 0; k < M; ++k) {
-            float s = 0.f, n = 0.f;
-            for (int w = 0; w < PM_THREADS / 32; ++w) s += part_s[w][k], n += part_n[w][k];
-            nk_out[k] = n;
-            if (n > 0.f) cosv += 1.f - s / fmaxf(n, 1.f);
+            const float p = pf[(int64_t)k * B + i];
+            const float* row = u + ((int64_t)k * B + i) * K;
+            const float x0 = lane < K ? row[lane] : 0.f, x1 = lane + 32 < K ? row[lane + 32] : 0.f;
+            const float dot = warp_sum(fmaf(x0, r.m[0], x1 * r.m[1]));
+            const float nu = sqrtf(warp_sum(fmaf(x0, x0, x1 * x1)));
+            const float sim = dot / (fmaxf(nu, PM_EPS) * fmaxf(r.nm, PM_EPS));
+            if (lane == 0) psim[(int64_t)k * B + i] = p * sim;
         }
-        cos_out[0] = cosv;
     }
 }
 
-__global__ void __launch_bounds__(PM_THREADS) paired_mean_cos_bwd_kernel(const float* __restrict__ u,
+// n_k, the masked sums of the cosines and the loss: one block, fixed order
+__global__ void __launch_bounds__(256) paired_cos_reduce_kernel(const float* __restrict__ pf,
+                                                                const float* __restrict__ psim, int M, int B,
+                                                                float* __restrict__ cos_out, float* __restrict__ nk_out) {
+    __shared__ float red_s[8], red_n[8];
+    __shared__ float cosv;
+    if (threadIdx.x == 0) cosv = 0.f;
+    for (int k = 0; k < M; ++k) {
+        float s = 0.f, n = 0.f;
+        for (int i = threadIdx.x; i < B; i += 256) s += psim[(int64_t)k * B + i], n += pf[(int64_t)k * B + i];
+        s = warp_sum(s), n = warp_sum(n);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = s, red_n[threadIdx.x >> 5] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float ts = 0.f, tn = 0.f;
+            for (int w = 0; w < 8; ++w) ts += red_s[w], tn += red_n[w];
+            nk_out[k] = tn;
+            if (tn > 0.f) cosv += 1.f - ts / fmaxf(tn, 1.f);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cos_out[0] = cosv;
+}
+
+__global__ void __launch_bounds__(PM_ROWS * 32) paired_mean_cos_bwd_kernel(const float* __restrict__ u,
                                                                          const float* __restrict__ pf,
                                                                          const float* __restrict__ nk, int M, int B,
                                                                          int K, const float* __restrict__ g_umean,
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(PM_THREADS) paired_mean_cos_bwd_kernel(const f
                                                                          float* __restrict__ g_u) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float gc = g_cos ? g_cos[0] : 0.f;
-    for (int i = warp; i < B; i += PM_THREADS / 32) {
+    for (int i = blockIdx.x * PM_ROWS + warp; i < B; i += gridDim.x * PM_ROWS) {
         const PmRow r = pm_mean(u, pf, M, B, K, i, lane);
         const float dm = fmaxf(r.nm, PM_EPS);
         // gradient reaching m_i: from the consumers of umean and from every cosine it takes part in
@@ -197,11 +200,16 @@ extern "C" int glue_kl_unit_normal_bwd(const float* mean, const float* std_, int
 }
 
 extern "C" int glue_paired_mean_cos_fwd(const float* ustack, const float* pmask, int32_t n_modalities, int64_t B,
-                                        int32_t K, float* umean, float* cos_loss, float* n_k, void* stream) {
-    if (!ustack || !pmask || !umean || !cos_loss || !n_k || B <= 0) return GLUE_E_BADARG;
+                                        int32_t K, float* umean, float* cos_loss, float* n_k, float* psim,
+                                        void* stream) {
+    if (!ustack || !pmask || !umean || !cos_loss || !n_k || !psim || B <= 0) return GLUE_E_BADARG;
     if (n_modalities < 1 || n_modalities > glue::PM_MAX_MOD || K < 1 || K > 64) return GLUE_E_UNSUPPORTED;
-    glue::paired_mean_cos_fwd_kernel<<<1, glue::PM_THREADS, 0, (cudaStream_t)stream>>>(
-        ustack, pmask, n_modalities, (int)B, K, umean, cos_loss, n_k);
+    const int grid = (int)((B + glue::PM_ROWS - 1) / glue::PM_ROWS);
+    glue::paired_mean_cos_rows_kernel<<<grid, glue::PM_ROWS * 32, 0, (cudaStream_t)stream>>>(
+        ustack, pmask, n_modalities, (int)B, K, umean, psim);
+    GLUE_CHECK_LAUNCH();
+    glue::paired_cos_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pmask, psim, n_modalities, (int)B, cos_loss,
+                                                                      n_k);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
@@ -211,7 +219,8 @@ extern "C" int glue_paired_mean_cos_bwd(const float* ustack, const float* pmask,
                                         const float* grad_cos, float* grad_ustack, void* stream) {
     if (!ustack || !pmask || !n_k || !grad_ustack || B <= 0) return GLUE_E_BADARG;
     if (n_modalities < 1 || n_modalities > glue::PM_MAX_MOD || K < 1 || K > 64) return GLUE_E_UNSUPPORTED;
-    glue::paired_mean_cos_bwd_kernel<<<1, glue::PM_THREADS, 0, (cudaStream_t)stream>>>(
+    const int grid = (int)((B + glue::PM_ROWS - 1) / glue::PM_ROWS);
+    glue::paired_mean_cos_bwd_kernel<<<grid, glue::PM_ROWS * 32, 0, (cudaStream_t)stream>>>(
         ustack, pmask, n_k, n_modalities, (int)B, K, grad_umean, grad_cos, grad_ustack);
     GLUE_CHECK_LAUNCH();
     return 0;

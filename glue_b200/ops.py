@@ -282,8 +282,9 @@ class _PairedMeanCosFn(torch.autograd.Function):
         umean = torch.empty(B, K, dtype=torch.float32, device=dev)
         cos = torch.empty((), dtype=torch.float32, device=dev)
         n_k = torch.empty(M, dtype=torch.float32, device=dev)
+        psim = torch.empty(M, B, dtype=torch.float32, device=dev)
         check(_lib.lib().glue_paired_mean_cos_fwd(ptr(ustack), ptr(pmask), M, B, K, ptr(umean), ptr(cos),
-                                                  ptr(n_k), current_stream(dev)), "paired_mean_cos_fwd")
+                                                  ptr(n_k), ptr(psim), current_stream(dev)), "paired_mean_cos_fwd")
         ctx.save_for_backward(ustack, pmask, n_k)
         return umean, cos
 
@@ -413,18 +414,22 @@ class _GraphNllFn(torch.autograd.Function):
         check(_lib.lib().glue_graphdec_bce_fwd(
             ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), n_edges, vnum, k, ptr(loss), None, None,
             ptr(coef), ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bce_fwd")
-        ctx.save_for_backward(v, eidx, esgn, coef)
+        if ctx.needs_input_grad[0]:
+            # the vertex-sorted incidence list of the backward pass depends on `eidx` only: sort it
+            # now, beside the rest of the forward pass, instead of on the tail of the backward pass
+            check(_lib.lib().glue_graphdec_sort_incidence(ptr(eidx), n_edges, vnum, ptr(ws), ws.numel(),
+                                                          current_stream(dev)), "graphdec_sort_incidence")
+        ctx.save_for_backward(v, eidx, esgn, coef, ws)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        v, eidx, esgn, coef = ctx.saved_tensors
+        v, eidx, esgn, coef, ws = ctx.saved_tensors
         dev = v.device
         n_edges, (vnum, k) = eidx.shape[1], v.shape
         grad_v = torch.empty_like(v)
-        ws = _graphdec_ws(n_edges, vnum, dev)
         up = _f32(grad_out, "grad_out")
-        check(_lib.lib().glue_graphdec_bwd_scaled(
+        check(_lib.lib().glue_graphdec_bwd_sorted(
             ptr(v), ptr(eidx), ptr(esgn), ptr(coef), ptr(up), n_edges, vnum, k, ptr(grad_v),
             ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bwd")
         return grad_v, None, None, None

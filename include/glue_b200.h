@@ -127,6 +127,15 @@ int glue_graphdec_bwd_scaled(const float *v, const int64_t *eidx, const float *e
                              const float *coef, const float *upstream, int64_t E, int64_t V,
                              int32_t K, float *grad_v, void *workspace, size_t workspace_bytes,
                              void *stream);
+/* The two halves of glue_graphdec_bwd_scaled.  The vertex-sorted incidence list depends on
+ * `eidx` only: glue_graphdec_sort_incidence can run right after the forward kernel (same
+ * workspace, kept alive), leaving memset + segmented reduction for the backward pass. */
+int glue_graphdec_sort_incidence(const int64_t *eidx, int64_t E, int64_t V, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+int glue_graphdec_bwd_sorted(const float *v, const int64_t *eidx, const float *esgn,
+                             const float *coef, const float *upstream, int64_t E, int64_t V,
+                             int32_t K, float *grad_v, void *workspace, size_t workspace_bytes,
+                             void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused data decoders -- replace forward + log_prob + (nan)mean + backward of
@@ -230,12 +239,14 @@ int glue_kl_unit_normal_bwd(const float *mean, const float *std_, int64_t n, flo
  *   umean_i  = sum_k p_ki u_ki / sum_k p_ki
  *   cos_loss = sum_k [n_k > 0] (1 - sum_i p_ki cos(u_ki, umean_i) / max(n_k, 1)),  n_k = sum_i p_ki
  * with cos as F.cosine_similarity (eps = 1e-8).  ustack: [M, B, K], pmask: [M, B]
- * (0 / 1 as fp32), umean: [B, K], cos_loss: [1], n_k: [M]; M <= 8, K <= 64.
- * bwd: grad_ustack [M, B, K] from grad_umean [B, K] (may be NULL) and the device
- * scalar grad_cos (may be NULL).  One block each way, fixed summation order.
+ * (0 / 1 as fp32), umean: [B, K], cos_loss: [1], n_k: [M], psim: [M, B] scratch;
+ * M <= 8, K <= 64.  bwd: grad_ustack [M, B, K] from grad_umean [B, K] (may be NULL)
+ * and the device scalar grad_cos (may be NULL).  One warp per cell; sums over cells
+ * in a fixed order.
  * ------------------------------------------------------------------------- */
 int glue_paired_mean_cos_fwd(const float *ustack, const float *pmask, int32_t n_modalities, int64_t B,
-                             int32_t K, float *umean, float *cos_loss, float *n_k, void *stream);
+                             int32_t K, float *umean, float *cos_loss, float *n_k, float *psim,
+                             void *stream);
 int glue_paired_mean_cos_bwd(const float *ustack, const float *pmask, const float *n_k,
                              int32_t n_modalities, int64_t B, int32_t K, const float *grad_umean,
                              const float *grad_cos, float *grad_ustack, void *stream);
