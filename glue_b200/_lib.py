@@ -42,6 +42,8 @@ EXPORTED_SYMBOLS = (
     "glue_kl_unit_normal_bwd",
     "glue_paired_mean_cos_fwd",
     "glue_paired_mean_cos_bwd",
+    "glue_act_bn_dropout_fwd",
+    "glue_act_bn_dropout_bwd",
     "glue_tc_selftest",
     "glue_tc_set_trace",
 )
@@ -171,6 +173,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_paired_mean_cos_bwd.restype = c_int32
     lib.glue_paired_mean_cos_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
                                              c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.glue_act_bn_dropout_fwd.restype = c_int32
+    lib.glue_act_bn_dropout_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_int64, c_int32, c_float, c_float, c_float, c_float, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.glue_act_bn_dropout_bwd.restype = c_int32
+    lib.glue_act_bn_dropout_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                            c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.glue_tc_set_trace.restype = None
     lib.glue_tc_set_trace.argtypes = [c_void_p]
 

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..num import EPS
+from ..utils import config
 from . import glue
 from .nn import GraphConv
 from .prob import ZIN, Bernoulli, EdgeBernoulli, FusedDataDistribution
@@ -89,6 +90,16 @@ class DataEncoder(glue.DataEncoder):
         self.loc = torch.nn.Linear(width, out_features)
         self.std_lin = torch.nn.Linear(width, out_features)
 
+    def _dropout_state(self, layer: int, device: torch.device) -> torch.Tensor:
+        r"""Philox state of hidden block ``layer`` for the fused kernel (seed drawn from torch's
+        generator at first use, call counter advanced on the device); not part of ``state_dict``."""
+        name = f"_dropout_state_{layer}"
+        state = getattr(self, name, None)
+        if state is None or state.device != device:
+            state = ops.new_dropout_state(device)
+            self.register_buffer(name, state, persistent=False)
+        return state
+
     def compute_l(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         raise NotImplementedError  # pragma: no cover
 
@@ -113,9 +124,16 @@ class DataEncoder(glue.DataEncoder):
             ptr = self.normalize(x, l)
         for layer in range(self.h_depth):
             ptr = getattr(self, f"linear_{layer}")(ptr)
-            ptr = getattr(self, f"act_{layer}")(ptr)
-            ptr = getattr(self, f"bn_{layer}")(ptr)
-            ptr = getattr(self, f"dropout_{layer}")(ptr)
+            act, bn = getattr(self, f"act_{layer}"), getattr(self, f"bn_{layer}")
+            dropout = getattr(self, f"dropout_{layer}")
+            if (config.USE_FUSED_MLP and ptr.is_cuda and ptr.dtype == torch.float32 and bn.training
+                    and bn.momentum is not None and type(act) is torch.nn.LeakyReLU):
+                # activation + batch normalisation + dropout in one launch each way
+                p = dropout.p if dropout.training else 0.0
+                ptr = ops.act_bn_dropout(ptr, bn, p, self._dropout_state(layer, ptr.device) if p > 0 else None,
+                                         negative_slope=act.negative_slope)
+            else:
+                ptr = dropout(bn(act(ptr)))
         loc = self.loc(ptr)
         std = F.softplus(self.std_lin(ptr)) + EPS
         return D.Normal(loc, std, validate_args=False), l

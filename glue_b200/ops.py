@@ -316,6 +316,74 @@ def paired_mean_cos(ustack: torch.Tensor, pmask: torch.Tensor) -> Tuple[torch.Te
     return _PairedMeanCosFn.apply(ustack, pmask)
 
 
+# ------------------------------------------------------------- hidden block of the data encoders
+
+
+class _ActBnDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, num_batches_tracked, rng_state,
+                slope, eps, momentum, p):
+        dev = z.device
+        B, H = z.shape
+        out = torch.empty_like(z)
+        mean = torch.empty(H, dtype=torch.float32, device=dev)
+        rstd = torch.empty(H, dtype=torch.float32, device=dev)
+        keep = torch.empty(B, H, dtype=torch.uint8, device=dev) if p > 0 else None
+        check(_lib.lib().glue_act_bn_dropout_fwd(
+            ptr(z), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(num_batches_tracked),
+            ptr(rng_state), B, H, slope, eps, momentum, p, ptr(out), ptr(mean), ptr(rstd), ptr(keep),
+            current_stream(dev)), "act_bn_dropout_fwd")
+        ctx.save_for_backward(z, gamma, mean, rstd, keep)
+        ctx.slope, ctx.p = slope, p
+        ctx.mark_non_differentiable(mean, rstd)
+        return out, mean, rstd, keep
+
+    @staticmethod
+    def backward(ctx, g_out, _g_mean, _g_rstd, _g_keep):
+        z, gamma, mean, rstd, keep = ctx.saved_tensors
+        dev = z.device
+        B, H = z.shape
+        g_out = _f32(g_out, "grad_out")
+        g_z = torch.empty_like(z)
+        g_gamma = torch.empty(H, dtype=torch.float32, device=dev)
+        g_beta = torch.empty(H, dtype=torch.float32, device=dev)
+        check(_lib.lib().glue_act_bn_dropout_bwd(
+            ptr(z), ptr(gamma), ptr(mean), ptr(rstd), ptr(keep), ptr(g_out), B, H, ctx.slope, ctx.p,
+            ptr(g_z), ptr(g_gamma), ptr(g_beta), current_stream(dev)), "act_bn_dropout_bwd")
+        return g_z, g_gamma, g_beta, None, None, None, None, None, None, None, None
+
+
+def act_bn_dropout(z: torch.Tensor, bn: torch.nn.BatchNorm1d, p: float, rng_state: Optional[torch.Tensor],
+                   negative_slope: float = 0.2, return_aux: bool = False):
+    r"""``dropout(bn(leaky_relu(z)))`` of a training-mode hidden block (``scglue/models/sc.py:62-178``)
+    in one launch each way.  ``bn``'s running statistics and batch counter are updated as
+    ``torch.nn.BatchNorm1d`` does; the keep mask is drawn from Philox4x32-10 keyed by
+    ``rng_state`` (``uint64 [3]``: seed, call counter, ticket; advanced on the device).
+    ``return_aux`` also returns ``(batch mean, 1 / sqrt(var + eps), keep mask)``."""
+    require_cuda(z, bn.weight, bn.bias)
+    if not bn.training or not bn.affine or bn.momentum is None:
+        raise ValueError("act_bn_dropout implements training-mode affine BatchNorm1d with a fixed momentum")
+    if p > 0 and rng_state is None:
+        raise ValueError("`rng_state` is required when p > 0")
+    z = _f32(z, "z")
+    if z.dim() != 2 or z.shape[1] != bn.num_features:
+        raise ValueError("`z` must be [batch, num_features]")
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    nbt = bn.num_batches_tracked if bn.track_running_stats else None
+    out, mean, rstd, keep = _ActBnDropoutFn.apply(z, bn.weight, bn.bias, rm, rv, nbt, rng_state,
+                                                  float(negative_slope), float(bn.eps), float(bn.momentum),
+                                                  float(p))
+    return (out, mean, rstd, keep) if return_aux else out
+
+
+def new_dropout_state(device, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    r"""``uint64 [3]`` Philox state for :func:`act_bn_dropout` (stored as int64): a seed drawn from
+    torch's (CPU) generator, call counter 0, ticket 0."""
+    seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, generator=generator)
+    return torch.cat([seed, torch.zeros(2, dtype=torch.int64)]).to(device)
+
+
 # ------------------------------------------------- edge-partitioned GraphConv (atlas scale)
 
 

@@ -252,6 +252,28 @@ int glue_paired_mean_cos_bwd(const float *ustack, const float *pmask, const floa
                              const float *grad_cos, float *grad_ustack, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Hidden block of the data encoders after its Linear layer
+ * (scglue/models/sc.py:62-178: Linear -> LeakyReLU(0.2) -> BatchNorm1d -> Dropout):
+ * activation, training-mode batch normalisation (batch statistics, running
+ * statistics and batch counter updated as torch.nn.BatchNorm1d does) and dropout
+ * in one launch; one launch for the backward pass.
+ *   z [B, H]: Linear output; gamma / beta / running_mean / running_var [H];
+ *   rng_state [3] (uint64: seed, call counter, ticket -- advanced on the device, so a
+ *   captured step draws a fresh mask at every replay; may be NULL when p_drop == 0);
+ *   out [B, H]; save_mean / save_rstd [H] and keep_mask [B, H] (bytes) feed the backward.
+ * bwd: grad_z [B, H], grad_gamma / grad_beta [H] from grad_out [B, H].
+ * ------------------------------------------------------------------------- */
+int glue_act_bn_dropout_fwd(const float *z, const float *gamma, const float *beta, float *running_mean,
+                            float *running_var, int64_t *num_batches_tracked, uint64_t *rng_state,
+                            int64_t B, int32_t H, float negative_slope, float eps, float momentum,
+                            float p_drop, float *out, float *save_mean, float *save_rstd,
+                            uint8_t *keep_mask, void *stream);
+int glue_act_bn_dropout_bwd(const float *z, const float *gamma, const float *save_mean,
+                            const float *save_rstd, const uint8_t *keep_mask, const float *grad_out,
+                            int64_t B, int32_t H, float negative_slope, float p_drop, float *grad_z,
+                            float *grad_gamma, float *grad_beta, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
  * M = 128) steps on caller-built shared-memory operand images and return the
  * accumulator tile out[128][N].  a_img / b_img are device buffers copied

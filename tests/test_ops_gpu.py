@@ -430,3 +430,59 @@ def test_paired_mean_cos_vs_torch(ops, M, B, K, empty_mod):
         assert g_only_cos.abs().max().item() < 1e-5 and g_only_cos_r.abs().max().item() < 1e-5
     else:
         assert_close(g_only_cos, g_only_cos_r, TOL, "d cos / d ustack")
+
+
+# ------------------------------------------------------------------ hidden block of the data encoders
+@pytest.mark.parametrize("B,H", [(128, 256), (37, 70), (2, 32), (300, 256)])
+def test_act_bn_dropout_without_dropout_equals_torch_modules(ops, B, H):
+    gen = torch.Generator().manual_seed(B + H)
+    z = torch.randn(B, H, generator=gen) * 2
+    ref_bn, bn = torch.nn.BatchNorm1d(H), torch.nn.BatchNorm1d(H).to(DEV)
+    with torch.no_grad():
+        for m in (ref_bn, bn):
+            m.weight.copy_(torch.rand(H, generator=torch.Generator().manual_seed(1)) + 0.5)
+            m.bias.copy_(torch.randn(H, generator=torch.Generator().manual_seed(2)))
+            m.running_mean.copy_(torch.randn(H, generator=torch.Generator().manual_seed(3)))
+    w = torch.randn(B, H, generator=gen)
+    zr = z.clone().requires_grad_(True)
+    yr = ref_bn(torch.nn.functional.leaky_relu(zr, 0.2))
+    gr = torch.autograd.grad((yr * w).sum(), [zr, ref_bn.weight, ref_bn.bias])
+    zd = z.to(DEV).requires_grad_(True)
+    y = ops.act_bn_dropout(zd, bn, 0.0, None)
+    g = torch.autograd.grad((y * w.to(DEV)).sum(), [zd, bn.weight, bn.bias])
+    assert_close(y, yr, 1e-5, "block output")
+    for name, a, b in zip(["z", "gamma", "beta"], g, gr):
+        assert_close(a, b, 1e-4, f"d / d {name}")
+    assert_close(bn.running_mean, ref_bn.running_mean, 1e-5, "running_mean")
+    assert_close(bn.running_var, ref_bn.running_var, 1e-5, "running_var")
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+
+
+def test_act_bn_dropout_masks(ops):
+    B, H, p = 256, 256, 0.2
+    z = torch.randn(B, H, generator=torch.Generator().manual_seed(0)).to(DEV).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(H).to(DEV)
+    state = ops.new_dropout_state(torch.device(DEV), generator=torch.Generator().manual_seed(5))
+    out, mean, rstd, keep = ops.act_bn_dropout(z, bn, p, state, return_aux=True)
+    assert state.tolist()[1:] == [1, 0], "call counter advanced, ticket back at zero"
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    # kept entries are the un-dropped block output scaled by 1 / (1 - p), dropped ones are zero
+    bn2 = torch.nn.BatchNorm1d(H).to(DEV)
+    full = bn2(torch.nn.functional.leaky_relu(z.detach(), 0.2))
+    assert_close(out, full * keep / (1 - p), 1e-5, "masked output")
+    # backward uses the same mask
+    w = torch.randn(B, H, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (g,) = torch.autograd.grad((out * w).sum(), [z])
+    z2 = z.detach().clone().requires_grad_(True)
+    bn3 = torch.nn.BatchNorm1d(H).to(DEV)
+    (g_ref,) = torch.autograd.grad((bn3(torch.nn.functional.leaky_relu(z2, 0.2)) * keep / (1 - p) * w).sum(), [z2])
+    assert_close(g, g_ref, 1e-4, "d / d z under the mask")
+    # a second call draws a different mask; the same state replays the same stream
+    _, _, _, keep_b = ops.act_bn_dropout(z, bn, p, state, return_aux=True)
+    assert not torch.equal(keep, keep_b)
+    state2 = ops.new_dropout_state(torch.device(DEV), generator=torch.Generator().manual_seed(5))
+    _, _, _, keep_c = ops.act_bn_dropout(z, bn, p, state2, return_aux=True)
+    assert torch.equal(keep, keep_c)
+    # columns and rows are not correlated in an obvious way
+    assert abs(keep.float().mean(0).std().item() - (p * (1 - p) / B) ** 0.5) < 0.01
