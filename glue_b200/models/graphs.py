@@ -124,6 +124,21 @@ class StepGraphs:
         self.replays += 1
         return entry["outputs"]
 
+    @staticmethod
+    def _recover_generator(device: torch.device, state: Optional[torch.Tensor]) -> None:
+        r"""An aborted capture leaves the device's default generator with a non-zero intra-graph
+        offset, and every later random draw raises.  Hand it the state object of a fresh generator
+        (same seed and offset as before the capture) so that eager training can go on."""
+        if state is None:
+            return
+        try:
+            fresh = torch.Generator(device=device)
+            fresh.set_state(state)
+            index = device.index if device.index is not None else torch.cuda.current_device()
+            torch.cuda.default_generators[index].graphsafe_set_state(fresh.graphsafe_get_state())
+        except Exception:  # best effort: the original error is what gets reported
+            pass
+
     def _capture(self, entry: Dict[str, Any], engine, data: List[torch.Tensor]) -> None:
         tr = self.trainer
         device = tr.net.device
@@ -134,6 +149,7 @@ class StepGraphs:
             torch.cuda.synchronize(device)
             if self.pool is None:
                 self.pool = torch.cuda.graph_pool_handle()
+            rng_before = torch.cuda.get_rng_state(device)  # (to recover the generator if the capture fails)
             graph = torch.cuda.CUDAGraph()
             launches0 = ops.kernel_launches()
             tr.capturing = True
@@ -148,10 +164,12 @@ class StepGraphs:
                               entry["native_kernels"])
         except Exception as e:  # capture is an optimisation: fall back to eager launches
             torch.cuda.synchronize(device)
+            self._recover_generator(device, locals().get("rng_before"))
             import traceback
             self.disabled_reason = f"{type(e).__name__}: {e}"
             self.logger.debug("capture traceback:\n%s", traceback.format_exc())
             self.last_traceback = traceback.format_exc()
             self.logger.warning("CUDA-graph capture of the training step failed (%s); "
-                                "continuing with eager launches", self.disabled_reason)
+                                "continuing with eager launches\n%s", self.disabled_reason,
+                                "".join(self.last_traceback.splitlines(keepends=True)[-24:]))
             entry["graph"] = None
