@@ -111,9 +111,14 @@ class StepGraphs:
             entry["seen"] += 1
             have_graph = any(e["graph"] is not None for e in self.entries.values())
             if entry["seen"] <= (self.WARMUP_STEPS_LATER if have_graph else self.WARMUP_STEPS):
+                # warm-up steps take the code path of the capture (device-scalar burn-in
+                # coefficient): every kernel the capture launches has been loaded by then -- a lazy
+                # module load inside a capture invalidates it
+                tr.anneal_buffer.fill_(anneal)
                 out = tr.eager_train_step(engine, data)
                 self._fingerprint = self._storage_fingerprint()  # the optimizer may re-adopt storage
                 return out
+            tr.anneal_buffer.fill_(anneal)
             self._capture(entry, engine, data)
             if entry["graph"] is None:
                 return tr.eager_train_step(engine, data)

@@ -212,7 +212,9 @@ class SCGLUETrainer(GLUETrainer):
                 jitter = self.noise(u_cat, "burnin") * u_cat.std(dim=0)
             # inside a captured step the coefficient is read from a device scalar
             # (fp32 product in both cases, so replayed and eager steps agree bit for bit)
-            if self.capturing:
+            if self.capturing or self.graphs.usable():
+                if not self.capturing:  # eager steps launch what a capture launches (see StepGraphs.step)
+                    self.anneal_buffer.fill_(anneal)
                 coeff = self.anneal_buffer * self.BURNIN_NOISE_EXAG
             else:
                 coeff = float(np.float32(anneal) * np.float32(self.BURNIN_NOISE_EXAG))
