@@ -222,3 +222,58 @@ def test_flat_rmsprop_refuses_cpu_parameters():
     from glue_b200.optim import FlatRMSprop
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FlatRMSprop([torch.nn.Parameter(torch.zeros(3))], lr=1e-3)
+
+
+def test_loss_terms_as_matrix_vector_product():
+    """SCGLUETrainer._combine: every reported term is a fixed linear combination of scalar components;
+    values and gradients must equal the term-by-term arithmetic of scglue.py:349-376."""
+    import types
+    from glue_b200.models.scglue import SCGLUETrainer
+    stub = types.SimpleNamespace(net=types.SimpleNamespace(device=torch.device("cpu")))
+    gen = torch.Generator().manual_seed(0)
+    comps = {n: torch.randn((), generator=gen).requires_grad_(True)
+             for n in ("dsc", "g_nll", "g_kl", "sup", "x_rna_nll", "x_rna_kl", "x_atac_nll", "x_atac_kl", "cos")}
+    lam_kl, lam_data, lam_graph, lam_align, lam_cos, mw = 0.04, 1.0, 0.02, 0.05, 0.02, {"rna": 1.0, "atac": 0.7}
+    rows = {"dsc_loss": {"dsc": 1.0}, "g_elbo": {"g_nll": 1.0, "g_kl": lam_kl},
+            "x_rna_elbo": {"x_rna_nll": 1.0, "x_rna_kl": lam_kl}, "cos_loss": {"cos": 1.0}}
+    vae = {"g_nll": lam_graph * 2, "g_kl": lam_graph * 2 * lam_kl, "cos": lam_cos}
+    for k in ("rna", "atac"):
+        vae[f"x_{k}_nll"], vae[f"x_{k}_kl"] = lam_data * mw[k], lam_data * mw[k] * lam_kl
+    rows["vae_loss"], rows["gen_loss"] = vae, dict(vae, dsc=-lam_align)
+    out = SCGLUETrainer._combine(stub, comps, rows)
+    c = comps
+    x_elbo = {k: c[f"x_{k}_nll"] + lam_kl * c[f"x_{k}_kl"] for k in ("rna", "atac")}
+    g_elbo = c["g_nll"] + lam_kl * c["g_kl"]
+    vae_ref = lam_data * sum(mw[k] * x_elbo[k] for k in mw) + lam_graph * 2 * g_elbo + lam_cos * c["cos"]
+    gen_ref = vae_ref - lam_align * c["dsc"]
+    assert torch.allclose(out["g_elbo"], g_elbo) and torch.allclose(out["x_rna_elbo"], x_elbo["rna"])
+    assert torch.allclose(out["vae_loss"], vae_ref, atol=1e-6) and torch.allclose(out["gen_loss"], gen_ref, atol=1e-6)
+    g = torch.autograd.grad(out["gen_loss"], list(comps.values()), allow_unused=True)
+    g_ref = torch.autograd.grad(gen_ref, list(comps.values()), allow_unused=True)
+    for name, a, b in zip(comps, g, g_ref):
+        a = torch.zeros(()) if a is None else a
+        b = torch.zeros(()) if b is None else b
+        assert torch.allclose(a, b, atol=1e-7), name
+    # the coefficient matrix is cached per set of weights
+    assert len(stub._combine_cache) == 1
+    SCGLUETrainer._combine(stub, comps, rows)
+    assert len(stub._combine_cache) == 1
+
+
+def test_paired_mean_and_cosine_reference_path_on_cpu():
+    """PairedSCGLUETrainer._umean without the fused kernel (CPU tensors): the formulas of
+    scglue.py:618-622 / 654-660, kept as the specification the CUDA kernel is tested against."""
+    import types
+    import torch.nn.functional as F
+    from glue_b200.models.scglue import PairedSCGLUETrainer
+    gen = torch.Generator().manual_seed(1)
+    usamp = {"rna": torch.randn(6, 4, generator=gen), "atac": torch.randn(6, 4, generator=gen)}
+    pmsk = torch.tensor([[1, 1], [1, 0], [0, 1], [1, 1], [1, 1], [0, 1]], dtype=torch.bool)
+    stub = types.SimpleNamespace(net=types.SimpleNamespace(keys=["rna", "atac"]), _pmsk=pmsk, normalize_u=False,
+                                 lam_cos=0.02)
+    ustack, umean, pf, cos = PairedSCGLUETrainer._umean(stub, usamp)
+    assert torch.allclose(umean[1], usamp["rna"][1]) and torch.allclose(umean[2], usamp["atac"][2])
+    assert torch.allclose(umean[0], 0.5 * (usamp["rna"][0] + usamp["atac"][0]))
+    want = sum(1 - (F.cosine_similarity(usamp[k], umean) * pf[i]).sum() / pf[i].sum()
+               for i, k in enumerate(["rna", "atac"]))
+    assert torch.allclose(cos, want)
