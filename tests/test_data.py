@@ -277,3 +277,73 @@ def test_paired_mean_and_cosine_reference_path_on_cpu():
     want = sum(1 - (F.cosine_similarity(usamp[k], umean) * pf[i]).sum() / pf[i].sum()
                for i, k in enumerate(["rna", "atac"]))
     assert torch.allclose(cos, want)
+
+
+@pytest.mark.parametrize("n,size,dtype", [(52000, 200000, np.float32), (152000, 104321, np.float32),
+                                          (7, 5000, np.float64), (1000, 4096, np.float64), (300, 100, np.float32)])
+def test_cdf_sampler_reproduces_randomstate_choice(n, size, dtype):
+    """_CdfSampler.choice must return what RandomState.choice(n, size, p=p) returns, draw for draw,
+    and leave the generator in the same state (the bucket table only short-cuts the binary search)."""
+    from glue_b200.models.data import _CdfSampler
+    w = np.random.RandomState(n).rand(n).astype(dtype)
+    w[:: max(2, n // 11)] = 0          # zero-probability entries
+    w[1] = w.sum() * 3                 # one dominant entry (many draws in one cdf step)
+    p = (w / w.sum()).astype(dtype)
+    sampler = _CdfSampler(p)
+    for seed in (0, 1):
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        want = a.choice(n, size, replace=True, p=p)
+        got = sampler.choice(b, size)
+        assert np.array_equal(got, want)
+        assert np.array_equal(a.random_sample(3), b.random_sample(3)), "generator state must match"
+
+
+def test_key_filter_has_no_false_negatives():
+    from glue_b200.models.data import _KeyFilter
+    rs = np.random.RandomState(3)
+    keys = np.unique(rs.randint(0, 2 ** 40, 150000).astype(np.int64))
+    filt = _KeyFilter(keys)
+    assert filt.maybe(keys).all()
+    probe = rs.randint(0, 2 ** 40, 500000).astype(np.int64)
+    maybe = filt.maybe(probe)
+    assert maybe[np.isin(probe, keys)].all()
+    assert maybe.mean() < 0.05, "the filter should reject almost every non-member"
+
+
+def test_negative_sampler_large_graph_matches_set_based_reference():
+    """The vectorised sampler against a literal restatement of scglue/models/data.py:794-820
+    (Python set of (i, j, s) tuples) on a graph large enough to take the table / filter paths."""
+    import networkx as nx
+    from glue_b200.models.data import GraphDataset
+    rs0 = np.random.RandomState(11)
+    n_v, n_e = 3000, 9000
+    g = nx.Graph()
+    names = [f"v{i}" for i in range(n_v)]
+    g.add_nodes_from(names)
+    for s, t, w in zip(rs0.randint(0, n_v, n_e), rs0.randint(0, n_v, n_e), rs0.uniform(0.05, 1, n_e)):
+        g.add_edge(names[s], names[t], weight=float(w), sign=1 if (s + t) % 5 else -1)
+    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in names)
+    ds = GraphDataset(g, names, neg_samples=10, weighted_sampling=True, deemphasize_loops=True)
+    assert ds.effective_enum * 10 >= 4096, "large enough for the bucket-table path"
+    got_idx, got_wt, got_sgn = ds.propose_shuffle(5)
+
+    rs = np.random.RandomState(5)
+    eset = {(i, j, s) for (i, j), s in zip(ds.eidx.T.tolist(), ds.esgn.tolist())}
+    pi, pj, pw, ps = ds.eidx[0], ds.eidx[1], ds.ewt, ds.esgn
+    psamp = rs.choice(ds.ewt.size, ds.effective_enum, replace=True, p=ds.eprob)
+    pi_, pj_, pw_, ps_ = pi[psamp], pj[psamp], pw[psamp], ps[psamp]
+    pw_ = np.ones_like(pw_)
+    ni_ = np.tile(pi_, ds.neg_samples)
+    nw_ = np.zeros(pw_.size * ds.neg_samples, dtype=pw_.dtype)
+    ns_ = np.tile(ps_, ds.neg_samples)
+    nj_ = rs.choice(ds.vnum, pj_.size * ds.neg_samples, replace=True, p=ds.vprob)
+    remain = np.where([item in eset for item in zip(ni_.tolist(), nj_.tolist(), ns_.tolist())])[0]
+    while remain.size:
+        newnj = rs.choice(ds.vnum, remain.size, replace=True, p=ds.vprob)
+        nj_[remain] = newnj
+        remain = remain[[item in eset for item in zip(ni_[remain].tolist(), newnj.tolist(), ns_[remain].tolist())]]
+    idx = np.stack([np.concatenate([pi_, ni_]), np.concatenate([pj_, nj_])])
+    w, s = np.concatenate([pw_, nw_]), np.concatenate([ps_, ns_])
+    perm = rs.permutation(idx.shape[1])
+    assert np.array_equal(got_idx, idx[:, perm])
+    assert np.array_equal(got_wt, w[perm]) and np.array_equal(got_sgn, s[perm])
