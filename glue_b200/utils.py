@@ -29,7 +29,10 @@ class _Settings:
         CUDNN_MODE="repeatability",
         MASKED_GPUS=[],
         ARRAY_SHUFFLE_NUM_WORKERS=0,
-        GRAPH_SHUFFLE_NUM_WORKERS=1,
+        # look-ahead threads of the negative sampler (reference default: 1 worker process).  Results
+        # do not depend on it; a graph epoch is ~35 ms of GPU time at the PBMC shape and 0.18 s of
+        # sampling, so a B200 needs several shuffles in flight
+        GRAPH_SHUFFLE_NUM_WORKERS=4,
         FORCE_TERMINATE_WORKER_PATIENCE=60,
         DATALOADER_NUM_WORKERS=0,
         DATALOADER_FETCHES_PER_WORKER=4,

@@ -347,3 +347,24 @@ def test_negative_sampler_large_graph_matches_set_based_reference():
     perm = rs.permutation(idx.shape[1])
     assert np.array_equal(got_idx, idx[:, perm])
     assert np.array_equal(got_wt, w[perm]) and np.array_equal(got_sgn, s[perm])
+
+
+def test_shuffle_lookahead_depth_does_not_change_the_stream():
+    """Shuffle n of a dataset uses seed random_seed + n whatever the number of look-ahead threads."""
+    from glue_b200.models.data import ArrayDataset
+    base = np.arange(1000)
+    streams = []
+    for workers in (0, 1, 3):
+        ds = ArrayDataset(base, getitem_size=10)
+        ds.prepare_shuffle(num_workers=workers, random_seed=7)
+        seq = []
+        for _ in range(5):
+            ds.shuffle()
+            seq.append(ds.shuffle_idx[0].copy())
+        assert len(ds._lookahead) == workers
+        ds.clean()
+        assert not ds.has_workers
+        streams.append(seq)
+    for seq in streams[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(seq, streams[0]))
+    assert np.array_equal(streams[0][2], np.random.RandomState(9).permutation(base))
