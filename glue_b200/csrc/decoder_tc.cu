@@ -150,7 +150,6 @@ struct TcParams {
     int acc;           // outputs accumulate (a previous cell block already wrote them)
     int chunk, nchunks;  // this launch handles cell block `chunk` of `nchunks`
     long long* trace;  // optional: clock64 stamps of CTA 0, [kernel 0..2][tile < 8][event < 16]
-    int dbg;           // timing experiments only (GLUE_TC_DBG): 1 = no x loads, 2 = no X stores / c_i reduce
     int pdl;           // launches carry the programmatic-dependent-launch attribute (GLUE_TC_PDL=0 switches it off)
 };
 
@@ -633,7 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
 #pragma unroll
                     for (int e8 = 0; e8 < 8; ++e8) {
                         const int cell = 8 * g + e8;
-                        xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell && !(P.dbg & 1))
+                        xn[e8] = (PHASE == 0 && jok && g < g_end && cell < ncell)
                                      ? __ldg(a.x + S.xoff[cell] + j) : 0.f;
                     }
                 }
@@ -959,7 +958,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main_kernel(TcParams P) {
                         gch[e8] = G;
                     }
                 }
-                if (GRAD && !(P.dbg & 2)) {
+                if (GRAD) {
                     // coefficient tile -> shared memory (bf16 hi / lo): rows = features, 128 B = 64 cells
                     uint32_t hh[4], ll[4];
 #pragma unroll
@@ -1266,9 +1265,7 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
     P.chunk = 0, P.nchunks = nchunks;
     {
-        const char* e = getenv("GLUE_TC_DBG");
-        P.dbg = e ? atoi(e) : 0;
-        e = getenv("GLUE_TC_PDL");
+        const char* e = getenv("GLUE_TC_PDL");
         P.pdl = e ? atoi(e) : TC_DEFAULT_PDL;
     }
     const bool nbf = is_nb_family(a.family);

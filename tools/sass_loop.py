@@ -1,10 +1,10 @@
 """Instruction mix of the epilogue group loop (the loop around the LDTM.x8) of one tc_main_kernel variant.
-usage: sass_loop.py "<0, 0, true, true, 8, true>" [dump]"""
+usage: sass_loop.py "<0, 0, true, true, true>" [dump]"""
 import collections, os, re, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 obj = os.path.join(root, "build/csrc/decoder_tc.o")
 want = sys.argv[1]
-# mangled template args: Li<FAM>ELi<PHASE>ELb<GRAD>ELb<NB1>ELi<EW>ELb<FAST>E
+# mangled template args: Li<FAM>ELi<PHASE>ELb<GRAD>ELb<NB1>ELb<FAST>E
 vals = [v.strip() for v in want.strip("<>").split(",")]
 enc = "".join(("Lb%dE" % (v == "true")) if v in ("true", "false") else "Li%sE" % v for v in vals)
 sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
