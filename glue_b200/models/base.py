@@ -23,7 +23,7 @@ from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional
 import dill
 import torch
 
-from ..utils import DelayedKeyboardInterrupt, config, logged
+from ..utils import config, logged
 
 # ----------------------------------------------------------------------- engine
 

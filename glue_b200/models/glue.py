@@ -7,14 +7,12 @@ import os
 from typing import Any, List, Mapping, Optional
 
 import torch
-import torch.distributions as D
 
 from .. import dist as gdist
 from ..num import normalize_edges
 from ..utils import config, logged
 from .base import Trainer, TrainingPlugin
-from .data import (AnnDataset, ArrayDataset, DataLoader, DevicePrefetcher, GraphDataset,
-                   ParallelDataLoader)
+from .data import ArrayDataset, DataLoader, DevicePrefetcher, GraphDataset, ParallelDataLoader
 from .nn import autodevice
 from .plugins import EarlyStopping, LRScheduler, Tensorboard
 

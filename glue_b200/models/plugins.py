@@ -5,13 +5,13 @@ restore, learning-rate reduction on plateau, optional Tensorboard logging.
 
 import pathlib
 import re
-from typing import Iterable, List, Optional
+from typing import List
 
 import torch
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from ..utils import config, logged
-from .base import COMPLETED, EPOCH_COMPLETED, TERMINATE, Engine, Trainer, TrainingPlugin
+from .base import COMPLETED, EPOCH_COMPLETED, TERMINATE, Engine, TrainingPlugin
 
 
 @logged

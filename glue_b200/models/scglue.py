@@ -14,7 +14,7 @@ sub-computations through the sm_100a kernels:
 import copy
 from itertools import chain
 from math import ceil
-from typing import Callable, List, Mapping, Optional, Tuple, Union
+from typing import Callable, List, Mapping, Optional, Union
 
 import networkx as nx
 import numpy as np
@@ -27,7 +27,7 @@ from ..num import normalize_edges
 from ..utils import AUTO, config, logged
 from . import sc
 from .base import Model
-from .data import AnnDataset, ArrayDataset, DataLoader, GraphDataset
+from .data import AnnDataset, DataLoader, GraphDataset
 from .glue import GLUE, GLUETrainer
 from .graphs import StepGraphs
 from .nn import freeze_running_stats
