@@ -175,6 +175,50 @@ def _check_fractions(fractions: List[float]) -> None:
 # ------------------------------------------------------------------------ AnnData
 
 
+class DeviceCSR:
+    r"""
+    A sparse ``[N, F]`` matrix resident on the device as CSR, densified per minibatch with static
+    shapes (no host read of the number of non-zeros): every requested row is read as
+    ``max_row_nnz`` (column, value) slots, slots beyond the row's length repeat its last entry --
+    duplicate writes of one value to one address -- and one ``scatter_`` fills the dense block.
+    ``fill`` is the value of structural zeros (NaN for ``nan_sparse`` modalities, ``data.py:397-436``).
+    Duck-types the one tensor method the loaders use: ``index_select(0, rows)``.
+    """
+
+    def __init__(self, csr, device: torch.device, fill: float = 0.0) -> None:
+        csr = csr.tocsr()
+        if not csr.has_canonical_format:  # (never touch the caller's matrix)
+            csr = csr.copy()
+            csr.sum_duplicates()
+        self.shape = tuple(csr.shape)
+        self.fill = fill
+        self.indptr = torch.as_tensor(csr.indptr.astype(np.int64)).to(device)
+        self.indices = torch.as_tensor(csr.indices.astype(np.int32)).to(device)
+        self.data = torch.as_tensor(csr.data).to(device)
+        self.max_row_nnz = int(np.diff(csr.indptr).max()) if csr.shape[0] else 0
+        self._slots = torch.arange(max(self.max_row_nnz, 1), device=device).unsqueeze(0)
+
+    @staticmethod
+    def nbytes_of(csr) -> int:
+        return int(csr.nnz) * (4 + csr.data.dtype.itemsize) + (csr.shape[0] + 1) * 8
+
+    def index_select(self, dim: int, rows: torch.Tensor) -> torch.Tensor:
+        if dim != 0:
+            raise ValueError("DeviceCSR selects rows only")
+        n, f = rows.shape[0], self.shape[1]
+        out = torch.full((n, f), self.fill, dtype=self.data.dtype, device=self.data.device)
+        if self.max_row_nnz == 0 or n == 0:
+            return out
+        start = self.indptr[rows]
+        count = self.indptr[rows + 1] - start
+        slot = torch.minimum(self._slots, (count - 1).clamp(min=0).unsqueeze(1))  # repeat the last entry
+        pos = (start.unsqueeze(1) + slot).clamp(max=self.data.shape[0] - 1)
+        empty = (count == 0).unsqueeze(1)
+        cols = torch.where(empty, torch.zeros_like(pos), self.indices[pos].long())
+        vals = torch.where(empty, out[:, :1], self.data[pos])  # rows without entries rewrite the fill
+        return out.scatter_(1, cols, vals)
+
+
 @logged
 class AnnDataset(Dataset):
     r"""
@@ -274,20 +318,27 @@ class AnnDataset(Dataset):
 
     # -- device residency ----------------------------------------------------------------
     def to_device(self, device: torch.device) -> "AnnDataset":
-        r"""Upload the per-modality arrays once; minibatches become device row gathers."""
+        r"""Upload the per-modality arrays once; minibatches become device row gathers.  Sparse
+        matrices are densified if everything then fits ``config.DEVICE_DATA_BUDGET_BYTES`` (a
+        minibatch is one ``index_select``); otherwise they stay CSR on the device
+        (:class:`DeviceCSR`, ~20 x smaller at 5 % density) and rows are densified per minibatch."""
         device = torch.device(device)
-        total = 0
-        for group in self.extracted_data:
-            for arr in group:
-                total += int(np.prod(arr.shape)) * 4
-        if total > config.DEVICE_DATA_BUDGET_BYTES:
-            raise MemoryError(
-                f"dense device-resident data would need {total / 2**30:.1f} GiB "
-                f"(> DEVICE_DATA_BUDGET_BYTES); keep the dataset on the host")
+        dense_bytes = sum(int(np.prod(arr.shape)) * 4 for group in self.extracted_data for arr in group)
+        keep_sparse = dense_bytes > config.DEVICE_DATA_BUDGET_BYTES
+        if keep_sparse:
+            total = sum(DeviceCSR.nbytes_of(arr) if scipy.sparse.issparse(arr) else int(np.prod(arr.shape)) * 4
+                        for group in self.extracted_data for arr in group)
+            if total > config.DEVICE_DATA_BUDGET_BYTES:
+                raise MemoryError(
+                    f"device-resident data would need {total / 2**30:.1f} GiB even with the sparse "
+                    f"matrices kept as CSR (> DEVICE_DATA_BUDGET_BYTES); keep the dataset on the host")
         dev_groups = []
         for group in self.extracted_data:
             dev_group = []
             for arr, nan_sparse in zip(group, self.nan_sparse):
+                if scipy.sparse.issparse(arr) and keep_sparse:
+                    dev_group.append(DeviceCSR(arr, device, fill=float("nan") if nan_sparse else 0.0))
+                    continue
                 dense = self._index_array(arr, slice(None), nan_sparse) \
                     if scipy.sparse.issparse(arr) else np.asarray(arr)
                 dev_group.append(torch.as_tensor(dense).to(device))

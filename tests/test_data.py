@@ -368,3 +368,51 @@ def test_shuffle_lookahead_depth_does_not_change_the_stream():
     for seq in streams[1:]:
         assert all(np.array_equal(a, b) for a, b in zip(seq, streams[0]))
     assert np.array_equal(streams[0][2], np.random.RandomState(9).permutation(base))
+
+
+@pytest.mark.parametrize("nan_sparse", [False, True])
+def test_device_csr_rows_equal_scipy_rows(nan_sparse):
+    """DeviceCSR.index_select(0, rows) == csr[rows] densified (NaN for structural zeros of
+    nan_sparse modalities), including empty rows, repeated rows and a stored explicit zero."""
+    import scipy.sparse
+    from glue_b200.models.data import AnnDataset, DeviceCSR
+    rs = np.random.RandomState(0)
+    dense = rs.poisson(0.2, (50, 37)).astype(np.float32)
+    dense[7] = 0          # empty rows
+    dense[49] = 0
+    dense[3] = rs.poisson(3, 37) + 1  # a full row (defines max_row_nnz)
+    csr = scipy.sparse.csr_matrix(dense)
+    csr.data[0] = 0.0     # an explicitly stored zero stays a value, not a structural zero
+    dev = DeviceCSR(csr, torch.device("cpu"), fill=float("nan") if nan_sparse else 0.0)
+    rows = np.array([3, 7, 0, 49, 3, 12, 48, 7])
+    got = dev.index_select(0, torch.as_tensor(rows)).numpy()
+    want = AnnDataset._index_array(csr, rows, nan_sparse)
+    assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True)
+    assert dev.index_select(0, torch.as_tensor(np.array([], dtype=np.int64))).shape == (0, 37)
+    empty = DeviceCSR(scipy.sparse.csr_matrix((5, 9), dtype=np.float32), torch.device("cpu"))
+    assert np.array_equal(empty.index_select(0, torch.tensor([1, 4])).numpy(), np.zeros((2, 9), np.float32))
+
+
+def test_anndataset_keeps_csr_on_device_when_dense_does_not_fit():
+    """to_device falls back from dense to CSR residency under a tight budget; fetched minibatches
+    are the same either way."""
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+    from glue_b200.models.data import AnnDataset, DeviceCSR
+    from glue_b200.utils import config
+    adatas, graph = make_synthetic(n_cells=(120, 120), n_feat=(40, 300), n_pairs=100, seed=3, rep_dim=8)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep")
+    cfgs = [a.uns[config.ANNDATA_KEY] for a in adatas.values()]
+    dense_ds = AnnDataset(list(adatas.values()), cfgs, mode="train").to_device("cpu")
+    old = config.DEVICE_DATA_BUDGET_BYTES
+    try:
+        config.DEVICE_DATA_BUDGET_BYTES = 120 * 340 * 4 // 2   # half of the dense count matrices
+        sparse_ds = AnnDataset(list(adatas.values()), cfgs, mode="train").to_device("cpu")
+    finally:
+        config.DEVICE_DATA_BUDGET_BYTES = old
+    assert any(isinstance(d, DeviceCSR) for group in sparse_ds.device_data for d in group)
+    rows = torch.as_tensor(np.random.RandomState(1).randint(0, 120, (16, 2)))
+    pmsk = torch.ones(16, 2, dtype=torch.bool)
+    for a, b in zip(dense_ds.fetch_device(rows, pmsk), sparse_ds.fetch_device(rows, pmsk)):
+        assert torch.equal(a, b)
