@@ -41,6 +41,31 @@ class EngineState:
         self.times: Dict[str, float] = {}
 
 
+class LossVector(Mapping):
+    r"""``{name: 0-dim tensor}`` backed by one device vector: the loss terms of a step come out of
+    one matrix-vector product (``SCGLUETrainer._combine``), and the engine averages them over an
+    epoch with one vector add per step instead of one add per term."""
+
+    def __init__(self, names: List[str], values: torch.Tensor) -> None:
+        self.names, self.values = list(names), values
+        self._index = {name: i for i, name in enumerate(self.names)}
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.values[self._index[name]]
+
+    def __iter__(self):
+        return iter(self.names)
+
+    def __len__(self) -> int:
+        return len(self.names)
+
+    def index(self, name: str) -> int:
+        return self._index[name]
+
+    def detach(self) -> "LossVector":
+        return LossVector(self.names, self.values.detach())
+
+
 class Engine:
     r"""Runs ``step(engine, batch)`` over a loader for a number of epochs and fires events."""
 
@@ -79,18 +104,32 @@ class Engine:
             tic = time.time()
             self.fire(EPOCH_STARTED)
             sums: Dict[str, torch.Tensor] = {}
+            vec_sum, vec_names = None, None  # steps that return a LossVector: one add per step
             count = 0
             for batch in loader:
                 state.iteration += 1
                 state.output = self.step(self, batch)
-                for key in self.tracked:
-                    val = state.output[key].detach()
-                    sums[key] = val.clone() if key not in sums else sums[key] + val
+                out = state.output
+                if isinstance(out, LossVector) and self.tracked and (vec_names is None or vec_names == out.names) \
+                        and not sums and all(key in out for key in self.tracked):
+                    vec = out.values.detach()
+                    vec_sum = vec.clone() if vec_sum is None else vec_sum + vec
+                    vec_names = out.names
+                else:
+                    if vec_sum is not None:  # (mixed output kinds within an epoch: fold the vector in)
+                        sums = {key: vec_sum[vec_names.index(key)].clone() for key in self.tracked}
+                        vec_sum = None
+                    for key in self.tracked:
+                        val = out[key].detach()
+                        sums[key] = val.clone() if key not in sums else sums[key] + val
                 count += 1
                 self.fire(ITERATION_COMPLETED)
                 if self.should_terminate:
                     break
-            if sums:  # one device->host read per epoch
+            if vec_sum is not None:  # one device->host read per epoch
+                host = (vec_sum.float() / max(count, 1)).tolist()
+                state.metrics = {key: host[vec_names.index(key)] for key in self.tracked}
+            elif sums:
                 keys = list(sums)
                 host = (torch.stack([sums[k].float() for k in keys]) / max(count, 1)).tolist()
                 state.metrics = dict(zip(keys, host))

@@ -28,6 +28,7 @@ import torch
 
 from .. import ops
 from ..utils import config, logged
+from .base import LossVector
 
 
 @logged
@@ -163,7 +164,8 @@ class StepGraphs:
                     outputs = tr.eager_train_step(engine, inputs)
             finally:
                 tr.capturing = False
-            entry.update(graph=graph, inputs=inputs, outputs=dict(outputs),
+            entry.update(graph=graph, inputs=inputs,
+                         outputs=outputs if isinstance(outputs, LossVector) else dict(outputs),
                          native_kernels=ops.kernel_launches() - launches0)
             self.logger.debug("captured a training step (%d native kernels)",
                               entry["native_kernels"])

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 from ..num import normalize_edges
 from ..utils import AUTO, config, logged
 from . import sc
-from .base import Model
+from .base import LossVector, Model
 from .data import AnnDataset, DataLoader, GraphDataset
 from .glue import GLUE, GLUETrainer
 from .graphs import StepGraphs
@@ -398,8 +398,7 @@ class SCGLUETrainer(GLUETrainer):
             if len(cache) > 8:
                 cache.clear()
             mat = cache[cache_key] = torch.tensor(flat, dtype=torch.float32, device=self.net.device)
-        out = mat @ torch.stack([comps[c].reshape(()) for c in keys])
-        return {n: out[i] for i, n in enumerate(names)}
+        return LossVector(names, mat @ torch.stack([comps[c].reshape(()) for c in keys]))
 
     def _prepare_extra(self, usamp) -> None:
         r"""Quantities shared by the per-modality extra terms (computed before the fork)."""
@@ -452,6 +451,8 @@ class SCGLUETrainer(GLUETrainer):
         self.vae_optim.step()
         # detached: the returned values feed metrics only, and a live autograd graph would keep
         # this step's AccumulateGrad nodes (bound to this stream) alive into a later capture
+        if isinstance(losses, LossVector):
+            return losses.detach()
         return {name: value.detach() for name, value in losses.items()}
 
     @torch.no_grad()

@@ -416,3 +416,19 @@ def test_anndataset_keeps_csr_on_device_when_dense_does_not_fit():
     pmsk = torch.ones(16, 2, dtype=torch.bool)
     for a, b in zip(dense_ds.fetch_device(rows, pmsk), sparse_ds.fetch_device(rows, pmsk)):
         assert torch.equal(a, b)
+
+
+def test_engine_averages_loss_vectors_like_dicts():
+    """Engine.run: steps that return a LossVector (one device vector) give the same epoch metrics as
+    steps that return a dict of scalars."""
+    from glue_b200.models.base import Engine, LossVector
+    names = ["dsc_loss", "vae_loss", "gen_loss", "g_nll"]
+    vals = [torch.tensor([1.0, 2.0, 3.0, 4.0]) * (i + 1) for i in range(5)]
+    as_vec = Engine(lambda eng, batch: LossVector(names, batch), tracked=["vae_loss", "g_nll"])
+    as_dict = Engine(lambda eng, batch: {n: batch[i] for i, n in enumerate(names)}, tracked=["vae_loss", "g_nll"])
+    m_vec = as_vec.run(vals, max_epochs=1).metrics
+    m_dict = as_dict.run(vals, max_epochs=1).metrics
+    assert m_vec == m_dict == {"vae_loss": 6.0, "g_nll": 12.0}
+    lv = LossVector(names, vals[0].clone().requires_grad_(True))
+    assert set(lv) == set(names) and len(lv) == 4 and float(lv["gen_loss"]) == 3.0
+    assert not lv.detach()["gen_loss"].requires_grad and dict(lv.items()).keys() == set(names)
