@@ -95,7 +95,7 @@ class Dataset(torch.utils.data.Dataset):
         raise NotImplementedError  # pragma: no cover
 
     def clean(self) -> None:
-        for thread, _ in getattr(self, "_lookahead", {}).values():
+        for thread, _ in (getattr(self, "_lookahead", None) or {}).values():
             thread.join()
         self._lookahead = {}
 
@@ -466,7 +466,8 @@ class AnnDataset(Dataset):
         subs = []
         for piece in pieces:
             sub = copy.copy(self)
-            sub._lookahead = None
+            # a split owns its shuffle state: no look-ahead threads / seeds shared with the parent
+            sub._lookahead, sub.shuffle_seed, sub._num_workers = {}, None, 0
             sub.view_idx, sub.size = piece, piece.size
             sub.shuffle_idx, sub.shuffle_pmsk = sub._get_idx_pmsk(piece)
             subs.append(sub)

@@ -432,3 +432,111 @@ def test_engine_averages_loss_vectors_like_dicts():
     lv = LossVector(names, vals[0].clone().requires_grad_(True))
     assert set(lv) == set(names) and len(lv) == 4 and float(lv["gen_loss"]) == 3.0
     assert not lv.detach()["gen_loss"].requires_grad and dict(lv.items()).keys() == set(names)
+
+
+def test_split_datasets_own_their_shuffle_state():
+    """AnnDataset.random_split -> prepare_shuffle(num_workers=2) -> shuffle -> clean on the subsets
+    (the sequence GLUETrainer.fit runs, scglue/models/glue.py:561-602): a split carries its own
+    look-ahead table and seed, and cleaning one split leaves the others alone."""
+    rna, atac, _ = _paired_adatas()
+    for a in (rna, atac):
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_obs_names=True)
+    ds = AnnDataset([rna, atac], [rna.uns[config.ANNDATA_KEY], atac.uns[config.ANNDATA_KEY]],
+                    mode="train", getitem_size=8)
+    ds.prepare_shuffle(num_workers=1, random_seed=0)      # the parent has threads in flight
+    train, val = ds.random_split([0.9, 0.1], random_state=0)
+    assert train._lookahead == {} and val._lookahead == {} and train._lookahead is not val._lookahead
+    assert train.shuffle_seed is None and not train.has_workers
+    with pytest.raises(RuntimeError, match="prepare_shuffle"):
+        train.shuffle()
+    for sub in (train, val):
+        sub.prepare_shuffle(num_workers=2, random_seed=3)
+        assert len(sub._lookahead) == 2
+    rows = []
+    for _ in range(3):
+        train.shuffle()
+        rows.append(train.shuffle_idx.copy())
+        assert sorted(train.shuffle_idx[:, 0][train.shuffle_pmsk[:, 0]]) == \
+            sorted(train._get_idx_pmsk(train.view_idx)[0][:, 0][train._get_idx_pmsk(train.view_idx)[1][:, 0]])
+    assert not np.array_equal(rows[0], rows[1])
+    val.shuffle()
+    train.clean()
+    assert not train.has_workers and val.has_workers and ds.has_workers
+    val.clean(), ds.clean()
+    # the same seeds without look-ahead give the same stream
+    train2, _ = ds.random_split([0.9, 0.1], random_state=0)
+    train2.prepare_shuffle(num_workers=0, random_seed=3)
+    for want in rows:
+        train2.shuffle()
+        assert np.array_equal(train2.shuffle_idx, want)
+    # a dataset whose table was lost (older pickles) still cleans
+    train2._lookahead = None
+    train2.clean()
+    assert train2._lookahead == {}
+
+
+def _stub_fit_model(monkeypatch, paired=True, n_batches=0):
+    """A (Paired)SCGLUEModel on the CPU whose trainer returns constant losses instead of launching
+    kernels: everything around the step -- split, shuffles, loaders, engine, plugins -- is real."""
+    from tests.synth import make_synthetic
+    from glue_b200.models import scglue as gs
+    from glue_b200.models.base import LossVector
+    monkeypatch.setattr(config, "CPU_ONLY", True)
+    adatas, graph = make_synthetic(n_cells=(96, 80), n_feat=(12, 30), n_pairs=40, seed=1, rep_dim=6,
+                                   paired=paired, n_batches=n_batches)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep",
+                                 use_obs_names=paired, use_batch="batch" if n_batches else None)
+    base = gs.PairedSCGLUETrainer if paired else gs.SCGLUETrainer
+
+    class StubTrainer(base):
+        seen = []
+
+        def _out(self, engine, data, kind):
+            n_mod = len(self.net.keys)
+            x = data[:n_mod]
+            eidx = data[-3]
+            StubTrainer.seen.append((kind, engine.state.epoch, tuple(t.shape[0] for t in x), eidx.shape[1]))
+            assert all(t.shape[1] == f for t, f in zip(x, (12, 30)))
+            vals = torch.arange(len(self.required_losses), dtype=torch.float32) + 1.0 / engine.state.epoch
+            return LossVector(self.required_losses, vals)
+
+        def train_step(self, engine, data):
+            return self._out(engine, data, "train")
+
+        def val_step(self, engine, data):
+            return self._out(engine, data, "val")
+
+    cls = gs.PairedSCGLUEModel if paired else gs.SCGLUEModel
+    monkeypatch.setattr(cls, "TRAINER_TYPE", StubTrainer)
+    vertices = sorted(graph.nodes)
+    model = cls(adatas, vertices, latent_dim=4, h_dim=8, random_seed=0)
+    model.compile()
+    return model, adatas, graph, StubTrainer
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_fit_plumbing_runs_on_cpu_with_a_stub_step(monkeypatch, tmp_path, paired):
+    """GLUETrainer.fit / Trainer.fit without a GPU: 90/10 split, block-shuffled loaders, the cycling
+    graph loader, per-epoch validation, LR scheduling / early stopping hooks, checkpoint directory,
+    clean-up of the shuffle threads (scglue/models/glue.py:486-667, base.py:117-214)."""
+    model, adatas, graph, stub = _stub_fit_model(monkeypatch, paired=paired)
+    stub.seen.clear()
+    model.fit(adatas, graph, data_batch_size=16, max_epochs=3, patience=2, reduce_lr_patience=1,
+              directory=tmp_path)
+    kinds = [k for k, *_ in stub.seen]
+    assert kinds.count("train") > 0 and kinds.count("val") > 0
+    epochs = sorted({e for k, e, *_ in stub.seen if k == "train"})
+    assert epochs == [1, 2, 3]
+    n_train = sum(1 for k, e, *_ in stub.seen if k == "train" and e == 1)
+    n_view = 96 if paired else 96 + 80
+    assert n_train == (round(n_view * 0.9) + 3) // 4 // 4   # blocks of 4 rows, 4 blocks per minibatch, drop_last
+    # (the one short block of the view can land in any minibatch)
+    assert all(b[0] == b[1] and 12 < b[0] <= 16 for k, e, b, _ in stub.seen if k == "train")
+    assert model.trainer.eidx is None and model.trainer.align_burnin is None   # cleared after fit
+    # a second fit on the same model works (datasets are rebuilt, threads were joined)
+    model.fit(adatas, graph, data_batch_size=16, max_epochs=1, patience=None, reduce_lr_patience=None,
+              directory=tmp_path)
+    # get_losses runs the validation step over one pass
+    losses = model.get_losses(adatas, graph, data_batch_size=32)
+    assert set(losses) == set(model.trainer.required_losses)
