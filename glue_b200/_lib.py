@@ -35,6 +35,9 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_workspace_bytes",
     "glue_decoder_nll_fwd_bwd",
     "glue_decoder_nll_fwd",
+    "glue_decoder_multi_workspace_bytes",
+    "glue_decoder_nll_multi_fwd_bwd",
+    "glue_decoder_nll_multi_fwd",
     "glue_decoder_log_prob",
     "glue_decoder_mean",
     "glue_rmsprop_flat",
@@ -61,6 +64,7 @@ class DecoderArgs(ctypes.Structure):
         ("K", c_int32),
         ("n_batches", c_int32),
         ("reduce", c_int32),
+        ("impl", c_int32),
         ("grad_scale", c_float),
         ("u", c_void_p),
         ("v", c_void_p),
@@ -86,6 +90,25 @@ class DecoderArgs(ctypes.Structure):
         ("workspace_bytes", c_size_t),
     ]
 
+
+MAX_TERMS = 3  # GLUE_DECODER_MAX_TERMS
+
+
+class DecoderMultiArgs(ctypes.Structure):
+    """Mirror of ``struct glue_decoder_multi_args``."""
+
+    _fields_ = [
+        ("shared", DecoderArgs),
+        ("n_terms", c_int32),
+        ("u", c_void_p * MAX_TERMS),
+        ("row_weight", c_void_p * MAX_TERMS),
+        ("grad_scale", c_float * MAX_TERMS),
+        ("loss", c_void_p * MAX_TERMS),
+        ("grad_u", c_void_p * MAX_TERMS),
+    ]
+
+
+ABI_VERSION = 3
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -146,6 +169,12 @@ def _declare(lib: ctypes.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = c_int32
         fn.argtypes = [POINTER(DecoderArgs), c_void_p]
+    lib.glue_decoder_multi_workspace_bytes.restype = c_size_t
+    lib.glue_decoder_multi_workspace_bytes.argtypes = [c_int32] * 6
+    for name in ("glue_decoder_nll_multi_fwd_bwd", "glue_decoder_nll_multi_fwd"):
+        fn = getattr(lib, name)
+        fn.restype = c_int32
+        fn.argtypes = [POINTER(DecoderMultiArgs), c_void_p]
     for name in ("glue_decoder_log_prob", "glue_decoder_mean"):
         fn = getattr(lib, name)
         fn.restype = c_int32
@@ -196,7 +225,7 @@ def lib() -> ctypes.CDLL:
             )
         handle = ctypes.CDLL(LIB_PATH)
         _declare(handle)
-        if handle.glue_abi_version() != 2:
+        if handle.glue_abi_version() != ABI_VERSION:
             raise RuntimeError("glue_b200: ABI version mismatch, rebuild the native library")
         _lib = handle
     return _lib

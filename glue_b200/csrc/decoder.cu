@@ -618,10 +618,17 @@ static int run(const glue_decoder_args* args, int mode, float* out, cudaStream_t
     return 0;
 }
 
-// GLUE_B200_DECODER=v1 pins the CUDA-core kernels (A/B comparisons, tests of both paths)
-static bool force_v1() {
-    const char* e = getenv("GLUE_B200_DECODER");
-    return e && e[0] == 'v' && e[1] == '1';
+// args->impl pins a decoder implementation (A/B comparisons, tests of every path).  Default: the
+// TMA-staged tensor-core kernels where they apply, then the per-row-staged ones, then CUDA cores.
+static int forced_version(const glue_decoder_args* a) { return a->impl & 0xff; }
+
+static glue_decoder_multi_args as_multi(const glue_decoder_args* args) {
+    glue_decoder_multi_args m = {};
+    m.shared = *args;
+    m.n_terms = 1;
+    m.u[0] = args->u, m.row_weight[0] = args->row_weight, m.grad_scale[0] = args->grad_scale;
+    m.loss[0] = args->loss, m.grad_u[0] = args->grad_u;
+    return m;
 }
 
 static int dispatch(const glue_decoder_args* args, int mode, float* out, void* stream) {
@@ -629,7 +636,12 @@ static int dispatch(const glue_decoder_args* args, int mode, float* out, void* s
     if (rc) return rc;
     if ((mode == MODE_LOGP || mode == MODE_MEAN) && !out) return GLUE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!force_v1() && tc_eligible(*args, mode)) {
+    const int forced = forced_version(args);
+    if (forced == 0 || forced == 3) {
+        const glue_decoder_multi_args m = as_multi(args);
+        if (tc3_eligible(m, mode) && args->workspace_bytes >= tc3_workspace_bytes(*args, 1)) return tc3_run(m, mode, st);
+    }
+    if (forced != 1 && tc_eligible(*args, mode)) {
         DecParams p;
         p.a = *args;
         p.out = out;
@@ -642,6 +654,21 @@ static int dispatch(const glue_decoder_args* args, int mode, float* out, void* s
     }
 }
 
+static int dispatch_multi(const glue_decoder_multi_args* m, int mode, void* stream) {
+    if (!m || m->n_terms < 1 || m->n_terms > GLUE_DECODER_MAX_TERMS) return GLUE_E_BADARG;
+    glue_decoder_args probe = m->shared;  // the shared fields are validated with the first term's
+    probe.u = m->u[0], probe.row_weight = m->row_weight[0], probe.loss = m->loss[0], probe.grad_u = m->grad_u[0];
+    probe.wmat = nullptr;
+    const int rc = validate(&probe, true);
+    if (rc) return rc;
+    for (int s = 0; s < m->n_terms; ++s)
+        if (!m->u[s]) return GLUE_E_BADARG;
+    const int forced = forced_version(&m->shared);
+    if ((forced != 0 && forced != 3) || !tc3_eligible(*m, mode)) return GLUE_E_UNSUPPORTED;
+    if (m->shared.workspace_bytes < tc3_workspace_bytes(m->shared, m->n_terms)) return GLUE_E_WORKSPACE;
+    return tc3_run(*m, mode, (cudaStream_t)stream);
+}
+
 }  // namespace glue
 
 extern "C" size_t glue_decoder_workspace_bytes(int32_t family, int32_t B, int32_t F, int32_t K,
@@ -652,9 +679,22 @@ extern "C" size_t glue_decoder_workspace_bytes(int32_t family, int32_t B, int32_
     if (B <= 0 || F <= 0 || KP == 0) return 0;
     int ncta, per;
     glue::plan(a, ncta, per);
-    const size_t v1 = glue::ws_layout(a, ncta, KP, nullptr, nullptr);
+    size_t need = glue::ws_layout(a, ncta, KP, nullptr, nullptr);
     const size_t v2 = glue::tc_workspace_bytes(a);
-    return v1 > v2 ? v1 : v2;
+    need = v2 > need ? v2 : need;
+    if (B <= 128) {
+        const size_t v3 = glue::tc3_workspace_bytes(a, 1);
+        need = v3 > need ? v3 : need;
+    }
+    return need;
+}
+
+extern "C" size_t glue_decoder_multi_workspace_bytes(int32_t family, int32_t B, int32_t F, int32_t K,
+                                                     int32_t n_batches, int32_t n_terms) {
+    glue_decoder_args a = {};
+    a.family = family, a.B = B, a.F = F, a.K = K, a.n_batches = n_batches;
+    if (B <= 0 || B > 128 || F <= 0 || K <= 0 || K > 64 || n_terms < 1 || n_terms > GLUE_DECODER_MAX_TERMS) return 0;
+    return glue::tc3_workspace_bytes(a, n_terms);
 }
 
 extern "C" int glue_decoder_nll_fwd_bwd(const glue_decoder_args* args, void* stream) {
@@ -662,6 +702,12 @@ extern "C" int glue_decoder_nll_fwd_bwd(const glue_decoder_args* args, void* str
 }
 extern "C" int glue_decoder_nll_fwd(const glue_decoder_args* args, void* stream) {
     return glue::dispatch(args, glue::MODE_LOSS, nullptr, stream);
+}
+extern "C" int glue_decoder_nll_multi_fwd_bwd(const glue_decoder_multi_args* args, void* stream) {
+    return glue::dispatch_multi(args, glue::MODE_GRAD, stream);
+}
+extern "C" int glue_decoder_nll_multi_fwd(const glue_decoder_multi_args* args, void* stream) {
+    return glue::dispatch_multi(args, glue::MODE_LOSS, stream);
 }
 extern "C" int glue_decoder_log_prob(const glue_decoder_args* args, float* out, void* stream) {
     return glue::dispatch(args, glue::MODE_LOGP, out, stream);

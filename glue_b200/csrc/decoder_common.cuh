@@ -188,6 +188,11 @@ bool tc_eligible(const glue_decoder_args& a, int mode);
 size_t tc_workspace_bytes(const glue_decoder_args& a);
 int tc_run(DecParams p, int mode, cudaStream_t st);
 
+// v3 (TMA-staged, several terms per launch sequence), decoder_tc3.cu
+bool tc3_eligible(const glue_decoder_multi_args& m, int mode);
+size_t tc3_workspace_bytes(const glue_decoder_args& a, int n_terms);
+int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st);
+
 // ---- small kernels shared by both paths (one copy per translation unit) ------------------------
 // one warp per row: lse_i = log sum_part psum * exp(pmax - M) + M
 static __global__ void dec_lse_kernel(DecWs ws, int nparts, int B) {

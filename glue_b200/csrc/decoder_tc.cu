@@ -27,9 +27,11 @@
 
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
+#include "tc_math.cuh"
 
 namespace glue {
 using namespace tc;
+using namespace tcm;
 
 namespace {
 
@@ -54,54 +56,6 @@ constexpr uint64_t DESC_MN_X = smem_desc_base(16384, 1024);   // MN-major X: two
 constexpr uint32_t IDESC_FWD = instr_desc_bf16(128, 128, 0, 0);
 constexpr uint32_t IDESC_D1 = instr_desc_bf16(128, 64, 0, 1);
 constexpr uint32_t IDESC_D2 = instr_desc_bf16(128, 64, 1, 1);
-
-constexpr float LOG2EF = 1.4426950408889634074f;
-constexpr float LN2F = 0.69314718055994530942f;
-
-// hardware approximations (flush-to-zero forms: one MUFU each)
-__device__ __forceinline__ float ex2f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2f(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcpf(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) --------
-struct f2 {
-    unsigned long long v;
-};
-__device__ __forceinline__ f2 pk(float lo, float hi) {
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void up(f2 x, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v));
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-    f2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-    return r;
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-    f2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-    f2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
 
 struct Bars {
     uint64_t v_full[2], v_empty[2], acc_full[2], acc_empty[2], x_full, x_empty, d1_full[2], d1_empty[2], d2_full;
@@ -1264,19 +1218,13 @@ int tc_run(DecParams p, int mode, cudaStream_t st) {
     const int nchunks = (a.B + 127) / 128;
     P.p = p, P.ntiles = ntiles, P.cell0 = 0, P.ncell = a.B, P.acc = 0, P.trace = g_trace;
     P.chunk = 0, P.nchunks = nchunks;
-    {
-        const char* e = getenv("GLUE_TC_PDL");
-        P.pdl = e ? atoi(e) : TC_DEFAULT_PDL;
-    }
+    P.pdl = TC_DEFAULT_PDL;
     const bool nbf = is_nb_family(a.family);
     const bool grad = mode == MODE_GRAD;
     const bool nb1 = a.n_batches == 1;
-    // kernel variant: GLUE_TC_VARIANT = 0 switches the streamlined NB pass B off (A/B runs, tests)
+    // kernel variant: impl bit 8 switches the streamlined NB pass B off (A/B runs, tests)
     int variant = TC_DEFAULT_VARIANT;
-    {
-        const char* e = getenv("GLUE_TC_VARIANT");
-        if (e) variant = atoi(e) & VARIANT_FAST;
-    }
+    if (a.impl & 0x100) variant &= ~VARIANT_FAST;
     if (!(a.family == GLUE_NB && nb1 && a.K <= 62 && (long long)a.B * (long long)a.F < (1ll << 31)))
         variant &= ~VARIANT_FAST;
     // Cells are handled in blocks of <= 128 (soft-max rows are independent); feature-side outputs

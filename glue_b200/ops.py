@@ -560,11 +560,17 @@ def graph_logits(v, eidx, esgn) -> torch.Tensor:
 # --------------------------------------------------------------- data decoder
 
 
+# Diagnostics: pin a decoder implementation for the calls that follow (``glue_decoder_args.impl``:
+# low byte 1 / 2 / 3 = CUDA-core / per-row-staged tcgen05 / TMA-staged tcgen05 kernels, bit 8 = without
+# the streamlined NB pass B).  0 = the library chooses.  Tests and A/B benches set it.
+DECODER_IMPL = 0
+
+
 class DecoderCall:
     r"""Argument marshalling for one ``glue_decoder_*`` call (keeps tensors alive)."""
 
     def __init__(self, family: str, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits,
-                 reduce: str = "nanmean", row_weight=None, grad_scale: float = 0.0):
+                 reduce: str = "nanmean", row_weight=None, grad_scale: float = 0.0, n_terms: int = 0):
         dev = require_cuda(u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, row_weight)
         if family not in FAMILY:
             raise ValueError(f"unknown decoder family {family!r}")
@@ -605,14 +611,20 @@ class DecoderCall:
         self.row_order = None
         if self.n_batches > 1 and self.b is not None:
             self.row_order = torch.sort(self.b, stable=True).indices.to(torch.int32)
-        nbytes = _lib.lib().glue_decoder_workspace_bytes(
-            FAMILY[family], self.B, self.F, self.K, self.n_batches)
+        if n_terms:
+            nbytes = _lib.lib().glue_decoder_multi_workspace_bytes(
+                FAMILY[family], self.B, self.F, self.K, self.n_batches, n_terms)
+            if nbytes == 0:
+                raise ValueError("glue_b200: shape outside the fused several-terms decoder path")
+        else:
+            nbytes = _lib.lib().glue_decoder_workspace_bytes(
+                FAMILY[family], self.B, self.F, self.K, self.n_batches)
         self.ws = _workspace(nbytes, dev)
 
     def args(self, **out) -> DecoderArgs:
         a = DecoderArgs()
         a.family, a.B, a.F, a.K = FAMILY[self.family], self.B, self.F, self.K
-        a.n_batches, a.reduce = self.n_batches, self.reduce
+        a.n_batches, a.reduce, a.impl = self.n_batches, self.reduce, DECODER_IMPL
         a.grad_scale = self.grad_scale
         a.u, a.v, a.vidx, a.b = ptr(self.u), ptr(self.v), ptr(self.vidx), ptr(self.b)
         a.row_order, a.l, a.x = ptr(self.row_order), ptr(self.l), ptr(self.x)
@@ -643,13 +655,15 @@ class _DecoderNllFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family, reduce,
-                unit_upstream, row_weight, upstream):
+                unit_upstream, row_weight, upstream, grad_enabled):
         call = DecoderCall(family, u, v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce,
                            row_weight, grad_scale=upstream)
         unit_upstream = unit_upstream or bool(upstream)
         loss = torch.empty((), dtype=torch.float32, device=call.device)
-        need_grad = any(t is not None and t.requires_grad
-                        for t in (u, v, scale_lin, bias, disp, zi_logits))
+        # (grad mode is always off inside Function.forward: the caller's mode comes in as a flag, so
+        # that validation / get_losses under no_grad take the loss-only kernels)
+        need_grad = grad_enabled and any(t is not None and t.requires_grad
+                                         for t in (u, v, scale_lin, bias, disp, zi_logits))
         L = _lib.lib()
         if need_grad:
             gu, gv, gs, gb, gd, gz = call.grad_buffers()
@@ -675,7 +689,7 @@ class _DecoderNllFn(torch.autograd.Function):
         if not ctx.unit_upstream:
             live = [g for g in grads if g is not None]
             torch._foreach_mul_(live, grad_out)
-        return (*grads, None, None, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None, None, None)
 
 
 def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
@@ -690,14 +704,126 @@ def decoder_nll(family: str, u, v, scale_lin, bias, disp, zi_logits=None, *, b=N
     ``unit_upstream=True`` promises that this loss enters the final objective with
     coefficient exactly 1, so backward hands the gradients over without rescaling;
     ``upstream=c`` promises coefficient exactly ``c`` (a non-zero Python number): the kernels
-    fold it into their weights, the returned loss stays unscaled.
+    fold it into their weights, the returned loss stays unscaled.  **Contract** of both: the
+    incoming autograd gradient is not read, so whatever is differentiated must contain this loss
+    with exactly that coefficient (``SCGLUETrainer.train_step`` differentiates ``gen_loss`` only;
+    anything else -- scaled losses, gradient accumulation with a factor, differentiating a single
+    term -- has to leave both arguments unset).
     ``row_weight`` (``[B]``, not differentiated) replaces the mean by
     ``-sum_i row_weight[i] sum_j log_prob[i, j]``: weighted / masked row subsets with static
     shapes (the paired-cell losses of ``scglue.py:603-640`` use ``mask / (n_masked * F)``)."""
     if x is None:
         raise ValueError("`x` is required")
     return _DecoderNllFn.apply(u, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family,
-                               reduce, unit_upstream, row_weight, upstream)
+                               reduce, unit_upstream, row_weight, upstream, torch.is_grad_enabled())
+
+
+# ------------------------------------------------- several loss terms of one modality per launch
+
+
+MAX_TERMS = _lib.MAX_TERMS
+
+
+class _DecoderNllMultiFn(torch.autograd.Function):
+    r"""``T`` loss terms ``-sum_i w_ti sum_j log_prob_t[i, j]`` that share ``x``, ``v``, ``b``, ``l`` and
+    the parameter tables, in one launch sequence; the gradients that come back are those of
+    ``sum_t upstream[t] * loss[t]`` (folded into the kernels' weights)."""
+
+    @staticmethod
+    def forward(ctx, v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family, reduce, upstreams,
+                grad_enabled, n_terms, *us_rws):
+        us, rws = us_rws[:n_terms], us_rws[n_terms:]
+        call = DecoderCall(family, us[0], v, vidx, b, l, x, scale_lin, bias, disp, zi_logits, reduce,
+                           rws[0], n_terms=n_terms)
+        dev = call.device
+        us = [_f32(u, "u") for u in us]
+        rws = [None if w is None else _f32(w, "row_weight").reshape(-1) for w in rws]
+        for u, w in zip(us, rws):
+            if u.shape != (call.B, call.K):
+                raise ValueError("every term's `u` must have shape [n_cells, latent_dim]")
+            if w is not None and w.numel() != call.B:
+                raise ValueError("`row_weight` must have one entry per cell")
+        losses = torch.empty(n_terms, dtype=torch.float32, device=dev)
+        need_grad = grad_enabled and any(t is not None and t.requires_grad
+                                         for t in (*us, v, scale_lin, bias, disp, zi_logits))
+        m = _lib.DecoderMultiArgs()
+        L = _lib.lib()
+        if need_grad:
+            _, gv, gs, gb, gd, gz = call.grad_buffers()
+            gus = [torch.empty_like(u) for u in us]
+            m.shared = call.args(grad_v=gv, grad_scale_lin=gs, grad_bias=gb, grad_disp=gd,
+                                 grad_zi_logits=gz)
+        else:
+            m.shared = call.args()
+        m.n_terms = n_terms
+        for t in range(n_terms):
+            m.u[t], m.row_weight[t] = ptr(us[t]), ptr(rws[t])
+            m.grad_scale[t] = float(upstreams[t])
+            m.loss[t] = losses.data_ptr() + 4 * t
+            m.grad_u[t] = ptr(gus[t]) if need_grad else None
+        ev = TIMER.start(f"decoder_multi{n_terms}_{family}_F{call.F}_B{call.B}", dev)
+        fn = L.glue_decoder_nll_multi_fwd_bwd if need_grad else L.glue_decoder_nll_multi_fwd
+        check(fn(ctypes.byref(m), call.stream()), "decoder_nll_multi")
+        TIMER.stop(ev, dev)
+        ctx.grads = (gv, gs, gb, gd, gz, gus) if need_grad else None
+        ctx.n_terms = n_terms
+        return losses
+
+    @staticmethod
+    def backward(ctx, _grad_losses):
+        if ctx.grads is None:
+            raise RuntimeError("decoder_nll_multi: no input required grad at forward time")
+        gv, gs, gb, gd, gz, gus = ctx.grads
+        ctx.grads = None
+        return (gv, gs, gb, gd, gz, None, None, None, None, None, None, None, None, None,
+                *gus, *([None] * ctx.n_terms))
+
+
+def decoder_multi_supported(family: str, B: int, F: int, K: int, n_batches: int, n_terms: int,
+                            reduce: str, row_weights) -> bool:
+    r"""Shapes the fused several-terms path takes (mirror of ``tc3_eligible``, decoder_tc3.cu)."""
+    if family not in FAMILY or not 1 <= n_terms <= MAX_TERMS:
+        return False
+    if B > 128 or K > 64 or K % 2 or n_batches > 24:
+        return False
+    if n_terms > 1 and reduce == "nanmean" and any(w is None for w in row_weights):
+        return False
+    return True
+
+
+def decoder_nll_multi(family: str, us, v, scale_lin, bias, disp, zi_logits=None, *, b=None, l=None,
+                      x=None, vidx=None, reduce: str = "mean", row_weights=None, upstreams=None):
+    r"""Several decoder loss terms of one modality that differ only in the cell embeddings ``us[t]``,
+    the per-cell weights ``row_weights[t]`` (``None`` = the plain ``reduce``) and their coefficient
+    ``upstreams[t]`` in the objective -- the reconstruction, joint-cross and real-cross terms of
+    ``PairedSCGLUETrainer`` (``scglue/models/scglue.py:603-652``).  Returns the tuple of (unscaled)
+    losses.  **Contract**: the objective that is differentiated must contain term ``t`` with
+    coefficient exactly ``upstreams[t]`` (the kernels fold it into their weights; the incoming
+    autograd gradients are not read).  Up to three terms run as one launch sequence that stages the
+    feature table once and reads ``x`` from HBM once; anything the fused path does not take is
+    evaluated term by term with :func:`decoder_nll`."""
+    n = len(us)
+    row_weights = list(row_weights) if row_weights is not None else [None] * n
+    if upstreams is None or any(not c for c in upstreams):
+        raise ValueError("`upstreams` (non-zero coefficient of every term in the objective) is required")
+    if x is None:
+        raise ValueError("`x` is required")
+    B, K = us[0].shape
+    nb, F = scale_lin.shape
+    out = []
+    for lo in range(0, n, MAX_TERMS):
+        grp = slice(lo, min(n, lo + MAX_TERMS))
+        g_us, g_rw, g_up = list(us[grp]), row_weights[grp], [float(c) for c in upstreams[grp]]
+        if decoder_multi_supported(family, B, F, K, nb, len(g_us), reduce, g_rw):
+            losses = _DecoderNllMultiFn.apply(v, scale_lin, bias, disp, zi_logits, vidx, b, l, x, family,
+                                              reduce, tuple(g_up), torch.is_grad_enabled(), len(g_us),
+                                              *g_us, *g_rw)
+            out.extend(losses.unbind(0))
+        else:
+            out.extend(decoder_nll(family, u, v, scale_lin, bias, disp, zi_logits, b=b, l=l, x=x, vidx=vidx,
+                                   reduce=reduce, row_weight=w, upstream=c)
+                       for u, w, c in zip(g_us, g_rw, g_up))
+    return tuple(out)
 
 
 class _DecoderLogProbFn(torch.autograd.Function):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLUE_B200_ABI_VERSION 2
+#define GLUE_B200_ABI_VERSION 3
 
 #define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
 #define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */
@@ -159,6 +159,11 @@ typedef struct glue_decoder_args {
     int32_t K;         /* latent dimension, 1..64                                    */
     int32_t n_batches; /* rows of the per-feature parameter tables                   */
     int32_t reduce;    /* 0: mean over non-NaN x (nanmean)  1: plain mean            */
+    int32_t impl;      /* 0: the library picks the kernels.  Diagnostics (A/B runs, tests of
+                          every path): low byte 1 = CUDA-core kernels, 2 = tcgen05 kernels
+                          with per-row operand staging, 3 = tcgen05 kernels with TMA-staged
+                          operands; bit 8 = without the streamlined NB pass B.  A pinned
+                          path that cannot take the call falls through to the next one.   */
     float grad_scale;  /* gradients are those of grad_scale * loss (the coefficient with
                           which the caller adds `loss` to its objective), `loss` itself is
                           reported unscaled; 0 is read as 1                             */
@@ -206,6 +211,35 @@ int glue_decoder_nll_fwd(const glue_decoder_args *args, void *stream);
  * (scglue/models/scglue.py:1355 decode_data): out is [B, F]. */
 int glue_decoder_log_prob(const glue_decoder_args *args, float *out, void *stream);
 int glue_decoder_mean(const glue_decoder_args *args, float *out, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Several loss terms of one modality in one launch sequence.  PairedSCGLUETrainer
+ * (scglue/models/scglue.py:603-652) evaluates up to three decoder terms per modality on the
+ * same observations: reconstruction from the cell's own embedding, from the mean embedding
+ * of its paired modalities (joint cross) and from the other modality's embedding (real
+ * cross).  They share x, v, b, l and the parameter tables and differ in u, the per-cell
+ * weights and the coefficient in the objective.  Fields of `shared` that are per term
+ * (u, row_weight, grad_scale, loss, grad_u) and wmat are ignored; grad_v and the
+ * parameter-table gradients receive the SUM over the terms of grad_scale[t] * d loss[t]
+ * (what autograd would accumulate), loss[t] is reported unscaled.  With reduce == 0
+ * (nanmean) and n_terms > 1 every term needs a row_weight.  B <= 128 cells.
+ * ------------------------------------------------------------------------- */
+#define GLUE_DECODER_MAX_TERMS 3
+typedef struct glue_decoder_multi_args {
+    glue_decoder_args shared;
+    int32_t n_terms; /* 1 .. GLUE_DECODER_MAX_TERMS */
+    const float *u[GLUE_DECODER_MAX_TERMS];          /* [B, K] each                    */
+    const float *row_weight[GLUE_DECODER_MAX_TERMS]; /* [B] each or NULL (uniform mean) */
+    float grad_scale[GLUE_DECODER_MAX_TERMS];        /* 0 is read as 1                  */
+    float *loss[GLUE_DECODER_MAX_TERMS];             /* [1] each, may be NULL           */
+    float *grad_u[GLUE_DECODER_MAX_TERMS];           /* [B, K] each, may be NULL        */
+} glue_decoder_multi_args;
+size_t glue_decoder_multi_workspace_bytes(int32_t family, int32_t B, int32_t F, int32_t K,
+                                          int32_t n_batches, int32_t n_terms);
+/* Returns GLUE_E_UNSUPPORTED when the shape is outside what the fused path takes (the
+ * caller then issues one glue_decoder_nll_fwd_bwd per term). */
+int glue_decoder_nll_multi_fwd_bwd(const glue_decoder_multi_args *args, void *stream);
+int glue_decoder_nll_multi_fwd(const glue_decoder_multi_args *args, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused RMSprop over a flat range -- replaces the multi-tensor launch sequence of

@@ -286,6 +286,111 @@ def test_decoder_full_size_properties(ops, family, F):
         assert_close(g, rg, TOL, f"{family} full-size gradient")
 
 
+MULTI_CASES = [
+    # family, B, F, K, n_batches, n_terms, extra_rows
+    ("NB", 128, 2000, 50, 1, 3, 0),
+    ("NB", 128, 700, 50, 1, 3, 300),
+    ("NB", 77, 391, 50, 1, 2, 0),
+    ("NB", 128, 1300, 50, 4, 3, 0),
+    ("ZINB", 128, 2000, 50, 1, 3, 0),
+    ("ZINB", 100, 600, 50, 20, 3, 0),
+    ("Normal", 128, 1000, 50, 3, 3, 0),
+    ("ZILN", 128, 1000, 50, 1, 3, 11),
+    ("NB", 128, 640, 64, 1, 3, 0),
+    ("NB", 128, 2000, 50, 1, 5, 0),   # more terms than one launch sequence takes: two groups
+]
+
+
+@pytest.mark.parametrize("family,B,F,K,nb,T,extra", MULTI_CASES)
+def test_decoder_multi_terms_vs_oracle(ops, family, B, F, K, nb, T, extra):
+    """Several loss terms of one modality in one launch sequence (reconstruction / joint-cross /
+    real-cross of PairedSCGLUETrainer, scglue.py:603-652): every loss, and the gradients of
+    sum_t c_t loss_t, against the CPU oracle evaluated term by term."""
+    u, v, b, l, x, params, vidx = _decoder_case(family, B, F, K, nb, seed=B * 1000 + F + T, extra_rows=extra)
+    gen = torch.Generator().manual_seed(T)
+    us = [u] + [torch.randn(B, K, generator=gen) * 0.5 for _ in range(T - 1)]
+    masks = [torch.ones(B)] + [(torch.rand(B, generator=gen) < 0.6).float() for _ in range(T - 1)]
+    masks[-1][:] = masks[-1] if masks[-1].sum() > 0 else 1.0
+    rws = [None] + [m / (m.sum().clamp(min=1.0) * F) for m in masks[1:]]
+    coefs = [1.0, 0.02, 0.02 * 0.7, 0.3, 1.7][:T]
+    # oracle
+    ous = [t.clone().requires_grad_(True) for t in us]
+    ov = v.clone().requires_grad_(True)
+    st = {f"u2x.m.{k}": p.clone().requires_grad_(True) for k, p in params.items()}
+    vv = ov if vidx is None else ov[vidx]
+    ref_losses = []
+    for t in range(T):
+        lp = oc.DECODER_LOG_PROB[family](st, "u2x.m.", ous[t], vv, b, l, x)
+        ref_losses.append(-lp.mean() if rws[t] is None else -(lp * rws[t].unsqueeze(1)).sum())
+    ref_grads = torch.autograd.grad(sum(c * ls for c, ls in zip(coefs, ref_losses)), ous + [ov] + list(st.values()))
+    # device
+    d = lambda t: None if t is None else t.to(DEV)
+    dus = [d(t).requires_grad_(True) for t in us]
+    dv = d(v).requires_grad_(True)
+    dp = [d(params[n]).requires_grad_(True) for n in PARAM_NAMES[family]]
+    zi = dp[3] if len(dp) == 4 else None
+
+    def run():
+        losses = ops.decoder_nll_multi(family, dus, dv, dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x), vidx=d(vidx),
+                                       reduce="mean", row_weights=[d(w) for w in rws], upstreams=coefs)
+        grads = torch.autograd.grad(sum(c * ls for c, ls in zip(coefs, losses)), dus + [dv] + dp)
+        return losses, grads
+
+    losses, grads = run()
+    for t in range(T):
+        assert_close(losses[t], ref_losses[t], TOL, f"{family} loss of term {t}")
+    names = [f"u{t}" for t in range(T)] + ["v"] + list(PARAM_NAMES[family])
+    for n, g, rg in zip(names, grads, ref_grads):
+        assert_close(g, rg, TOL, f"{family} multi d/d{n}")
+    losses2, grads2 = run()
+    assert all(torch.equal(a, b_) for a, b_ in zip(losses, losses2))
+    assert all(torch.equal(a, b_) for a, b_ in zip(grads, grads2)), "run-to-run deterministic"
+    # loss-only path (validation under no_grad)
+    with torch.no_grad():
+        val = ops.decoder_nll_multi(family, dus, dv, dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x), vidx=d(vidx),
+                                    reduce="mean", row_weights=[d(w) for w in rws], upstreams=coefs)
+    for t in range(T):
+        assert_close(val[t], ref_losses[t], TOL, f"{family} no-grad loss of term {t}")
+
+
+def test_decoder_multi_full_size(ops):
+    """Three NB terms at the ATAC shape of BASELINE configs 1 / 2 (B = 128, F = 50 000) against three
+    single-term calls of the same kernels and against the oracle."""
+    family, B, F, K = "NB", 128, 50000, 50
+    u, v, b, l, x, params, vidx = _decoder_case(family, B, F, K, 1, seed=7)
+    gen = torch.Generator().manual_seed(3)
+    us = [u, torch.randn(B, K, generator=gen) * 0.5, torch.randn(B, K, generator=gen) * 0.5]
+    masks = [(torch.rand(B, generator=gen) < 0.7).float() for _ in range(3)]
+    rws = [m / (m.sum() * F) for m in masks]
+    coefs = [1.0, 0.02, 0.02]
+    d = lambda t: None if t is None else t.to(DEV)
+    dus = [d(t).requires_grad_(True) for t in us]
+    dv = d(v).requires_grad_(True)
+    dp = [d(params[n]).requires_grad_(True) for n in PARAM_NAMES[family]]
+    losses = ops.decoder_nll_multi(family, dus, dv, dp[0], dp[1], dp[2], None, b=d(b), l=d(l), x=d(x),
+                                   reduce="mean", row_weights=[d(w) for w in rws], upstreams=coefs)
+    grads = torch.autograd.grad(sum(c * ls for c, ls in zip(coefs, losses)), dus + [dv] + dp)
+    singles = [ops.decoder_nll(family, dus[t], dv, dp[0], dp[1], dp[2], None, b=d(b), l=d(l), x=d(x), reduce="mean",
+                               row_weight=d(rws[t])) for t in range(3)]
+    sgrads = torch.autograd.grad(sum(c * ls for c, ls in zip(coefs, singles)), dus + [dv] + dp)
+    for t in range(3):
+        assert_close(losses[t], singles[t], 1e-5, f"loss of term {t} vs single-term call")
+    for g, sg in zip(grads, sgrads):
+        assert_close(g, sg, 2e-5, "fused vs term-by-term gradients")
+    ous = [t.clone().requires_grad_(True) for t in us]
+    ov = v.clone().requires_grad_(True)
+    st = {f"u2x.m.{k}": p.clone().requires_grad_(True) for k, p in params.items()}
+    ref = []
+    for t in range(3):
+        lp = oc.DECODER_LOG_PROB[family](st, "u2x.m.", ous[t], ov, b, l, x)
+        ref.append(-(lp * rws[t].unsqueeze(1)).sum())
+    ref_grads = torch.autograd.grad(sum(c * ls for c, ls in zip(coefs, ref)), ous + [ov] + list(st.values()))
+    for t in range(3):
+        assert_close(losses[t], ref[t], TOL, f"loss of term {t} vs oracle")
+    for g, rg in zip(grads, ref_grads):
+        assert_close(g, rg, TOL, "full-size multi-term gradient vs oracle")
+
+
 def test_decoder_rejects_cpu_tensors(ops):
     u, v = torch.randn(4, 50), torch.randn(6, 50)
     p = torch.zeros(1, 6)

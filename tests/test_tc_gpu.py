@@ -2,7 +2,7 @@
 
 * ``glue_tc_selftest`` pins the UMMA operand conventions (K-major / MN-major descriptors over the
   128-byte-swizzled [rows][64 bf16] tiles) against a plain matrix product;
-* the tensor-core decoder is compared with the CUDA-core decoder (``GLUE_B200_DECODER=v1``) on the
+* the tensor-core decoder is compared with the CUDA-core decoder (``impl`` 1) on the
   same inputs -- both are also compared with the oracle in tests/test_ops_gpu.py.
 """
 import ctypes
@@ -92,7 +92,21 @@ def test_umma_d2_mn_major_times_mn_major(native_lib):
     assert_close(out, X.T @ V, 1e-5, "d/du partial")
 
 
-# ------------------------------------------------------------------ v2 against v1
+# ------------------------------------------------------------------ v2 / v3 against v1
+import contextlib
+
+
+@contextlib.contextmanager
+def _impl(ops, impl):
+    """Pin a decoder implementation (``glue_decoder_args.impl``) for the calls inside the block."""
+    old = ops.DECODER_IMPL
+    ops.DECODER_IMPL = impl
+    try:
+        yield
+    finally:
+        ops.DECODER_IMPL = old
+
+
 def _run_decoder(ops, family, case, reduce):
     from tests.test_ops_gpu import _device_nll
     return _device_nll(ops, family, *case, reduce)
@@ -105,28 +119,29 @@ def _run_decoder(ops, family, case, reduce):
     # more than 128 cells: cell blocks of 128, feature-side outputs accumulate over the blocks
     ("NB", 512, 4000, 50, 1), ("NB", 300, 1000, 50, 3), ("ZINB", 257, 700, 50, 1), ("Normal", 130, 900, 16, 1),
 ])
-def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F, K, nb):
+@pytest.mark.parametrize("ver", [2, 3])
+def test_tensor_core_decoder_matches_cuda_core_decoder(native_lib, family, B, F, K, nb, ver):
+    """``ver``: 2 = per-row-staged tcgen05 kernels, 3 = TMA-staged ones (<= 128 cells; larger calls
+    fall through to 2), each against the CUDA-core kernels (``impl`` 1)."""
     from glue_b200 import ops
     from tests.test_ops_gpu import PARAM_NAMES, _decoder_case
     case = _decoder_case(family, B, F, K, nb, seed=B + F)
-    os.environ["GLUE_B200_DECODER"] = "v1"
-    try:
+    with _impl(ops, 1):
         l1, g1 = _run_decoder(ops, family, case, "nanmean")
-    finally:
-        os.environ.pop("GLUE_B200_DECODER")
-    l2, g2 = _run_decoder(ops, family, case, "nanmean")
+    with _impl(ops, ver):
+        l2, g2 = _run_decoder(ops, family, case, "nanmean")
+        l3, g3 = _run_decoder(ops, family, case, "nanmean")
     assert_close(l2, l1, 1e-4, "loss")
     for n, a, b in zip(["u", "v"] + list(PARAM_NAMES[family]), g2, g1):
-        assert_close(a, b, 1e-4, f"{family} d/d{n} (v2 vs v1)")
-    l3, g3 = _run_decoder(ops, family, case, "nanmean")
-    assert torch.equal(l2, l3) and all(torch.equal(a, b) for a, b in zip(g2, g3)), "v2 must be deterministic"
+        assert_close(a, b, 1e-4, f"{family} d/d{n} (v{ver} vs v1)")
+    assert torch.equal(l2, l3) and all(torch.equal(a, b) for a, b in zip(g2, g3)), "must be deterministic"
 
 
 # ------------------------------------------------------------------ kernel variants of the main pass
-# GLUE_TC_VARIANT: bit 0 = streamlined NB pass B (32-bit unpredicated x loads, quadratic gamma terms
-# for the counts 0 / 1 / 2, c_i from the tensor cores; the default for NB with one parameter row).
-# It must agree with the base kernel (GLUE_TC_VARIANT=0), which the tests above / test_ops_gpu.py
-# tie to the CUDA-core decoder and to the oracle.
+# variant 1 = streamlined NB pass B (32-bit unpredicated x loads, quadratic gamma terms for the counts
+# 0 / 1 / 2, c_i from the tensor cores; the default for NB with one parameter row).  It must agree
+# with the base kernel (variant 0 = ``impl`` bit 8), which the tests above / test_ops_gpu.py tie to the
+# CUDA-core decoder and to the oracle.  Both tcgen05 implementations (``ver`` 2 / 3) have the pair.
 def _variant_case(B, F, K, seed, sparse, nan_frac, extra_rows):
     from tests.test_ops_gpu import _decoder_case
     u, v, b, l, x, params, vidx = _decoder_case("NB", B, F, K, 1, seed=seed, extra_rows=extra_rows)
@@ -140,19 +155,16 @@ def _variant_case(B, F, K, seed, sparse, nan_frac, extra_rows):
     return u, v, b, l, x, params, vidx
 
 
-def _run_variant(ops, variant, case, reduce, row_weight=None):
+def _run_variant(ops, variant, case, reduce, row_weight=None, ver=2):
     u, v, b, l, x, params, vidx = case
     d = lambda t: None if t is None else t.to(DEV)
     du, dv = d(u).requires_grad_(True), d(v).requires_grad_(True)
     dp = [d(params[n]).requires_grad_(True) for n in ("scale_lin", "bias", "log_theta")]
-    os.environ["GLUE_TC_VARIANT"] = str(variant)
-    try:
+    with _impl(ops, ver | (0 if variant else 0x100)):
         loss = ops.decoder_nll("NB", du, dv, dp[0], dp[1], dp[2], None, b=d(b), l=d(l), x=d(x), vidx=d(vidx),
                                reduce=reduce, row_weight=d(row_weight))
         grads = torch.autograd.grad(loss, [du, dv] + dp)
         torch.cuda.synchronize()
-    finally:
-        os.environ.pop("GLUE_TC_VARIANT")
     return loss, grads
 
 
@@ -175,9 +187,11 @@ VARIANT_CASES = [
 ]
 
 
+@pytest.mark.parametrize("ver", [2, 3])
 @pytest.mark.parametrize("variant", [1])
 @pytest.mark.parametrize("B,F,K,sparse,nan_frac,extra,reduce,weighted", VARIANT_CASES)
-def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, sparse, nan_frac, extra, reduce, weighted):
+def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, sparse, nan_frac, extra, reduce, weighted,
+                                              ver):
     from glue_b200 import ops
     case = _variant_case(B, F, K, seed=7 * B + F, sparse=sparse, nan_frac=nan_frac, extra_rows=extra)
     if nan_frac and reduce == "mean":
@@ -187,23 +201,24 @@ def test_main_pass_variants_match_base_kernel(native_lib, variant, B, F, K, spar
         rw = torch.rand(B, generator=torch.Generator().manual_seed(B)) * (torch.arange(B) % 3 != 0)
         if nan_frac:
             case[4].nan_to_num_(nan=1.0)
-    l0, g0 = _run_variant(ops, 0, case, reduce, rw)
-    l1, g1 = _run_variant(ops, variant, case, reduce, rw)
+    l0, g0 = _run_variant(ops, 0, case, reduce, rw, ver)
+    l1, g1 = _run_variant(ops, variant, case, reduce, rw, ver)
     assert torch.isfinite(l0).all() and torch.isfinite(l1).all()
     assert_close(l1, l0, 2e-5, f"loss (variant {variant})")
     for n, a, b in zip(["u", "v", "scale_lin", "bias", "log_theta"], g1, g0):
         assert_close(a, b, 1e-4, f"d/d{n} (variant {variant} vs base)")
-    l2, g2 = _run_variant(ops, variant, case, reduce, rw)
+    l2, g2 = _run_variant(ops, variant, case, reduce, rw, ver)
     assert torch.equal(l1, l2) and all(torch.equal(a, b) for a, b in zip(g1, g2)), "variants must be deterministic"
 
 
+@pytest.mark.parametrize("ver", [2, 3])
 @pytest.mark.parametrize("variant", [0, 1])
-def test_main_pass_variants_vs_oracle(native_lib, variant):
+def test_main_pass_variants_vs_oracle(native_lib, variant, ver):
     from glue_b200 import ops
     from tests.test_ops_gpu import TOL, _oracle_nll
     case = _variant_case(128, 1500, 50, seed=11, sparse=True, nan_frac=0.005, extra_rows=0)
     ref_loss, _, ref_grads = _oracle_nll("NB", *case, "nanmean")
-    loss, grads = _run_variant(ops, variant, case, "nanmean")
+    loss, grads = _run_variant(ops, variant, case, "nanmean", ver=ver)
     assert_close(loss, ref_loss, TOL, "nll vs oracle")
     for n, g, rg in zip(["u", "v", "scale_lin", "bias", "log_theta"], grads, ref_grads):
         assert_close(g, rg, TOL, f"d/d{n} vs oracle (variant {variant})")
