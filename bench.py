@@ -388,14 +388,13 @@ def main():
     B, K, F = cfg["batch"], cfg["latent_dim"], cfg["n_peaks"]
     keys = net.keys
     x_of = {k: [batch[i] for batch in dev_pool] for i, k in enumerate(keys)}
-    blocker = torch.randn(8192, 8192, device=device)
 
     def time_calls(fn, n=24):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize(device)
-        for _ in range(4):
-            blocker @ blocker
+        torch.cuda._sleep(12_000_000)  # a spinning blocker: the launches below queue behind it (a GEMM blocker
+        # would pull the SM clock down under the power cap and inflate what is timed behind it)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(n):

@@ -85,7 +85,25 @@ struct Ws3 {
     int* badpart;            // [ncta][S]
     float* rescale;          // [1]
     unsigned int* counters;  // [4]
+    long long* trace;        // [3 kernels][16 units][16 events] clock64 stamps of CTA 0 (impl bit 9), else NULL
 };
+
+// diagnostic timeline (impl bit 9): kernel 0 = pass A, 1 = pass B, 2 = pass C; unit 15 holds kernel-wide events
+#define T3(kern, unit, ev)                                                                       \
+    do {                                                                                         \
+        if (P.ws.trace != nullptr && blockIdx.x == 0 && (unit) < 16)                             \
+            P.ws.trace[((kern) * 16 + (unit)) * 16 + (ev)] = clock64();                          \
+    } while (0)
+
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define T3NS(kern, ev)                                                                           \
+    do {                                                                                         \
+        if (P.ws.trace != nullptr && blockIdx.x == 0) P.ws.trace[((kern) * 16 + 15) * 16 + (ev)] = globaltimer_ns(); \
+    } while (0)
 
 struct P3 {
     glue_decoder_args a;  // shared fields (u, row_weight, grad_scale, loss, grad_u are per term below)
@@ -100,7 +118,7 @@ struct P3 {
 
 struct Bars3 {
     uint64_t v_full[2], v_empty[2], u_full[2], u_empty[2], acc_full[2], acc_empty[2], coef_full[2];
-    uint64_t x_full, x_empty, d1_full, d1_empty, d2_full;
+    uint64_t x_full[4], x_empty, d1_full, d1_empty, d2_full;  // x_full: per block of 32 cells
 };
 
 struct __align__(1024) SmemMain3 {
@@ -108,6 +126,8 @@ struct __align__(1024) SmemMain3 {
     uint8_t v[2][2][OP_BYTES];  // [stage][hi, lo]
     uint8_t x_hi[2 * OP_BYTES], x_lo[2 * OP_BYTES];  // [cell block of 64][128 feature rows][128 B]
     float stage[4][32][33];     // d/dv rows on their way out, one block per converter warp
+    int rowidx[4][32];          // row of d/dv (= row of v) of every feature row of the tile being written out (-1: none)
+    float pgrad[4][128];        // parameter-table gradient partials of the upper-half epilogue threads
     alignas(16) uint32_t xoff32[136];  // element offset of every cell's row of x (streamlined path); 8 pad entries
     alignas(16) int xrow[128];         // row of x of every cell
     alignas(16) int bidx[128];
@@ -143,6 +163,16 @@ static_assert(offsetof(SmemMain3, wrow) % 16 == 0 && offsetof(SmemMain3, lse) % 
               "vector loads of the per-cell tables");
 static_assert(offsetof(SmemStats3, ptab) % 16 == 0, "bulk copy destination");
 
+// predicated global store (no branch: a run of these keeps its loads and address arithmetic batched)
+__device__ __forceinline__ void st_global_pred(float* ptr, float val, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "@p st.global.f32 [%0], %1;\n\t}" ::"l"(ptr),
+        "f"(val), "r"((int)pred)
+        : "memory");
+}
+
 __device__ __forceinline__ int orig_row(const glue_decoder_args& a, int pos) {
     return a.row_order ? a.row_order[pos] : pos;
 }
@@ -153,25 +183,29 @@ __device__ __forceinline__ int orig_row(const glue_decoder_args& a, int pos) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void write_part(uint8_t* img, int64_t row, int64_t nrows, int part, const float* src, int K,
                                            int colx, float extra) {
-    float vals[4];
+    float vals[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = 4 * part + q;
-        vals[q] = (src != nullptr && k < K) ? __ldg(src + k) : 0.f;
-        if (k == colx) vals[q] = extra;
+    for (int q = 0; q < 4; ++q) {  // (rows are 8-byte aligned: K is even)
+        const int k = 8 * part + 2 * q;
+        float2 pr = make_float2(0.f, 0.f);
+        if (src != nullptr && k < K) pr = __ldg(reinterpret_cast<const float2*>(src + k));
+        vals[2 * q] = pr.x, vals[2 * q + 1] = pr.y;
     }
-    uint32_t h0, l0, h1, l1;
-    split2(vals[0], vals[1], h0, l0);
-    split2(vals[2], vals[3], h1, l1);
-    *reinterpret_cast<uint2*>(img + row * ROW_BYTES + part * 8) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(img + (nrows + row) * ROW_BYTES + part * 8) = make_uint2(l0, l1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (8 * part + q == colx) vals[q] = extra;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split2(vals[2 * q], vals[2 * q + 1], h[q], l[q]);
+    *reinterpret_cast<uint4*>(img + row * ROW_BYTES + part * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(img + (nrows + row) * ROW_BYTES + part * 16) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __global__ void __launch_bounds__(256) presplit_kernel(P3 P) {
     const glue_decoder_args& a = P.a;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int part = (int)(gid & 15);
-    const int64_t row = gid >> 4;
+    const int part = (int)(gid & 7);
+    const int64_t row = gid >> 3;
     const int64_t nv = P.Fpad, nu = (int64_t)P.S * 128;
     if (gid < 4) P.ws.counters[gid] = 0u;
     if (row < nv) {
@@ -181,14 +215,14 @@ __global__ void __launch_bounds__(256) presplit_kernel(P3 P) {
         if (j < a.F) {
             const int64_t vr = a.vidx ? a.vidx[j] : j;
             src = a.v + vr * a.K;
-            if (P.cinv) {
+            if (P.cinv && part == (a.K >> 3)) {
                 const float sp = softplusf(a.scale_lin[j]);
                 extra = sp > 1e-18f ? 1.f / sp : 0.f;
             }
         }
         write_part(P.ws.vimg, row, nv, part, src, a.K, P.cinv ? a.K : -1, extra);
-        if (part == 0 && P.ws.ptab != nullptr) {
-            for (int b = 0; b < a.n_batches; ++b) {
+        if (P.ws.ptab != nullptr) {
+            for (int b = part; b < a.n_batches; b += 8) {
                 float2 pr = make_float2(0.f, -INFINITY);
                 if (j < a.F) {
                     const int64_t off = (int64_t)b * a.F + j;
@@ -219,32 +253,41 @@ __device__ __forceinline__ void issue_logits(uint32_t tmem_acc, const uint8_t* a
                       (c | ks) ? 1u : 0u);
 }
 
-// operand loads of one CTA, in consumption order: the v tile of feature tile `it`, then the u block of
-// each of its units (two-slot ring)
+// operand loads of one CTA, in consumption order: per feature tile the v tile, then the u block of each
+// of its units (two-slot ring).  Loads [op_begin, op_end) of that sequence; the first ones wait for
+// nothing and are issued before the per-cell tables are complete (tma_prologue_ops).
 template <typename SM>
-__device__ __forceinline__ void tma_producer(SM& S, const CUtensorMap* mapV, const CUtensorMap* mapU, const P3& P,
-                                             int ntl, int cta, int ncta, bool with_ptab) {
-    const int nS = P.S;
-    for (int it = 0; it < ntl; ++it) {
-        const int vs = it & 1, f0 = (cta + it * ncta) * 128;
-        mbar_wait(&S.bars.v_empty[vs], ((it >> 1) & 1) ^ 1);
-        const uint32_t pbytes = with_ptab ? (uint32_t)P.a.n_batches * 1024u : 0u;
-        mbar_arrive_expect_tx(&S.bars.v_full[vs], 2 * OP_BYTES + pbytes);
-        tma_load_2d(S.v[vs][0], mapV, 0, f0, &S.bars.v_full[vs]);
-        tma_load_2d(S.v[vs][1], mapV, 0, P.Fpad + f0, &S.bars.v_full[vs]);
-        if constexpr (std::is_same<SM, SmemStats3>::value) {
-            if (with_ptab)
-                for (int b = 0; b < P.a.n_batches; ++b)
-                    bulk_load(&S.ptab[vs][b][0], P.ws.ptab + (int64_t)b * P.Fpad + f0, 1024u, &S.bars.v_full[vs]);
-        }
-        for (int seg = 0; seg < nS; ++seg) {
-            const int n = it * nS + seg, us = n & 1;
+__device__ __forceinline__ void tma_ops(SM& S, const CUtensorMap* mapV, const CUtensorMap* mapU, const P3& P, int cta,
+                                        int ncta, bool with_ptab, int kern, int op_begin, int op_end) {
+    const int nS = P.S, per = 1 + nS;
+    for (int op = op_begin; op < op_end; ++op) {
+        const int it = op / per, k = op - it * per;
+        if (k == 0) {
+            const int vs = it & 1, f0 = (cta + it * ncta) * 128;
+            mbar_wait(&S.bars.v_empty[vs], ((it >> 1) & 1) ^ 1);
+            const uint32_t pbytes = with_ptab ? (uint32_t)P.a.n_batches * 1024u : 0u;
+            mbar_arrive_expect_tx(&S.bars.v_full[vs], 2 * OP_BYTES + pbytes);
+            tma_load_2d(S.v[vs][0], mapV, 0, f0, &S.bars.v_full[vs]);
+            tma_load_2d(S.v[vs][1], mapV, 0, P.Fpad + f0, &S.bars.v_full[vs]);
+            T3(kern, it * nS, 0);
+            if constexpr (std::is_same<SM, SmemStats3>::value) {
+                if (with_ptab)
+                    for (int b = 0; b < P.a.n_batches; ++b)
+                        bulk_load(&S.ptab[vs][b][0], P.ws.ptab + (int64_t)b * P.Fpad + f0, 1024u, &S.bars.v_full[vs]);
+            }
+        } else {
+            const int seg = k - 1, n = it * nS + seg, us = n & 1;
             mbar_wait(&S.bars.u_empty[us], ((n >> 1) & 1) ^ 1);
             mbar_arrive_expect_tx(&S.bars.u_full[us], 2 * OP_BYTES);
             tma_load_2d(S.u[us][0], mapU, 0, seg * 128, &S.bars.u_full[us]);
             tma_load_2d(S.u[us][1], mapU, 0, (nS + seg) * 128, &S.bars.u_full[us]);
+            T3(kern, n, 1);
         }
     }
+}
+__device__ __forceinline__ int tma_prologue_ops(int nS, int ntl) {
+    const int total = ntl * (1 + nS), free_ops = nS == 1 ? 4 : 3;  // v0 u0 v1 u1 | v0 u0 u1: fresh buffers
+    return total < free_ops ? total : free_ops;
 }
 
 template <typename SM>
@@ -258,7 +301,7 @@ __device__ __forceinline__ void init_bars(SM& S, bool grad, int v_empty_count) {
         mbar_init(&S.bars.acc_empty[s], grad ? CONV_THREADS / 32 : EPI_WARPS);
         mbar_init(&S.bars.coef_full[s], EPI_WARPS);
     }
-    mbar_init(&S.bars.x_full, CONV_THREADS / 32);
+    for (int cb = 0; cb < 4; ++cb) mbar_init(&S.bars.x_full[cb], CONV_THREADS / 32);
     mbar_init(&S.bars.x_empty, 1);
     mbar_init(&S.bars.d1_full, 1);
     mbar_init(&S.bars.d1_empty, CONV_THREADS / 32);
@@ -280,6 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int ntl = (P.ntiles - cta + ncta - 1) / ncta;
     const int nS = P.S, nunits = ntl * nS;
+    if (t == 0) T3(0, 15, 0);
 
     if (t == 0) init_bars(S, false, EPI_WARPS);
     if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, 256);
@@ -292,9 +336,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    if (t == 0) T3(0, 15, 1);
 
     if (warp == TMA_WARP) {
-        if (lane == 0) tma_producer(S, &mapV, &mapU, P, ntl, cta, ncta, true);
+        if (lane == 0) tma_ops(S, &mapV, &mapU, P, cta, ncta, true, 0, 0, ntl * (1 + nS));
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             for (int n = 0; n < nunits; ++n) {
@@ -306,6 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 issue_logits(tmem_base + COL_ACC + as * 128, S.u[us][0], S.u[us][1], S.v[vs][0], S.v[vs][1]);
                 umma_commit(&S.bars.acc_full[as]);
                 umma_commit(&S.bars.u_empty[us]);
+                T3(0, n, 2);
                 // (the parameter table of the stage is read by the epilogue: released there)
             }
         }
@@ -320,8 +366,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const int it = n / nS, seg = n - it * nS, vs = it & 1, as = n & 1;
             const int f0 = (cta + it * ncta) * 128;
             const int nvalid = min(128, a.F - f0);
+            if (t == 0) T3(0, n, 5);
             mbar_wait(&S.bars.acc_full[as], (n >> 1) & 1);
             tc_fence_after();
+            if (t == 0) T3(0, n, 6);
             float mm = -INFINITY, ss = 0.f;
 #pragma unroll
             for (int s = 0; s < MAXSEG; ++s)
@@ -355,6 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
             for (int s = 0; s < MAXSEG; ++s)
                 if (s == seg) m[s] = mm, ssum[s] = ss;
+            if (t == 0) T3(0, n, 7);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -375,6 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
+    if (t == 0) T3(0, 15, 5);
 }
 
 // lse (natural log) from the base-2 per-(CTA, column half) partials; block = 32 rows x 32 strided
@@ -437,34 +487,57 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int ncell = P.ncell;
     const int nS = P.S, nunits = ntl * nS;
     const int ngrp = (ncell + 7) >> 3;
+    constexpr int KRN = 1 + PHASE;
+    if (t == 0) T3(KRN, 15, 0);
+    if (t == 0) T3NS(KRN, 13);
 
     if (t == 0) init_bars(S, GRAD, 1);
+    if (warp == TMA_WARP && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapU) : "memory");
+    }
+    __syncthreads();  // barriers are live: the operand loads start while the per-cell tables are filled
     if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
     if (t < 128) {
         const bool ok = t < ncell;
         const int orig = ok ? orig_row(a, t) : 0;
-        S.bidx[t] = (ok && a.b) ? (int)a.b[orig] : 0;
+        // every load first
+        const int bi = (ok && a.b) ? (int)a.b[orig] : 0;
+        const float li = (ok && a.l) ? a.l[orig] : 1.f;
+        float lsev[MAXSEG], cv[MAXSEG], rwv[MAXSEG];
+#pragma unroll
+        for (int s = 0; s < MAXSEG; ++s) {
+            const bool on = ok && s < nS;
+            lsev[s] = (on && NBF) ? P.ws.lse[s * 128 + t] : 0.f;
+            cv[s] = (on && PHASE == 1) ? P.ws.c[s * 128 + t] : 0.f;
+            rwv[s] = (on && P.term[s].row_weight) ? P.term[s].row_weight[orig] : 0.f;
+        }
+        S.bidx[t] = bi;
         S.xrow[t] = orig;
         S.xoff32[t] = (uint32_t)((long long)orig * a.F);  // (FAST: B F < 2^31 checked by the host)
         if (t < 8) S.xoff32[128 + t] = 0u;
         S.zeros[t] = 0.f;
-        S.l[t] = (ok && a.l) ? a.l[orig] : 1.f;
-        for (int s = 0; s < nS; ++s) {
-            S.lse[s][t] = (ok && NBF) ? -(P.ws.lse[s * 128 + t] * LOG2EF) : 0.f;  // -lse in base 2
-            S.c[s][t] = (ok && PHASE == 1) ? P.ws.c[s * 128 + t] : 0.f;
-            S.c_acc[s][t] = 0.f;
-            const Term& T = P.term[s];
-            S.wrow[s][t] = ok ? (T.row_weight ? -T.row_weight[orig] * T.gscale : T.w0) : 0.f;
-        }
+        S.l[t] = li;
+#pragma unroll
+        for (int s = 0; s < MAXSEG; ++s)
+            if (s < nS) {
+                S.lse[s][t] = -(lsev[s] * LOG2EF);  // -lse in base 2
+                S.c[s][t] = cv[s];
+                S.c_acc[s][t] = 0.f;
+                const Term& T = P.term[s];
+                S.wrow[s][t] = ok ? (T.row_weight ? -rwv[s] * T.gscale : T.w0) : 0.f;
+            }
     }
+    if (warp == TMA_WARP && lane == 0) tma_ops(S, &mapV, &mapU, P, cta, ncta, false, KRN, 0, tma_prologue_ops(nS, ntl));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    if (t == 0) T3(KRN, 15, 1);
 
     if (warp == TMA_WARP) {
         // ===== operand loads =====
-        if (lane == 0) tma_producer(S, &mapV, &mapU, P, ntl, cta, ncta, false);
+        if (lane == 0) tma_ops(S, &mapV, &mapU, P, cta, ncta, false, KRN, tma_prologue_ops(nS, ntl), ntl * (1 + nS));
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -476,6 +549,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 tc_fence_after();
                 issue_logits(tmem_base + COL_ACC + as * 128, S.v[vs][0], S.v[vs][1], S.u[us][0], S.u[us][1]);
                 umma_commit(&S.bars.acc_full[as]);
+                T3(KRN, n, 2);
                 if (!GRAD) {
                     umma_commit(&S.bars.u_empty[us]);
                     if (seg == nS - 1) umma_commit(&S.bars.v_empty[vs]);
@@ -487,22 +561,33 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 if (n + 1 < nunits) issue_fwd(n + 1);
                 if (GRAD) {
                     const int it = n / nS, seg = n - it * nS, vs = it & 1, us = n & 1;
-                    mbar_wait(&S.bars.x_full, n & 1);
-                    if (seg == 0) mbar_wait(&S.bars.d1_empty, (it & 1) ^ 1);
-                    tc_fence_after();
                     const uint32_t xh = smem_u32(S.x_hi), xl = smem_u32(S.x_lo);
                     const uint32_t uh = smem_u32(S.u[us][0]), ul = smem_u32(S.u[us][1]);
                     const uint32_t vh = smem_u32(S.v[vs][0]), vl = smem_u32(S.v[vs][1]);
                     const uint32_t xs[3] = {xl, xh, xh};
-                    // D1[feature, k] (+)= sum_cell X[feature, cell] U[cell, k]   (all terms of the tile)
+                    // D1[feature, k] (+)= sum_cell X[feature, cell] U[cell, k]   (all terms of the tile);
+                    // issued per block of 32 cells as the converters finish it
                     {
                         const uint32_t bs[3] = {uh, ul, uh};
                         const uint32_t d1 = tmem_base + COL_D1;
+                        for (uint32_t cb = 0; cb < 4; ++cb) {
+                            mbar_wait(&S.bars.x_full[cb], n & 1);
+                            if (cb == 0) {
+                                T3(KRN, n, 3);
+                                if (seg == 0) mbar_wait(&S.bars.d1_empty, (it & 1) ^ 1);
+                            }
+                            tc_fence_after();
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            for (uint32_t ks = 0; ks < nks1; ++ks)
-                                umma_bf16(d1, smem_desc(DESC_K, xs[c] + (ks >> 2) * OP_BYTES + (ks & 3) * 32),
-                                          smem_desc(DESC_MN1, bs[c] + ks * 2048), IDESC_D1, (seg | c | ks) ? 1u : 0u);
+                            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                for (uint32_t kq = 0; kq < 2; ++kq) {
+                                    const uint32_t ks = 2 * cb + kq;
+                                    if (ks < nks1)
+                                        umma_bf16(d1, smem_desc(DESC_K, xs[c] + (ks >> 2) * OP_BYTES + (ks & 3) * 32),
+                                                  smem_desc(DESC_MN1, bs[c] + ks * 2048), IDESC_D1,
+                                                  (seg | cb | c | kq) ? 1u : 0u);
+                                }
+                        }
                         umma_commit(&S.bars.u_empty[us]);  // (logits of this unit and the next were issued before)
                         if (seg == nS - 1) umma_commit(&S.bars.d1_full);
                     }
@@ -518,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                           smem_desc(DESC_MN1, bs[c] + ks * 2048), IDESC_D2, (it | c | ks) ? 1u : 0u);
                         umma_commit(&S.bars.x_empty);
                         if (seg == nS - 1) umma_commit(&S.bars.v_empty[vs]);
+                        T3(KRN, n, 4);
                     }
                 }
             }
@@ -532,9 +618,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const uint32_t lane_addr = (uint32_t)(32 * cq) << 16;
         const bool add_v = (PHASE == 1);
         auto prefetch_x = [&](int itn) {
-            if (PHASE != 0 || itn >= ntl) return;
+            if (itn >= ntl) return;
             const int f0 = (cta + itn * ncta) * 128;
             const int nvalid = min(128, a.F - f0);
+            if (NB1 && ct < 16) {  // the tile's parameter rows (512 B per table)
+                const float* tabs[4] = {a.scale_lin, a.bias, a.disp, a.zi_logits};
+                const float* tp = tabs[ct >> 2];
+                const int o = 32 * (ct & 3);
+                if (tp != nullptr && o < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + f0 + o));
+            }
+            if (PHASE != 0) return;
             for (int cell = ct; cell < ncell; cell += CONV_THREADS) {
                 const float* px = a.x + (int64_t)S.xrow[cell] * a.F + f0;
                 for (int o = 0; o < nvalid; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
@@ -542,43 +635,80 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
         };
         auto readout_d1 = [&](int itp) {
+            // my row of d/dv; rows leave with consecutive lanes on consecutive addresses (transposed
+            // through the warp's staging block, 32 columns at a time).  Shared-memory reads are
+            // collected in registers before the global stores (the compiler keeps generic-pointer
+            // stores and shared loads in program order).  Pass C adds to what pass B wrote: the old
+            // values of the first 32 columns are requested before the tile is waited for.
+            const bool tr0 = ct == 0 && itp == 0;
+            if (tr0) T3(KRN, 15, 6);
+            const int j = (cta + itp * ncta) * 128 + frow;
+            int myrow = -1;
+            if (j < a.F && a.grad_v) myrow = (int)(a.vidx ? a.vidx[j] : (long long)j);
+            S.rowidx[cq][lane] = myrow;
+            __syncwarp();
+            const int* rowidx = S.rowidx[cq];
+            float(*st)[33] = S.stage[cq];
+            float old[32];
+            // (row indices are re-read from shared memory where they are needed: at most 64 values per
+            // thread are live at any point, nothing is demoted to local memory)
+            auto load_old = [&](int kk) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int row = rowidx[r];
+                    old[r] = (add_v && kk < a.K && row >= 0) ? __ldcg(a.grad_v + (long long)row * a.K + kk) : 0.f;
+                }
+            };
+            auto store_rows = [&](int kk) {
+                float vals[32];
+                int rows[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    rows[r] = rowidx[r];
+                    vals[r] = st[r][lane] + old[r];
+                }
+                asm volatile("" ::: "memory");  // every shared-memory read before the first global store
+                const bool kok = kk < a.K;
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    st_global_pred(a.grad_v + (long long)rows[r] * a.K + kk, vals[r], kok && rows[r] >= 0);
+            };
+            load_old(lane);
+            if (tr0) T3(KRN, 15, 7);
             mbar_wait(&S.bars.d1_full, itp & 1);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_base + lane_addr + COL_D1, r0);
-            tmem_ld32(tmem_base + lane_addr + COL_D1 + 32, r1);
-            tmem_ld_wait();
+            if (tr0) T3(KRN, 15, 8);
+            if (ct == 0) T3(KRN, itp * nS + nS - 1, 13);
+            {
+                uint32_t r0[32];
+                tmem_ld32(tmem_base + lane_addr + COL_D1, r0);
+                tmem_ld_wait();
+                if (tr0) T3(KRN, 15, 9);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) st[lane][k] = __uint_as_float(r0[k]);
+            }
+            __syncwarp();
+            if (tr0) T3(KRN, 15, 10);
+            store_rows(lane);
+            __syncwarp();
+            if (tr0) T3(KRN, 15, 11);
+            if (a.K > 32) {
+                load_old(32 + lane);
+                uint32_t r1[32];
+                tmem_ld32(tmem_base + lane_addr + COL_D1 + 32, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) st[lane][k] = __uint_as_float(r1[k]);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.bars.d1_empty);
-            // my row of d/dv; rows leave with consecutive lanes on consecutive addresses
-            const int j = (cta + itp * ncta) * 128 + frow;
-            long long myoff = -1;
-            if (j < a.F && a.grad_v) myoff = (a.vidx ? a.vidx[j] : (long long)j) * a.K;
-            float(*st)[33] = S.stage[cq];
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                if (32 * half >= a.K) break;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) st[lane][k] = __uint_as_float(half ? r1[k] : r0[k]);
-                __syncwarp();
-                const int kk = 32 * half + lane;
-                const bool kok = kk < a.K;
-#pragma unroll 1
-                for (int rb = 0; rb < 32; rb += 8) {
-                    long long off[8];
-                    float old[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {  // every load before the first store
-                        off[i] = __shfl_sync(FULL, myoff, rb + i);
-                        old[i] = (add_v && kok && off[i] >= 0) ? a.grad_v[off[i] + kk] : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (kok && off[i] >= 0) a.grad_v[off[i] + kk] = st[rb + i][lane] + old[i];
-                }
+            if (tr0) T3(KRN, 15, 12);
+            if (a.K > 32) {
+                store_rows(32 + lane);
                 __syncwarp();
             }
+            if (ct == 0) T3(KRN, itp * nS + nS - 1, 14);
         };
         if (GRAD) {
             prefetch_x(0);
@@ -587,7 +717,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 if (seg == 0) prefetch_x(it + 1);
                 mbar_wait(&S.bars.coef_full[as], (n >> 1) & 1);
                 tc_fence_after();
+                if (ct == 0) T3(KRN, n, 10);
                 mbar_wait(&S.bars.x_empty, (n & 1) ^ 1);  // gradient products of the previous unit are done with X
+                if (ct == 0) T3(KRN, n, 11);
 #pragma unroll 1
                 for (int cb = 0; cb < 4; ++cb) {
                     uint32_t d[32];
@@ -611,14 +743,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         st_shared_v4(smem_u32(S.x_hi) + off, hh[0], hh[1], hh[2], hh[3]);
                         st_shared_v4(smem_u32(S.x_lo) + off, ll[0], ll[1], ll[2], ll[3]);
                     }
+                    fence_proxy_async();
+                    if (cb == 3) tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (cb == 3) mbar_arrive(&S.bars.acc_empty[as]);
+                        mbar_arrive(&S.bars.x_full[cb]);
+                    }
                 }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&S.bars.acc_empty[as]);
-                    mbar_arrive(&S.bars.x_full);
-                }
+                if (ct == 0) T3(KRN, n, 12);
                 if (seg == 0 && it > 0) readout_d1(it - 1);  // (its products were committed a unit ago)
             }
             readout_d1(ntl - 1);
@@ -665,6 +798,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             if (wd) a.grad_disp[off] = od + vd;
             if (wz) a.grad_zi_logits[off] = oz + vz;
         };
+        // several parameter rows: read-modify-write per run of cells with one batch index; the first run
+        // of the upper-half thread is written after a barrier (fixed order of the two updates of an entry)
         auto flush = [&]() {
             if (GRAD && cur_b >= 0 && jok) {
                 const int64_t off = (int64_t)cur_b * a.F + j;
@@ -672,9 +807,28 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 if (h == 1 && !pend) {
                     pend = true, pend_off = off, pend_b = gb, pend_s = vs, pend_d = gd, pend_z = gz;
                 } else {
-                    write_param(off, gb, vs, gd, gz, (PHASE == 1) || !NB1 || h == 1);
+                    write_param(off, gb, vs, gd, gz, true);
                 }
             }
+            gb = gs = gd = gz = 0.f;
+        };
+        // single parameter row: the two threads of a feature meet in shared memory, the lower-half thread
+        // writes (pass C adds to what pass B wrote; those values were requested when the tile started)
+        float old_b = 0.f, old_s = 0.f;
+        auto flush_nb1 = [&]() {
+            const float vs = gs * fp.sg;
+            if (h == 1) {
+                S.pgrad[0][frow] = gb, S.pgrad[1][frow] = vs, S.pgrad[2][frow] = gd, S.pgrad[3][frow] = gz;
+            }
+            named_bar_sync(4 + q, 64);  // the two warps of this TMEM lane quarter
+            if (h == 0 && jok) {
+                const int64_t off = j;
+                if (a.grad_bias) a.grad_bias[off] = (gb + S.pgrad[0][frow]) + old_b;
+                if (a.grad_scale_lin) a.grad_scale_lin[off] = (vs + S.pgrad[1][frow]) + old_s;
+                if (PHASE == 0 && a.grad_disp) a.grad_disp[off] = gd + S.pgrad[2][frow];
+                if (PHASE == 0 && ZI && a.grad_zi_logits) a.grad_zi_logits[off] = gz + S.pgrad[3][frow];
+            }
+            named_bar_sync(4 + q, 64);  // (pgrad is free again)
             gb = gs = gd = gz = 0.f;
         };
 
@@ -689,6 +843,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 gb = gs = gd = gz = 0.f;
                 ngb2 = pk(0.f, 0.f), ngs2 = pk(0.f, 0.f), gd2 = pk(0.f, 0.f);
                 if (NB1) {
+                    if (GRAD && PHASE == 1 && h == 0 && jok) {
+                        old_b = a.grad_bias ? __ldcg(a.grad_bias + j) : 0.f;
+                        old_s = a.grad_scale_lin ? __ldcg(a.grad_scale_lin + j) : 0.f;
+                    }
                     fp = load_params<FAM>(a, 0, j, jok);
                     cur_b = 0;
                     s2 = fp.s * LOG2EF, b2 = fp.bias * LOG2EF;  // logits in base 2
@@ -737,8 +895,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const float* lsep = S.lse[seg];
             const float* auxp = PHASE == 0 ? S.l : S.c[seg];
             load_x(g_begin);
+            if (t == 0) T3(KRN, n, 5);
             mbar_wait(&S.bars.acc_full[as], (n >> 1) & 1);
             tc_fence_after();
+            if (t == 0) T3(KRN, n, 6);
 #pragma unroll 1
             for (int g = g_begin; g < g_end; ++g) {
                 const int c0 = g * 8;
@@ -992,6 +1152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     }
                 }
             }
+            if (t == 0) T3(KRN, n, 7);
             {  // loss of the unit
                 float a0, a1;
                 up(loss2, a0, a1);
@@ -1010,34 +1171,38 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.bars.acc_empty[as]);
             }
+            if (t == 0) T3(KRN, n, 8);
             const bool last_of_tile = seg == nS - 1;
-            if (GRAD && (last_of_tile || !NB1)) {
-                if (NB1) {  // packed accumulators of the fast paths (they hold -G sums)
-                    float a0, a1;
-                    up(ngb2, a0, a1);
-                    gb -= a0 + a1;
-                    up(ngs2, a0, a1);
-                    gs -= a0 + a1;
-                    up(gd2, a0, a1);
-                    gd += a0 + a1;
-                }
+            if (GRAD && NB1 && last_of_tile) {
+                float a0, a1;  // packed accumulators of the fast paths (they hold -G sums)
+                up(ngb2, a0, a1);
+                gb -= a0 + a1;
+                up(ngs2, a0, a1);
+                gs -= a0 + a1;
+                up(gd2, a0, a1);
+                gd += a0 + a1;
+                flush_nb1();
+            }
+            if (GRAD && !NB1) {
                 flush();
                 named_bar_sync(1, EPI_T);
                 if (pend) write_param(pend_off, pend_b, pend_s, pend_d, pend_z, true);
                 pend = false;
-                // several parameter rows: the next unit of this tile updates the same table entries
-                if (!NB1 && nS > 1) named_bar_sync(1, EPI_T);
+                // the next unit of this tile updates the same table entries
+                if (nS > 1) named_bar_sync(1, EPI_T);
             }
             if (GRAD && NBF && PHASE == 0 && !(FAST || (NB1 && P.cinv))) {
-                if (NB1 && !last_of_tile) named_bar_sync(1, EPI_T);  // (cw of this unit is complete)
+                if (NB1) named_bar_sync(1, EPI_T);  // (cw of this unit is complete)
                 if (t < ncell)
                     S.c_acc[seg][t] += (S.cw[n & 1][0][t] + S.cw[n & 1][1][t]) + (S.cw[n & 1][2][t] + S.cw[n & 1][3][t]);
             }
         }
+        if (t == 0) T3(KRN, 15, 2);
         if (GRAD) {
             // d/du partials of this CTA: rows = cells, one 64-column accumulator per term
             mbar_wait(&S.bars.d2_full, 0);
             tc_fence_after();
+            if (t == 0) T3(KRN, 15, 3);
             for (int s = 0; s < nS; ++s) {
                 uint32_t r[DC];
                 tmem_ld32(tmem_base + lane_addr + COL_D2 + 64 * s + DC * h, r);
@@ -1091,6 +1256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc_fence_before();
     if (PHASE == 0) __threadfence();
     __syncthreads();
+    if (t == 0) T3(KRN, 15, 4);
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
     if (PHASE == 0) {
         // ---- the last CTA to arrive reduces the per-CTA partials: c_i, losses, nanmean factor -----
@@ -1138,22 +1304,35 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
         }
     }
+    if (t == 0) T3(KRN, 15, 5);
+    if (t == 0) T3NS(KRN, 14);
 }
 
-// d/du = sum over CTAs of the D2 partials; grid = S * ncell blocks, 256 threads = 64 latent columns x
-// 4 strided sub-sums combined in a fixed order
-__global__ void __launch_bounds__(256) grad_u3_kernel(P3 P, int ncta) {
+// d/du = sum over CTAs of the D2 partials; grid = S * ncell blocks, 1024 threads = 64 latent columns x
+// 16 strided sub-sums (<= 10 loads in flight per thread) combined in a fixed order
+__global__ void __launch_bounds__(1024) grad_u3_kernel(P3 P, int ncta) {
     const glue_decoder_args& a = P.a;
     const int s = blockIdx.x / P.ncell, pos = blockIdx.x - s * P.ncell;
     const int k = threadIdx.x & 63, sub = threadIdx.x >> 6;
-    __shared__ float part[4][64];
+    __shared__ float part[16][64];
+    float vals[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int q = sub + 16 * i;
+        vals[i] = q < ncta ? __ldcg(P.ws.apart + (((int64_t)q * P.S + s) * 128 + pos) * 64 + k) : 0.f;
+    }
     float acc = 0.f;
-    for (int q = sub; q < ncta; q += 4) acc += P.ws.apart[(((int64_t)q * P.S + s) * 128 + pos) * 64 + k];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc += vals[i];
     part[sub][k] = acc;
     __syncthreads();
     float* gu = P.term[s].grad_u;
-    if (sub == 0 && k < a.K && gu)
-        gu[(int64_t)orig_row(a, pos) * a.K + k] = (part[0][k] + part[1][k]) + (part[2][k] + part[3][k]);
+    if (sub == 0 && k < a.K && gu) {
+        float tot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tot += part[q][k];
+        gu[(int64_t)orig_row(a, pos) * a.K + k] = tot;
+    }
 }
 
 // only does work when NaN observations were skipped (nanmean denominator; single term)
@@ -1190,6 +1369,7 @@ size_t ws_layout(const glue_decoder_args& a, int S, int ncta, int Fpad, char* ba
         return ptr;
     };
     Ws3 w;
+    w.trace = (long long*)take(3 * 16 * 16 * 8, 1024);  // (first: tools find it at the aligned base)
     w.vimg = (uint8_t*)take((size_t)2 * Fpad * ROW_BYTES, 1024);
     w.uimg = (uint8_t*)take((size_t)2 * S * 128 * ROW_BYTES, 1024);
     w.ptab = (float2*)take((size_t)a.n_batches * Fpad * sizeof(float2), 256);
@@ -1328,6 +1508,10 @@ int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st) {
     const bool fast = a.family == GLUE_NB && nb1 && a.K <= 62 && small && !(a.impl & 0x100);
     P.cinv = (nbf && nb1 && a.K <= 62 && grad) ? 1 : 0;
     if (!nbf) P.ws.ptab = nullptr;
+    if (a.impl & 0x200)
+        GLUE_CUDA(cudaMemsetAsync(P.ws.trace, 0, 3 * 16 * 16 * 8, st));
+    else
+        P.ws.trace = nullptr;
 
     CUtensorMap mapV, mapU;
     int rc = make_map(&mapV, P.ws.vimg, (uint64_t)2 * P.Fpad);
@@ -1343,7 +1527,7 @@ int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st) {
         if (a.grad_zi_logits) GLUE_CUDA(cudaMemsetAsync(a.grad_zi_logits, 0, tab, st));
     }
     {
-        const int64_t nthreads = ((int64_t)P.Fpad + (int64_t)P.S * 128) * 16;
+        const int64_t nthreads = ((int64_t)P.Fpad + (int64_t)P.S * 128) * 8;
         presplit_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(P);
         GLUE_CHECK_LAUNCH();
     }
@@ -1364,7 +1548,7 @@ int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st) {
                      : launch_family<false>(a.family, 1, true, fast, mapV, mapU, P, ncta, st);
             if (rc) return rc;
         }
-        grad_u3_kernel<<<P.S * P.ncell, 256, 0, st>>>(P, ncta);
+        grad_u3_kernel<<<P.S * P.ncell, 1024, 0, st>>>(P, ncta);  // ncta <= 160
         GLUE_CHECK_LAUNCH();
         if (P.S == 1 && a.reduce == 0 && !m.row_weight[0]) {
             rescale3_kernel<<<sm_count(), 256, 0, st>>>(P);

@@ -318,24 +318,21 @@ class SCGLUETrainer(GLUETrainer):
         # the data encoders: it runs beside them
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
             x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
-        # one stream per decoder call (per modality: the reconstruction term and, for paired data,
-        # the joint-cross / real-cross terms): each call is a short sequence of one-CTA-per-SM
-        # kernels, so the calls of a small modality (16 CTAs for 2 000 genes) and the prologue of
-        # the next large kernel fill the SMs that the tail of a large one (50 000 peaks) leaves idle
+        # one stream per modality: the reconstruction term and, for paired data, the joint-cross /
+        # real-cross terms of a modality share its observations, feature embeddings and decoder
+        # parameters and run as ONE fused launch sequence (the feature table is staged once, the
+        # observations are read from HBM once); the modalities run side by side, so the small one
+        # (16 CTAs for 2 000 genes) fills the SMs that the tail of the large one leaves idle
         self._prepare_extra(usamp)
-        jobs = []
-        for k in net.keys:
-            jobs.append((k, "nll", lambda k=k: self._data_nll(
-                k, usamp[k], vsamp, xbch[k], l[k], x[k], self.DATA_REDUCE,
-                upstream=self.lam_data * self.modality_weight[k])))
-            jobs.extend((k, kind, thunk) for kind, thunk in self._extra_thunks_for(k, data, usamp, vsamp, l))
-        results = self._parallel([thunk for _, _, thunk in jobs])
-        x_nll = {k: res for (k, kind, _), res in zip(jobs, results) if kind == "nll"}
-        self._extra_parts = {k: {} for k in net.keys}
-        for (k, kind, _), res in zip(jobs, results):  # (several real-cross terms add up in job order)
-            if kind != "nll":
-                self._extra_parts[k][kind] = res if kind not in self._extra_parts[k] \
-                    else self._extra_parts[k][kind] + res
+        results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
+        x_nll, self._extra_parts = {}, {k: {} for k in net.keys}
+        for k, terms in zip(net.keys, results):
+            for kind, res in terms:  # (several real-cross terms add up in term order)
+                if kind == "nll":
+                    x_nll[k] = res
+                else:
+                    parts = self._extra_parts[k]
+                    parts[kind] = res if kind not in parts else parts[kind] + res
         if dsc_stream is not None:  # the alignment term needs the updated discriminator
             torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
         u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
@@ -400,13 +397,38 @@ class SCGLUETrainer(GLUETrainer):
             mat = cache[cache_key] = torch.tensor(flat, dtype=torch.float32, device=self.net.device)
         return LossVector(names, mat @ torch.stack([comps[c].reshape(()) for c in keys]))
 
+    def _modality_nlls(self, k: str, data, usamp, vsamp, l):
+        r"""Every decoder-based loss term whose *target* modality is ``k`` as ``[(kind, value), ...]``:
+        the reconstruction term ``"nll"`` (``scglue.py:342-347``) followed by the extra terms of
+        :meth:`_extra_terms_for`.  Kernel-backed decoders evaluate all of them in one fused launch
+        sequence (``ops.decoder_nll_multi``); other decoders term by term."""
+        net = self.net
+        x, xrep, xbch, *_ = data
+        specs = [("nll", usamp[k], None, self.lam_data * self.modality_weight[k])]
+        specs += self._extra_terms_for(k, data, usamp, vsamp, l)
+        decoder, idx = net.u2x[k], getattr(net, f"{k}_idx")
+        fused = (isinstance(decoder, sc._FusedDecoder) and config.USE_FUSED_TERMS and len(specs) > 1
+                 and all(c for *_, c in specs))
+        if fused:
+            from .. import ops
+            rws = [w for _, _, w, _ in specs]  # (None: the plain ``DATA_REDUCE`` of the reconstruction term)
+            values = ops.decoder_nll_multi(
+                decoder.FAMILY, [u for _, u, _, _ in specs], vsamp, decoder.scale_lin, decoder.bias,
+                getattr(decoder, decoder.DISPERSION), decoder.zi_logits if decoder.ZERO_INFLATED else None,
+                b=xbch[k], l=l[k], x=x[k], vidx=idx, reduce=self.DATA_REDUCE, row_weights=rws,
+                upstreams=[c for *_, c in specs])
+            return [(kind, val) for (kind, *_), val in zip(specs, values)]
+        return [(kind, self._data_nll(k, u, vsamp, xbch[k], l[k], x[k],
+                                      self.DATA_REDUCE if w is None else "mean", row_weight=w, upstream=c))
+                for kind, u, w, c in specs]
+
     def _prepare_extra(self, usamp) -> None:
         r"""Quantities shared by the per-modality extra terms (computed before the fork)."""
 
-    def _extra_thunks_for(self, k: str, data, usamp, vsamp, l):
+    def _extra_terms_for(self, k: str, data, usamp, vsamp, l):
         r"""Extra decoder-based loss terms whose *target* modality is ``k``, as
-        ``[(kind, thunk), ...]`` (each evaluated on its own stream beside the reconstruction
-        term); combined by :meth:`_extra_losses`."""
+        ``[(kind, u [B, K], row_weight [B], coefficient in gen_loss), ...]``; combined by
+        :meth:`_extra_losses`."""
         return []
 
     def _extra_losses(self, data, usamp, vsamp, l):
@@ -534,32 +556,27 @@ class PairedSCGLUETrainer(SCGLUETrainer):
                 cos = cos + torch.where(n > 0, 1 - sim, zero)
         return ustack, umean, pf, cos
 
-    def _extra_thunks_for(self, k: str, data, usamp, vsamp, l):
+    def _extra_terms_for(self, k: str, data, usamp, vsamp, l):
         r"""Joint-cross and real-cross reconstruction of modality ``k`` (``scglue.py:624-652``) as
-        independent decoder calls ``[("joint" | "real", thunk), ...]``.  Row subsets (observed in
-        ``k``; observed in both modalities of an ordered pair) enter as per-cell weights
+        ``[("joint" | "real", u, row_weight, coefficient), ...]``.  Row subsets (observed in ``k``;
+        observed in both modalities of an ordered pair) enter as per-cell weights
         ``mask / (n_masked * n_features)``: the mean over the subset without compacting rows --
         static shapes, no host read of the subset sizes."""
         net = self.net
-        x, xrep, xbch, *_ = data
+        x = data[0]
         keys = net.keys
         i = keys.index(k)
         _, umean, pf, _ = self._shared_extra
-
-        def subset_nll(usrc, maskf, lam):
-            w = maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
-            return self._data_nll(k, usrc, vsamp, xbch[k], l[k], x[k], "mean", row_weight=w,
-                                  upstream=lam * self.modality_weight[k])
-
-        thunks = []
+        weight = lambda maskf: maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
+        terms = []
         if self.lam_joint_cross:
-            thunks.append(("joint", lambda: subset_nll(umean, pf[i], self.lam_joint_cross)))
+            terms.append(("joint", umean, weight(pf[i]), self.lam_joint_cross * self.modality_weight[k]))
         if self.lam_real_cross:
             for j, ks in enumerate(keys):
                 if i != j:
-                    thunks.append(("real", lambda j=j, ks=ks: subset_nll(usamp[ks], pf[i] * pf[j],
-                                                                          self.lam_real_cross)))
-        return thunks
+                    terms.append(("real", usamp[ks], weight(pf[i] * pf[j]),
+                                  self.lam_real_cross * self.modality_weight[k]))
+        return terms
 
     def _extra_losses(self, data, usamp, vsamp, l):
         keys = self.net.keys

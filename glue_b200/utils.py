@@ -59,6 +59,9 @@ class _Settings:
         OVERLAP_DISCRIMINATOR=True,
         # fused kernels for the scalar tail of the objective (data-encoder KL, paired mean + cosine term)
         USE_FUSED_OBJECTIVE=True,
+        # the decoder loss terms of one modality (reconstruction, joint cross, real cross) as one fused
+        # launch sequence that shares the staged feature table and the observations
+        USE_FUSED_TERMS=True,
         # activation + BatchNorm + dropout of the data encoders' hidden blocks in one launch each way
         # (the dropout masks then come from the kernel's own Philox stream, not from torch's)
         USE_FUSED_MLP=True,

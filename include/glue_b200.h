@@ -162,8 +162,10 @@ typedef struct glue_decoder_args {
     int32_t impl;      /* 0: the library picks the kernels.  Diagnostics (A/B runs, tests of
                           every path): low byte 1 = CUDA-core kernels, 2 = tcgen05 kernels
                           with per-row operand staging, 3 = tcgen05 kernels with TMA-staged
-                          operands; bit 8 = without the streamlined NB pass B.  A pinned
-                          path that cannot take the call falls through to the next one.   */
+                          operands; bit 8 = without the streamlined NB pass B; bit 9 = CTA 0
+                          of the TMA-staged kernels writes a clock64 timeline into the
+                          first 6 KB of the (1024-byte aligned) workspace.  A pinned path
+                          that cannot take the call falls through to the next one.        */
     float grad_scale;  /* gradients are those of grad_scale * loss (the coefficient with
                           which the caller adds `loss` to its objective), `loss` itself is
                           reported unscaled; 0 is read as 1                             */

@@ -24,15 +24,14 @@ IMPLS = [int(v) for v in os.environ.get("IMPLS", "2,3").split(",")]
 FAMILY = os.environ.get("FAMILY", "NB")
 NB = int(os.environ.get("NBATCH", "1"))
 out = {}
-blocker = torch.randn(8192, 8192, device=dev)
 
 
 def timed(fn):
     for i in range(3):
         fn(i)
     torch.cuda.synchronize()
-    for _ in range(6):
-        blocker @ blocker  # keeps the GPU busy while the launches below are queued
+    torch.cuda._sleep(12_000_000)  # a spinning blocker: the launches below queue behind it (a GEMM blocker
+    # would pull the SM clock down under the power cap and inflate what is timed behind it)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(ITERS):

@@ -14,13 +14,12 @@ for name, V, E in (("cfg1", 52000, 100000), ("atlas", 200000, 1000000)):
     enorm = num.normalize_edges(eidx, ewt)
     csr = ops.GraphCSR(*(torch.as_tensor(a).to(dev) for a in (eidx, enorm, esgn)), V)
     xs = [torch.randn(V, 50, device=dev) for _ in range(8)]
-    blocker = torch.randn(8192, 8192, device=dev)
     for part, tag in ((csr.fwd, "fwd"), (csr.bwd, "bwd")):
         for i in range(3):
             ops._spmm(part, xs[i])
         torch.cuda.synchronize()
-        for _ in range(4):
-            blocker @ blocker
+        torch.cuda._sleep(12_000_000)  # a spinning blocker: the launches below queue behind it (a GEMM blocker
+        # would pull the SM clock down under the power cap and inflate what is timed behind it)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(32):

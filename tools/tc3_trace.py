@@ -1,0 +1,64 @@
+"""Timeline of CTA 0 of the TMA-staged decoder kernels (impl bit 9: clock64 stamps in the workspace).
+
+    F=50000 TERMS=3 python tools/tc3_trace.py
+
+Prints, per kernel (0 = pass A, 1 = pass B, 2 = pass C) and unit, the stamps relative to the kernel's
+entry, in cycles."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import __graft_entry__ as entry
+
+entry.build()
+from glue_b200 import ops
+
+dev = torch.device("cuda:0")
+B, K, F = 128, 50, int(os.environ.get("F", "50000"))
+T = int(os.environ.get("TERMS", "1"))
+us = [(torch.randn(B, K, device=dev) * 0.5).requires_grad_(True) for _ in range(T)]
+v = (torch.randn(F, K, device=dev) * 0.5).requires_grad_(True)
+x = torch.poisson(torch.full((B, F), 0.05, device=dev))
+l = x.sum(1, keepdim=True) + 1
+ps = [torch.zeros(1, F, device=dev, requires_grad=True) for _ in range(3)]
+rws = [torch.rand(B, device=dev) / (B * F) for _ in range(T)]
+
+captured = []
+orig = ops._workspace
+
+
+def grab(nbytes, device):
+    ws = orig(nbytes, device)
+    captured.append(ws)
+    return ws
+
+
+ops._workspace = grab
+EV = {0: "tmaV", 1: "tmaU", 2: "mma_fwd", 3: "mma_xfull", 4: "mma_grad", 5: "epi_wait", 6: "epi_acc", 7: "epi_loop_end",
+      8: "epi_arrived", 10: "cv_coef", 11: "cv_xempty", 12: "cv_done", 13: "ro_start", 14: "ro_done"}
+KEV = {0: "entry", 1: "setup_done", 2: "epi_units_done", 3: "d2_ready", 4: "all_joined", 5: "end", 6: "ro0_begin",
+       7: "ro0_rows", 8: "ro0_d1full", 9: "ro0_ld0", 10: "ro0_sts0", 11: "ro0_stg0", 12: "ro0_arrive"}
+for rep in range(3):
+    captured.clear()
+    ops.DECODER_IMPL = 3 | 0x200
+    losses = ops.decoder_nll_multi("NB", us, v, ps[0], ps[1], ps[2], None, l=l, x=x, reduce="mean", row_weights=rws,
+                                   upstreams=[1.0] * T)
+    torch.cuda.synchronize()
+ws = captured[-1]
+off = (-ws.data_ptr()) % 1024
+tr = ws[off:off + 3 * 16 * 16 * 8].view(torch.int64).cpu().reshape(3, 16, 16)
+for k in range(3):
+    t0 = int(tr[k, 15, 0])
+    if t0 == 0:
+        continue
+    if int(tr[k, 15, 13]):
+        ns = int(tr[k, 15, 14]) - int(tr[k, 15, 13])
+        cyc = int(tr[k, 15, 5]) - t0
+        print(f"kernel {k}: CTA 0 lived {ns} ns = {cyc} cycles -> {cyc / max(ns, 1):.3f} GHz")
+    print(f"kernel {k}: " + "  ".join(f"{KEV[e]}={int(tr[k, 15, e]) - t0}" for e in range(1, 13) if int(tr[k, 15, e])))
+    for n in range(15):
+        row = tr[k, n]
+        if not int(row.abs().sum()):
+            continue
+        print(f"  unit {n:2d}: " + "  ".join(f"{EV[e]}={int(row[e]) - t0}" for e in sorted(EV) if int(row[e])))
