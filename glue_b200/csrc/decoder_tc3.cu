@@ -100,6 +100,12 @@ __device__ __forceinline__ long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// per-CTA lifetime (globaltimer, ns): [3 kernels][160 CTAs][entry, exit] behind the event table
+#define T3CTA(kern, which)                                                                       \
+    do {                                                                                         \
+        if (P.ws.trace != nullptr && blockIdx.x < 160)                                           \
+            P.ws.trace[768 + ((kern) * 160 + blockIdx.x) * 2 + (which)] = globaltimer_ns();      \
+    } while (0)
 #define T3NS(kern, ev)                                                                           \
     do {                                                                                         \
         if (P.ws.trace != nullptr && blockIdx.x == 0) P.ws.trace[((kern) * 16 + 15) * 16 + (ev)] = globaltimer_ns(); \
@@ -490,6 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     constexpr int KRN = 1 + PHASE;
     if (t == 0) T3(KRN, 15, 0);
     if (t == 0) T3NS(KRN, 13);
+    if (t == 0) T3CTA(KRN, 0);
 
     if (t == 0) init_bars(S, GRAD, 1);
     if (warp == TMA_WARP && lane == 0) {
@@ -1306,6 +1313,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     if (t == 0) T3(KRN, 15, 5);
     if (t == 0) T3NS(KRN, 14);
+    if (t == 0) T3CTA(KRN, 1);
 }
 
 // d/du = sum over CTAs of the D2 partials; grid = S * ncell blocks, 1024 threads = 64 latent columns x
@@ -1369,7 +1377,7 @@ size_t ws_layout(const glue_decoder_args& a, int S, int ncta, int Fpad, char* ba
         return ptr;
     };
     Ws3 w;
-    w.trace = (long long*)take(3 * 16 * 16 * 8, 1024);  // (first: tools find it at the aligned base)
+    w.trace = (long long*)take(16384, 1024);  // (first: tools find it at the aligned base)
     w.vimg = (uint8_t*)take((size_t)2 * Fpad * ROW_BYTES, 1024);
     w.uimg = (uint8_t*)take((size_t)2 * S * 128 * ROW_BYTES, 1024);
     w.ptab = (float2*)take((size_t)a.n_batches * Fpad * sizeof(float2), 256);
@@ -1509,7 +1517,7 @@ int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st) {
     P.cinv = (nbf && nb1 && a.K <= 62 && grad) ? 1 : 0;
     if (!nbf) P.ws.ptab = nullptr;
     if (a.impl & 0x200)
-        GLUE_CUDA(cudaMemsetAsync(P.ws.trace, 0, 3 * 16 * 16 * 8, st));
+        GLUE_CUDA(cudaMemsetAsync(P.ws.trace, 0, 16384, st));
     else
         P.ws.trace = nullptr;
 

@@ -47,7 +47,17 @@ for rep in range(3):
     torch.cuda.synchronize()
 ws = captured[-1]
 off = (-ws.data_ptr()) % 1024
-tr = ws[off:off + 3 * 16 * 16 * 8].view(torch.int64).cpu().reshape(3, 16, 16)
+raw = ws[off:off + 16384].view(torch.int64).cpu()
+tr = raw[:768].reshape(3, 16, 16)
+cta = raw[768:768 + 3 * 160 * 2].reshape(3, 160, 2)
+for k in range(3):
+    live = cta[k][cta[k, :, 0] > 0]
+    if len(live):
+        t_first = int(live[:, 0].min())
+        dur = (live[:, 1] - live[:, 0])
+        print(f"kernel {k}: {len(live)} CTAs; entry spread {int(live[:, 0].max()) - t_first} ns; lifetime min/mean/max "
+              f"{int(dur.min())}/{int(dur.float().mean())}/{int(dur.max())} ns; last exit - first entry "
+              f"{int(live[:, 1].max()) - t_first} ns; slowest CTAs {dur.argsort(descending=True)[:6].tolist()}")
 for k in range(3):
     t0 = int(tr[k, 15, 0])
     if t0 == 0:
