@@ -1,26 +1,41 @@
 #!/usr/bin/env python
-"""Benchmark of the SCGLUE training step (BASELINE.json metric: train cells/s, with the
-fused NB decoder's fraction of the HBM roofline).
+"""Benchmark of the SCGLUE training step (BASELINE.json metric: train cells/s, with the fused
+decoder's fraction of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgN]
 
 A *step* is one ``train_step`` (discriminator update + generator update, RMSprop) on one
-minibatch of 128 cells per modality.  Workload = BASELINE.json ``configs[1]``:
-PairedSCGLUE, RNA + ATAC, synthetic 10x-Multiome-PBMC shape (10 000 paired cells, 2 000
-HVGs, 50 000 peaks, 100 k-edge guidance graph + self-loops, NB decoders, 50-d latent).
-"A cell" = one view row (one RNA row + one ATAC row).
+minibatch per rank.  "A cell" = one view row of the dataset (one row per modality).
 
-``value``  : steps over minibatches already resident in HBM (device-resident pipeline).
-``e2e``    : the same steps through the reference-facing call ``trainer.train_step(engine,
-             host_batch)`` with pinned host tensors: H2D of the dense minibatch and a D2H read
-             of the loss are inside the timed region.
-``roofline``: the dominant kernel sequence (fused NB decoder fwd+bwd at F = 50 000) timed with
-             CUDA events on the launching stream (the training step itself is one CUDA-graph
-             launch, so the kernel is timed in its own region of the same run), algorithmic
-             bytes / time vs the measured HBM copy bandwidth.
+Workloads (BASELINE.json ``configs``; ``--config``, default ``cfg2`` = the configuration the
+metric is quoted on; the others are extra lines, run through ``gpurun`` and kept under
+``profiles/``):
+
+  cfg1  SCGLUE RNA + ATAC, unpaired, PBMC shape (10 k + 10 k cells, 2 000 genes, 50 000 peaks,
+        100 k-edge guidance graph + self-loops), NB decoders, batch 128
+  cfg2  PairedSCGLUE, same shape, all cells paired, joint-cross / real-cross / cosine terms
+  cfg3  triple omics: RNA NB 2 000 + ATAC NB 150 000 + methylation ZILN 48 000 (sign -1 edges),
+        200 k vertices
+  cfg4  ZINB decoders with 20 batches (``use_batch``), PBMC feature shape
+  cfg5  atlas shape: 4 000 HVGs + 196 000 peaks, h_dim 512, batch 512 per GPU, 1.2 M edges
+
+The step cost does not depend on how many cells the dataset holds, so cfg3-cfg5 materialise a
+bounded number of synthetic cells (``config.cells_materialised``); features, graph, batch and
+model sizes are the configuration's.
+
+``value``   : steps over minibatches already resident in HBM (device-resident pipeline).
+``e2e``     : the same steps through the reference-facing call ``trainer.train_step(engine,
+              host_batch)`` with pinned host tensors: H2D of the minibatch and a D2H read of the
+              loss are inside the timed region.
+``fit_e2e`` : wall-clock cells/s of a real ``model.fit`` (negative sampler, loaders, validation,
+              plugins) on the materialised dataset.
+``roofline``: the dominant kernel sequence -- the fused decoder call of the largest modality as
+              the step issues it (all its loss terms in one launch sequence) -- timed with CUDA
+              events on the launching stream (the step itself is one CUDA-graph launch, so the
+              sequence is timed in its own region of the same run); algorithmic bytes / time vs
+              the measured HBM copy bandwidth.
 ``cpu_baseline`` / ``--impl reference``: the CPU port of the reference's train_step
-             (``oracle/scglue_cpu.py``, pinned against the unmodified reference) on the
-             host cores.
+              (``oracle/scglue_cpu.py``, pinned against the unmodified reference) on the host cores.
 """
 import argparse
 import json
@@ -40,14 +55,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="cfg2_paired_scglue_pbmc", n_cells=10000, n_genes=2000, n_peaks=50000,
-                n_pairs=50000, latent_dim=50, h_dim=256, rep_dim=100, batch=128, neg_samples=10,
-                rna_rate=0.26, atac_rate=0.05, seed=0)
+# modality: (name, feature prefix, prob_model, n_features, density of the count matrix)
+_PBMC = [("rna", "g", "NB", 2000, 0.26), ("atac", "p", "NB", 50000, 0.05)]
+WORKLOADS = {
+    "cfg1": dict(name="cfg1_scglue_pbmc", paired=False, modalities=_PBMC, n_cells=10000, cells_total=20000,
+                 n_pairs=50000, h_dim=256, batch=128),
+    "cfg2": dict(name="cfg2_paired_scglue_pbmc", paired=True, modalities=_PBMC, n_cells=10000, cells_total=10000,
+                 n_pairs=50000, h_dim=256, batch=128),
+    "cfg3": dict(name="cfg3_triple_omics", paired=False,
+                 modalities=[("rna", "g", "NB", 2000, 0.26), ("atac", "p", "NB", 150000, 0.02),
+                             ("met", "m", "ZILN", 48000, 0.5)],
+                 n_cells=4000, cells_total=30000, n_pairs=150000, h_dim=256, batch=128),
+    "cfg4": dict(name="cfg4_zinb_batches", paired=False,
+                 modalities=[("rna", "g", "ZINB", 2000, 0.26), ("atac", "p", "ZINB", 50000, 0.05)],
+                 n_cells=10000, cells_total=100000, n_pairs=50000, h_dim=256, batch=128, n_batches=20),
+    "cfg5": dict(name="cfg5_atlas", paired=False,
+                 modalities=[("rna", "g", "NB", 4000, 0.15), ("atac", "p", "NB", 196000, 0.01)],
+                 n_cells=4000, cells_total=4700000, n_pairs=500000, h_dim=512, batch=512, align_burnin=0),
+}
+for _w in WORKLOADS.values():
+    _w.update(latent_dim=50, rep_dim=100, neg_samples=10, seed=0)
 
 
 # ----------------------------------------------------------------------- workload
 def make_workload(cfg):
-    """Seeded synthetic data: CSR fp32 counts, 100-d encoder inputs, bipartite guidance graph."""
+    """Seeded synthetic data: CSR fp32 counts (log-normal values with exact zeros for the ZILN
+    modality), 100-d encoder inputs, guidance graph: gene--peak pairs (sign +1), one gene per
+    methylation feature (sign -1), self-loops."""
     import networkx as nx
     import pandas as pd
     import scipy.sparse
@@ -56,40 +90,50 @@ def make_workload(cfg):
 
     rs = np.random.RandomState(cfg["seed"])
     n = cfg["n_cells"]
-    cells = [f"cell{i}" for i in range(n)]
-    adatas = {}
-    for key, prefix, f, rate in (("rna", "g", cfg["n_genes"], cfg["rna_rate"]),
-                                 ("atac", "p", cfg["n_peaks"], cfg["atac_rate"])):
+    adatas, names = {}, {}
+    for key, prefix, prob, f, rate in cfg["modalities"]:
+        cells = [f"cell{i}" for i in range(n)] if cfg["paired"] else [f"{key}_cell{i}" for i in range(n)]
         nnz = int(n * f * rate)
-        rows = rs.randint(0, n, nnz)
-        cols = rs.randint(0, f, nnz)
-        vals = (1 + rs.poisson(0.3, nnz)).astype(np.float32)
+        rows, cols = rs.randint(0, n, nnz), rs.randint(0, f, nnz)
+        if prob == "ZILN":
+            vals = np.exp(rs.randn(nnz)).astype(np.float32)
+        else:
+            vals = (1 + rs.poisson(0.3, nnz)).astype(np.float32)
         x = scipy.sparse.coo_matrix((vals, (rows, cols)), shape=(n, f)).tocsr()
         x.sum_duplicates()
         x = (x + scipy.sparse.csr_matrix((np.ones(n, np.float32), (np.arange(n), np.zeros(n, int))),
-                                         shape=(n, f))).tocsr().astype(np.float32)
-        names = [f"{prefix}{i}" for i in range(f)]
-        adatas[key] = AnnData(X=x, obs=pd.DataFrame(index=cells), var=pd.DataFrame(index=names),
+                                         shape=(n, f))).tocsr().astype(np.float32)  # no empty library
+        names[key] = [f"{prefix}{i}" for i in range(f)]
+        obs = pd.DataFrame(index=cells)
+        if cfg.get("n_batches"):
+            obs["batch"] = rs.randint(0, cfg["n_batches"], n).astype(str)
+        adatas[key] = AnnData(X=x, obs=obs, var=pd.DataFrame(index=names[key]),
                               obsm={"X_rep": rs.randn(n, cfg["rep_dim"]).astype(np.float32)})
     g = nx.Graph()
-    genes, peaks = list(adatas["rna"].var_names), list(adatas["atac"].var_names)
-    g.add_nodes_from(genes + peaks)
+    for key in names:
+        g.add_nodes_from(names[key])
+    genes = names["rna"]
+    peaks = names["atac"]
     src, dst = rs.randint(0, len(genes), cfg["n_pairs"]), rs.randint(0, len(peaks), cfg["n_pairs"])
     wts = rs.uniform(0.05, 1.0, cfg["n_pairs"])
-    g.add_edges_from((genes[s], peaks[t], {"weight": float(w), "sign": 1})
-                     for s, t, w in zip(src, dst, wts))
-    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in genes + peaks)
+    g.add_edges_from((genes[s], peaks[t], {"weight": float(w), "sign": 1}) for s, t, w in zip(src, dst, wts))
+    if "met" in names:  # gene-body methylation represses: weight 1, sign -1
+        met = names["met"]
+        owner = rs.randint(0, len(genes), len(met))
+        g.add_edges_from((genes[s], m, {"weight": 1.0, "sign": -1}) for s, m in zip(owner, met))
+    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in list(g.nodes))
     return adatas, g
 
 
 def build_model(cfg, adatas, graph):
     from glue_b200 import models
 
-    for a in adatas.values():
-        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep",
-                                 use_obs_names=True)
-    model = models.PairedSCGLUEModel(adatas, sorted(graph.nodes), latent_dim=cfg["latent_dim"],
-                                     h_dim=cfg["h_dim"], random_seed=cfg["seed"])
+    for (key, _, prob, _, _) in cfg["modalities"]:
+        models.configure_dataset(adatas[key], prob, use_highly_variable=False, use_rep="X_rep",
+                                 use_obs_names=cfg["paired"], use_batch="batch" if cfg.get("n_batches") else None)
+    cls = models.PairedSCGLUEModel if cfg["paired"] else models.SCGLUEModel
+    # (vertices sorted as fit_SCGLUE does, scglue/models/__init__.py:217-273)
+    model = cls(adatas, sorted(graph.nodes), latent_dim=cfg["latent_dim"], h_dim=cfg["h_dim"], random_seed=cfg["seed"])
     model.compile()
     return model
 
@@ -100,8 +144,7 @@ def make_loaders(model, adatas, graph, cfg, device_resident):
     from glue_b200.utils import config
 
     net, trainer = model.net, model.trainer
-    data = AnnDataset([adatas[k] for k in net.keys], [model.modalities[k] for k in net.keys],
-                      mode="train")
+    data = AnnDataset([adatas[k] for k in net.keys], [model.modalities[k] for k in net.keys], mode="train")
     gds = GraphDataset(graph, model.vertices, neg_samples=cfg["neg_samples"],
                        weighted_sampling=True, deemphasize_loops=True)
     if device_resident:
@@ -115,6 +158,20 @@ def make_loaders(model, adatas, graph, cfg, device_resident):
     gds.prepare_shuffle(num_workers=0, random_seed=cfg["seed"])
     loader = trainer._loaders(data, gds, fetches, fetches, cfg["seed"], True, True, shard=True)
     return gds, loader, graph_batch
+
+
+def config_block(cfg, world, gds_edges=None, e_mb=None, extra=None):
+    """The ``config`` object of the JSON line: identical keys for both arms."""
+    feats = {key: f for key, _, _, f, _ in cfg["modalities"]}
+    out = {"workload": cfg["name"], "trainer": "PairedSCGLUE" if cfg["paired"] else "SCGLUE",
+           "prob_models": {key: prob for key, _, prob, _, _ in cfg["modalities"]},
+           "features": feats, "vertices": int(sum(feats.values())), "cells": cfg["cells_total"],
+           "cells_materialised": cfg["n_cells"] * (1 if cfg["paired"] else len(feats)),
+           "n_batches": cfg.get("n_batches", 0), "h_dim": cfg["h_dim"], "latent_dim": cfg["latent_dim"],
+           "graph_edges": gds_edges, "edge_minibatch": e_mb, "batch_per_gpu": cfg["batch"],
+           "global_batch": cfg["batch"] * world, "parallelism": f"dp{world}"}
+    out.update(extra or {})
+    return out
 
 
 class _Engine:
@@ -178,19 +235,29 @@ def cpu_step_runner(cfg, model, host_batches, gds, threads):
     torch.set_num_threads(threads)
     net = model.net
     state = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
-    step_cfg = oc.StepConfig(net.keys, {k: "NB" for k in net.keys}, {k: True for k in net.keys},
-                             {k: 1 for k in net.keys}, paired=True, lam_joint_cross=0.02,
-                             lam_real_cross=0.02, lam_cos=0.02, align_burnin=57)
+    probs = {key: prob for key, _, prob, _, _ in cfg["modalities"]}
+    paired = cfg["paired"]
+    burnin = cfg.get("align_burnin", 57)
+    step_cfg = oc.StepConfig(net.keys, probs, {k: probs[k] in ("NB", "ZINB") for k in net.keys},
+                             {k: max(cfg.get("n_batches", 0), 1) for k in net.keys}, paired=paired,
+                             lam_joint_cross=0.02 if paired else 0.0, lam_real_cross=0.02 if paired else 0.0,
+                             lam_cos=0.02 if paired else 0.0, align_burnin=burnin or None)
     full = (torch.as_tensor(gds.eidx), torch.as_tensor(normalize_edges(gds.eidx, gds.ewt)),
             torch.as_tensor(gds.esgn))
     trainer = oc.CpuTrainer(step_cfg, state, full, lr=2e-3)
     K = len(net.keys)
 
     def to_batch(data):
+        from glue_b200.models.data import is_packed_sparse, unpack_sparse_rows
         data = [t.cpu() for t in data]
+        for i, k in enumerate(net.keys):  # (host batches carry sparse count rows packed)
+            if is_packed_sparse(data[i]):
+                data[i] = unpack_sparse_rows(data[i], data[2 * K + i].shape[0], getattr(net, f"{k}_idx").shape[0])
         groups = [dict(zip(net.keys, data[i * K:(i + 1) * K])) for i in range(5)]
-        return dict(x=groups[0], xrep=groups[1], xbch=groups[2], xdwt=groups[4], pmsk=data[5 * K],
-                    eidx=data[5 * K + 1], ewt=data[5 * K + 2], esgn=data[5 * K + 3])
+        rest = data[5 * K:]
+        pmsk = rest[0] if len(rest) == 4 else None
+        return dict(x=groups[0], xrep=groups[1], xbch=groups[2], xdwt=groups[4], pmsk=pmsk,
+                    eidx=rest[-3], ewt=rest[-2], esgn=rest[-1])
 
     batches = [to_batch(b) for b in host_batches]
 
@@ -219,6 +286,12 @@ def traffic_from_profile(name):
     return None
 
 
+def decoder_bytes(B, F, K, n_param_tables, n_batches, n_terms):
+    """x rows count once per term, v / dv and the parameter tables once per fused call."""
+    return (n_terms * B * F * 4 + 2 * F * K * 4 + 2 * n_param_tables * n_batches * F * 4
+            + n_terms * (2 * B * K * 4 + 16 * B))
+
+
 # ------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -226,13 +299,15 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true", help="skip the fit_e2e measurement")
     ap.add_argument("--partition-graph", action="store_true",
-                    help="N > 1: edge-partitioned GraphConv (row-block aggregate + all-gather)")
+                    help="N > 1: run the steps with the edge-partitioned GraphConv (row-block aggregate + all-gather)")
     ap.add_argument("--profile", action="store_true",
                     help="only the device-resident steps (short run for ncu launch lists)")
     args = ap.parse_args()
-    cfg = dict(WORKLOAD)
+    cfg = dict(WORKLOADS[args.config])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -240,7 +315,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        return run_reference(args, cfg)
+        return run_reference(args, cfg, world)
 
     import __graft_entry__ as entry
     if local_rank == 0:
@@ -265,9 +340,11 @@ def main():
     trainer, net = model.trainer, model.net
     gds, dev_loader, graph_batch = make_loaders(model, adatas, graph, cfg, device_resident=True)
     trainer.set_full_graph(gds)
-    trainer.align_burnin = max(math.ceil(8.0 / 2e-3 / (cfg["n_cells"] * 0.9 / cfg["batch"])), 8)  # AUTO rule
+    view_cells = cfg["n_cells"] * (1 if cfg["paired"] else len(cfg["modalities"]))
+    auto_burnin = max(math.ceil(8.0 / 2e-3 / (view_cells * 0.9 / cfg["batch"])), 8)  # AUTO rule
+    trainer.align_burnin = cfg.get("align_burnin", auto_burnin)
 
-    # pools of distinct minibatches: 8 x 27 MB of inputs per pass, i.e. larger than L2
+    # pools of distinct minibatches: larger than L2 in total
     pool_n = 8
     it = iter(dev_loader)
     dev_pool = [next(it) for _ in range(pool_n)]
@@ -282,6 +359,7 @@ def main():
                                   if t.dim() and t.shape[0] == cfg["batch"] else t for t in batch]
         dev_pool[3], host_pool[5] = cut(dev_pool[3], False), cut(host_pool[5], True)
     h2d = sum(t.numel() * t.element_size() for t in host_pool[0])
+    pool_mb = pool_n * h2d / 1e6
     e_mb = int(dev_pool[0][-1].numel())
 
     def sync():
@@ -379,15 +457,19 @@ def main():
     e2e_gap_ms = sum(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1)) / max(1, len(marks) - 1)
     e2e_value = cells / (ms_e2e * 1e-3)
 
+    # --- N > 1: edge-partitioned GraphConv against the replicated one, atlas graph shape ------
+    partitioned = measure_partitioned(device, world, rank) if world > 1 else None
+
     if rank != 0:
         return
 
     # --- the native kernels, timed alone on this stream -----------------------------------
     # CUDA events around back-to-back calls queued behind a blocker (so the host launch path is
-    # off the clock); x cycles through the 8 pooled minibatches (8 x 25.6 MB > L2).
-    B, K, F = cfg["batch"], cfg["latent_dim"], cfg["n_peaks"]
+    # off the clock); x cycles through the pooled minibatches (more than L2 in total).
+    B, K = cfg["batch"], cfg["latent_dim"]
     keys = net.keys
     x_of = {k: [batch[i] for batch in dev_pool] for i, k in enumerate(keys)}
+    xbch_of = {k: [batch[2 * len(keys) + i] for batch in dev_pool] for i, k in enumerate(keys)}
 
     def time_calls(fn, n=24):
         for i in range(3):
@@ -403,24 +485,48 @@ def main():
         torch.cuda.synchronize(device)
         return a.elapsed_time(b) * 1e3 / n
 
-    ktimes = {}
+    ktimes, kbytes = {}, {}
     vtab = (torch.randn(len(model.vertices), K, device=device) * 0.3).requires_grad_(True)
+    n_terms = 3 if (cfg["paired"] and len(keys) == 2) else 1
     for k in keys:
         dec, idx = net.u2x[k], getattr(net, f"{k}_idx")
-        u = (torch.randn(B, K, device=device) * 0.5).requires_grad_(True)
-        bz = torch.zeros(B, dtype=torch.int64, device=device)
-        ls = [x.sum(1, keepdim=True) for x in x_of[k]]
+        fam = dec.FAMILY
+        Fk = x_of[k][0].shape[1]
+        us = [(torch.randn(B, K, device=device) * 0.5).requires_grad_(True) for _ in range(n_terms)]
+        rws = [None] + [torch.rand(B, device=device) / (B * Fk) for _ in range(n_terms - 1)]
+        need_l = fam in ("NB", "ZINB")
+        ls = [x.sum(1, keepdim=True) if need_l else None for x in x_of[k]]
+        disp = getattr(dec, dec.DISPERSION)
+        zi = dec.zi_logits if dec.ZERO_INFLATED else None
+        nb = dec.scale_lin.shape[0]
+        npar = 4 if zi is not None else 3
 
-        def dec_call(i, dec=dec, idx=idx, u=u, ls=ls, k=k):
+        def dec_single(i, dec=dec, idx=idx, us=us, ls=ls, k=k, fam=fam, disp=disp, zi=zi):
             xb = x_of[k][i % pool_n]
             n = xb.shape[0]  # the block-shuffled loader can yield a short minibatch
-            return ops.decoder_nll("NB", u[:n], vtab, dec.scale_lin, dec.bias, dec.log_theta, None,
-                                   b=bz[:n], l=ls[i % pool_n], x=xb, vidx=idx, reduce="mean")
+            return ops.decoder_nll(fam, us[0][:n], vtab, dec.scale_lin, dec.bias, disp, zi,
+                                   b=xbch_of[k][i % pool_n], l=ls[i % pool_n], x=xb, vidx=idx, reduce="mean")
 
-        ktimes[f"decoder_fwd_bwd_NB_F{x_of[k][0].shape[1]}_B{B}"] = (time_calls(dec_call), 3)
-    csr = ops.csr_for(trainer.eidx, trainer.enorm, trainer.esgn, len(model.vertices))
+        def dec_fused(i, dec=dec, idx=idx, us=us, ls=ls, k=k, fam=fam, disp=disp, zi=zi, rws=rws):
+            xb = x_of[k][i % pool_n]
+            n = xb.shape[0]
+            return ops.decoder_nll_multi(fam, [u[:n] for u in us], vtab, dec.scale_lin, dec.bias, disp, zi,
+                                         b=xbch_of[k][i % pool_n], l=ls[i % pool_n], x=xb, vidx=idx, reduce="mean",
+                                         row_weights=[None if w is None else w[:n] for w in rws],
+                                         upstreams=[1.0, 0.02, 0.02][:n_terms])
+
+        name1 = f"decoder_fwd_bwd_{fam}_F{Fk}_B{B}"
+        ktimes[name1] = (time_calls(dec_single), 0 if n_terms > 1 else 1)
+        kbytes[name1] = decoder_bytes(B, Fk, K, npar, nb, 1)
+        if n_terms > 1:
+            name3 = f"decoder_fused{n_terms}_fwd_bwd_{fam}_F{Fk}_B{B}"
+            ktimes[name3] = (time_calls(dec_fused), 1)
+            kbytes[name3] = decoder_bytes(B, Fk, K, npar, nb, n_terms)
+    V, E = len(model.vertices), int(gds.eidx.shape[1])
+    csr = ops.csr_for(trainer.eidx, trainer.enorm, trainer.esgn, V)
     ktimes["graphconv_fwd"] = (time_calls(lambda i: ops._spmm(csr.fwd, vtab.detach())), 2)
     ktimes["graphconv_bwd"] = (time_calls(lambda i: ops._spmm(csr.bwd, vtab.detach())), 1)
+    kbytes["graphconv_fwd"] = kbytes["graphconv_bwd"] = 2 * V * K * 4 + 8 * E + 4 * (V + 1)
     eb = dev_pool[0]
     s_eidx, s_ewt, s_esgn = eb[-3], eb[-2], eb[-1]
 
@@ -430,22 +536,30 @@ def main():
         return g
 
     ktimes["graph_nll_fwd_bwd"] = (time_calls(gnll), 1)
+    kbytes["graph_nll_fwd_bwd"] = e_mb * 16 + min(2 * e_mb, V) * K * 4 + V * K * 4
 
     # --- roofline of the dominant kernel sequence ------------------------------------------
-    dom = f"decoder_fwd_bwd_NB_F{F}_B{B}"
-    alg_bytes = B * F * 4 + 2 * F * K * 4 + 2 * 3 * 1 * F * 4 + 2 * B * K * 4 + 16 * B
     peak, peak_src = peaks()
-    us, per_step = ktimes[dom]
     step_us = ms * 1e3 / args.steps
-    roof = {"bound": "hbm", "kernel": "fused NB decoder fwd+bwd (ATAC, B=128, F=50000), tcgen05 path",
-            "achieved": alg_bytes / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": alg_bytes / (us * 1e-6) / 1e9 / peak, "traffic": traffic_from_profile(dom),
-            "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "launch_us": us,
-            "calls_per_step": per_step, "share_of_step": per_step * us / step_us,
-            "how": "CUDA events around 24 back-to-back calls on the launching stream, x from "
-                   "8 pooled minibatches (HBM resident, > L2)"}
-    kernels = {name: {"us_per_call": t, "calls_per_step": n, "share_of_step": n * t / step_us}
+    dom = max((n for n in ktimes if n.startswith("decoder") and ktimes[n][1]), key=lambda n: ktimes[n][0])
+    us_dom, per_step = ktimes[dom]
+    roof = {"bound": "hbm", "kernel": f"{dom}: fused decoder call of the largest modality as the step issues it "
+                                       f"({n_terms} loss term(s) in one launch sequence), tcgen05 + TMA path",
+            "achieved": kbytes[dom] / (us_dom * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": kbytes[dom] / (us_dom * 1e-6) / 1e9 / peak, "traffic": traffic_from_profile(dom),
+            "peak_source": peak_src, "algorithmic_bytes": kbytes[dom], "launch_us": us_dom,
+            "calls_per_step": per_step, "share_of_step": per_step * us_dom / step_us,
+            "how": "CUDA events around 24 back-to-back calls on the launching stream behind a spinning blocker, "
+                   f"x from {pool_n} pooled minibatches (HBM resident, {pool_mb:.0f} MB > L2)"}
+    kernels = {name: {"us_per_call": t, "calls_per_step": n, "share_of_step": n * t / step_us,
+                      "algorithmic_bytes": kbytes.get(name),
+                      "frac_of_hbm_peak": kbytes[name] / (t * 1e-6) / 1e9 / peak if name in kbytes else None}
                for name, (t, n) in sorted(ktimes.items())}
+
+    # --- a real fit: sampler + loaders + validation + plugins, wall clock -------------------
+    fit_e2e = None
+    if not args.no_fit and world == 1:
+        fit_e2e = measure_fit(cfg, adatas, graph, device)
 
     # --- CPU baseline (bounded sample of the same workload) --------------------------------
     cpu = None
@@ -453,7 +567,7 @@ def main():
         cores = os.cpu_count() or 1
         run = cpu_step_runner(cfg, model, host_pool, gds, cores)
         run(1)
-        n_cpu = 5
+        n_cpu = 5 if cfg["batch"] * max(f for *_, f, _ in cfg["modalities"]) < 2e7 else 2
         secs = run(n_cpu, offset=1)
         cpu = {"value": cfg["batch"] * n_cpu / secs, "unit": "cells/s", "cores": cores,
                "kind": "port", "ms_per_step": secs * 1e3 / n_cpu,
@@ -465,27 +579,101 @@ def main():
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": cfg["name"], "cells": cfg["n_cells"], "genes": cfg["n_genes"],
-                   "peaks": cfg["n_peaks"], "graph_edges": int(gds.eidx.shape[1]),
-                   "edge_minibatch": e_mb, "batch_per_gpu": cfg["batch"],
-                   "global_batch": cfg["batch"] * world, "latent_dim": K,
-                   "parallelism": f"dp{world}" + ("+graph-partition" if args.partition_graph else ""),
-                   "l2": f"inputs cycle through {pool_n} minibatches (8 x 27 MB > 126 MB L2)"},
+        "config": config_block(cfg, world, E, e_mb, {
+            "parallelism": f"dp{world}" + ("+graph-partition" if args.partition_graph else ""),
+            "l2": f"inputs cycle through {pool_n} minibatches ({pool_n} x {h2d / 1e6:.0f} MB > 126 MB L2)"}),
         "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "feed": e2e_feed,
                 "ms_per_step_by_feed": {k: v / args.steps for k, v in e2e_runs.items()},
                 "gpu_ms_inside_steps": e2e_step_gpu_ms, "gpu_ms_between_steps": e2e_gap_ms},
+        "fit_e2e": fit_e2e,
         "gpu_launches": int(launches),
         "cuda_graph": {k: ginfo[k] for k in ("graphs", "kernels_per_step", "disabled")},
         "clocks": clocks.summary(),
         "roofline": roof,
         "kernels": kernels,
+        "partitioned_graphconv": partitioned,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
 
 
-def run_reference(args, cfg):
+def measure_fit(cfg, adatas, graph, device):
+    """Wall-clock throughput of ``model.fit`` itself: negative sampler, block-shuffled loaders,
+    device-resident row gathers, per-epoch validation, metric read-back, plugins.  A fresh model;
+    the first epoch (graph capture, allocator warm-up) is timed separately."""
+    from glue_b200.utils import config
+    model = build_model(cfg, adatas, graph)
+    view_cells = cfg["n_cells"] * (1 if cfg["paired"] else len(cfg["modalities"]))
+    kw = dict(data_batch_size=cfg["batch"], patience=None, reduce_lr_patience=None)
+    if "align_burnin" in cfg:
+        kw["align_burnin"] = cfg["align_burnin"]
+    old = config.PRINT_LOSS_INTERVAL
+    config.PRINT_LOSS_INTERVAL = 1000
+    try:
+        tic = time.perf_counter()
+        model.fit(adatas, graph, max_epochs=1, **kw)
+        torch.cuda.synchronize(device)
+        first = time.perf_counter() - tic
+        epochs = 4
+        tic = time.perf_counter()
+        model.fit(adatas, graph, max_epochs=epochs, **kw)
+        torch.cuda.synchronize(device)
+        wall = time.perf_counter() - tic
+    finally:
+        config.PRINT_LOSS_INTERVAL = old
+    fetches = config.DATALOADER_FETCHES_PER_BATCH
+    block = max(1, round(cfg["batch"] / fetches))
+    n_train = round(view_cells * 0.9)
+    steps = (math.ceil(n_train / block)) // fetches  # drop_last over blocks
+    trained = steps * cfg["batch"] * epochs
+    return {"value": trained / wall, "unit": "cells/s", "epochs": epochs, "train_steps_per_epoch": steps,
+            "wall_s": wall, "first_fit_s_1_epoch": first,
+            "includes": "dataset + graph construction, negative sampling, loaders, validation every epoch, "
+                        "metric read-back, checkpoint directory; 4 epochs after a 1-epoch fit (graph capture)"}
+
+
+def measure_partitioned(device, world, rank, V=200000, E=1000000, K=50, n=20):
+    """GraphConv forward at the atlas graph shape: replicated (every rank aggregates all rows) vs
+    edge-partitioned by target-row blocks + all-gather (``ops.PartitionedGraphCSR``); device time, max
+    over ranks."""
+    from glue_b200 import ops
+    rs = np.random.RandomState(1)
+    src = np.concatenate([rs.randint(0, V, E), np.arange(V)])
+    dst = np.concatenate([rs.randint(0, V, E), np.arange(V)])
+    eidx = torch.as_tensor(np.stack([src, dst]).astype(np.int64), device=device)
+    enorm = torch.rand(eidx.shape[1], device=device)
+    esgn = torch.ones(eidx.shape[1], device=device)
+    csr = ops.GraphCSR(eidx, enorm, esgn, V)
+    part = ops.PartitionedGraphCSR(csr, rank, world)
+    xs = [torch.randn(V, K, device=device) for _ in range(8)]
+
+    def run(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize(device)
+        torch.distributed.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize(device)
+        t = torch.tensor([a.elapsed_time(b) * 1e3 / n], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        rep = run(lambda i: ops.graph_conv(xs[i % 8], csr))
+        par = run(lambda i: ops.graph_conv_partitioned(xs[i % 8], part))
+        same = bool(torch.equal(ops.graph_conv(xs[0], csr), ops.graph_conv_partitioned(xs[0], part)))
+    bytes_ = 2 * V * K * 4 + 8 * int(eidx.shape[1]) + 4 * (V + 1)
+    return {"vertices": V, "edges": int(eidx.shape[1]), "replicated_us": rep, "partitioned_us": par,
+            "bit_identical": same, "algorithmic_bytes": bytes_,
+            "note": "forward aggregation only; partitioned = local row block + all-gather of [V/N, K] blocks"}
+
+
+def run_reference(args, cfg, world):
     """The reference's CPU path (port pinned against the unmodified reference) on host cores."""
     from glue_b200.utils import config
     config.CPU_ONLY = True
@@ -494,10 +682,11 @@ def run_reference(args, cfg):
     gds, host_loader, _ = make_loaders(model, adatas, graph, cfg, device_resident=False)
     it = iter(host_loader)
     host_pool = [next(it) for _ in range(8)]
+    e_mb = int(host_pool[0][-1].numel())
     cores = os.cpu_count() or 1
     run = cpu_step_runner(cfg, model, host_pool, gds, cores)
-    warmup = max(1, min(args.warmup, 3))
-    steps = max(1, min(args.steps, 40))  # bounded: ~1 s per step on 8+ cores
+    warmup = max(args.warmup, 3)           # (the same rule as the GPU arm)
+    steps = max(1, min(args.steps, 40))    # bounded: ~0.3 s per step on 16 cores
     run(warmup)
     secs = run(steps, offset=warmup)
     value = cfg["batch"] * steps / secs
@@ -507,7 +696,10 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "train_cells_per_s", "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": secs * 1e3 / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": cfg["name"], "batch_per_gpu": cfg["batch"]},
+        "data": "synthetic",
+        "config": config_block(cfg, max(world, args.gpus), int(gds.eidx.shape[1]), e_mb, {
+            "parallelism": f"dp{max(world, args.gpus)}",
+            "l2": "host arm: CPU caches, no flush"}),
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,

@@ -99,3 +99,32 @@ class RankStridedBatches:
                 break
             if i % self.world == self.rank:
                 yield batch
+
+
+def mean_over_ranks(values: List[float], device: torch.device = None) -> List[float]:
+    r"""Element-wise mean of a list of host floats over all ranks (identity when not
+    distributed).  Training-loop decisions that every rank takes on its own copy of a
+    metric -- learning-rate reduction, early stopping, the non-finite guard -- must see the
+    same number everywhere, or one rank changes its learning rate / leaves the loop while the
+    others wait in the next gradient all-reduce."""
+    if not is_distributed() or not values:
+        return list(values)
+    on_gpu = td.get_backend() == "nccl"
+    t = torch.tensor(values, dtype=torch.float64,
+                     device=device if (on_gpu and device is not None) else ("cuda" if on_gpu else "cpu"))
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return (t / world_size()).tolist()
+
+
+def broadcast_object(obj, src: int = 0):
+    r"""``obj`` of rank ``src`` on every rank (identity when not distributed)."""
+    if not is_distributed():
+        return obj
+    box = [obj]
+    td.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def barrier() -> None:
+    if is_distributed():
+        td.barrier()

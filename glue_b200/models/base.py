@@ -70,9 +70,12 @@ class Engine:
     r"""Runs ``step(engine, batch)`` over a loader for a number of epochs and fires events."""
 
     def __init__(self, step: Callable[["Engine", Any], Mapping[str, torch.Tensor]],
-                 tracked: Optional[List[str]] = None) -> None:
+                 tracked: Optional[List[str]] = None, sync_metrics: bool = False) -> None:
         self.step = step
         self.tracked = list(tracked or [])
+        # data parallel: epoch metrics are averaged over the ranks so that every rank's plugins
+        # (LR scheduling, early stopping, the non-finite guard) take the same decisions
+        self.sync_metrics = sync_metrics
         self.state = EngineState()
         self.should_terminate = False
         self._handlers: Dict[str, List[Callable]] = defaultdict(list)
@@ -133,6 +136,10 @@ class Engine:
                 keys = list(sums)
                 host = (torch.stack([sums[k].float() for k in keys]) / max(count, 1)).tolist()
                 state.metrics = dict(zip(keys, host))
+            if self.sync_metrics and state.metrics:
+                from .. import dist as gdist
+                keys = list(state.metrics)
+                state.metrics = dict(zip(keys, gdist.mean_over_ranks([state.metrics[k] for k in keys])))
             state.times["EPOCH_COMPLETED"] = time.time() - tic
             self.fire(EPOCH_COMPLETED)
             state.times["EPOCH_COMPLETED"] = time.time() - tic
@@ -170,10 +177,15 @@ class Trainer:
             directory: Optional[os.PathLike] = None,
             plugins: Optional[List["TrainingPlugin"]] = None) -> None:
         r"""Training loop with per-epoch validation and plugins (``base.py:117-214``)."""
-        directory = pathlib.Path(directory or tempfile.mkdtemp(prefix=config.TMP_PREFIX))
+        from .. import dist as gdist
+        if directory is None:  # (data parallel: one directory, chosen by rank 0)
+            directory = gdist.broadcast_object(
+                tempfile.mkdtemp(prefix=config.TMP_PREFIX) if gdist.rank() == 0 else None)
+        directory = pathlib.Path(directory)
         self.logger.info('Using training directory: "%s"', directory)
-        train_engine = Engine(self.train_step, self.required_losses)
-        val_engine = Engine(self.val_step, self.required_losses) if val_loader else None
+        sync = gdist.is_distributed()
+        train_engine = Engine(self.train_step, self.required_losses, sync_metrics=sync)
+        val_engine = Engine(self.val_step, self.required_losses, sync_metrics=sync) if val_loader else None
 
         @train_engine.on(EPOCH_COMPLETED)
         def _nonfinite_guard(engine):  # TerminateOnNan, at epoch granularity

@@ -6,6 +6,7 @@ import itertools
 import os
 from typing import Any, List, Mapping, Optional
 
+import numpy as np
 import torch
 
 from .. import dist as gdist
@@ -125,6 +126,7 @@ class GLUETrainer(Trainer):
         self.dsc_optim = self._make_optim([net.du])
         self.align_burnin: Optional[int] = None
         self.eidx = self.enorm = self.esgn = None  # full graph used by the graph encoder
+        self.full_graph_digest: Optional[str] = None
         self._vae_bucket = self._dsc_bucket = None
 
     def _vae_modules(self) -> List[torch.nn.Module]:
@@ -161,14 +163,29 @@ class GLUETrainer(Trainer):
 
     def set_full_graph(self, graph: GraphDataset) -> None:
         r"""Normalise the full guidance graph and keep it on the device
-        (``glue.py:555-559``); cleared again at the end of :meth:`fit`."""
+        (``glue.py:555-559``); cleared again at the end of :meth:`fit`.
+
+        The device tensors of the most recent graph are kept behind the scenes, keyed by a digest
+        of its edges: captured training steps have the CSR arrays of a specific graph baked in
+        (``full_graph_digest`` is part of their key), and a second ``fit`` on the same graph finds
+        the same tensors -- same CSR cache entry, same captures -- instead of re-uploading."""
+        import hashlib
         device = self.net.device
-        self.enorm = torch.as_tensor(normalize_edges(graph.eidx, graph.ewt), device=device)
-        self.esgn = torch.as_tensor(graph.esgn, device=device)
-        self.eidx = torch.as_tensor(graph.eidx, device=device)
+        enorm = normalize_edges(graph.eidx, graph.ewt)
+        h = hashlib.blake2b(digest_size=16)
+        for arr in (graph.eidx, enorm, graph.esgn):
+            h.update(np.ascontiguousarray(arr).tobytes())
+        digest = h.hexdigest()
+        kept = getattr(self, "_full_graph_kept", None)
+        if kept is None or kept[0] != (digest, str(device)):
+            kept = ((digest, str(device)), torch.as_tensor(graph.eidx, device=device),
+                    torch.as_tensor(enorm, device=device), torch.as_tensor(graph.esgn, device=device))
+            self._full_graph_kept = kept
+        (self.full_graph_digest, _), self.eidx, self.enorm, self.esgn = kept
 
     def clear_full_graph(self) -> None:
         self.eidx = self.enorm = self.esgn = None
+        self.full_graph_digest = None
 
     # -- fit / get_losses ------------------------------------------------------------------
     def _loaders(self, data, graph, data_batch: int, graph_batch: int, random_seed: int,
@@ -180,6 +197,9 @@ class GLUETrainer(Trainer):
         the common batch sequence while every rank sees the same edge minibatches."""
         def make(ds, batch, drop_last, strided):
             on_device = getattr(ds, "device", None) is not None
+            if hasattr(ds, "sparse_items"):  # host-resident count matrices feeding a GPU travel sparse
+                ds.sparse_items = (config.SPARSE_HOST_BATCHES and not on_device
+                                   and self.net.device.type == "cuda")
             pin = (config.DATALOADER_PIN_MEMORY and not config.CPU_ONLY and not on_device
                    and torch.cuda.is_available())
             gen = torch.Generator().manual_seed(random_seed)

@@ -67,8 +67,10 @@ class StepGraphs:
             "lam_data", "lam_kl", "lam_graph", "lam_align", "lam_sup", "lam_joint_cross",
             "lam_real_cross", "lam_cos") if hasattr(tr, name))
         weights += tuple(float(v) for v in tr.modality_weight.values())
+        # (the guidance graph's CSR arrays are baked into a capture: another graph is another key)
         return (tuple((tuple(t.shape), t.dtype) for t in data), bool(anneal), bool(tr.freeze_u),
-                lrs, tr.dsc_steps, weights, bool(tr.normalize_u), tr.align_burnin)
+                lrs, tr.dsc_steps, weights, bool(tr.normalize_u), tr.align_burnin,
+                getattr(tr, "full_graph_digest", None))
 
     def _storage_fingerprint(self) -> tuple:
         r"""Addresses of the first and last parameter of every optimizer: a capture is only valid
@@ -155,6 +157,9 @@ class StepGraphs:
             torch.cuda.synchronize(device)
             if self.pool is None:
                 self.pool = torch.cuda.graph_pool_handle()
+            # whatever the step caches across calls must exist before the capture: memory allocated
+            # inside it belongs to the graph's pool and is only meaningful during a replay
+            tr.prepare_capture()
             rng_before = torch.cuda.get_rng_state(device)  # (to recover the generator if the capture fails)
             graph = torch.cuda.CUDAGraph()
             launches0 = ops.kernel_launches()

@@ -10,6 +10,7 @@ from typing import List
 import torch
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
+from .. import dist as gdist
 from ..utils import config, logged
 from .base import COMPLETED, EPOCH_COMPLETED, TERMINATE, Engine, TrainingPlugin
 
@@ -21,6 +22,8 @@ class Tensorboard(TrainingPlugin):
 
     def attach(self, net, trainer, train_engine, val_engine, train_loader, val_loader,
                directory) -> None:
+        if gdist.rank() != 0:  # data parallel: metrics are rank-averaged, one writer is enough
+            return
         try:
             from torch.utils.tensorboard import SummaryWriter
         except Exception:  # pragma: no cover
@@ -58,10 +61,16 @@ class EarlyStopping(TrainingPlugin):
 
     def attach(self, net, trainer, train_engine, val_engine, train_loader, val_loader,
                directory) -> None:
+        # Data parallel: parameters and optimizer state are identical on every rank (averaged
+        # gradients) and so are the rank-averaged metrics, hence every rank takes the same keep /
+        # stop decisions; rank 0 alone touches the files, all ranks restore the same checkpoint.
         directory = pathlib.Path(directory)
-        directory.mkdir(parents=True, exist_ok=True)
-        for item in directory.glob("checkpoint_*.pt"):
-            item.unlink()
+        writer = gdist.rank() == 0
+        if writer:
+            directory.mkdir(parents=True, exist_ok=True)
+            for item in directory.glob("checkpoint_*.pt"):
+                item.unlink()
+        gdist.barrier()
         score_engine = val_engine if val_engine else train_engine
         saved: List[tuple] = []  # (score, epoch)
         tracker = {"best": None, "stale": 0}
@@ -75,13 +84,15 @@ class EarlyStopping(TrainingPlugin):
             score = -score_engine.state.metrics[self.monitor]
             # keep the n best checkpoints (ties: the newer one wins, like ignite's Checkpoint)
             if len(saved) < config.CHECKPOINT_SAVE_NUMBERS or score >= min(saved)[0]:
-                torch.save({"net": net.state_dict(), "trainer": trainer.state_dict()},
-                           directory / f"checkpoint_{epoch}.pt")
+                if writer:
+                    torch.save({"net": net.state_dict(), "trainer": trainer.state_dict()},
+                               directory / f"checkpoint_{epoch}.pt")
                 saved.append((score, epoch))
                 if len(saved) > config.CHECKPOINT_SAVE_NUMBERS:
                     worst = min(saved)
                     saved.remove(worst)
-                    (directory / f"checkpoint_{worst[1]}.pt").unlink(missing_ok=True)
+                    if writer:
+                        (directory / f"checkpoint_{worst[1]}.pt").unlink(missing_ok=True)
             if tracker["best"] is None or score > tracker["best"]:
                 tracker["best"], tracker["stale"] = score, 0
             else:
@@ -93,6 +104,7 @@ class EarlyStopping(TrainingPlugin):
         def _on_end(engine: Engine) -> None:
             nan_flag = any(v != v or abs(v) == float("inf")
                            for v in engine.state.metrics.values())
+            gdist.barrier()  # rank 0 has finished writing
             ckpts = sorted((int(re.match(r"checkpoint_(\d+)\.pt", p.name).group(1))
                             for p in directory.glob("checkpoint_*.pt")), reverse=True)
             if ckpts and nan_flag and engine.state.epoch == ckpts[0]:

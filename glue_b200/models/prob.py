@@ -15,6 +15,10 @@ from .. import ops
 from ..num import EPS
 
 
+def _zero_nan_grad(grad: torch.Tensor) -> torch.Tensor:
+    return grad.nan_to_num()
+
+
 class NB(D.NegativeBinomial):
     r"""Negative binomial -- the reference uses ``torch.distributions.NegativeBinomial``
     directly (``scglue/models/sc.py:397``); this alias completes the ``prob`` namespace."""
@@ -56,6 +60,11 @@ class ZIN(D.Normal):
     r"""Zero-inflated normal (``scglue/models/prob.py:52-87``)."""
 
     def __init__(self, zi_logits, loc, scale):
+        # as the reference (``prob.py:70-75``): NaN gradients (NaN observations, or the unselected
+        # branch of the ``where`` below overflowing) are zeroed on their way into the parameters
+        for t in (zi_logits, loc, scale):
+            if t.requires_grad:
+                t.register_hook(_zero_nan_grad)
         super().__init__(loc, scale, validate_args=False)
         self.zi_logits = zi_logits
 

@@ -132,6 +132,7 @@ class SCGLUETrainer(GLUETrainer):
         """
         device, keys = self.net.device, self.net.keys
         K = len(keys)
+        data = self.unpack_data(data)
         move = lambda t: t.to(device, non_blocking=True)
         groups = [dict(zip(keys, map(move, data[i * K:(i + 1) * K]))) for i in range(5)]
         x, xrep, xbch, xlbl, xdwt = groups
@@ -143,6 +144,30 @@ class SCGLUETrainer(GLUETrainer):
         if self.PAIRED:
             return x, xrep, xbch, xlbl, xdwt, xflag, pmsk, eidx, ewt, esgn
         return x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn
+
+    def prepare_capture(self) -> None:
+        r"""Build, outside the capture, what the step looks up in process-wide caches: the CSR of the
+        full guidance graph (``ops.csr_for``)."""
+        g2v = self.net.g2v
+        if self.eidx is not None and hasattr(g2v, "vrepr") and g2v.vrepr.is_cuda:
+            from .. import ops
+            ops.csr_for(self.eidx, self.enorm, self.esgn, g2v.vrepr.shape[0])
+
+    def unpack_data(self, data: List[torch.Tensor]) -> List[torch.Tensor]:
+        r"""Count matrices that arrive as packed sparse rows (``data.SparseRows``: host-resident
+        datasets) are moved to the device and densified there; everything else passes through."""
+        from .data import is_packed_sparse, unpack_sparse_rows
+        K = len(self.net.keys)
+        if not any(is_packed_sparse(t) for t in data[:K]):
+            return data
+        device = self.net.device
+        data = list(data)
+        for i, k in enumerate(self.net.keys):
+            if is_packed_sparse(data[i]):
+                n_rows = data[2 * K + i].shape[0]  # (one batch index per cell)
+                n_cols = getattr(self.net, f"{k}_idx").shape[0]
+                data[i] = unpack_sparse_rows(data[i].to(device, non_blocking=True), n_rows, n_cols)
+        return data
 
     # -- shared pieces of the objective ----------------------------------------------------
     def _parallel(self, thunks):
@@ -440,6 +465,7 @@ class SCGLUETrainer(GLUETrainer):
     def train_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
         r"""One discriminator + one generator update.  On CUDA, steps whose input signature
         has been seen before are replayed from a captured graph (:class:`StepGraphs`)."""
+        data = self.unpack_data(data)
         if self.graphs.usable():
             return self.graphs.step(engine, data)
         return self.eager_train_step(engine, data)

@@ -134,6 +134,10 @@ def csr_for(eidx: torch.Tensor, enorm: torch.Tensor, esgn: torch.Tensor, vnum: i
         _CSR_CACHE.move_to_end(key)
         return hit[0]
     csr = GraphCSR(eidx, enorm, esgn, vnum)
+    if torch.cuda.is_current_stream_capturing():
+        # arrays allocated during a CUDA-graph capture live in the graph's private pool and hold
+        # their values only while that graph replays: usable by this capture, never by anyone else
+        return csr
     _CSR_CACHE[key] = (csr, eidx, enorm, esgn)
     while len(_CSR_CACHE) > _CSR_CACHE_SIZE:
         _CSR_CACHE.popitem(last=False)

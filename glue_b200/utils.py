@@ -59,6 +59,9 @@ class _Settings:
         OVERLAP_DISCRIMINATOR=True,
         # fused kernels for the scalar tail of the objective (data-encoder KL, paired mean + cosine term)
         USE_FUSED_OBJECTIVE=True,
+        # host-resident datasets: sparse count matrices travel to the device as (position, value) pairs
+        # and are densified there, instead of being densified on the host and copied as [B, F] fp32
+        SPARSE_HOST_BATCHES=True,
         # the decoder loss terms of one modality (reconstruction, joint cross, real cross) as one fused
         # launch sequence that shares the staged feature table and the observations
         USE_FUSED_TERMS=True,

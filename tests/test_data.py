@@ -540,3 +540,41 @@ def test_fit_plumbing_runs_on_cpu_with_a_stub_step(monkeypatch, tmp_path, paired
     # get_losses runs the validation step over one pass
     losses = model.get_losses(adatas, graph, data_batch_size=32)
     assert set(losses) == set(model.trainer.required_losses)
+
+
+def test_packed_sparse_host_batches_equal_dense_batches():
+    """Host-resident datasets hand sparse count rows to the device as (position, value) pairs
+    (``SparseRows``); unpacked they must be the dense minibatch of ``AnnDataset.__getitem__``
+    (scglue/models/data.py:397-436) bit for bit, including all-zero batches and padded buckets."""
+    from tests.synth import make_synthetic
+    from glue_b200.models.data import SparseRows, is_packed_sparse, unpack_sparse_rows
+    adatas, graph = make_synthetic(n_cells=(150, 150), n_feat=(40, 700), n_pairs=100, seed=3, rep_dim=8)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep")
+    cfgs = [a.uns[config.ANNDATA_KEY] for a in adatas.values()]
+
+    def batches(sparse):
+        ds = AnnDataset(list(adatas.values()), cfgs, mode="train", getitem_size=8)
+        ds.sparse_items = sparse
+        ds.prepare_shuffle(num_workers=0, random_seed=2)
+        return list(DataLoader(ds, batch_size=4, shuffle=True, generator=torch.Generator().manual_seed(2)))
+
+    dense, packed = batches(False), batches(True)
+    assert len(dense) == len(packed)
+    seen_packed = 0
+    for d, p in zip(dense, packed):
+        for i, (td, tp) in enumerate(zip(d, p)):
+            if is_packed_sparse(tp) and i < 2:
+                seen_packed += 1
+                assert tp.shape[1] % SparseRows.BUCKET == 0
+                got = unpack_sparse_rows(tp, td.shape[0], td.shape[1])
+                assert got.dtype == td.dtype and torch.equal(got, td)
+            else:
+                assert torch.equal(td, tp)
+    assert seen_packed == 2 * len(dense)
+    # an all-zero block
+    zero = SparseRows(scipy.sparse.csr_matrix((5, 9), dtype=np.float32))
+    assert torch.equal(unpack_sparse_rows(SparseRows.pack([zero, zero]), 10, 9), torch.zeros(10, 9))
+    # direct indexing keeps the reference's contract: dense tensors
+    ds = AnnDataset(list(adatas.values()), cfgs, mode="train", getitem_size=8)
+    assert all(isinstance(t, torch.Tensor) and not is_packed_sparse(t) for t in ds[0])

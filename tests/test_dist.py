@@ -109,3 +109,60 @@ def test_partitioned_graphconv_gloo():
     assert out[0][0] and out[1][0], "all-gathered row blocks must equal the unpartitioned result"
     assert out[0][1] and out[1][1], "backward must apply the whole transposed graph locally"
     assert (out[0][2], out[0][3]) == (51, 0) and (out[1][2], out[1][3]) == (50, 51)
+
+
+def _fit_worker(rank, world, port, out, tmpdir):
+    """Two ranks drive the real fit plumbing (loaders, engine, LR scheduler, early stopping) with a
+    stub step whose validation loss differs per rank: rank 0 alone would see steady improvement,
+    rank 1 alone a plateau.  With rank-averaged epoch metrics both take the same decisions."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as td
+    from glue_b200 import dist as gdist
+    from glue_b200 import models
+    from glue_b200.models import scglue as gs
+    from glue_b200.models.base import LossVector
+    from glue_b200.utils import config
+    from tests.synth import make_synthetic
+    gdist.init_from_env(backend="gloo")
+    config.CPU_ONLY = True
+    adatas, graph = make_synthetic(n_cells=(96, 96), n_feat=(12, 30), n_pairs=40, seed=1, rep_dim=6, paired=True)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep", use_obs_names=True)
+    steps = []
+
+    class StubTrainer(gs.PairedSCGLUETrainer):
+        def _vec(self, engine, val):
+            e = engine.state.epoch
+            # rank 0: 1/e (always improving); rank 1: constant after epoch 2
+            score = 1.0 / e if rank == 0 else (1.0 if e <= 2 else 0.9)
+            vals = torch.full((len(self.required_losses),), score if val else 1.0)
+            return LossVector(self.required_losses, vals)
+
+        def train_step(self, engine, data):
+            steps.append(engine.state.epoch)
+            return self._vec(engine, False)
+
+        def val_step(self, engine, data):
+            return self._vec(engine, True)
+
+    gs.PairedSCGLUEModel.TRAINER_TYPE = StubTrainer
+    model = gs.PairedSCGLUEModel(adatas, sorted(graph.nodes), latent_dim=4, h_dim=8, random_seed=0)
+    model.compile()
+    model.fit(adatas, graph, data_batch_size=16, max_epochs=12, patience=3, reduce_lr_patience=1,
+              align_burnin=1, directory=None)
+    lr = model.trainer.vae_optim.param_groups[0]["lr"]
+    out[rank] = (max(steps), len(steps), lr)
+    td.barrier()
+    td.destroy_process_group()
+
+
+def test_data_parallel_fit_takes_the_same_decisions_on_every_rank(tmp_path):
+    """ADVICE (round 1): LR scheduling / early stopping acted on rank-local validation metrics, so one
+    rank could reduce its LR or leave the loop alone.  Epoch metrics are now averaged over the ranks."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fit_worker, args=(world, port, out, str(tmp_path)), nprocs=world, join=True)
+    assert out[0] == out[1], f"ranks diverged: {dict(out)}"
+    assert out[0][0] >= 3

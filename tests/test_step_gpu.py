@@ -274,3 +274,42 @@ def test_training_continues_correctly_after_save(native_lib):
     assert model.trainer.graphs.replays > replays
     opt = model.trainer.vae_optim
     assert all(p.data_ptr() == v.data_ptr() for p, v in zip(opt._plist, opt._pviews))
+
+
+def test_repeated_fits_with_step_graphs_equal_eager_fits(native_lib):
+    """Round-2 regression: a minibatch signature seen exactly once in the first ``fit`` (the short last
+    block) is captured at its first occurrence in the second ``fit``; the CSR of the guidance graph used to
+    be built -- and cached process-wide -- inside that capture, i.e. in the graph's private memory pool, and
+    the next eager consumer (validation) read garbage.  Two fits with captured steps must give what two
+    fits with eager steps give (dropout 0: same arithmetic, same order), and stay finite."""
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+    from glue_b200.utils import config
+
+    def run(use_graphs):
+        adatas, graph = make_synthetic(n_cells=(330, 290), n_feat=(40, 900), n_pairs=400, seed=5, rep_dim=12)
+        for a in adatas.values():
+            models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep")
+        old = config.USE_CUDA_GRAPHS
+        config.USE_CUDA_GRAPHS = use_graphs
+        try:
+            model = models.SCGLUEModel(adatas, sorted(graph.nodes), latent_dim=16, h_dim=32, dropout=0.0,
+                                       random_seed=2)
+            model.compile()
+            kw = dict(data_batch_size=32, max_epochs=1, patience=None, reduce_lr_patience=None, align_burnin=50)
+            for _ in range(3):
+                model.fit(adatas, graph, **kw)
+            losses = model.get_losses(adatas, graph)
+            n_graphs = model.trainer.graphs.info()["graphs"]
+            return model.encode_graph(graph), model.encode_data("rna", adatas["rna"]), losses, n_graphs
+        finally:
+            config.USE_CUDA_GRAPHS = old
+
+    v_g, u_g, l_g, n_graphs = run(True)
+    v_e, u_e, l_e, _ = run(False)
+    assert n_graphs >= 1, "the captured path must have been exercised"
+    assert np.isfinite(v_g).all() and np.isfinite(u_g).all() and np.isfinite(list(l_g.values())).all()
+    assert_close(v_g, v_e, 1e-4, "vertex embeddings after three fits (graphs vs eager)")
+    assert_close(u_g, u_e, 1e-4, "cell embeddings after three fits (graphs vs eager)")
+    for k in l_e:
+        assert abs(l_g[k] - l_e[k]) <= 1e-4 * max(1.0, abs(l_e[k])), k
