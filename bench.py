@@ -600,9 +600,24 @@ def main():
 
 def measure_fit(cfg, adatas, graph, device):
     """Wall-clock throughput of ``model.fit`` itself: negative sampler, block-shuffled loaders,
-    device-resident row gathers, per-epoch validation, metric read-back, plugins.  A fresh model;
-    the first epoch (graph capture, allocator warm-up) is timed separately."""
+    device-resident row gathers, per-epoch validation, metric read-back, plugins.  A fresh model is
+    fitted once for one epoch (graph capture, allocator warm-up) and once more for five epochs;
+    ``value`` is the steady state (epochs 2-5 of the second fit, wall clock between the ends of
+    epochs), ``setup_s`` what precedes its first step: dataset and graph construction, upload."""
+    from glue_b200.models.base import EPOCH_COMPLETED, EPOCH_STARTED, TrainingPlugin
     from glue_b200.utils import config
+
+    class EpochClock(TrainingPlugin):
+        def __init__(self):
+            self.started, self.ended = [], []
+
+        def attach(self, net, trainer, train_engine, val_engine, train_loader, val_loader, directory):
+            def end(engine):
+                torch.cuda.synchronize(device)
+                self.ended.append(time.perf_counter())
+            train_engine.add_event_handler(EPOCH_STARTED, lambda engine: self.started.append(time.perf_counter()))
+            train_engine.add_event_handler(EPOCH_COMPLETED, end)
+
     model = build_model(cfg, adatas, graph)
     view_cells = cfg["n_cells"] * (1 if cfg["paired"] else len(cfg["modalities"]))
     kw = dict(data_batch_size=cfg["batch"], patience=None, reduce_lr_patience=None)
@@ -612,12 +627,14 @@ def measure_fit(cfg, adatas, graph, device):
     config.PRINT_LOSS_INTERVAL = 1000
     try:
         tic = time.perf_counter()
-        model.fit(adatas, graph, max_epochs=1, **kw)
+        first_clock = EpochClock()
+        run_fit(model, adatas, graph, cfg, kw, 1, first_clock)
         torch.cuda.synchronize(device)
         first = time.perf_counter() - tic
-        epochs = 4
+        epochs = 5
+        clock = EpochClock()
         tic = time.perf_counter()
-        model.fit(adatas, graph, max_epochs=epochs, **kw)
+        run_fit(model, adatas, graph, cfg, kw, epochs, clock)
         torch.cuda.synchronize(device)
         wall = time.perf_counter() - tic
     finally:
@@ -626,11 +643,31 @@ def measure_fit(cfg, adatas, graph, device):
     block = max(1, round(cfg["batch"] / fetches))
     n_train = round(view_cells * 0.9)
     steps = (math.ceil(n_train / block)) // fetches  # drop_last over blocks
-    trained = steps * cfg["batch"] * epochs
-    return {"value": trained / wall, "unit": "cells/s", "epochs": epochs, "train_steps_per_epoch": steps,
-            "wall_s": wall, "first_fit_s_1_epoch": first,
-            "includes": "dataset + graph construction, negative sampling, loaders, validation every epoch, "
-                        "metric read-back, checkpoint directory; 4 epochs after a 1-epoch fit (graph capture)"}
+    steady_s = clock.ended[-1] - clock.ended[0]
+    trained = steps * cfg["batch"] * (epochs - 1)
+    return {"value": trained / steady_s, "unit": "cells/s", "epochs_timed": epochs - 1,
+            "train_steps_per_epoch": steps, "s_per_epoch": steady_s / (epochs - 1),
+            "setup_s": clock.started[0] - tic, "fit_wall_s": wall, "first_fit_s_1_epoch": first,
+            "includes": "per epoch: negative sampling of the guidance graph, block-shuffled loaders, device row "
+                        "gathers, the training steps, validation on the held-out 10 %, metric read-back; "
+                        "setup_s: dataset + graph construction and upload before the first step"}
+
+
+def run_fit(model, adatas, graph, cfg, kw, epochs, clock):
+    """``model.fit`` with an extra plugin (the public ``fit`` takes none): same code path, the clock rides
+    along through ``GLUETrainer.fit(plugins=...)``."""
+    from glue_b200.models import glue as glue_mod
+    orig = glue_mod.GLUETrainer.fit
+
+    def fit_with_clock(self, *a, **k):
+        k["plugins"] = list(k.get("plugins") or []) + [clock]
+        return orig(self, *a, **k)
+
+    glue_mod.GLUETrainer.fit = fit_with_clock
+    try:
+        model.fit(adatas, graph, max_epochs=epochs, **kw)
+    finally:
+        glue_mod.GLUETrainer.fit = orig
 
 
 def measure_partitioned(device, world, rank, V=200000, E=1000000, K=50, n=20):

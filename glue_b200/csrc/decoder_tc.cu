@@ -1144,8 +1144,12 @@ size_t tc_ws_layout(const glue_decoder_args& a, int ncta, char* base, DecWs* ws)
 }
 
 int tc_grid(const glue_decoder_args& a, int& ntiles) {
+    // the fewest CTAs with the makespan of a full grid (see grid_for in decoder_tc3.cu)
     ntiles = (a.F + 127) / 128;
-    return ntiles < sm_count() ? ntiles : sm_count();
+    const int sms = sm_count();
+    if (ntiles <= sms) return ntiles;
+    const int per_cta = (ntiles + sms - 1) / sms;
+    return (ntiles + per_cta - 1) / per_cta;
 }
 
 template <int FAM, int PHASE, bool GRAD, bool NB1, bool FAST>

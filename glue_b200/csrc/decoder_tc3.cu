@@ -1396,9 +1396,16 @@ size_t ws_layout(const glue_decoder_args& a, int S, int ncta, int Fpad, char* ba
     return align_up(off, 1024) + 1024;  // (+ slack to align the base itself)
 }
 
+// Persistent CTAs, feature tiles strided over them.  The fewest CTAs that still give every CTA at most
+// ceil(ntiles / #SM) tiles: the makespan is that of a full grid (391 tiles: 3 per CTA with 148 CTAs and
+// with 131), and the SMs left over take the kernels that run beside this call on other streams -- the
+// decoder call of a small modality (16 CTAs at 2 000 genes) would otherwise wait for, or delay, a full wave.
 int grid_for(int F, int& ntiles) {
     ntiles = (F + 127) / 128;
-    return ntiles < sm_count() ? ntiles : sm_count();
+    const int sms = sm_count();
+    if (ntiles <= sms) return ntiles;
+    const int per_cta = (ntiles + sms - 1) / sms;
+    return (ntiles + per_cta - 1) / per_cta;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 
-cfg = dict(bench.WORKLOAD)
+cfg = dict(bench.WORKLOADS[os.environ.get("CONFIG", "cfg2")])
 adatas, graph = bench.make_workload(cfg)
 model = bench.build_model(cfg, adatas, graph)
 trainer = model.trainer
