@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "glue_graphenc_workspace_bytes",
     "glue_graphenc_head_fwd",
     "glue_graphenc_head_bwd",
+    "glue_graphenc_head_bwd_impl",
+    "glue_graphenc_head_fwd_impl",
     "glue_graphdec_workspace_bytes",
     "glue_graphdec_bce_fwd",
     "glue_graphdec_bwd",
@@ -141,6 +143,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_graphenc_head_bwd.restype = c_int32
     lib.glue_graphenc_head_bwd.argtypes = [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 6 + [
         c_size_t, c_void_p]
+
+    lib.glue_graphenc_head_fwd_impl.restype = c_int32
+    lib.glue_graphenc_head_fwd_impl.argtypes = [c_void_p] * 6 + [c_int64, c_int32] + [c_void_p] * 5 + [
+        c_size_t, c_int32, c_void_p]
+    lib.glue_graphenc_head_bwd_impl.restype = c_int32
+    lib.glue_graphenc_head_bwd_impl.argtypes = [c_void_p] * 8 + [c_int64, c_int32] + [c_void_p] * 6 + [
+        c_size_t, c_int32, c_void_p]
 
     lib.glue_graphdec_workspace_bytes.restype = c_size_t
     lib.glue_graphdec_workspace_bytes.argtypes = [c_int64, c_int64]

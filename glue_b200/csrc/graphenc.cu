@@ -292,6 +292,328 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_kernel(EncArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------- backward, tensor cores
+// Same outputs as graphenc_bwd_kernel with the four K x K products per tile on warp-level tensor
+// cores: mma.sync m16n8k8 TF32, every fp32 product rebuilt from three TF32 products
+// (big*big + big*small + small*big, ~2^-21 relative) so that the 1e-4 parity bar holds.
+//   dgrad   g_ptr[64 x K]  = d1[64 x K] W_loc[K x K] + d2[64 x K] W_std[K x K]
+//           warp w: rows 16 (w & 3) .., output columns of half (w >> 2)
+//   wgrad   gW_m[K x K]   += d_m^T[K x 64] x[64 x K]      (m = loc, std)
+//           warp w: matrix (w >> 2), output rows 16 (w & 3) .., all column tiles; accumulators
+//           stay in registers over all tiles of the CTA
+// Fragment layouts (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3;
+//   A[16 x 8] row-major: a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4)
+//   B[8 x 8]  col-major: b0 (t, g) b1 (t + 4, g)
+//   C[16 x 8]:           c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1)
+// Shared-memory strides: A-pattern reads (row g, col t) are conflict free for strides = 4 mod 32,
+// B-pattern reads (row t, col g) for strides = 8 mod 32.
+constexpr int MM_KP = 64;    // padded latent dim (K <= 64)
+constexpr int MM_DS = 68;    // stride of d1 / d2 (A operand of dgrad; 2-way conflicts as A^T of wgrad)
+constexpr int MM_BS = 72;    // stride of x and of the weight matrices (B operands)
+
+struct MmaSmem {
+    float x[TR][MM_BS];
+    float d1[TR][MM_DS];
+    float d2[TR][MM_DS];
+    float wl_big[MM_KP][MM_BS], wl_small[MM_KP][MM_BS];  // [o][i], TF32 split of the weights
+    float ws_big[MM_KP][MM_BS], ws_small[MM_KP][MM_BS];
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
+    big = to_tf32(x);
+    small = to_tf32(x - __uint_as_float(big));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A B with A, B given as (big, small) TF32 pairs: small terms first
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t bb0,
+                                       uint32_t bb1, uint32_t bs0, uint32_t bs1) {
+    mma_tf32(c, as, bb0, bb1);
+    mma_tf32(c, ab, bs0, bs1);
+    mma_tf32(c, ab, bb0, bb1);
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a, int KPW /* 52 or 64: partial layout */) {
+    extern __shared__ float4 enc_smem_raw[];
+    MmaSmem& S = *reinterpret_cast<MmaSmem*>(enc_smem_raw);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+    const int K = a.K;
+    const int nk8 = (K + 7) >> 3;  // 8-wide tiles covering K
+    // weights -> shared memory, split once
+    for (int idx = t; idx < MM_KP * MM_KP; idx += ENC_THREADS) {
+        const int o = idx >> 6, i = idx & 63;
+        const bool ok = o < K && i < K;
+        uint32_t b, sm;
+        split_tf32(ok ? a.w_loc[o * K + i] : 0.f, b, sm);
+        S.wl_big[o][i] = __uint_as_float(b), S.wl_small[o][i] = __uint_as_float(sm);
+        split_tf32(ok ? a.w_std[o * K + i] : 0.f, b, sm);
+        S.ws_big[o][i] = __uint_as_float(b), S.ws_small[o][i] = __uint_as_float(sm);
+    }
+    const float ckl = a.kl_coef ? __ldg(a.kl_coef) : 0.f;
+    // wgrad accumulators of this warp: matrix wm, output rows 16 mt .., column tiles 0 .. nk8 - 1
+    const int wm = warp >> 2, mt = warp & 3;
+    float gw[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) gw[n][0] = gw[n][1] = gw[n][2] = gw[n][3] = 0.f;
+    float gbias = 0.f;  // threads 0..63: column t of d1; 64..127: column t - 64 of d2
+    const int64_t ntiles = (a.V + TR - 1) / TR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();  // previous tile's reads are done
+        const int64_t row0 = tile * TR;
+        // x tile and the two upstream-gradient tiles, zero padded to 64 columns
+        for (int idx = t; idx < TR * (MM_KP / 2); idx += ENC_THREADS) {
+            const int r = idx >> 5, o = 2 * (idx & 31);
+            const int64_t row = row0 + r;
+            float2 xv = make_float2(0.f, 0.f), dm = xv, ds = xv;
+            if (row < a.V && o < K) {
+                const int64_t off = row * K + o;
+                xv = __ldg(reinterpret_cast<const float2*>(a.ptr + off));
+                const float2 gv = a.grad_vsamp ? __ldg(reinterpret_cast<const float2*>(a.grad_vsamp + off))
+                                               : make_float2(0.f, 0.f);
+                const float2 nz = a.noise ? __ldg(reinterpret_cast<const float2*>(a.noise + off)) : make_float2(0.f, 0.f);
+                const float2 m = __ldg(reinterpret_cast<const float2*>(a.mu + off));
+                const float2 sg = __ldg(reinterpret_cast<const float2*>(a.sigma + off));
+                dm = make_float2(fmaf(ckl, m.x, gv.x), fmaf(ckl, m.y, gv.y));
+                const float dsg0 = fmaf(gv.x, nz.x, ckl * (sg.x - 1.f / sg.x));
+                const float dsg1 = fmaf(gv.y, nz.y, ckl * (sg.y - 1.f / sg.y));
+                ds = make_float2(dsg0 * (1.f - expf(-(sg.x - GLUE_EPS))), dsg1 * (1.f - expf(-(sg.y - GLUE_EPS))));
+            }
+            *reinterpret_cast<float2*>(&S.x[r][o]) = xv;
+            *reinterpret_cast<float2*>(&S.d1[r][o]) = dm;
+            *reinterpret_cast<float2*>(&S.d2[r][o]) = ds;
+        }
+        __syncthreads();
+        // ---- bias gradients: column sums of d1 / d2
+        if (t < 128) {
+            const float(*d)[MM_DS] = t < 64 ? S.d1 : S.d2;
+            const int col = t & 63;
+            float s = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < TR; ++r) s += d[r][col];
+            gbias += s;
+        }
+        // ---- dgrad: rows 16 mt .. of this tile, column tiles [n_lo, n_hi)
+        {
+            const int n_lo = wm == 0 ? 0 : (nk8 + 1) / 2, n_hi = wm == 0 ? (nk8 + 1) / 2 : nk8;
+            float acc[4][4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+            for (int mat = 0; mat < 2; ++mat) {
+                const float(*d)[MM_DS] = mat == 0 ? S.d1 : S.d2;
+                const float(*wb)[MM_BS] = mat == 0 ? S.wl_big : S.ws_big;
+                const float(*wsm)[MM_BS] = mat == 0 ? S.wl_small : S.ws_small;
+                for (int ks = 0; ks < nk8; ++ks) {
+                    const int k0 = 8 * ks, r0 = 16 * mt;
+                    uint32_t ab[4], as[4];
+                    split_tf32(d[r0 + g][k0 + tq], ab[0], as[0]);
+                    split_tf32(d[r0 + g + 8][k0 + tq], ab[1], as[1]);
+                    split_tf32(d[r0 + g][k0 + tq + 4], ab[2], as[2]);
+                    split_tf32(d[r0 + g + 8][k0 + tq + 4], ab[3], as[3]);
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        const int nt = n_lo + n;
+                        if (nt < n_hi) {
+                            const int n0 = 8 * nt;
+                            mma_3x(acc[n], ab, as, __float_as_uint(wb[k0 + tq][n0 + g]),
+                                   __float_as_uint(wb[k0 + tq + 4][n0 + g]), __float_as_uint(wsm[k0 + tq][n0 + g]),
+                                   __float_as_uint(wsm[k0 + tq + 4][n0 + g]));
+                        }
+                    }
+                }
+            }
+            if (a.grad_ptr) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const int nt = n_lo + n;
+                    if (nt >= n_hi) continue;
+                    const int col = 8 * nt + 2 * tq;
+                    if (col >= K) continue;  // (K even: col + 1 < K as well)
+                    const int64_t r_lo = row0 + 16 * mt + g, r_hi = r_lo + 8;
+                    if (r_lo < a.V) *reinterpret_cast<float2*>(a.grad_ptr + r_lo * K + col) = make_float2(acc[n][0], acc[n][1]);
+                    if (r_hi < a.V) *reinterpret_cast<float2*>(a.grad_ptr + r_hi * K + col) = make_float2(acc[n][2], acc[n][3]);
+                }
+            }
+        }
+        // ---- wgrad: gW_wm[16 mt + ., :] += d_wm^T x over the 64 rows of the tile
+        {
+            const float(*d)[MM_DS] = wm == 0 ? S.d1 : S.d2;
+            const int m0 = 16 * mt;
+            for (int ks = 0; ks < TR / 8; ++ks) {
+                const int k0 = 8 * ks;  // rows of the tile
+                uint32_t ab[4], as[4];  // A[m = o][k = r] = d[r][o]
+                split_tf32(d[k0 + tq][m0 + g], ab[0], as[0]);
+                split_tf32(d[k0 + tq][m0 + g + 8], ab[1], as[1]);
+                split_tf32(d[k0 + tq + 4][m0 + g], ab[2], as[2]);
+                split_tf32(d[k0 + tq + 4][m0 + g + 8], ab[3], as[3]);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    if (n < nk8) {
+                        const int n0 = 8 * n;
+                        uint32_t bb0, bs0, bb1, bs1;  // B[k = r][n = i] = x[r][i]
+                        split_tf32(S.x[k0 + tq][n0 + g], bb0, bs0);
+                        split_tf32(S.x[k0 + tq + 4][n0 + g], bb1, bs1);
+                        mma_3x(gw[n], ab, as, bb0, bb1, bs0, bs1);
+                    }
+                }
+            }
+        }
+    }
+    // per-CTA partials in the layout of graphenc_wgrad_reduce_kernel<KPW>: [2][KPW][KPW + 1]
+    {
+        float* base = a.gwpart + (size_t)blockIdx.x * 2 * KPW * (KPW + 1) + (size_t)wm * KPW * (KPW + 1);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            if (n >= nk8) continue;
+            const int i0 = 8 * n + 2 * tq;
+            const int o_lo = 16 * mt + g, o_hi = o_lo + 8;
+            if (i0 < K) {
+                if (o_lo < K) base[o_lo * (KPW + 1) + i0] = gw[n][0], base[o_lo * (KPW + 1) + i0 + 1] = gw[n][1];
+                if (o_hi < K) base[o_hi * (KPW + 1) + i0] = gw[n][2], base[o_hi * (KPW + 1) + i0 + 1] = gw[n][3];
+            }
+        }
+        if (t < 128) {
+            const int col = t & 63, m = t >> 6;
+            if (col < K) a.gwpart[(size_t)blockIdx.x * 2 * KPW * (KPW + 1) + (size_t)m * KPW * (KPW + 1) +
+                                  col * (KPW + 1) + KPW] = gbias;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------- forward, tensor cores
+// mu = x W_loc^T + b_loc, s = x W_std^T + b_std per 64-vertex tile on mma.sync m16n8k8 TF32 x 3 (as the
+// backward kernel above), then the epilogue of graphenc_fwd_kernel from the accumulator fragments.
+//   warp w: rows 16 (w & 3) .., output-column tiles of half (w >> 2), both matrices (the epilogue needs
+//   mu and sigma of the same element)
+// A = x tile [64 x K] (stride 68 = 4 mod 32), B[k = i][n = o] = W[o][i]: the weights are kept
+// transposed, [i][o], with stride 72 = 8 mod 32 (conflict-free B-pattern reads).
+struct MmaFwdSmem {
+    float x[TR][MM_DS];
+    float wlT_big[MM_KP][MM_BS], wlT_small[MM_KP][MM_BS];  // [i][o]
+    float wsT_big[MM_KP][MM_BS], wsT_small[MM_KP][MM_BS];
+    float bl[MM_KP], bs[MM_KP];
+    double red[ENC_THREADS / 32];
+    unsigned int ticket;
+};
+
+__global__ void __launch_bounds__(ENC_THREADS) graphenc_fwd_mma_kernel(EncArgs a) {
+    extern __shared__ float4 enc_smem_raw[];
+    MmaFwdSmem& S = *reinterpret_cast<MmaFwdSmem*>(enc_smem_raw);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+    const int K = a.K;
+    const int nk8 = (K + 7) >> 3;
+    for (int idx = t; idx < MM_KP * MM_KP; idx += ENC_THREADS) {
+        const int o = idx >> 6, i = idx & 63;
+        const bool ok = o < K && i < K;
+        uint32_t b, sm;
+        split_tf32(ok ? a.w_loc[o * K + i] : 0.f, b, sm);
+        S.wlT_big[i][o] = __uint_as_float(b), S.wlT_small[i][o] = __uint_as_float(sm);
+        split_tf32(ok ? a.w_std[o * K + i] : 0.f, b, sm);
+        S.wsT_big[i][o] = __uint_as_float(b), S.wsT_small[i][o] = __uint_as_float(sm);
+    }
+    for (int o = t; o < MM_KP; o += ENC_THREADS) {
+        S.bl[o] = o < K ? a.b_loc[o] : 0.f;
+        S.bs[o] = o < K ? a.b_std[o] : 0.f;
+    }
+    const int mt = warp & 3, ch = warp >> 2;
+    const int n_lo = ch == 0 ? 0 : (nk8 + 1) / 2, n_hi = ch == 0 ? (nk8 + 1) / 2 : nk8;
+    double kl_acc = 0.0;
+    const int64_t ntiles = (a.V + TR - 1) / TR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();  // previous tile's reads are done (first pass: weights are in place after the next one)
+        const int64_t row0 = tile * TR;
+        for (int idx = t; idx < TR * (MM_KP / 2); idx += ENC_THREADS) {
+            const int r = idx >> 5, o = 2 * (idx & 31);
+            const int64_t row = row0 + r;
+            float2 xv = make_float2(0.f, 0.f);
+            if (row < a.V && o < K) xv = __ldg(reinterpret_cast<const float2*>(a.ptr + row * K + o));
+            *reinterpret_cast<float2*>(&S.x[r][o]) = xv;
+        }
+        __syncthreads();
+        float am[4][4], as_[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) am[n][q] = as_[n][q] = 0.f;
+        const int r0 = 16 * mt;
+        for (int ks = 0; ks < nk8; ++ks) {
+            const int k0 = 8 * ks;
+            uint32_t ab[4], asm_[4];
+            split_tf32(S.x[r0 + g][k0 + tq], ab[0], asm_[0]);
+            split_tf32(S.x[r0 + g + 8][k0 + tq], ab[1], asm_[1]);
+            split_tf32(S.x[r0 + g][k0 + tq + 4], ab[2], asm_[2]);
+            split_tf32(S.x[r0 + g + 8][k0 + tq + 4], ab[3], asm_[3]);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int nt = n_lo + n;
+                if (nt < n_hi) {
+                    const int n0 = 8 * nt;
+                    mma_3x(am[n], ab, asm_, __float_as_uint(S.wlT_big[k0 + tq][n0 + g]),
+                           __float_as_uint(S.wlT_big[k0 + tq + 4][n0 + g]), __float_as_uint(S.wlT_small[k0 + tq][n0 + g]),
+                           __float_as_uint(S.wlT_small[k0 + tq + 4][n0 + g]));
+                    mma_3x(as_[n], ab, asm_, __float_as_uint(S.wsT_big[k0 + tq][n0 + g]),
+                           __float_as_uint(S.wsT_big[k0 + tq + 4][n0 + g]), __float_as_uint(S.wsT_small[k0 + tq][n0 + g]),
+                           __float_as_uint(S.wsT_small[k0 + tq + 4][n0 + g]));
+                }
+            }
+        }
+        float kl_row = 0.f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int nt = n_lo + n;
+            if (nt >= n_hi) continue;
+            const int col = 8 * nt + 2 * tq;
+            if (col >= K) continue;  // (K even: col + 1 < K as well)
+            const float bl0 = S.bl[col], bl1 = S.bl[col + 1], bs0 = S.bs[col], bs1 = S.bs[col + 1];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // rows r0 + g and r0 + g + 8
+                const int64_t row = row0 + r0 + g + 8 * hh;
+                if (row >= a.V) continue;
+                const int64_t off = row * K + col;
+                float2 nz = make_float2(0.f, 0.f);
+                if (a.noise) nz = __ldg(reinterpret_cast<const float2*>(a.noise + off));
+                const float m0 = am[n][2 * hh] + bl0, m1 = am[n][2 * hh + 1] + bl1;
+                const float g0 = softplusf(as_[n][2 * hh] + bs0) + GLUE_EPS, g1 = softplusf(as_[n][2 * hh + 1] + bs1) + GLUE_EPS;
+                *reinterpret_cast<float2*>(a.mu + off) = make_float2(m0, m1);
+                *reinterpret_cast<float2*>(a.sigma + off) = make_float2(g0, g1);
+                *reinterpret_cast<float2*>(a.vsamp + off) = make_float2(fmaf(nz.x, g0, m0), fmaf(nz.y, g1, m1));
+                kl_row += (-logf(g0) + 0.5f * (g0 * g0 + m0 * m0) - 0.5f) +
+                          (-logf(g1) + 0.5f * (g1 * g1 + m1 * m1) - 0.5f);
+            }
+        }
+        kl_acc += (double)kl_row;
+    }
+    // KL: deterministic block reduction, per-CTA partial, last CTA sums the partials in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kl_acc += __shfl_xor_sync(FULL, kl_acc, o);
+    if (lane == 0) S.red[warp] = kl_acc;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < ENC_THREADS / 32; ++w) s += S.red[w];
+        a.klpart[blockIdx.x] = s;
+        __threadfence();
+        S.ticket = atomicAdd(a.counter, 1u);
+    }
+    __syncthreads();
+    if (S.ticket == gridDim.x - 1 && t == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned q = 0; q < gridDim.x; ++q) s += __ldcg(a.klpart + q);
+        a.kl_sum[0] = (float)s;
+        *a.counter = 0u;  // ready for the next call on this workspace
+    }
+}
+
 // fixed-order sum of the per-CTA weight-gradient partials; one thread per (matrix, out, in | bias)
 template <int KP>
 __global__ void graphenc_wgrad_reduce_kernel(EncArgs a, int ncta) {
@@ -337,22 +659,36 @@ size_t enc_ws_layout(int64_t V, int KP, char* base, EncArgs* a) {
 }
 
 template <int KP>
-int run_fwd(EncArgs a, cudaStream_t st) {
-    const size_t smem = sizeof(EncSmem<KP>);
-    auto k = graphenc_fwd_kernel<KP>;
-    GLUE_SMEM_ONCE(k, smem);
-    k<<<enc_grid(a.V), ENC_THREADS, smem, st>>>(a);
+int run_fwd(EncArgs a, cudaStream_t st, int impl) {
+    if (impl != 1) {  // default: warp-level tensor cores (TF32 x 3)
+        const size_t smem = sizeof(MmaFwdSmem);
+        GLUE_SMEM_ONCE(graphenc_fwd_mma_kernel, smem);
+        graphenc_fwd_mma_kernel<<<enc_grid(a.V), ENC_THREADS, smem, st>>>(a);
+    } else {
+        const size_t smem = sizeof(EncSmem<KP>);
+        auto k = graphenc_fwd_kernel<KP>;
+        GLUE_SMEM_ONCE(k, smem);
+        k<<<enc_grid(a.V), ENC_THREADS, smem, st>>>(a);
+    }
     GLUE_CHECK_LAUNCH();
     return 0;
 }
 
 template <int KP>
-int run_bwd(EncArgs a, cudaStream_t st) {
-    const size_t smem = sizeof(EncSmem<KP>);
-    auto k = graphenc_bwd_kernel<KP>;
-    GLUE_SMEM_ONCE(k, smem);
+int run_bwd(EncArgs a, cudaStream_t st, int impl) {
     const int ncta = enc_grid(a.V);
-    k<<<ncta, ENC_THREADS, smem, st>>>(a);
+    // impl: 0 = default (warp-level tensor cores, TF32 x 3), 1 = FFMA kernel, 2 = tensor cores
+    const bool use_mma = impl != 1;
+    if (use_mma) {
+        const size_t smem = sizeof(MmaSmem);
+        GLUE_SMEM_ONCE(graphenc_bwd_mma_kernel, smem);
+        graphenc_bwd_mma_kernel<<<ncta, ENC_THREADS, smem, st>>>(a, KP);
+    } else {
+        const size_t smem = sizeof(EncSmem<KP>);
+        auto k = graphenc_bwd_kernel<KP>;
+        GLUE_SMEM_ONCE(k, smem);
+        k<<<ncta, ENC_THREADS, smem, st>>>(a);
+    }
     GLUE_CHECK_LAUNCH();
     const int total = 2 * KP * (KP + 1);
     graphenc_wgrad_reduce_kernel<KP><<<(total + 255) / 256, 256, 0, st>>>(a, ncta);
@@ -369,10 +705,10 @@ extern "C" size_t glue_graphenc_workspace_bytes(int64_t V, int32_t K) {
     return glue::enc_ws_layout(V, KP, nullptr, nullptr);
 }
 
-extern "C" int glue_graphenc_head_fwd(const float* ptr, const float* w_loc, const float* b_loc, const float* w_std,
-                                      const float* b_std, const float* noise, int64_t V, int32_t K, float* mu,
-                                      float* sigma, float* vsamp, float* kl_sum, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+extern "C" int glue_graphenc_head_fwd_impl(const float* ptr, const float* w_loc, const float* b_loc, const float* w_std,
+                                           const float* b_std, const float* noise, int64_t V, int32_t K, float* mu,
+                                           float* sigma, float* vsamp, float* kl_sum, void* workspace,
+                                           size_t workspace_bytes, int32_t impl, void* stream) {
     using namespace glue;
     if (!ptr || !w_loc || !b_loc || !w_std || !b_std || !mu || !sigma || !vsamp || !kl_sum || !workspace)
         return GLUE_E_BADARG;
@@ -386,14 +722,22 @@ extern "C" int glue_graphenc_head_fwd(const float* ptr, const float* w_loc, cons
     enc_ws_layout(V, KP, (char*)workspace, &a);
     cudaStream_t st = (cudaStream_t)stream;
     GLUE_CUDA(cudaMemsetAsync(a.counter, 0, 16, st));
-    return KP == 52 ? run_fwd<52>(a, st) : run_fwd<64>(a, st);
+    return KP == 52 ? run_fwd<52>(a, st, impl) : run_fwd<64>(a, st, impl);
 }
 
-extern "C" int glue_graphenc_head_bwd(const float* ptr, const float* w_loc, const float* w_std, const float* noise,
-                                      const float* mu, const float* sigma, const float* grad_vsamp,
-                                      const float* kl_coef, int64_t V, int32_t K, float* grad_ptr,
-                                      float* grad_w_loc, float* grad_b_loc, float* grad_w_std, float* grad_b_std,
-                                      void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int glue_graphenc_head_fwd(const float* ptr, const float* w_loc, const float* b_loc, const float* w_std,
+                                      const float* b_std, const float* noise, int64_t V, int32_t K, float* mu,
+                                      float* sigma, float* vsamp, float* kl_sum, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    return glue_graphenc_head_fwd_impl(ptr, w_loc, b_loc, w_std, b_std, noise, V, K, mu, sigma, vsamp, kl_sum, workspace,
+                                       workspace_bytes, 0, stream);
+}
+
+extern "C" int glue_graphenc_head_bwd_impl(const float* ptr, const float* w_loc, const float* w_std, const float* noise,
+                                           const float* mu, const float* sigma, const float* grad_vsamp,
+                                           const float* kl_coef, int64_t V, int32_t K, float* grad_ptr,
+                                           float* grad_w_loc, float* grad_b_loc, float* grad_w_std, float* grad_b_std,
+                                           void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
     using namespace glue;
     if (!ptr || !w_loc || !w_std || !mu || !sigma || !workspace) return GLUE_E_BADARG;
     if (V <= 0 || K <= 0) return GLUE_E_BADARG;
@@ -409,5 +753,15 @@ extern "C" int glue_graphenc_head_bwd(const float* ptr, const float* w_loc, cons
     if (workspace_bytes < enc_ws_layout(V, KP, nullptr, nullptr)) return GLUE_E_WORKSPACE;
     enc_ws_layout(V, KP, (char*)workspace, &a);
     cudaStream_t st = (cudaStream_t)stream;
-    return KP == 52 ? run_bwd<52>(a, st) : run_bwd<64>(a, st);
+    return KP == 52 ? run_bwd<52>(a, st, impl) : run_bwd<64>(a, st, impl);
+}
+
+extern "C" int glue_graphenc_head_bwd(const float* ptr, const float* w_loc, const float* w_std, const float* noise,
+                                      const float* mu, const float* sigma, const float* grad_vsamp,
+                                      const float* kl_coef, int64_t V, int32_t K, float* grad_ptr,
+                                      float* grad_w_loc, float* grad_b_loc, float* grad_w_std, float* grad_b_std,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    return glue_graphenc_head_bwd_impl(ptr, w_loc, w_std, noise, mu, sigma, grad_vsamp, kl_coef, V, K, grad_ptr,
+                                       grad_w_loc, grad_b_loc, grad_w_std, grad_b_std, workspace, workspace_bytes, 0,
+                                       stream);
 }

@@ -182,6 +182,11 @@ def graph_conv(inp: torch.Tensor, csr: GraphCSR) -> torch.Tensor:
 # --------------------------------------------------------------- graph encoder head
 
 
+# Diagnostics: pin the kernel of the graph-encoder head's backward pass (0 = the library picks,
+# 1 = FFMA, 2 = warp-level tensor cores); tests and A/B benches set it.
+GRAPHENC_IMPL = 0
+
+
 class _GraphEncHeadFn(torch.autograd.Function):
     r"""``(vsamp, kl_sum, mu, sigma)`` of the graph encoder's Gaussian head in one launch; the
     backward pass produces every gradient from ``d L / d vsamp`` and ``d L / d kl_sum``."""
@@ -195,9 +200,10 @@ class _GraphEncHeadFn(torch.autograd.Function):
         kl = torch.empty((), dtype=torch.float32, device=dev)
         ws = _workspace(L.glue_graphenc_workspace_bytes(V, K), dev)
         ev = TIMER.start("graphenc_head_fwd", dev)
-        check(L.glue_graphenc_head_fwd(ptr(ptr_), ptr(w_loc), ptr(b_loc), ptr(w_std), ptr(b_std),
-                                       ptr(noise), V, K, ptr(mu), ptr(sigma), ptr(vsamp), ptr(kl),
-                                       ptr(ws), ws.numel(), current_stream(dev)), "graphenc_head_fwd")
+        check(L.glue_graphenc_head_fwd_impl(ptr(ptr_), ptr(w_loc), ptr(b_loc), ptr(w_std), ptr(b_std),
+                                            ptr(noise), V, K, ptr(mu), ptr(sigma), ptr(vsamp), ptr(kl),
+                                            ptr(ws), ws.numel(), GRAPHENC_IMPL, current_stream(dev)),
+              "graphenc_head_fwd")
         TIMER.stop(ev, dev)
         ctx.save_for_backward(ptr_, w_loc, w_std, noise, mu, sigma)
         ctx.mark_non_differentiable(mu, sigma)
@@ -216,10 +222,10 @@ class _GraphEncHeadFn(torch.autograd.Function):
         ws = _workspace(L.glue_graphenc_workspace_bytes(V, K), dev)
         g_vsamp = None if g_vsamp is None else _f32(g_vsamp, "grad_vsamp")
         g_kl = None if g_kl is None else _f32(g_kl, "grad_kl")
-        check(L.glue_graphenc_head_bwd(ptr(ptr_), ptr(w_loc), ptr(w_std), ptr(noise), ptr(mu),
-                                       ptr(sigma), ptr(g_vsamp), ptr(g_kl), V, K, ptr(g_ptr),
-                                       ptr(g_wl), ptr(g_bl), ptr(g_ws), ptr(g_bs), ptr(ws), ws.numel(),
-                                       current_stream(dev)), "graphenc_head_bwd")
+        check(L.glue_graphenc_head_bwd_impl(ptr(ptr_), ptr(w_loc), ptr(w_std), ptr(noise), ptr(mu),
+                                            ptr(sigma), ptr(g_vsamp), ptr(g_kl), V, K, ptr(g_ptr),
+                                            ptr(g_wl), ptr(g_bl), ptr(g_ws), ptr(g_bs), ptr(ws), ws.numel(),
+                                            GRAPHENC_IMPL, current_stream(dev)), "graphenc_head_bwd")
         return g_ptr, g_wl, g_bl, g_ws, g_bs, None
 
 

@@ -94,6 +94,19 @@ int glue_graphenc_head_bwd(const float *ptr, const float *w_loc, const float *w_
                            float *grad_ptr, float *grad_w_loc, float *grad_b_loc,
                            float *grad_w_std, float *grad_b_std, void *workspace,
                            size_t workspace_bytes, void *stream);
+/* Same, with the kernels pinned (A/B runs, tests of both paths): impl 0 = the library picks (the
+ * K x K products per 64-vertex tile on warp-level tensor cores, three TF32 products per fp32
+ * product), 1 = FFMA kernels, 2 = tensor-core kernels. */
+int glue_graphenc_head_fwd_impl(const float *ptr, const float *w_loc, const float *b_loc,
+                                const float *w_std, const float *b_std, const float *noise, int64_t V,
+                                int32_t K, float *mu, float *sigma, float *vsamp, float *kl_sum,
+                                void *workspace, size_t workspace_bytes, int32_t impl, void *stream);
+int glue_graphenc_head_bwd_impl(const float *ptr, const float *w_loc, const float *w_std,
+                                const float *noise, const float *mu, const float *sigma,
+                                const float *grad_vsamp, const float *kl_coef, int64_t V, int32_t K,
+                                float *grad_ptr, float *grad_w_loc, float *grad_b_loc,
+                                float *grad_w_std, float *grad_b_std, void *workspace,
+                                size_t workspace_bytes, int32_t impl, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * GraphDecoder + Bernoulli log-prob + pos/neg balanced mean -- replaces

@@ -399,11 +399,14 @@ def test_decoder_rejects_cpu_tensors(ops):
 
 
 # ------------------------------------------------------------------ graph encoder head
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("V,K,with_noise", [(37, 50, True), (5000, 50, True), (52000, 50, True),
                                             (1000, 16, False), (777, 64, True), (300, 2, True)])
-def test_graph_encoder_head_vs_torch(ops, V, K, with_noise):
+def test_graph_encoder_head_vs_torch(ops, V, K, with_noise, impl, monkeypatch):
     """Fused Gaussian head (Linear x2 + softplus + sample + KL) against the ATen formulation of
-    scglue/models/sc.py:44-46 and scglue/models/scglue.py:329-340, values and every gradient."""
+    scglue/models/sc.py:44-46 and scglue/models/scglue.py:329-340, values and every gradient;
+    ``impl``: backward pass with the FFMA kernel (1) / on warp-level tensor cores (2, the default)."""
+    monkeypatch.setattr(ops, "GRAPHENC_IMPL", impl)
     import torch.distributions as D
     import torch.nn.functional as F
     gen = torch.Generator().manual_seed(V + K)
