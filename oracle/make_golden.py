@@ -295,7 +295,127 @@ def golden_step(ref, graph, paired: bool):
     np.savez_compressed(os.path.join(GOLDEN_DIR, f"step_{tag}.npz"), **out)
 
 
+def golden_step_config(ref, graph, tag, keys, prefix, prob, rep_dim, n_batches, B=16):
+    """One full train_step of the reference ``SCGLUETrainer`` for a BASELINE-config shaped model:
+    ``cfg3`` = three modalities, one of them ZILN, guidance edges of both signs;
+    ``cfg4`` = ZINB decoders with 20 batches (``use_batch``).  Same layout as ``step_scglue.npz``
+    plus ``keys`` / ``prob__<k>`` so that the test builds the model from the file alone."""
+    torch.manual_seed(31 + len(keys) + max(n_batches.values()))
+    K, h_dim = 50, 32
+    vertices = list(graph["vertices"])
+    V = len(vertices)
+    feat_idx = {k: [i for i, v in enumerate(vertices) if v.startswith(prefix[k])] for k in keys}
+    net = _build_reference_net(ref, V, K, feat_idx, prob, rep_dim, h_dim, n_batches)
+    with torch.no_grad():
+        net.g2v.vrepr.copy_(torch.randn(V, K) * 0.3)
+        for p in net.u2x.parameters():
+            p.copy_(torch.randn_like(p) * 0.3)
+    mw = {k: 1.0 + 0.5 * i for i, k in enumerate(keys)}
+    trainer = ref.models.scglue.SCGLUETrainer(
+        net, lam_data=1.0, lam_kl=1.0, lam_graph=0.02, lam_align=0.05, lam_sup=0.02, dsc_steps=1,
+        normalize_u=False, modality_weight=mw, optim="RMSprop", lr=2e-3)
+    trainer.eidx = torch.as_tensor(graph["eidx"])
+    trainer.enorm = torch.as_tensor(graph["enorm_keepvar"])
+    trainer.esgn = torch.as_tensor(graph["esgn"])
+    assert (graph["esgn"] < 0).any(), "the golden graph must carry sign -1 edges"
+    trainer.align_burnin = 4
+    epoch = 2
+    init_state = {k: v.clone() for k, v in net.state_dict().items()}
+
+    x, xrep = {}, {}
+    for k in keys:
+        F = len(feat_idx[k])
+        if prob[k] in ("NB", "ZINB"):
+            x[k] = torch.poisson(torch.rand(B, F) * 2.0 + 0.2)
+            x[k][:, 0] += 1.0  # no empty libraries
+        else:  # ZILN: positive continuous values with exact zeros
+            x[k] = torch.exp(torch.randn(B, F)) * (torch.rand(B, F) > 0.45)
+        xrep[k] = torch.randn(B, rep_dim[k]) if rep_dim[k] else torch.empty(B, 0)
+    xbch = {k: torch.randint(0, n_batches[k], (B,)) for k in keys}
+    xlbl = {k: torch.full((B,), -1, dtype=torch.int64) for k in keys}
+    xdwt = {k: torch.rand(B) + 0.5 for k in keys}
+    xflag = {k: torch.full((B,), i, dtype=torch.int64) for i, k in enumerate(keys)}
+    mb = slice(0, 200)
+    s_eidx = torch.as_tensor(graph["samp5_eidx"][:, mb])
+    s_ewt = torch.as_tensor(graph["samp5_ewt"][mb])
+    s_esgn = torch.as_tensor(graph["samp5_esgn"][mb])
+    data = (x, xrep, xbch, xlbl, xdwt, xflag, s_eidx, s_ewt, s_esgn)
+
+    def draw_noise(seed, full):
+        torch.manual_seed(seed)
+        u_eps = {k: torch.randn(B, K) for k in keys}
+        burn = torch.randn(len(keys) * B, K)
+        v_eps = torch.randn(V, K) if full else None
+        return oc.Noise(u_eps=u_eps, v_eps=v_eps, burnin_eps=burn)
+
+    net.train()
+    out = {}
+    torch.manual_seed(101)
+    losses = trainer.compute_losses(data, epoch, dsc_only=True)
+    net.zero_grad(set_to_none=True)
+    losses["dsc_loss"].backward()
+    out["dsc_only_loss"] = _np(losses["dsc_loss"])
+    for n, p in net.du.named_parameters():
+        out[f"dscgrad__du.{n}"] = _np(p.grad)
+    trainer.dsc_optim.step()
+    torch.manual_seed(202)
+    losses = trainer.compute_losses(data, epoch)
+    net.zero_grad(set_to_none=True)
+    losses["gen_loss"].backward()
+    for k, v in losses.items():
+        out[f"loss__{k}"] = _np(v)
+    for n, p in net.named_parameters():
+        if p.grad is not None:
+            out[f"gengrad__{n}"] = _np(p.grad)
+    trainer.vae_optim.step()
+    for k, v in net.state_dict().items():
+        out[f"final__{k}"] = _np(v)
+
+    cfg = oc.StepConfig(keys, prob, {k: prob[k] in ("NB", "ZINB") for k in keys}, n_batches,
+                        modality_weight=mw, paired=False, align_burnin=4)
+    state = {k: v.clone() for k, v in init_state.items()}
+    batch = dict(x=x, xrep=xrep, xbch=xbch, xdwt=xdwt, pmsk=None, eidx=s_eidx, ewt=s_ewt, esgn=s_esgn)
+    cpu = oc.CpuTrainer(cfg, state, (trainer.eidx, trainer.enorm, trainer.esgn), lr=2e-3)
+    o_losses = cpu.train_step(batch, epoch, noise_dsc=draw_noise(101, False), noise_gen=draw_noise(202, True))
+    for k, v in losses.items():
+        _close(o_losses[k], v, f"{tag} loss {k}", rtol=1e-5, atol=1e-6)
+    for k, v in net.state_dict().items():
+        _close(state[k], v, f"{tag} post-step {k}", rtol=1e-4, atol=1e-6)
+
+    for k, v in init_state.items():
+        out[f"init__{k}"] = _np(v)
+    for k in keys:
+        out[f"x__{k}"], out[f"xrep__{k}"], out[f"xbch__{k}"], out[f"xdwt__{k}"] = (
+            _np(x[k]), _np(xrep[k]), _np(xbch[k]), _np(xdwt[k]))
+        out[f"prob__{k}"] = np.array(prob[k])
+        out[f"mw__{k}"] = np.array(mw[k])
+    for seed, full, name in ((101, False, "dsc"), (202, True, "gen")):
+        nz = draw_noise(seed, full)
+        for k in keys:
+            out[f"noise_{name}__u_{k}"] = _np(nz.u_eps[k])
+        out[f"noise_{name}__burnin"] = _np(nz.burnin_eps)
+        if full:
+            out[f"noise_{name}__v"] = _np(nz.v_eps)
+    out.update(keys=np.array(keys), pmsk=np.ones((B, len(keys)), dtype=bool), eidx=_np(s_eidx), ewt=_np(s_ewt),
+               esgn=_np(s_esgn), epoch=epoch, align_burnin=4)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"step_{tag}.npz"), **out)
+
+
+def golden_new_configs(ref, graph):
+    golden_step_config(ref, graph, "cfg3", ["rna", "atac", "met"], {"rna": "g", "atac": "p", "met": "z"},
+                       {"rna": "NB", "atac": "NB", "met": "ZILN"}, {"rna": 0, "atac": 10, "met": 0},
+                       {"rna": 1, "atac": 1, "met": 1})
+    golden_step_config(ref, graph, "cfg4", ["rna", "atac"], {"rna": "g", "atac": "p"},
+                       {"rna": "ZINB", "atac": "ZINB"}, {"rna": 0, "atac": 10}, {"rna": 20, "atac": 20})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "new-configs":
+        # (adds step_cfg3.npz / step_cfg4.npz without rewriting the round-1 fixtures)
+        ref = refstub.load()
+        torch.set_num_threads(1)
+        golden_new_configs(ref, dict(np.load(os.path.join(GOLDEN_DIR, "graph.npz"), allow_pickle=False)))
+        return
     if not refstub.available():
         sys.exit("reference checkout not found; golden vectors can only be regenerated "
                  "in the build container")
@@ -306,6 +426,7 @@ def main():
     golden_modules(ref, graph)
     golden_step(ref, graph, paired=False)
     golden_step(ref, graph, paired=True)
+    golden_new_configs(ref, graph)
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

@@ -266,24 +266,31 @@ def test_decoder_golden(ops, golden, family):
         assert_close(g, rg, TOL, "log_prob backward")
 
 
-@pytest.mark.parametrize("family,F", [("NB", 50000), ("ZINB", 50000), ("Normal", 48000)])
-def test_decoder_full_size_properties(ops, family, F):
-    """BASELINE-size (B=128, F=50k) checks that do not need the slow oracle everywhere:
-    fused loss == mean of the materialised log_prob; gradients agree with the oracle on
-    a feature sub-range for Normal (separable) and are deterministic for all."""
-    B, K = 128, 50
-    case = _decoder_case(family, B, F, K, 1, seed=99)
+@pytest.mark.parametrize("family,B,F,nb,nan_frac", [
+    ("NB", 128, 50000, 1, 0.0), ("ZINB", 128, 50000, 1, 0.0), ("Normal", 128, 48000, 1, 0.0),
+    ("ZINB", 128, 50000, 20, 0.0),    # BASELINE config 4: 20 batches at the full ATAC width
+    ("ZILN", 128, 48000, 1, 0.05),    # config 3: methylation modality, 5 % NaN (nan_sparse / nanmean)
+    ("NB", 512, 50000, 1, 0.0),       # config 5: atlas batch (four cell blocks, feature-side accumulation)
+])
+def test_decoder_full_size_properties(ops, family, B, F, nb, nan_frac):
+    """BASELINE-size checks: fused loss == (nan)mean of the materialised log_prob; every gradient agrees
+    with the CPU oracle; results are deterministic."""
+    K = 50
+    case = _decoder_case(family, B, F, K, nb, seed=99, nan_frac=nan_frac)
     u, v, b, l, x, params, vidx = case
     loss, grads = _device_nll(ops, family, *case, "nanmean")
     d = lambda t: None if t is None else t.to(DEV)
     dp = [d(params[n]) for n in PARAM_NAMES[family]]
     zi = dp[3] if len(dp) == 4 else None
-    logp = ops.decoder_log_prob(family, d(u), d(v), dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x))
-    assert_close(loss, -logp.double().mean().float(), TOL, "fused loss vs materialised mean")
+    if not nan_frac:
+        logp = ops.decoder_log_prob(family, d(u), d(v), dp[0], dp[1], dp[2], zi, b=d(b), l=d(l), x=d(x))
+        assert_close(loss, -logp.double().mean().float(), TOL, "fused loss vs materialised mean")
     ref_loss, _, ref_grads = _oracle_nll(family, *case, "nanmean")
     assert_close(loss, ref_loss, TOL)
-    for g, rg in zip(grads, ref_grads):
-        assert_close(g, rg, TOL, f"{family} full-size gradient")
+    for n, g, rg in zip(["u", "v"] + list(PARAM_NAMES[family]), grads, ref_grads):
+        assert_close(g, rg, TOL, f"{family} full-size gradient d/d{n}")
+    loss2, grads2 = _device_nll(ops, family, *case, "nanmean")
+    assert torch.equal(loss, loss2) and all(torch.equal(a, c) for a, c in zip(grads, grads2))
 
 
 MULTI_CASES = [

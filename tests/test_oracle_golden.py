@@ -122,3 +122,39 @@ def test_full_step_golden(golden, paired):
             continue
         gref = g.get(f"dscgrad__{k}") if k.startswith("du.") else g.get(f"gengrad__{k}")
         assert_post_step_close(v.detach().numpy(), g[f"final__{k}"], gref, 1e-4, k)
+
+
+@pytest.mark.parametrize("tag", ["cfg3", "cfg4"])
+def test_full_step_golden_new_configs(golden, tag):
+    """The oracle against the reference-generated steps at the shapes of BASELINE configs 3 / 4: three
+    modalities with a ZILN decoder and guidance edges of both signs; ZINB decoders with 20 batches."""
+    g = golden(f"step_{tag}")
+    graph = golden("graph")
+    t = torch.as_tensor
+    keys = [str(k) for k in g["keys"]]
+    prob = {k: str(g[f"prob__{k}"]) for k in keys}
+    n_batches = {k: int(g[f"init__u2x.{k}.scale_lin"].shape[0]) for k in keys}
+    state = {k[len("init__"):]: t(v).clone() for k, v in g.items() if k.startswith("init__")}
+    cfg = oc.StepConfig(keys, prob, {k: prob[k] in ("NB", "ZINB") for k in keys}, n_batches,
+                        modality_weight={k: float(g[f"mw__{k}"]) for k in keys}, paired=False,
+                        align_burnin=int(g["align_burnin"]))
+    batch = dict(x={k: t(g[f"x__{k}"]) for k in keys}, xrep={k: t(g[f"xrep__{k}"]) for k in keys},
+                 xbch={k: t(g[f"xbch__{k}"]) for k in keys}, xdwt={k: t(g[f"xdwt__{k}"]) for k in keys},
+                 pmsk=None, eidx=t(g["eidx"]), ewt=t(g["ewt"]), esgn=t(g["esgn"]))
+    noise = {name: oc.Noise(u_eps={k: t(g[f"noise_{name}__u_{k}"]) for k in keys},
+                            burnin_eps=t(g[f"noise_{name}__burnin"]),
+                            v_eps=t(g["noise_gen__v"]) if name == "gen" else None)
+             for name in ("dsc", "gen")}
+    full = (t(graph["eidx"]), t(graph["enorm_keepvar"]), t(graph["esgn"]))
+    assert (graph["esgn"] < 0).any()
+    trainer = oc.CpuTrainer(cfg, state, full, lr=2e-3)
+    losses = trainer.train_step(batch, int(g["epoch"]), noise_dsc=noise["dsc"], noise_gen=noise["gen"])
+    for k, v in losses.items():
+        assert np.allclose(v.detach(), g[f"loss__{k}"], rtol=1e-5, atol=1e-6), k
+    from tests.util import assert_post_step_close
+    for k, v in state.items():
+        if not v.dtype.is_floating_point:
+            assert np.array_equal(v.numpy(), g[f"final__{k}"]), k
+            continue
+        gref = g.get(f"dscgrad__{k}") if k.startswith("du.") else g.get(f"gengrad__{k}")
+        assert_post_step_close(v.detach().numpy(), g[f"final__{k}"], gref, 1e-4, k)

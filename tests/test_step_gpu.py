@@ -35,22 +35,30 @@ def build(golden_npz, paired):
     g = golden_npz
     init = {k[len("init__"):]: torch.as_tensor(v) for k, v in g.items() if k.startswith("init__")}
     V, K = init["g2v.vrepr"].shape
-    keys = ["rna", "atac"]
-    prob = {"rna": "NB", "atac": "ZINB" if paired else "NB"}
-    dec = {"NB": sc.NBDataDecoder, "ZINB": sc.ZINBDataDecoder}
+    if "keys" in g:  # fixtures of the BASELINE-config shapes describe themselves
+        keys = [str(k) for k in g["keys"]]
+        prob = {k: str(g[f"prob__{k}"]) for k in keys}
+        mw = {k: float(g[f"mw__{k}"]) for k in keys}
+    else:
+        keys = ["rna", "atac"]
+        prob = {"rna": "NB", "atac": "ZINB" if paired else "NB"}
+        mw = {"rna": 1.0, "atac": 2.0}
+    dec = {"NB": sc.NBDataDecoder, "ZINB": sc.ZINBDataDecoder, "ZILN": sc.ZILNDataDecoder,
+           "Normal": sc.NormalDataDecoder}
     x2u, u2x, idx = {}, {}, {}
     for k in keys:
         in_dim = init[f"x2u.{k}.linear_0.weight"].shape[1]
         h_dim = init[f"x2u.{k}.linear_0.weight"].shape[0]
-        x2u[k] = sc.NBDataEncoder(in_dim, K, h_depth=2, h_dim=h_dim, dropout=0.0)
+        enc = sc.NBDataEncoder if prob[k] in ("NB", "ZINB") else sc.VanillaDataEncoder
+        x2u[k] = enc(in_dim, K, h_depth=2, h_dim=h_dim, dropout=0.0)
         nb, F = init[f"u2x.{k}.scale_lin"].shape
         u2x[k] = dec[prob[k]](F, n_batches=nb)
         idx[k] = init[f"{k}_idx"]
-    du = sc.Discriminator(K, 2, n_batches=0, h_depth=2, h_dim=h_dim, dropout=0.0)
+    du = sc.Discriminator(K, len(keys), n_batches=0, h_depth=2, h_dim=h_dim, dropout=0.0)
     net = SCGLUE(sc.GraphEncoder(V, K), sc.GraphDecoder(), x2u, u2x, idx, du, sc.Prior())
     net.load_state_dict(init)
     common = dict(lam_data=1.0, lam_kl=1.0, lam_graph=0.02, lam_align=0.05, lam_sup=0.02,
-                  dsc_steps=1, normalize_u=False, modality_weight={"rna": 1.0, "atac": 2.0},
+                  dsc_steps=1, normalize_u=False, modality_weight=mw,
                   optim="RMSprop", lr=2e-3)
     if paired:
         trainer = PairedSCGLUETrainer(net, lam_joint_cross=0.02, lam_real_cross=0.02,
@@ -60,9 +68,13 @@ def build(golden_npz, paired):
     return net, trainer, keys
 
 
-@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("paired", [False, True, "cfg3", "cfg4"])
 def test_train_step_matches_reference(native_lib, golden, paired):
-    g = golden("step_paired" if paired else "step_scglue")
+    """``paired``: False / True = the round-1 fixtures (SCGLUE / PairedSCGLUE, two modalities); "cfg3" = three
+    modalities with a ZILN decoder and sign -1 guidance edges, "cfg4" = ZINB decoders with 20 batches."""
+    tag = paired if isinstance(paired, str) else None
+    paired = paired is True
+    g = golden(f"step_{tag}" if tag else ("step_paired" if paired else "step_scglue"))
     graph = golden("graph")
     net, trainer, keys = build(g, paired)
     dev = net.device
@@ -313,3 +325,52 @@ def test_repeated_fits_with_step_graphs_equal_eager_fits(native_lib):
     assert_close(u_g, u_e, 1e-4, "cell embeddings after three fits (graphs vs eager)")
     for k in l_e:
         assert abs(l_g[k] - l_e[k]) <= 1e-4 * max(1.0, abs(l_e[k])), k
+
+
+@pytest.mark.parametrize("keep_sparse", [False, True])
+@pytest.mark.parametrize("nan_sparse", [False, True])
+def test_device_resident_minibatches_equal_host_minibatches(native_lib, keep_sparse, nan_sparse):
+    """Row f1 of the scope table: a minibatch gathered on the device (dense ``index_select`` or
+    ``DeviceCSR`` densify, ``AnnDataset.to_device``) is, bit for bit, the minibatch the host path of the
+    reference builds (``AnnDataset.__getitem__``, scglue/models/data.py:397-436), including NaN for the
+    structural zeros of ``nan_sparse`` modalities; and so is the packed-sparse host feed after unpacking."""
+    from tests.synth import make_synthetic
+    from glue_b200 import models
+    from glue_b200.models.data import AnnDataset, DataLoader, DeviceCSR, is_packed_sparse, unpack_sparse_rows
+    from glue_b200.utils import config
+    adatas, graph = make_synthetic(n_cells=(300, 260), n_feat=(70, 900), n_pairs=200, seed=4, rep_dim=8)
+    for k, a in adatas.items():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep",
+                                 nan_sparse=nan_sparse and k == "atac")
+    cfgs = [a.uns[config.ANNDATA_KEY] for a in adatas.values()]
+
+    def batches(device=None, sparse_items=False):
+        ds = AnnDataset(list(adatas.values()), cfgs, mode="train", getitem_size=8)
+        if device is not None:
+            old = config.DEVICE_DATA_BUDGET_BYTES
+            if keep_sparse:
+                config.DEVICE_DATA_BUDGET_BYTES = 300 * 970 * 4 // 2
+            try:
+                ds.to_device(device)
+            finally:
+                config.DEVICE_DATA_BUDGET_BYTES = old
+            if keep_sparse:
+                assert any(isinstance(t, DeviceCSR) for grp in ds.device_data for t in grp)
+        ds.sparse_items = sparse_items
+        ds.prepare_shuffle(num_workers=0, random_seed=6)
+        return list(DataLoader(ds, batch_size=4, shuffle=True, generator=torch.Generator().manual_seed(6)))
+
+    host = batches()
+    dev = batches(torch.device(DEV))
+    packed = batches(sparse_items=True)
+    assert len(host) == len(dev) == len(packed) > 5
+    for hb, db, pb in zip(host, dev, packed):
+        for i, (h, d_, p) in enumerate(zip(hb, db, pb)):
+            assert d_.is_cuda and d_.dtype == h.dtype
+            assert torch.equal(torch.nan_to_num(d_.cpu(), nan=-7.0), torch.nan_to_num(h, nan=-7.0)), i
+            assert torch.equal(torch.isnan(d_.cpu()), torch.isnan(h)), i
+            if is_packed_sparse(p) and i < 2:
+                got = unpack_sparse_rows(p.to(DEV), h.shape[0], h.shape[1]).cpu()
+                assert torch.equal(got, h), i
+            else:
+                assert torch.equal(torch.nan_to_num(p, nan=-7.0), torch.nan_to_num(h, nan=-7.0)), i
