@@ -1,6 +1,15 @@
 r"""
 Cell-level utilities that ``fit_SCGLUE`` needs between its two training stages
 (``scglue/data.py:705-836``).
+
+``estimate_balancing_weight`` has two halves in the reference: (1) cluster every dataset --
+``scanpy.pp.neighbors`` (cosine kNN graph) + ``scanpy.tl.leiden`` -- and (2) match the clusters across
+datasets and turn the match mass into per-cell weights.  Half (2) is restated here exactly (pinned by
+``tests/test_data.py`` against ``oracle/balancing.py``, a line-by-line numpy restatement of
+``scglue/data.py:783-836``).  Half (1) depends on scanpy / leidenalg / igraph, none of which is in this
+image: **documented divergence** -- the built-in clustering is spherical k-means on the same cosine
+geometry; callers who have scanpy can cluster with leiden themselves and pass the labels through
+``use_clusters`` (an ``obs`` column), which makes the whole function the reference's.
 """
 
 from typing import Optional
@@ -25,12 +34,16 @@ def _cluster(rep: np.ndarray, resolution: float, seed: int = 0) -> np.ndarray:
 @logged
 def estimate_balancing_weight(*adatas, use_rep: str = None, use_batch: Optional[str] = None,
                               resolution: float = 1.0, cutoff: float = 0.5, power: float = 4.0,
-                              key_added: str = "balancing_weight") -> None:
+                              key_added: str = "balancing_weight",
+                              use_clusters: Optional[str] = None) -> None:
     r"""
     Per-cell weights that balance matched cell populations across datasets: cluster each
     dataset, match cluster centroids by thresholded cosine similarity raised to ``power``,
     and weight every cell by its cluster's total match mass divided by the cluster size;
     weights are normalised to mean 1 and stored in ``adata.obs[key_added]``.
+
+    ``use_clusters``: name of an ``obs`` column with precomputed cluster labels (e.g. leiden labels from
+    scanpy, as the reference computes them); default: built-in spherical k-means (see module docstring).
     """
     if use_rep is None:
         raise ValueError("Missing required argument `use_rep`!")
@@ -43,19 +56,37 @@ def estimate_balancing_weight(*adatas, use_rep: str = None, use_batch: Optional[
         for level in levels[0]:
             masks = [np.asarray(a.obs[use_batch] == level) for a in adatas]
             weights = _balance([np.asarray(a.obsm[use_rep])[m] for a, m in zip(adatas, masks)],
-                               resolution, cutoff, power)
+                               _labels(adatas, masks, use_rep, use_clusters, resolution), cutoff, power)
             for adata, mask, w in zip(adatas, masks, weights):
                 col = adata.obs[key_added].to_numpy(copy=True)
                 col[mask] = w
                 adata.obs[key_added] = col
         return
-    weights = _balance([np.asarray(a.obsm[use_rep]) for a in adatas], resolution, cutoff, power)
+    weights = _balance([np.asarray(a.obsm[use_rep]) for a in adatas],
+                       _labels(adatas, [None] * len(adatas), use_rep, use_clusters, resolution), cutoff, power)
     for adata, w in zip(adatas, weights):
         adata.obs[key_added] = w
 
 
-def _balance(reps, resolution, cutoff, power):
-    labels = [_cluster(rep, resolution) for rep in reps]
+def _labels(adatas, masks, use_rep, use_clusters, resolution):
+    r"""Integer cluster labels per dataset (restricted to ``masks``): the given ``obs`` column or the
+    built-in clustering."""
+    out = []
+    for adata, mask in zip(adatas, masks):
+        sel = slice(None) if mask is None else mask
+        if use_clusters:
+            if use_clusters not in adata.obs:
+                raise ValueError(f"Cluster labels '{use_clusters}' cannot be found in input data!")
+            out.append(pd.factorize(np.asarray(adata.obs[use_clusters])[sel], sort=True)[0])
+        else:
+            out.append(_cluster(np.asarray(adata.obsm[use_rep])[sel], resolution))
+    return out
+
+
+def _balance(reps, labels, cutoff, power):
+    r"""``scglue/data.py:783-836`` given the cluster labels: l2-normalised cluster means, pairwise cosine
+    with cutoff and power, product over dataset pairs, per-cluster match mass / cluster size, mean-1
+    normalisation over cells."""
     cents, sizes = [], []
     for rep, lab in zip(reps, labels):
         k = lab.max() + 1

@@ -578,3 +578,37 @@ def test_packed_sparse_host_batches_equal_dense_batches():
     # direct indexing keeps the reference's contract: dense tensors
     ds = AnnDataset(list(adatas.values()), cfgs, mode="train", getitem_size=8)
     assert all(isinstance(t, torch.Tensor) and not is_packed_sparse(t) for t in ds[0])
+
+
+def test_balancing_arithmetic_matches_reference_restatement_given_clusters():
+    """The cluster-matching half of estimate_balancing_weight (scglue/data.py:793-836) against
+    oracle/balancing.py, for two and for three datasets, with the clusters given (``use_clusters``: what a
+    scanpy user would get from leiden); the clustering half is a documented divergence (glue_b200/data.py)."""
+    import pandas as pd
+    from glue_b200.anndata_lite import AnnData
+    from glue_b200.data import estimate_balancing_weight
+    from oracle.balancing import balancing_weights
+    rs = np.random.RandomState(1)
+    centers = rs.randn(5, 10) * 3
+    def make(counts, seed):
+        r = np.random.RandomState(seed)
+        lab = np.repeat(np.arange(len(counts)), counts)
+        rep = centers[lab % 5] + r.randn(lab.size, 10) * 0.4
+        order = r.permutation(lab.size)
+        lab, rep = lab[order], rep[order]
+        a = AnnData(X=np.zeros((lab.size, 1), dtype=np.float32), obs=pd.DataFrame({"cl": lab.astype(str)},
+                    index=[f"c{i}" for i in range(lab.size)]), var=pd.DataFrame(index=["f0"]),
+                    obsm={"X_emb": rep.astype(np.float32)})
+        return a, lab
+    sets = [make([40, 25, 60, 10], 2), make([15, 50, 30, 30, 20], 3), make([33, 33, 33], 4)]
+    for group in (sets[:2], sets):
+        adatas = [a for a, _ in group]
+        estimate_balancing_weight(*adatas, use_rep="X_emb", use_clusters="cl", cutoff=0.5, power=4.0)
+        # pd.factorize(sort=True) orders the string labels "0", "1", ... like the integers 0 .. 4
+        want = balancing_weights([np.asarray(a.obsm["X_emb"], dtype=float) for a in adatas], [lab for _, lab in group])
+        for a, w in zip(adatas, want):
+            got = np.asarray(a.obs["balancing_weight"], dtype=float)
+            assert np.allclose(got, w, rtol=1e-6, atol=1e-9)
+            assert abs(got.mean() - 1) < 1e-9
+    with pytest.raises(ValueError, match="cannot be found"):
+        estimate_balancing_weight(*[a for a, _ in sets[:2]], use_rep="X_emb", use_clusters="nope")
