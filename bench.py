@@ -475,8 +475,14 @@ def main():
         for i in range(3):
             fn(i)
         torch.cuda.synchronize(device)
-        torch.cuda._sleep(12_000_000)  # a spinning blocker: the launches below queue behind it (a GEMM blocker
-        # would pull the SM clock down under the power cap and inflate what is timed behind it)
+        t0 = time.perf_counter()
+        for i in range(n):
+            fn(i)
+        host_s = time.perf_counter() - t0  # what the Python launch path needs to enqueue the n calls
+        torch.cuda.synchronize(device)
+        # a spinning blocker the n launches queue behind, long enough to cover their enqueue time (a GEMM
+        # blocker would pull the SM clock down under the power cap and inflate what is timed behind it)
+        torch.cuda._sleep(max(12_000_000, int(host_s * 1.5 * 2.0e9)))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(n):
@@ -549,7 +555,8 @@ def main():
             "frac": kbytes[dom] / (us_dom * 1e-6) / 1e9 / peak, "traffic": traffic_from_profile(dom),
             "peak_source": peak_src, "algorithmic_bytes": kbytes[dom], "launch_us": us_dom,
             "calls_per_step": per_step, "share_of_step": per_step * us_dom / step_us,
-            "how": "CUDA events around 24 back-to-back calls on the launching stream behind a spinning blocker, "
+            "how": "CUDA events around 24 back-to-back calls on the launching stream behind a spinning blocker "
+                   "that outlasts their enqueue time, "
                    f"x from {pool_n} pooled minibatches (HBM resident, {pool_mb:.0f} MB > L2)"}
     kernels = {name: {"us_per_call": t, "calls_per_step": n, "share_of_step": n * t / step_us,
                       "algorithmic_bytes": kbytes.get(name),

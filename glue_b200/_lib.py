@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = (
     "glue_graphdec_bwd_scaled",
     "glue_graphdec_sort_incidence",
     "glue_graphdec_bwd_sorted",
+    "glue_graph_nll_fwd",
+    "glue_graph_nll_bwd",
     "glue_decoder_workspace_bytes",
     "glue_decoder_nll_fwd_bwd",
     "glue_decoder_nll_fwd",
@@ -170,6 +172,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_graphdec_bwd_sorted.restype = c_int32
     lib.glue_graphdec_bwd_sorted.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.glue_graph_nll_fwd.restype = c_int32
+    lib.glue_graph_nll_fwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+        c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]
+    lib.glue_graph_nll_bwd.restype = c_int32
+    lib.glue_graph_nll_bwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
         c_void_p, c_void_p, c_size_t, c_void_p]
 
     lib.glue_decoder_workspace_bytes.restype = c_size_t

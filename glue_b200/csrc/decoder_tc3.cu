@@ -54,6 +54,7 @@ constexpr uint32_t COL_ACC = 0;   // logits: 2 x 128 columns
 constexpr uint32_t COL_D1 = 256;  // d/dv tile: 64 columns (accumulates over the terms of a tile)
 constexpr uint32_t COL_D2 = 320;  // d/du: 64 columns per term
 constexpr uint32_t TMEM_COLS = 512;
+constexpr size_t TRACE_BYTES = 32768;  // diagnostic stamps (impl bit 9): 768 + 960 + 1440 int64 values
 
 constexpr uint64_t DESC_K = smem_desc_base(16, 1024);
 constexpr uint64_t DESC_MN1 = smem_desc_base(1024, 1024);
@@ -105,6 +106,12 @@ __device__ __forceinline__ long long globaltimer_ns() {
     do {                                                                                         \
         if (P.ws.trace != nullptr && blockIdx.x < 160)                                           \
             P.ws.trace[768 + ((kern) * 160 + blockIdx.x) * 2 + (which)] = globaltimer_ns();      \
+    } while (0)
+// per-CTA epilogue accounting (warp 0 lane 0): [3 kernels][160 CTAs][smid, loop cycles, wait cycles] at 1728
+#define T3EPI(kern, which, val)                                                                  \
+    do {                                                                                         \
+        if (P.ws.trace != nullptr && blockIdx.x < 160)                                           \
+            P.ws.trace[1728 + ((kern) * 160 + blockIdx.x) * 3 + (which)] = (long long)(val);     \
     } while (0)
 #define T3NS(kern, ev)                                                                           \
     do {                                                                                         \
@@ -774,6 +781,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int g_begin = (ngrp * h + NH - 1) / NH;
         const int g_end = (ngrp * (h + 1) + NH - 1) / NH;
         const bool skip_nan = a.reduce == 0 && P.term[0].row_weight == nullptr;  // nanmean semantics (single term)
+        long long t_loop = 0, t_wait = 0;
         float loss_seg[MAXSEG];
         int bad_seg[MAXSEG];
 #pragma unroll
@@ -788,7 +796,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         bool pend = false;
         int64_t pend_off = 0;
         float pend_b = 0.f, pend_s = 0.f, pend_d = 0.f, pend_z = 0.f;
-        float s2 = 0.f, b2 = 0.f, lg1 = 0.f, dg1 = 0.f, lg2 = 0.f, dg2 = 0.f;
+        float s2 = 0.f, b2 = 0.f, lg1 = 0.f, dg1 = 0.f, lg2 = 0.f, dg2 = 0.f, lg3 = 0.f, dg3 = 0.f;
         f2 ngb2 = pk(0.f, 0.f), ngs2 = pk(0.f, 0.f), gd2 = pk(0.f, 0.f);
 
         auto write_param = [&](int64_t off, float vb, float vs, float vd, float vz, bool add) {
@@ -863,6 +871,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         lg1 = fp.disp, dg1 = ti;
                         lg2 = logf(fp.th * (fp.th + 1.f)) - 0.69314718055994530942f;
                         dg2 = ti + 1.f / (fp.th + 1.f);
+                        lg3 = lg2 + logf(fp.th + 2.f) - 1.09861228866810969140f;  // - log 3
+                        dg3 = dg2 + 1.f / (fp.th + 2.f);
                     }
                 }
             }
@@ -894,17 +904,27 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const f2 S2 = pk(s2, s2), B2 = pk(b2, b2), NS2 = pk(-fp.s, -fp.s), TH2 = pk(fp.th, fp.th);
             const f2 EPS2 = pk(GLUE_EPS, GLUE_EPS), M1 = pk(-1.f, -1.f), LN2_2 = pk(LN2F, LN2F);
             const f2 NLN2 = pk(-LN2F, -LN2F), DISP2 = pk(fp.disp, fp.disp);
-            const float lq_c2 = 0.5f * lg2 - lg1, lq_c1 = lg1 - lq_c2;
-            const float dq_c2 = 0.5f * dg2 - dg1, dq_c1 = dg1 - dq_c2;
-            const f2 LQ1 = pk(lq_c1, lq_c1), LQ2 = pk(lq_c2, lq_c2), DQ1 = pk(dq_c1, dq_c1), DQ2 = pk(dq_c2, dq_c2);
-            const f2 M2 = pk(-2.f, -2.f);
+            // FAST: log-gamma / digamma differences of the counts 0 .. 3 as the cubic x (c1 + c2 x + c3 x^2)
+            // through their exact values (sparse count data: 3 is still common, 4 and more is rare)
+            const float ld1 = lg1, ld2 = 0.5f * lg2, ld3 = lg3 * (1.f / 3.f);
+            const float lq_c3 = 0.5f * ((ld3 - ld2) - (ld2 - ld1)), lq_c2 = (ld2 - ld1) - 3.f * lq_c3;
+            const float lq_c1 = ld1 - lq_c2 - lq_c3;
+            const float dd1 = dg1, dd2 = 0.5f * dg2, dd3 = dg3 * (1.f / 3.f);
+            const float dq_c3 = 0.5f * ((dd3 - dd2) - (dd2 - dd1)), dq_c2 = (dd2 - dd1) - 3.f * dq_c3;
+            const float dq_c1 = dd1 - dq_c2 - dq_c3;
+            const f2 LQ1 = pk(lq_c1, lq_c1), LQ2 = pk(lq_c2, lq_c2), LQ3 = pk(lq_c3, lq_c3);
+            const f2 DQ1 = pk(dq_c1, dq_c1), DQ2 = pk(dq_c2, dq_c2), DQ3 = pk(dq_c3, dq_c3);
+            const f2 M2 = pk(-2.f, -2.f), M3 = pk(-3.f, -3.f);
             const float* wsrc = (FAST && !jok) ? S.zeros : S.wrow[seg];
             const float* lsep = S.lse[seg];
             const float* auxp = PHASE == 0 ? S.l : S.c[seg];
             load_x(g_begin);
             if (t == 0) T3(KRN, n, 5);
+            const long long tw0 = clock64();
             mbar_wait(&S.bars.acc_full[as], (n >> 1) & 1);
             tc_fence_after();
+            const long long tw1 = clock64();
+            t_wait += tw1 - tw0;
             if (t == 0) T3(KRN, n, 6);
 #pragma unroll 1
             for (int g = g_begin; g < g_end; ++g) {
@@ -951,7 +971,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     for (int pr_ = 0; pr_ < 4; ++pr_) {
                         const f2 x2 = pk(xv[2 * pr_], xv[2 * pr_ + 1]);
                         float p0, p1;
-                        up(mul2(mul2(x2, add2(x2, M1)), add2(x2, M2)), p0, p1);  // x (x - 1) (x - 2)
+                        up(mul2(mul2(x2, add2(x2, M1)), mul2(add2(x2, M2), add2(x2, M3))), p0, p1);  // x (x-1) (x-2) (x-3)
                         rb |= __float_as_uint(p0) | __float_as_uint(p1);
                         xq[2 * pr_] = xv[2 * pr_], xq[2 * pr_ + 1] = xv[2 * pr_ + 1];
                     }
@@ -962,7 +982,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             if (skip_nan && x != x) {
                                 bad_acc += (jok && c0 + e8 < ncell) ? 1 : 0;
                                 xv[e8] = 0.f, xq[e8] = 0.f, wv[e8] = 0.f;
-                            } else if (!(x == 0.f || x == 1.f || x == 2.f)) {
+                            } else if (!(x == 0.f || x == 1.f || x == 2.f || x == 3.f)) {
                                 float lg_t, dg_t;
                                 nb_gamma_terms_t<true>(x, fp.th, lg_t, dg_t);
                                 xq[e8] = 0.f;
@@ -991,12 +1011,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         const f2 dlt2 = fma2(l2t, NLN2, DISP2);                        // log theta - log(m + theta)
                         const f2 xl2 = mul2(fma2(l2t, M1, l2m), LN2_2);                // log m - log(m + theta)
                         const f2 ndd2 = fma2(add2(x2, TH2), sig2, mul2(x2, M1));       // -(x - (x + theta) sig)
-                        const f2 lgq2 = mul2(xq2, fma2(LQ2, xq2, LQ1));
+                        const f2 lgq2 = mul2(xq2, fma2(fma2(LQ3, xq2, LQ2), xq2, LQ1));
                         const f2 lp2 = fma2(TH2, dlt2, fma2(x2, xl2, lgq2));
                         loss2 = fma2(W2, lp2, loss2);
                         if (GRAD) {
                             const f2 rat2 = mul2(mu2, mul2(r2, mt2));
-                            const f2 dgq2 = mul2(xq2, fma2(DQ2, xq2, DQ1));
+                            const f2 dgq2 = mul2(xq2, fma2(fma2(DQ3, xq2, DQ2), xq2, DQ1));
                             const f2 tl2 = fma2(TH2, add2(dlt2, dgq2), ndd2);
                             const f2 nG2 = mul2(W2, mul2(ndd2, rat2));
                             ngb2 = add2(ngb2, nG2);
@@ -1159,6 +1179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     }
                 }
             }
+            t_loop += clock64() - tw1;
             if (t == 0) T3(KRN, n, 7);
             {  // loss of the unit
                 float a0, a1;
@@ -1205,6 +1226,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
         }
         if (t == 0) T3(KRN, 15, 2);
+        if (t == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            T3EPI(KRN, 0, smid);
+            T3EPI(KRN, 1, t_loop);
+            T3EPI(KRN, 2, t_wait);
+        }
         if (GRAD) {
             // d/du partials of this CTA: rows = cells, one 64-column accumulator per term
             mbar_wait(&S.bars.d2_full, 0);
@@ -1377,7 +1405,7 @@ size_t ws_layout(const glue_decoder_args& a, int S, int ncta, int Fpad, char* ba
         return ptr;
     };
     Ws3 w;
-    w.trace = (long long*)take(16384, 1024);  // (first: tools find it at the aligned base)
+    w.trace = (long long*)take(TRACE_BYTES, 1024);  // (first: tools find it at the aligned base)
     w.vimg = (uint8_t*)take((size_t)2 * Fpad * ROW_BYTES, 1024);
     w.uimg = (uint8_t*)take((size_t)2 * S * 128 * ROW_BYTES, 1024);
     w.ptab = (float2*)take((size_t)a.n_batches * Fpad * sizeof(float2), 256);
@@ -1524,7 +1552,7 @@ int tc3_run(const glue_decoder_multi_args& m, int mode, cudaStream_t st) {
     P.cinv = (nbf && nb1 && a.K <= 62 && grad) ? 1 : 0;
     if (!nbf) P.ws.ptab = nullptr;
     if (a.impl & 0x200)
-        GLUE_CUDA(cudaMemsetAsync(P.ws.trace, 0, 16384, st));
+        GLUE_CUDA(cudaMemsetAsync(P.ws.trace, 0, TRACE_BYTES, st));
     else
         P.ws.trace = nullptr;
 

@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(GD_THREADS)
 graphdec_fwd_kernel(const float* __restrict__ v, const int64_t* __restrict__ eidx,
                     const float* __restrict__ esgn, const float* __restrict__ ewt, int64_t E, int K,
                     bool vec2, float* __restrict__ out_logits, float* __restrict__ out_nll,
-                    float* __restrict__ out_coef, float* __restrict__ partial) {
+                    float* __restrict__ out_coef, float* __restrict__ partial,
+                    unsigned int* __restrict__ ticket, float* __restrict__ scales,
+                    float* __restrict__ out_loss) {
     const int sub = threadIdx.x & (GD_LPE - 1);
     const int64_t grp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GD_LPE;
     const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / GD_LPE;
@@ -266,6 +268,36 @@ graphdec_fwd_kernel(const float* __restrict__ v, const int64_t* __restrict__ eid
         float acc = 0.f;
         for (int w = 0; w < GD_THREADS / 32; ++w) acc += red[w][threadIdx.x];
         partial[(int64_t)blockIdx.x * 4 + threadIdx.x] = acc;
+    }
+    if (ticket == nullptr) return;
+    // fused finalize: the last CTA to arrive reduces the per-block partials in a fixed order (thread <->
+    // component t & 3 and one of 64 strided sub-sums, shuffle tree per component, then the 8 warps in
+    // order) and publishes the balanced loss of scglue.py:332-338 and the two class weights
+    __shared__ bool last;
+    __shared__ double wsum[GD_THREADS / 32][4];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int c = threadIdx.x & 3;
+    double a = 0.0;
+    for (int b = threadIdx.x >> 2; b < (int)gridDim.x; b += GD_THREADS / 4) a += (double)__ldcg(partial + (int64_t)b * 4 + c);
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) a += __shfl_xor_sync(FULL, a, o);  // lanes with equal (t & 3)
+    if (lane < 4) wsum[wid][c] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < GD_THREADS / 32; ++w)
+            for (int q = 0; q < 4; ++q) acc[q] += wsum[w][q];
+        const double n_neg = acc[2], n_pos = acc[3];
+        const double avgc = (n_pos > 0) + (n_neg > 0);
+        const double inv_neg = 1.0 / (fmax(n_neg, 1.0) * avgc), inv_pos = 1.0 / (fmax(n_pos, 1.0) * avgc);
+        if (out_loss) out_loss[0] = (float)(acc[0] * inv_neg + acc[1] * inv_pos);
+        scales[0] = (float)inv_neg;
+        scales[1] = (float)inv_pos;
     }
 }
 
@@ -318,7 +350,8 @@ __global__ void graphdec_incidence_kernel(const int64_t* __restrict__ eidx, int6
 // list position so that short segments (the common case) still fill the warp.
 __global__ void __launch_bounds__(GD_THREADS)
 graphdec_bwd_kernel(const float* __restrict__ v, const int64_t* __restrict__ eidx,
-                    const float* __restrict__ esgn, const float* __restrict__ coef,
+                    const float* __restrict__ esgn, const float* __restrict__ ewt,
+                    const float* __restrict__ coef, const float* __restrict__ scales,
                     const float* __restrict__ upstream, const int32_t* __restrict__ key,
                     const int32_t* __restrict__ entry, int64_t E, int K,
                     float* __restrict__ grad_v) {
@@ -337,7 +370,9 @@ graphdec_bwd_kernel(const float* __restrict__ v, const int64_t* __restrict__ eid
             const int32_t q_ent = entry[p];
             const int64_t e = q_ent < E ? q_ent : q_ent - E;
             const int64_t other = q_ent < E ? eidx[E + e] : eidx[e];
-            const float w = coef[e] * esgn[e] * up;
+            float cf = coef[e];
+            if (scales) cf *= scales[ewt[e] != 0.f ? 1 : 0];  // (class weights of the fused forward)
+            const float w = cf * esgn[e] * up;
             const float* row = v + other * K;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -351,6 +386,107 @@ graphdec_bwd_kernel(const float* __restrict__ v, const int64_t* __restrict__ eid
             if (c < K) grad_v[(int64_t)vert * K + c] = acc[q];
         }
     }
+}
+
+// Second generation (K <= 64).  The sorted list is turned into a CSR over vertices right after the sort
+// (graphdec_segments_kernel, still in the forward pass: it depends on `eidx` only): segptr[w] .. segptr[w + 1]
+// are the list positions of vertex w, meta[p] = (other endpoint, edge) of position p.  The backward kernel
+// then runs one 8-lane group per *vertex*: the lanes resolve up to 8 entries side by side (coefficient,
+// sign, class weight by ewt[e] != 0 -- coefficients arrive unscaled from the fused forward) and broadcast
+// them, the source rows of 2 entries are gathered at a time; every row of grad_v is written by its own
+// group (zeros for untouched vertices: no memset).  Sums run in list order, as in the kernel above
+// (bit-identical results).
+__global__ void graphdec_segments_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ entry,
+                                         const int64_t* __restrict__ eidx, int64_t E, int64_t V,
+                                         int32_t* __restrict__ segptr, int2* __restrict__ meta) {
+    const int64_t n = 2 * E;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i < n) {
+        const int32_t ent = entry[i];
+        const int64_t e = ent < E ? ent : ent - E;
+        meta[i] = make_int2((int32_t)(ent < E ? eidx[E + e] : eidx[e]), (int32_t)e);
+    }
+    const int64_t prev = i == 0 ? -1 : (int64_t)key[i - 1];
+    const int64_t cur = i == n ? V : (int64_t)key[i];
+    for (int64_t r = prev + 1; r <= cur; ++r) segptr[r] = (int32_t)i;  // vertices whose run starts at i
+}
+
+template <bool VEC2>
+__global__ void __launch_bounds__(GD_THREADS, 4)
+graphdec_bwd3_kernel(const float* __restrict__ v, const float* __restrict__ esgn, const float* __restrict__ ewt,
+                     const float* __restrict__ coef, const float* __restrict__ scales,
+                     const float* __restrict__ upstream, const int32_t* __restrict__ segptr,
+                     const int2* __restrict__ meta, int64_t V, int K, float* __restrict__ grad_v) {
+    constexpr int Q = VEC2 ? 4 : 8;  // columns per lane: float2 q * 8 + sub, or float q * 8 + sub
+    constexpr int NJ = 2;            // source rows gathered at a time
+    using T = typename VecT<VEC2 ? 2 : 1>::type;
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GD_LPE;
+    if (r >= V) return;
+    const int beg = __ldg(segptr + r), end = __ldg(segptr + r + 1);
+    const int ncol = VEC2 ? (K >> 1) : K;
+    bool act[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) act[q] = q * 8 + sub < ncol;
+    T acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        if constexpr (VEC2) acc[q] = make_float2(0.f, 0.f); else acc[q] = 0.f;
+    }
+    if (beg < end) {
+        const float up = upstream ? upstream[0] : 1.f;
+        const float sc_neg = scales ? scales[0] : 1.f, sc_pos = scales ? scales[1] : 1.f;
+        const T* vbase = reinterpret_cast<const T*>(v) + sub;
+        for (int p = beg; p < end; p += 8) {
+            const int m = min(8, end - p);
+            int other = 0;
+            float w = 0.f;
+            if (sub < m) {
+                const int2 mt = __ldg(meta + p + sub);
+                other = mt.x;
+                float cf = coef[mt.y];
+                if (scales) cf *= (ewt[mt.y] != 0.f ? sc_pos : sc_neg);
+                w = cf * esgn[mt.y] * up;
+            }
+#pragma unroll
+            for (int jb = 0; jb < 8; jb += NJ) {
+                if (jb < m) {
+                    T x[NJ][Q];
+                    float wj[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int src = min(jb + j, m - 1);  // (beyond the run: a valid row, unused)
+                        const int oj = __shfl_sync(gmask, other, src, 8);
+                        wj[j] = __shfl_sync(gmask, w, src, 8);
+                        const T* row = vbase + (int64_t)oj * ncol;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q)
+                            if (act[q]) x[j][q] = __ldg(row + q * 8);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        if (jb + j < m) {
+#pragma unroll
+                            for (int q = 0; q < Q; ++q)
+                                if (act[q]) {
+                                    if constexpr (VEC2) {
+                                        acc[q].x = fmaf(wj[j], x[j][q].x, acc[q].x);
+                                        acc[q].y = fmaf(wj[j], x[j][q].y, acc[q].y);
+                                    } else {
+                                        acc[q] = fmaf(wj[j], x[j][q], acc[q]);
+                                    }
+                                }
+                        }
+                }
+            }
+        }
+    }
+    T* dst = reinterpret_cast<T*>(grad_v + r * K) + sub;
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+        if (act[q]) dst[q * 8] = acc[q];
 }
 
 }  // namespace glue
@@ -424,6 +560,11 @@ extern "C" int glue_csr_build(const int64_t* key, const int64_t* other, const fl
     return 0;
 }
 
+// workspace head: per-block partials of the forward kernel (4 floats each), then 8 words for the ticket
+// and the class weights of the fused finalize
+constexpr int GD_MAX_BLOCKS = 148 * 16 - 2;
+constexpr int GD_TAIL_OFFSET = 148 * 16 * 4 - 8;  // in floats
+
 static int graphdec_grid(int64_t E) {
     const int64_t per_block = GD_THREADS / GD_LPE;
     const int64_t want = (E + per_block - 1) / per_block;
@@ -432,10 +573,11 @@ static int graphdec_grid(int64_t E) {
 }
 
 extern "C" size_t glue_graphdec_workspace_bytes(int64_t E, int64_t V) {
-    (void)V;
     if (E <= 0) return 256;
+    if (V < 0) V = 0;
     const size_t partial = align_up((size_t)148 * 16 * 4 * sizeof(float), 256);  // <= 2368 blocks
-    return partial + 4 * align_up((size_t)E * 8, 256) + align_up(sort_temp_bytes(2 * E), 256);
+    return partial + 4 * align_up((size_t)E * 8, 256) + align_up(sort_temp_bytes(2 * E), 256) +
+           align_up((size_t)(V + 1) * 4, 256) + align_up((size_t)E * 16, 256);  // segptr, meta
 }
 
 extern "C" int glue_graphdec_bce_fwd(const float* v, const int64_t* eidx, const float* esgn,
@@ -447,11 +589,11 @@ extern "C" int glue_graphdec_bce_fwd(const float* v, const int64_t* eidx, const 
     if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = graphdec_grid(E);
-    if (grid > 148 * 16) return GLUE_E_UNSUPPORTED;
+    if (grid > GD_MAX_BLOCKS) return GLUE_E_UNSUPPORTED;
     float* partial = (float*)workspace;
     const bool vec2 = (K % 2 == 0) && ((uintptr_t)v % 8 == 0);
     graphdec_fwd_kernel<<<grid, GD_THREADS, 0, st>>>(v, eidx, esgn, ewt, E, K, vec2, out_logits,
-                                                     out_nll, out_coef, partial);
+                                                     out_nll, out_coef, partial, nullptr, nullptr, nullptr);
     GLUE_CHECK_LAUNCH();
     const int fin_blocks = out_coef ? (int)((E + 4095) / 4096 < 64 ? (E + 4095) / 4096 : 64) : 1;
     graphdec_finalize_kernel<<<fin_blocks < 1 ? 1 : fin_blocks, 1024, 0, st>>>(partial, grid, ewt, E, out_loss,
@@ -469,15 +611,46 @@ struct GdSortBufs {
     int32_t *k_in, *k_out, *p_in, *p_out;
     void* temp;
     size_t temp_bytes;
+    int32_t* segptr;  // [V + 1] list positions of every vertex's run
+    int2* meta;       // [2 E] (other endpoint, edge) per list position
 };
-GdSortBufs gd_sort_bufs(void* workspace, int64_t E) {
+GdSortBufs gd_sort_bufs(void* workspace, int64_t E, int64_t V) {
     char* ws = (char*)workspace + align_up((size_t)148 * 16 * 4 * sizeof(float), 256);
     const size_t seg = align_up((size_t)E * 8, 256);
     GdSortBufs b;
     b.k_in = (int32_t*)ws, b.k_out = (int32_t*)(ws + seg);
     b.p_in = (int32_t*)(ws + 2 * seg), b.p_out = (int32_t*)(ws + 3 * seg);
     b.temp = ws + 4 * seg, b.temp_bytes = sort_temp_bytes(2 * E);
+    char* tail = ws + 4 * seg + align_up(b.temp_bytes, 256);
+    b.segptr = (int32_t*)tail;
+    b.meta = (int2*)(tail + align_up((size_t)(V + 1) * 4, 256));
     return b;
+}
+}  // namespace
+
+namespace {
+// K <= 64: one group per vertex over the segment CSR; wider rows: the one-entry-at-a-time kernel + memset
+int graphdec_bwd_launch(const float* v, const int64_t* eidx, const float* esgn, const float* ewt, const float* coef,
+                        const float* scales, const float* upstream, const GdSortBufs& b, int64_t E, int64_t V, int K,
+                        float* grad_v, cudaStream_t st) {
+    if (K <= 64) {
+        const bool vec2 = (K % 2 == 0) && (((uintptr_t)v | (uintptr_t)grad_v) % 8 == 0);
+        const unsigned vblocks = (unsigned)((V * GD_LPE + GD_THREADS - 1) / GD_THREADS);
+        if (vec2)
+            graphdec_bwd3_kernel<true><<<vblocks, GD_THREADS, 0, st>>>(v, esgn, ewt, coef, scales, upstream, b.segptr,
+                                                                       b.meta, V, K, grad_v);
+        else
+            graphdec_bwd3_kernel<false><<<vblocks, GD_THREADS, 0, st>>>(v, esgn, ewt, coef, scales, upstream, b.segptr,
+                                                                        b.meta, V, K, grad_v);
+        GLUE_CHECK_LAUNCH();
+        return 0;
+    }
+    const int64_t blocks = (2 * E * GD_LPE + GD_THREADS - 1) / GD_THREADS;
+    GLUE_CUDA(cudaMemsetAsync(grad_v, 0, (size_t)V * K * sizeof(float), st));
+    graphdec_bwd_kernel<<<(unsigned)blocks, GD_THREADS, 0, st>>>(v, eidx, esgn, ewt, coef, scales, upstream, b.k_out,
+                                                                 b.p_out, E, K, grad_v);
+    GLUE_CHECK_LAUNCH();
+    return 0;
 }
 }  // namespace
 
@@ -491,7 +664,7 @@ extern "C" int glue_graphdec_sort_incidence(const int64_t* eidx, int64_t E, int6
     if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
     if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const GdSortBufs b = gd_sort_bufs(workspace, E);
+    const GdSortBufs b = gd_sort_bufs(workspace, E, V);
     const int threads = 256;
     graphdec_incidence_kernel<<<(unsigned)((2 * E + threads - 1) / threads), threads, 0, st>>>(eidx, E, b.k_in,
                                                                                                b.p_in);
@@ -499,6 +672,9 @@ extern "C" int glue_graphdec_sort_incidence(const int64_t* eidx, int64_t E, int6
     size_t temp_bytes = b.temp_bytes;
     GLUE_CUDA(cub::DeviceRadixSort::SortPairs(b.temp, temp_bytes, b.k_in, b.k_out, b.p_in, b.p_out, (int)(2 * E), 0,
                                               bits_for(V), st));
+    graphdec_segments_kernel<<<(unsigned)((2 * E + 1 + threads - 1) / threads), threads, 0, st>>>(
+        b.k_out, b.p_out, eidx, E, V, b.segptr, b.meta);
+    GLUE_CHECK_LAUNCH();
     return 0;
 }
 
@@ -512,14 +688,44 @@ extern "C" int glue_graphdec_bwd_sorted(const float* v, const int64_t* eidx, con
     if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
     if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const GdSortBufs b = gd_sort_bufs(workspace, E);
-    GLUE_CUDA(cudaMemsetAsync(grad_v, 0, (size_t)V * K * sizeof(float), st));
-    const int64_t groups = 2 * E;
-    const int64_t blocks = (groups * GD_LPE + GD_THREADS - 1) / GD_THREADS;
-    graphdec_bwd_kernel<<<(unsigned)blocks, GD_THREADS, 0, st>>>(v, eidx, esgn, coef, upstream, b.k_out, b.p_out, E,
-                                                                 K, grad_v);
+    const GdSortBufs b = gd_sort_bufs(workspace, E, V);
+    return graphdec_bwd_launch(v, eidx, esgn, nullptr, coef, nullptr, upstream, b, E, V, K, grad_v, st);
+}
+
+// ---- fused-finalize pair (what graph_nll of the training step calls) ---------------------------
+// Forward: one launch -- the last CTA to arrive reduces the partials, writes the loss and leaves the two
+// class weights in the workspace; out_coef stays *unscaled* (sigma(logit) - ewt).  With prepare_bwd the
+// vertex-sorted incidence list follows on the same stream.  Backward: glue_graph_nll_bwd applies the
+// class weights while it resolves the entries; it writes every row of grad_v itself.
+extern "C" int glue_graph_nll_fwd(const float* v, const int64_t* eidx, const float* esgn, const float* ewt,
+                                  int64_t E, int64_t V, int32_t K, float* out_loss, float* out_coef,
+                                  int32_t prepare_bwd, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!v || !eidx || !esgn || !ewt || !out_loss || E <= 0 || V <= 0 || K <= 0 || !workspace) return GLUE_E_BADARG;
+    if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = graphdec_grid(E);
+    if (grid > GD_MAX_BLOCKS) return GLUE_E_UNSUPPORTED;
+    float* partial = (float*)workspace;
+    float* tail = partial + GD_TAIL_OFFSET;  // [0]: ticket, [1..2]: class weights
+    GLUE_CUDA(cudaMemsetAsync(tail, 0, 4, st));
+    const bool vec2 = (K % 2 == 0) && ((uintptr_t)v % 8 == 0);
+    graphdec_fwd_kernel<<<grid, GD_THREADS, 0, st>>>(v, eidx, esgn, ewt, E, K, vec2, nullptr, nullptr, out_coef,
+                                                     partial, (unsigned int*)tail, tail + 1, out_loss);
     GLUE_CHECK_LAUNCH();
+    if (prepare_bwd) return glue_graphdec_sort_incidence(eidx, E, V, workspace, workspace_bytes, stream);
     return 0;
+}
+
+extern "C" int glue_graph_nll_bwd(const float* v, const int64_t* eidx, const float* esgn, const float* ewt,
+                                  const float* coef, const float* upstream, int64_t E, int64_t V, int32_t K,
+                                  float* grad_v, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!v || !eidx || !esgn || !ewt || !coef || !grad_v || E <= 0 || V <= 0 || K <= 0 || !workspace)
+        return GLUE_E_BADARG;
+    if (2 * E >= ((int64_t)1 << 31) || V >= ((int64_t)1 << 31)) return GLUE_E_UNSUPPORTED;
+    if (workspace_bytes < glue_graphdec_workspace_bytes(E, V)) return GLUE_E_WORKSPACE;
+    const GdSortBufs b = gd_sort_bufs(workspace, E, V);
+    const float* scales = (const float*)workspace + GD_TAIL_OFFSET + 1;
+    return graphdec_bwd_launch(v, eidx, esgn, ewt, coef, scales, upstream, b, E, V, K, grad_v, (cudaStream_t)stream);
 }
 
 extern "C" int glue_graphdec_bwd_scaled(const float* v, const int64_t* eidx, const float* esgn,

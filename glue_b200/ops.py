@@ -483,34 +483,37 @@ def _graphdec_ws(n_edges: int, vnum: int, device) -> torch.Tensor:
 
 class _GraphNllFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, v, eidx, esgn, ewt):
+    def forward(ctx, v, eidx, esgn, ewt, grad_enabled):
         dev = v.device
         n_edges, (vnum, k) = eidx.shape[1], v.shape
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        coef = torch.empty(n_edges, dtype=torch.float32, device=dev)
+        # (grad mode is always off inside Function.forward: the caller's mode comes in as a flag, so that
+        # validation under no_grad does not sort the incidence list)
+        need_grad = bool(grad_enabled and ctx.needs_input_grad[0])
+        coef = torch.empty(n_edges, dtype=torch.float32, device=dev) if need_grad else None
         ws = _graphdec_ws(n_edges, vnum, dev)
-        check(_lib.lib().glue_graphdec_bce_fwd(
-            ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), n_edges, vnum, k, ptr(loss), None, None,
-            ptr(coef), ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bce_fwd")
-        if ctx.needs_input_grad[0]:
-            # the vertex-sorted incidence list of the backward pass depends on `eidx` only: sort it
-            # now, beside the rest of the forward pass, instead of on the tail of the backward pass
-            check(_lib.lib().glue_graphdec_sort_incidence(ptr(eidx), n_edges, vnum, ptr(ws), ws.numel(),
-                                                          current_stream(dev)), "graphdec_sort_incidence")
-        ctx.save_for_backward(v, eidx, esgn, coef, ws)
+        # one launch: the last CTA publishes the loss and the class weights; the vertex-sorted
+        # incidence list of the backward pass depends on `eidx` only and is sorted right behind it,
+        # beside the rest of the forward pass, instead of on the tail of the backward pass
+        check(_lib.lib().glue_graph_nll_fwd(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), n_edges, vnum, k, ptr(loss),
+            ptr(coef) if need_grad else None, 1 if need_grad else 0, ptr(ws), ws.numel(),
+            current_stream(dev)), "graph_nll_fwd")
+        if need_grad:
+            ctx.save_for_backward(v, eidx, esgn, ewt, coef, ws)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        v, eidx, esgn, coef, ws = ctx.saved_tensors
+        v, eidx, esgn, ewt, coef, ws = ctx.saved_tensors
         dev = v.device
         n_edges, (vnum, k) = eidx.shape[1], v.shape
         grad_v = torch.empty_like(v)
         up = _f32(grad_out, "grad_out")
-        check(_lib.lib().glue_graphdec_bwd_sorted(
-            ptr(v), ptr(eidx), ptr(esgn), ptr(coef), ptr(up), n_edges, vnum, k, ptr(grad_v),
-            ptr(ws), ws.numel(), current_stream(dev)), "graphdec_bwd")
-        return grad_v, None, None, None
+        check(_lib.lib().glue_graph_nll_bwd(
+            ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), ptr(coef), ptr(up), n_edges, vnum, k, ptr(grad_v),
+            ptr(ws), ws.numel(), current_stream(dev)), "graph_nll_bwd")
+        return grad_v, None, None, None, None
 
 
 class _GraphLogitsFn(torch.autograd.Function):
@@ -558,7 +561,7 @@ def graph_nll(v, eidx, esgn, ewt) -> torch.Tensor:
     r"""Balanced Bernoulli NLL of the sampled edges -- replaces ``GraphDecoder.forward``
     + ``Bernoulli.log_prob`` + the pos/neg averaging of ``scglue/models/scglue.py:331-338``
     (without its ``.item()`` host sync)."""
-    return _GraphNllFn.apply(*_graph_args(v, eidx, esgn, ewt))
+    return _GraphNllFn.apply(*_graph_args(v, eidx, esgn, ewt), torch.is_grad_enabled())
 
 
 def graph_logits(v, eidx, esgn) -> torch.Tensor:

@@ -150,6 +150,22 @@ int glue_graphdec_bwd_sorted(const float *v, const int64_t *eidx, const float *e
                              int32_t K, float *grad_v, void *workspace, size_t workspace_bytes,
                              void *stream);
 
+/* The pair the training step calls (scglue/models/scglue.py:331-338 and its autograd backward).
+ * glue_graph_nll_fwd: ONE kernel (+ a 4-byte memset): the last CTA to arrive reduces the per-block
+ * sums in a fixed order, writes out_loss and leaves the two class weights in the workspace;
+ * out_coef [E] (may be NULL) = sigma(logit) - ewt, NOT yet class-weighted.  prepare_bwd != 0 also
+ * builds the vertex-sorted incidence list in the workspace (glue_graphdec_sort_incidence), which
+ * must then stay alive until glue_graph_nll_bwd has run.
+ * glue_graph_nll_bwd: grad_v [V, K] = d (upstream[0] * out_loss) / d v by segmented reduction;
+ * class weights are applied per entry (by ewt[e] != 0), untouched vertices get zero rows from the
+ * kernel itself (no memset), sums run in list order (bit-reproducible). */
+int glue_graph_nll_fwd(const float *v, const int64_t *eidx, const float *esgn, const float *ewt,
+                       int64_t E, int64_t V, int32_t K, float *out_loss, float *out_coef,
+                       int32_t prepare_bwd, void *workspace, size_t workspace_bytes, void *stream);
+int glue_graph_nll_bwd(const float *v, const int64_t *eidx, const float *esgn, const float *ewt,
+                       const float *coef, const float *upstream, int64_t E, int64_t V, int32_t K,
+                       float *grad_v, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Fused data decoders -- replace forward + log_prob + (nan)mean + backward of
  *   NB     scglue/models/sc.py:372-397 + torch NegativeBinomial.log_prob

@@ -123,6 +123,41 @@ def test_graph_nll_vs_oracle(ops, V, E, K, pos_frac):
     assert torch.equal(g, g2), "segmented-reduction backward must be deterministic"
 
 
+@pytest.mark.parametrize("V,E,K", [(3000, 6000, 50), (3000, 6000, 64), (500, 3000, 7), (400, 2000, 72)])
+def test_graph_nll_hub_segments_and_untouched_rows(ops, V, E, K):
+    """A hub vertex with thousands of incidences (segments longer than one chunk of the walk), long runs of
+    untouched vertices in the middle and at both ends of the table: every row of the gradient is written
+    (zeros where no sampled edge ends), sums match the oracle and are bit-reproducible."""
+    rs = np.random.RandomState(V + K)
+    lo, hi = V // 10, V // 2  # only vertices in [lo, hi) occur, except the hub
+    eidx = rs.randint(lo, hi, (2, E)).astype(np.int64)
+    hub = lo + 3
+    eidx[0, rs.rand(E) < 0.3] = hub
+    eidx[1, rs.rand(E) < 0.1] = hub
+    eidx[:, (eidx[0] >= lo + 100) & (eidx[0] < lo + 400)] = lo + 50  # a hole of 300 untouched vertices
+    eidx[1, (eidx[1] >= lo + 100) & (eidx[1] < lo + 400)] = lo + 51
+    esgn = np.where(rs.rand(E) < 0.3, -1.0, 1.0).astype(np.float32)
+    ewt = (rs.rand(E) < 1 / 11).astype(np.float32)
+    v = torch.randn(V, K, generator=torch.Generator().manual_seed(5)) * 0.3
+    ref_v = v.clone().requires_grad_(True)
+    ref = oc.graph_nll(ref_v, torch.as_tensor(eidx), torch.as_tensor(esgn), torch.as_tensor(ewt))
+    (ref_g,) = torch.autograd.grad(ref, ref_v)
+    dv = v.to(DEV).requires_grad_(True)
+    grads = []
+    for _ in range(2):
+        loss = ops.graph_nll(dv, _cuda(eidx), _cuda(esgn), _cuda(ewt))
+        junk = torch.full((V, K), float("nan"), device=DEV)  # the gradient buffer reuses this block
+        del junk
+        (g,) = torch.autograd.grad(loss, dv)
+        grads.append(g)
+    assert_close(loss, ref, TOL, "graph nll")
+    assert_close(grads[0], ref_g, TOL, "graph nll grad")
+    untouched = np.setdiff1d(np.arange(V), np.unique(eidx))
+    assert len(untouched) > V // 2
+    assert torch.equal(grads[0][_cuda(untouched)], torch.zeros(len(untouched), K, device=DEV))
+    assert torch.equal(grads[0], grads[1])
+
+
 def test_graph_decoder_golden(ops, golden):
     g, m = golden("graph"), golden("modules")
     v = _cuda(m["gd_v"]).requires_grad_(True)

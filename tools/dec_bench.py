@@ -9,6 +9,7 @@ joint cross, real cross) as one fused launch sequence vs. three single-term call
 import json
 import os
 import sys
+import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
@@ -30,8 +31,14 @@ def timed(fn):
     for i in range(3):
         fn(i)
     torch.cuda.synchronize()
-    torch.cuda._sleep(12_000_000)  # a spinning blocker: the launches below queue behind it (a GEMM blocker
+    t0 = time.perf_counter()
+    for i in range(ITERS):
+        fn(i)
+    host_s = time.perf_counter() - t0  # enqueue time of the timed calls
+    torch.cuda.synchronize()
+    # a spinning blocker the launches below queue behind, longer than their enqueue time (a GEMM blocker
     # would pull the SM clock down under the power cap and inflate what is timed behind it)
+    torch.cuda._sleep(max(12_000_000, int(host_s * 1.5 * 2.0e9)))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(ITERS):
@@ -47,6 +54,9 @@ for name, F, rate in (("atac", 50000, 0.05), ("rna", 2000, 0.3), ("atac150k", 15
     us = [(torch.randn(B, K, device=dev) * 0.5).requires_grad_(True) for _ in range(3)]
     v = (torch.randn(F, K, device=dev) * 0.5).requires_grad_(True)
     xs = [torch.poisson(torch.full((B, F), rate, device=dev)) for _ in range(8)]
+    if os.environ.get("XDIST") == "bench":  # bench.py's counts: non-zeros at `rate`, values 1 + Poisson(0.3)
+        xs = [(torch.rand(B, F, device=dev) < rate).float() * (1 + torch.poisson(torch.full((B, F), 0.3, device=dev)))
+              for _ in range(8)]
     ls = [x.sum(1, keepdim=True) + 1 for x in xs]
     npar = 4 if FAMILY in ("ZINB", "ZILN") else 3
     ps = [torch.zeros(NB, F, device=dev, requires_grad=True) for _ in range(npar)]

@@ -20,6 +20,8 @@ T = int(os.environ.get("TERMS", "1"))
 us = [(torch.randn(B, K, device=dev) * 0.5).requires_grad_(True) for _ in range(T)]
 v = (torch.randn(F, K, device=dev) * 0.5).requires_grad_(True)
 x = torch.poisson(torch.full((B, F), 0.05, device=dev))
+if os.environ.get("XDIST") == "bench":  # bench.py's counts: 5 % non-zeros, values 1 + Poisson(0.3)
+    x = (torch.rand(B, F, device=dev) < 0.05).float() * (1 + torch.poisson(torch.full((B, F), 0.3, device=dev)))
 l = x.sum(1, keepdim=True) + 1
 ps = [torch.zeros(1, F, device=dev, requires_grad=True) for _ in range(3)]
 rws = [torch.rand(B, device=dev) / (B * F) for _ in range(T)]
@@ -47,9 +49,19 @@ for rep in range(3):
     torch.cuda.synchronize()
 ws = captured[-1]
 off = (-ws.data_ptr()) % 1024
-raw = ws[off:off + 16384].view(torch.int64).cpu()
+raw = ws[off:off + 32768].view(torch.int64).cpu()
 tr = raw[:768].reshape(3, 16, 16)
 cta = raw[768:768 + 3 * 160 * 2].reshape(3, 160, 2)
+epi = raw[1728:1728 + 3 * 160 * 3].reshape(3, 160, 3)
+for k in (1, 2):
+    live = cta[k][:, 0] > 0
+    if live.any():
+        dur = (cta[k][:, 1] - cta[k][:, 0])
+        print(f"kernel {k}: per CTA (cta, smid, lifetime ns, epilogue loop cycles, logits-wait cycles), slowest 8 and fastest 4 of the 3-tile CTAs:")
+        three = [c for c in range(160) if live[c] and c < (int(live.sum()) if False else 9999)]
+        order = sorted(three, key=lambda c: -int(dur[c]))
+        for c in order[:8] + order[60:64]:
+            print(f"    cta {c:3d} smid {int(epi[k, c, 0]):3d}  {int(dur[c]):7d} ns  loop {int(epi[k, c, 1]):7d}  wait {int(epi[k, c, 2]):7d}")
 for k in range(3):
     live = cta[k][cta[k, :, 0] > 0]
     if len(live):
