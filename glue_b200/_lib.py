@@ -51,6 +51,10 @@ EXPORTED_SYMBOLS = (
     "glue_paired_mean_cos_bwd",
     "glue_act_bn_dropout_fwd",
     "glue_act_bn_dropout_bwd",
+    "glue_mlp_hidden_fwd",
+    "glue_mlp_heads_fwd",
+    "glue_mlp_heads_bwd",
+    "glue_mlp_hidden_bwd",
     "glue_tc_selftest",
     "glue_tc_set_trace",
 )
@@ -228,6 +232,18 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.glue_act_bn_dropout_bwd.restype = c_int32
     lib.glue_act_bn_dropout_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                             c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.glue_mlp_hidden_fwd.restype = c_int32
+    lib.glue_mlp_hidden_fwd.argtypes = [c_void_p, c_int64] + [c_void_p] * 8 + [c_int64, c_int32, c_int32] + [
+        c_float] * 4 + [c_void_p] * 6
+    lib.glue_mlp_heads_fwd.restype = c_int32
+    lib.glue_mlp_heads_fwd.argtypes = [c_void_p, c_int64] + [c_void_p] * 4 + [c_int64, c_int32, c_int32] + [
+        c_void_p] * 4
+    lib.glue_mlp_heads_bwd.restype = c_int32
+    lib.glue_mlp_heads_bwd.argtypes = [c_void_p, c_int64] + [c_void_p] * 3 + [c_int64, c_int32, c_int32] + [
+        c_void_p] * 6
+    lib.glue_mlp_hidden_bwd.restype = c_int32
+    lib.glue_mlp_hidden_bwd.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_int32] + [c_void_p] * 6 + [
+        c_int64, c_int32, c_int64, c_int32, c_float, c_float] + [c_void_p] * 6
     lib.glue_tc_set_trace.restype = None
     lib.glue_tc_set_trace.argtypes = [c_void_p]
 

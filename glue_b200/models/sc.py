@@ -100,6 +100,29 @@ class DataEncoder(glue.DataEncoder):
             self.register_buffer(name, state, persistent=False)
         return state
 
+    def _fused_forward(self, ptr: torch.Tensor):
+        r"""The whole MLP in ``h_depth + 1`` launches each way (``ops.encoder_mlp``) when the shapes
+        allow it (a training-mode minibatch of <= 128 cells, widths <= 256); ``None`` otherwise."""
+        if not (config.USE_FUSED_MLP and config.USE_FUSED_ENCODER and self.h_depth >= 1 and ptr.is_cuda):
+            return None
+        lins = [getattr(self, f"linear_{i}") for i in range(self.h_depth)]
+        bns = [getattr(self, f"bn_{i}") for i in range(self.h_depth)]
+        acts = [getattr(self, f"act_{i}") for i in range(self.h_depth)]
+        drops = [getattr(self, f"dropout_{i}") for i in range(self.h_depth)]
+        if any(not bn.training or bn.momentum is None or not bn.affine for bn in bns):
+            return None
+        if any(type(a) is not torch.nn.LeakyReLU for a in acts) or len({a.negative_slope for a in acts}) != 1:
+            return None
+        ps = {d.p if d.training else 0.0 for d in drops}
+        if len(ps) != 1 or ptr.requires_grad:
+            return None
+        if not ops.encoder_mlp_supported(ptr, [lin.weight for lin in lins], self.loc.out_features):
+            return None
+        p = ps.pop()
+        rngs = [self._dropout_state(i, ptr.device) if p > 0 else None for i in range(self.h_depth)]
+        return ops.encoder_mlp(ptr, lins, bns, (self.loc, self.std_lin), p, rngs,
+                               negative_slope=acts[0].negative_slope)
+
     def compute_l(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         raise NotImplementedError  # pragma: no cover
 
@@ -122,6 +145,9 @@ class DataEncoder(glue.DataEncoder):
             if l is None:
                 l = self.compute_l(x)
             ptr = self.normalize(x, l)
+        fused = self._fused_forward(ptr)
+        if fused is not None:
+            return D.Normal(fused[0], fused[1], validate_args=False), l
         for layer in range(self.h_depth):
             ptr = getattr(self, f"linear_{layer}")(ptr)
             act, bn = getattr(self, f"act_{layer}"), getattr(self, f"bn_{layer}")

@@ -387,6 +387,124 @@ def act_bn_dropout(z: torch.Tensor, bn: torch.nn.BatchNorm1d, p: float, rng_stat
     return (out, mean, rstd, keep) if return_aux else out
 
 
+# ------------------------------------------------------------- whole data-encoder MLP
+
+
+def encoder_mlp_supported(x: torch.Tensor, weights, n_out: int) -> bool:
+    r"""Shapes the fused encoder kernels take (``include/glue_b200.h``): at most 128 rows, every
+    operand width a multiple of 4 and at most 256, fp32, 16-byte aligned rows."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] > 128 or x.shape[0] < 2:
+        return False
+    widths = [x.shape[1]] + [w.shape[0] for w in weights] + [2 * n_out]
+    if any(w % 4 or w > 256 or w <= 0 for w in widths):
+        return False
+    return x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+
+
+class _EncoderMlpFn(torch.autograd.Function):
+    r"""``h_depth`` hidden blocks + both heads; tensors: x, then per block (W, b, gamma, beta), then
+    (Wloc, bloc, Wstd, bstd).  ``blocks`` carries the per-block BatchNorm buffers / dropout states."""
+
+    @staticmethod
+    def forward(ctx, grad_enabled, blocks, slope, p, x, *params):
+        L = _lib.lib()
+        dev, st = x.device, current_stream(x.device)
+        depth = len(blocks)
+        B = x.shape[0]
+        wloc, bloc, wstd, bstd = params[4 * depth:]
+        need_grad = bool(grad_enabled and any(t.requires_grad for t in params))
+        saved, aux = [], []
+        cur = x
+        for i, blk in enumerate(blocks):
+            W, b, gamma, beta = params[4 * i:4 * i + 4]
+            H, Din = W.shape
+            out = torch.empty(B, H, dtype=torch.float32, device=dev)
+            z = torch.empty(B, H, dtype=torch.float32, device=dev) if need_grad else None
+            mean = torch.empty(H, dtype=torch.float32, device=dev) if need_grad else None
+            rstd = torch.empty(H, dtype=torch.float32, device=dev) if need_grad else None
+            keep = torch.empty(B, H, dtype=torch.uint8, device=dev) if (need_grad and p > 0) else None
+            check(L.glue_mlp_hidden_fwd(
+                ptr(cur), cur.stride(0), ptr(W), ptr(b), ptr(gamma), ptr(beta), ptr(blk["running_mean"]),
+                ptr(blk["running_var"]), ptr(blk["num_batches_tracked"]), ptr(blk["rng"]) if p > 0 else None,
+                B, Din, H, slope, blk["eps"], blk["momentum"], p, ptr(z), ptr(out), ptr(mean), ptr(rstd),
+                ptr(keep), st), "mlp_hidden_fwd")
+            saved += [cur, z, mean, rstd]
+            aux.append(keep)
+            cur = out
+        O, H = wloc.shape
+        loc = torch.empty(B, O, dtype=torch.float32, device=dev)
+        std = torch.empty(B, O, dtype=torch.float32, device=dev)
+        spre = torch.empty(B, O, dtype=torch.float32, device=dev) if need_grad else None
+        check(L.glue_mlp_heads_fwd(ptr(cur), cur.stride(0), ptr(wloc), ptr(bloc), ptr(wstd), ptr(bstd), B, H, O,
+                                   ptr(loc), ptr(std), ptr(spre), st), "mlp_heads_fwd")
+        if need_grad:
+            ctx.save_for_backward(cur, spre, *saved, *[k for k in aux if k is not None], *params)
+            ctx.depth, ctx.slope, ctx.p, ctx.has_keep = depth, slope, p, p > 0
+        ctx.need_grad = need_grad
+        return loc, std
+
+    @staticmethod
+    def backward(ctx, g_loc, g_std):
+        if not ctx.need_grad:
+            raise RuntimeError("encoder_mlp was run without gradient buffers")
+        L = _lib.lib()
+        t = ctx.saved_tensors
+        depth, slope, p = ctx.depth, ctx.slope, ctx.p
+        h, spre = t[0], t[1]
+        saved = t[2:2 + 4 * depth]
+        n_keep = depth if ctx.has_keep else 0
+        keeps = t[2 + 4 * depth:2 + 4 * depth + n_keep]
+        params = t[2 + 4 * depth + n_keep:]
+        wloc, bloc, wstd, bstd = params[4 * depth:]
+        dev, st = h.device, current_stream(h.device)
+        B, (O, H) = h.shape[0], wloc.shape
+        g_loc = torch.zeros(B, O, dtype=torch.float32, device=dev) if g_loc is None else _f32(g_loc, "grad_loc")
+        g_std = torch.zeros(B, O, dtype=torch.float32, device=dev) if g_std is None else _f32(g_std, "grad_std")
+        G = torch.empty(B, 2 * O, dtype=torch.float32, device=dev)
+        g_wloc, g_bloc, g_wstd, g_bstd = (torch.empty_like(w) for w in (wloc, bloc, wstd, bstd))
+        check(L.glue_mlp_heads_bwd(ptr(h), h.stride(0), ptr(g_loc), ptr(g_std), ptr(spre), B, H, O, ptr(G),
+                                   ptr(g_wloc), ptr(g_bloc), ptr(g_wstd), ptr(g_bstd), st), "mlp_heads_bwd")
+        grads = [None] * (4 * depth)
+        above, k_above, wa0, wa1, n0 = G, 2 * O, wloc, wstd, O
+        for i in reversed(range(depth)):
+            W, b, gamma, beta = params[4 * i:4 * i + 4]
+            inp, z, mean, rstd = saved[4 * i:4 * i + 4]
+            Hi, Din = W.shape
+            dz = torch.empty(B, Hi, dtype=torch.float32, device=dev) if i > 0 else None
+            gW, gb = torch.empty_like(W), torch.empty_like(b)
+            gg = torch.empty_like(gamma) if gamma is not None else None
+            gbeta = torch.empty_like(beta) if beta is not None else None
+            check(L.glue_mlp_hidden_bwd(
+                ptr(above), k_above, ptr(wa0), ptr(wa1), n0, ptr(z), ptr(gamma), ptr(mean), ptr(rstd),
+                ptr(keeps[i]) if n_keep else None, ptr(inp), inp.stride(0), Din, B, Hi, slope, p, ptr(dz), ptr(gW),
+                ptr(gb), ptr(gg), ptr(gbeta), st), "mlp_hidden_bwd")
+            grads[4 * i:4 * i + 4] = [gW, gb, gg, gbeta]
+            above, k_above, wa0, wa1, n0 = dz, Hi, W, None, Hi
+        return (None, None, None, None, None, *grads, g_wloc, g_bloc, g_wstd, g_bstd)
+
+
+def encoder_mlp(x: torch.Tensor, linears, bns, heads, p: float, rng_states, negative_slope: float = 0.2):
+    r"""``(loc, std)`` of a data encoder (``scglue/models/sc.py:136-178``) in ``h_depth + 1`` launches
+    each way: ``linears`` / ``bns`` are the ``Linear`` / training-mode ``BatchNorm1d`` modules of the
+    hidden blocks, ``heads = (loc, std_lin)``, ``rng_states[i]`` the Philox state of block ``i``'s
+    dropout (as :func:`act_bn_dropout`).  The input takes no gradient."""
+    require_cuda(x)
+    if x.requires_grad:
+        raise ValueError("encoder_mlp does not differentiate its input")
+    blocks, params = [], []
+    for lin, bn, rng in zip(linears, bns, rng_states):
+        if not bn.training or not bn.affine or bn.momentum is None:
+            raise ValueError("encoder_mlp implements training-mode affine BatchNorm1d with a fixed momentum")
+        track = bn.track_running_stats
+        blocks.append({"running_mean": bn.running_mean if track else None,
+                       "running_var": bn.running_var if track else None,
+                       "num_batches_tracked": bn.num_batches_tracked if track else None,
+                       "rng": rng, "eps": float(bn.eps), "momentum": float(bn.momentum)})
+        params += [lin.weight, lin.bias, bn.weight, bn.bias]
+    params += [heads[0].weight, heads[0].bias, heads[1].weight, heads[1].bias]
+    return _EncoderMlpFn.apply(torch.is_grad_enabled(), blocks, float(negative_slope), float(p), x, *params)
+
+
 def new_dropout_state(device, generator: Optional[torch.Generator] = None) -> torch.Tensor:
     r"""``uint64 [3]`` Philox state for :func:`act_bn_dropout` (stored as int64): a seed drawn from
     torch's (CPU) generator, call counter 0, ticket 0."""

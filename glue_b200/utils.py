@@ -68,6 +68,9 @@ class _Settings:
         # activation + BatchNorm + dropout of the data encoders' hidden blocks in one launch each way
         # (the dropout masks then come from the kernel's own Philox stream, not from torch's)
         USE_FUSED_MLP=True,
+        # the whole data-encoder MLP (Linear layers included) in h_depth + 1 launches each way
+        # (training-mode minibatches of <= 128 cells, layer widths <= 256; needs USE_FUSED_MLP)
+        USE_FUSED_ENCODER=True,
     )
 
     def __init__(self) -> None:

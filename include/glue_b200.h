@@ -339,6 +339,46 @@ int glue_act_bn_dropout_bwd(const float *z, const float *gamma, const float *sav
                             float *grad_gamma, float *grad_beta, void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * Whole data-encoder MLP (scglue/models/sc.py:62-178: h_depth x [Linear -> LeakyReLU(0.2) ->
+ * BatchNorm1d -> Dropout], then the `loc` / `std_lin` heads; forward at sc.py:136-178) -- one launch
+ * per hidden block and one for both heads, forward and backward.  B <= 128 rows, every operand width
+ * (Din, H, k_above) a multiple of 4 and <= 256, 16-byte aligned tensors; other shapes return
+ * GLUE_E_UNSUPPORTED and the caller uses the per-op path (Linear + glue_act_bn_dropout_*).
+ *
+ * glue_mlp_hidden_fwd: out = dropout(bn(leaky_relu(in W^T + bias))); gamma == NULL skips the
+ *   BatchNorm (discriminator blocks, sc.py:576-624).  z [B, H] (the Linear output), save_mean /
+ *   save_rstd [H] and keep_mask [B, H] feed the backward pass and may be NULL when no gradient is
+ *   needed.  BatchNorm state and rng_state exactly as glue_act_bn_dropout_fwd (same masks).
+ * glue_mlp_heads_fwd: loc = in Wloc^T + bloc, std = softplus(in Wstd^T + bstd) + 1e-7;
+ *   spre [B, O] = the pre-activation of std (for the backward; may be NULL).
+ * glue_mlp_heads_bwd: from d_loc, d_std [B, O]: G [B, 2 O] = [d_loc | d_std sigmoid(spre)], and
+ *   the gradients of both heads' weights [O, H] and biases [O].
+ * glue_mlp_hidden_bwd (top block first): g_above [B, k_above] is the gradient reaching the output
+ *   of the layer above this block (G of the heads, or dz of the block above) and
+ *   w_above0 / w_above1 that layer's weights ([n0, H] and [k_above - n0, H]; w_above1 NULL when
+ *   n0 == k_above): the kernel forms g_above W_above restricted to its columns, runs dropout /
+ *   BatchNorm / LeakyReLU backward and writes dz [B, H] (NULL: not needed), dW [H, Din] = dz^T in,
+ *   db, dgamma, dbeta [H].  All reductions over the batch run in a fixed order.
+ * ------------------------------------------------------------------------- */
+int glue_mlp_hidden_fwd(const float *in, int64_t ld_in, const float *W, const float *bias,
+                        const float *gamma, const float *beta, float *running_mean, float *running_var,
+                        int64_t *num_batches_tracked, uint64_t *rng_state, int64_t B, int32_t Din,
+                        int32_t H, float negative_slope, float eps, float momentum, float p_drop, float *z,
+                        float *out, float *save_mean, float *save_rstd, uint8_t *keep_mask, void *stream);
+int glue_mlp_heads_fwd(const float *in, int64_t ld_in, const float *Wloc, const float *bloc,
+                       const float *Wstd, const float *bstd, int64_t B, int32_t H, int32_t O, float *loc,
+                       float *std, float *spre, void *stream);
+int glue_mlp_heads_bwd(const float *h, int64_t ld_h, const float *d_loc, const float *d_std,
+                       const float *spre, int64_t B, int32_t H, int32_t O, float *G, float *dWloc,
+                       float *dbloc, float *dWstd, float *dbstd, void *stream);
+int glue_mlp_hidden_bwd(const float *g_above, int32_t k_above, const float *w_above0,
+                        const float *w_above1, int32_t n0, const float *z, const float *gamma,
+                        const float *save_mean, const float *save_rstd, const uint8_t *keep_mask,
+                        const float *in, int64_t ld_in, int32_t Din, int64_t B, int32_t H,
+                        float negative_slope, float p_drop, float *dz, float *dW, float *db, float *dgamma,
+                        float *dbeta, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * Diagnostic: run `nk` tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate,
  * M = 128) steps on caller-built shared-memory operand images and return the
  * accumulator tile out[128][N].  a_img / b_img are device buffers copied

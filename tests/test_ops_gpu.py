@@ -636,3 +636,134 @@ def test_act_bn_dropout_masks(ops):
     assert torch.equal(keep, keep_c)
     # columns and rows are not correlated in an obvious way
     assert abs(keep.float().mean(0).std().item() - (p * (1 - p) / B) ** 0.5) < 0.01
+
+
+# ------------------------------------------------------------------ whole data-encoder MLP
+def _make_encoders(in_dim, h_dim, depth, p, n):
+    """``n`` data encoders with identical weights (non-trivial BatchNorm affine and running statistics)."""
+    from glue_b200.models import sc
+    torch.manual_seed(in_dim + h_dim + depth)
+    encs = [sc.VanillaDataEncoder(in_dim, 50, h_depth=depth, h_dim=h_dim, dropout=p)]
+    with torch.no_grad():
+        for i in range(depth):
+            bn = getattr(encs[0], f"bn_{i}")
+            bn.weight.copy_(torch.rand(h_dim) + 0.5), bn.bias.copy_(torch.randn(h_dim) * 0.3)
+            bn.running_mean.copy_(torch.randn(h_dim) * 0.1)
+    for _ in range(n - 1):
+        other = sc.VanillaDataEncoder(in_dim, 50, h_depth=depth, h_dim=h_dim, dropout=p)
+        other.load_state_dict(encs[0].state_dict())
+        encs.append(other)
+    return encs
+
+
+def _encoder_run(enc, x, wl, ws):
+    u, _ = enc(x, x)
+    loss = (u.mean * wl).sum() + (u.stddev * ws).sum()
+    names = [n for n, _ in enc.named_parameters()]
+    grads = torch.autograd.grad(loss, [p for _, p in enc.named_parameters()])
+    return u.mean, u.stddev, dict(zip(names, grads))
+
+
+def _assert_encoder_grads(got, want, tol=1e-4):
+    for name in want:
+        if name.startswith("linear_") and name.endswith(".bias"):
+            # a bias in front of BatchNorm has gradient zero up to rounding (the batch mean removes it):
+            # compared on the scale of the layer's weight gradient
+            scale = want[name.replace(".bias", ".weight")].abs().max().item()
+            assert (got[name].cpu() - want[name].cpu()).abs().max().item() <= tol * scale, f"d / d {name}"
+        else:
+            assert_close(got[name], want[name], tol, f"d / d {name}")
+
+
+@pytest.mark.parametrize("B,in_dim,h_dim,depth", [(128, 100, 256, 2), (77, 100, 256, 2), (128, 52, 64, 1),
+                                                  (128, 256, 256, 3), (8, 100, 32, 2)])
+def test_fused_encoder_mlp_vs_torch_modules(ops, B, in_dim, h_dim, depth):
+    """Whole-MLP kernels (3 launches each way) against the reference formulation with torch modules on the
+    CPU (scglue/models/sc.py:136-178), dropout off: outputs, every parameter gradient, BatchNorm state."""
+    from glue_b200.utils import config
+    ref, enc = _make_encoders(in_dim, h_dim, depth, 0.0, 2)
+    enc = enc.to(DEV)
+    gen = torch.Generator().manual_seed(B)
+    x = torch.randn(B, in_dim, generator=gen)
+    wl, ws = torch.randn(B, 50, generator=gen), torch.randn(B, 50, generator=gen)
+    want = _encoder_run(ref, x, wl, ws)
+    launches = ops.kernel_launches()
+    assert config.USE_FUSED_ENCODER
+    got = _encoder_run(enc, x.to(DEV), wl.to(DEV), ws.to(DEV))
+    assert ops.kernel_launches() - launches == 2 * (depth + 1), "h_depth + 1 launches each way"
+    assert_close(got[0], want[0], 1e-5, "loc")
+    assert_close(got[1], want[1], 1e-5, "std")
+    _assert_encoder_grads(got[2], want[2])
+    for i in range(depth):
+        a, b = getattr(enc, f"bn_{i}"), getattr(ref, f"bn_{i}")
+        assert_close(a.running_mean, b.running_mean, 1e-5, "running_mean")
+        assert_close(a.running_var, b.running_var, 1e-5, "running_var")
+        assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+    again = _encoder_run(_make_encoders(in_dim, h_dim, depth, 0.0, 1)[0].to(DEV), x.to(DEV), wl.to(DEV), ws.to(DEV))
+    assert torch.equal(again[0], got[0]) and all(torch.equal(again[2][n], got[2][n]) for n in got[2]), \
+        "fixed-order reductions: bit-reproducible"
+
+
+def _encoder_fp64(enc, x, keeps, p, wl, ws):
+    """float64 restatement of the encoder forward under given keep masks; returns loc, std, parameter gradients."""
+    import torch.nn.functional as F
+    params = {n: q.detach().double().requires_grad_(True) for n, q in enc.named_parameters()}
+    h = x.double()
+    for i, keep in enumerate(keeps):
+        bn = getattr(enc, f"bn_{i}")
+        a = F.leaky_relu(h @ params[f"linear_{i}.weight"].T + params[f"linear_{i}.bias"], 0.2)
+        y = (a - a.mean(0)) / torch.sqrt(a.var(0, unbiased=False) + bn.eps)
+        h = (y * params[f"bn_{i}.weight"] + params[f"bn_{i}.bias"]) * keep.double() / (1 - p)
+    loc = h @ params["loc.weight"].T + params["loc.bias"]
+    std = F.softplus(h @ params["std_lin.weight"].T + params["std_lin.bias"]) + 1e-7
+    grads = torch.autograd.grad((loc * wl.double()).sum() + (std * ws.double()).sum(), list(params.values()))
+    return loc, std, dict(zip(params, grads))
+
+
+@pytest.mark.parametrize("B", [128, 100])
+def test_fused_encoder_mlp_with_dropout(ops, B, monkeypatch):
+    """With dropout on, the fused kernels and the per-op path (torch Linear + the hidden-block kernel) draw the
+    same Philox masks from the same state.  Under those masks the fused outputs and gradients match a float64
+    restatement to 1e-4 (the per-op path, cuBLAS products, is checked against the same restatement), the call
+    counters advance alike; under no_grad (discriminator pass) the fused path gives the same values."""
+    from glue_b200.utils import config
+    p = 0.2
+    fused, per_op = (e.to(DEV) for e in _make_encoders(100, 256, 2, p, 2))
+    dev = torch.device(DEV)
+    for i in range(2):  # same seeds
+        per_op._dropout_state(i, dev).copy_(fused._dropout_state(i, dev))
+    gen = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 100, generator=gen).to(DEV)
+    wl, ws = torch.randn(B, 50, generator=gen).to(DEV), torch.randn(B, 50, generator=gen).to(DEV)
+    for step in range(2):
+        keeps = []
+        for i in range(2):  # the masks of this call: a function of (seed, call, row, column) only
+            state = fused._dropout_state(i, dev).clone()
+            keeps.append(ops.act_bn_dropout(torch.zeros(B, 256, device=DEV), torch.nn.BatchNorm1d(256).to(DEV), p,
+                                            state, return_aux=True)[3])
+        ref = _encoder_fp64(fused, x, keeps, p, wl, ws)
+        got = _encoder_run(fused, x, wl, ws)
+        monkeypatch.setattr(config, "USE_FUSED_ENCODER", False)
+        other = _encoder_run(per_op, x, wl, ws)
+        monkeypatch.setattr(config, "USE_FUSED_ENCODER", True)
+        ref_g = {n: g.float() for n, g in ref[2].items()}
+        assert_close(got[0], ref[0].float(), 1e-5, "loc")
+        assert_close(got[1], ref[1].float(), 1e-5, "std")
+        _assert_encoder_grads(got[2], ref_g)
+        # (the per-op path: same masks, hence the same values; its cuBLAS weight gradients are only good to a
+        # few 1e-4 of the float64 result at B = 100, the fused kernels to 1e-6)
+        assert_close(other[0], ref[0].float(), 1e-5, "per-op loc")
+        _assert_encoder_grads(other[2], ref_g, tol=3e-3)
+        for i in range(2):
+            assert fused._dropout_state(i, dev).tolist() == per_op._dropout_state(i, dev).tolist()
+    with torch.no_grad():
+        u_f, _ = fused(x, x)
+        monkeypatch.setattr(config, "USE_FUSED_ENCODER", False)
+        u_p, _ = per_op(x, x)
+    assert_close(u_f.mean, u_p.mean, 1e-5, "loc under no_grad")
+    assert_close(u_f.stddev, u_p.stddev, 1e-5, "std under no_grad")
+    fused.eval()  # BatchNorm on its running statistics: the torch modules take over
+    monkeypatch.setattr(config, "USE_FUSED_ENCODER", True)
+    launches = ops.kernel_launches()
+    fused(x, x)
+    assert ops.kernel_launches() == launches
