@@ -29,6 +29,7 @@
 //   C (16 x 8):       c0 (g, 2 t)  c1 (g, 2 t + 1)  c2 (g + 8, 2 t)  c3 (g + 8, 2 t + 1)
 #include "common.cuh"
 #include "philox.cuh"
+#include "tc_common.cuh"
 
 namespace glue {
 namespace {
@@ -65,33 +66,43 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// small terms first
-__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t bb0,
-                                       uint32_t bb1, uint32_t bs0, uint32_t bs1) {
-    mma_tf32(c, as, bb0, bb1);
-    mma_tf32(c, ab, bs0, bs1);
-    mma_tf32(c, ab, bb0, bb1);
-}
-
-// rows [0, rows_pad) x k floats (k4 of them copied, the rest zeros) into dst[row][ld]; row r from row_ptr(r);
-// 4 threads per row, 128 rows per sweep
+// rows [0, 128) x k floats into dst[row][ld]: the first n_rows rows come from row_ptr(r) as ONE bulk copy each
+// (cp.async.bulk, k4 floats, completing on `bar`; a first version issued 16-byte cp.async and spent 4 k cycles on
+// issuing them), the padding columns [k4, k) and the rows beyond n_rows are zero-filled with plain stores.
+// Every thread then waits on `bar` (phase `parity`).  `reuse`: the destination was read through the generic proxy
+// before (the caller has synchronised the CTA): order those reads before the asynchronous writes.
 template <typename RowPtr>
-__device__ __forceinline__ void stage_rows(float* dst, int ld, int k4, int k, int rows_pad, RowPtr row_ptr) {
-    const int q4 = k >> 2, qc = k4 >> 2;
-    for (int r = threadIdx.x >> 2; r < rows_pad; r += MF_THREADS / 4) {
-        const float* src = row_ptr(r);
+__device__ __forceinline__ void stage_rows(float* dst, int ld, int k4, int k, int n_rows, RowPtr row_ptr, uint64_t* bar,
+                                           bool reuse) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)n_rows * (uint32_t)k4 * 4u);
+    if (lane < 8) {  // row = 16 lane + warp: 8 copies per warp (a warp issues its bulk copies one lane at a time)
+        const int r = 16 * lane + warp;
         float* d = dst + r * ld;
-        for (int q = threadIdx.x & 3; q < q4; q += 4) {
-            if (src != nullptr && q < qc)
-                cp_async16(d + 4 * q, src + 4 * q);
-            else
-                *reinterpret_cast<float4*>(d + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n_rows) {
+            if (reuse) tc::fence_proxy_async();
+            tc::bulk_load(d, row_ptr(r), (uint32_t)k4 * 4u, bar);
+        } else {
+            for (int q = 0; q < k; q += 4) *reinterpret_cast<float4*>(d + q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    } else if (lane < 16 && k > k4) {
+        const int r = 16 * (lane - 8) + warp;
+        if (r < n_rows)
+            for (int q = k4; q < k; q += 4) *reinterpret_cast<float4*>(dst + r * ld + q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+__device__ __forceinline__ void init_bar(uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
 }
 
 // C[16 wr + {g, g + 8}][8 nt + {2 t, 2 t + 1}] += sum_k A[row][k] Bt[col][k] over the 8-wide steps [s_begin, s_end);
-// A fp32 [128][ld] split on the fly, Bt pre-split TF32 big / small [16][ld]
+// A fp32 [128][ld] split on the fly, Bt pre-split TF32 big / small [16][ld].  The three TF32 products of an fp32
+// product go to three accumulators (one dependent mma per step and accumulator instead of three); the two small
+// ones are added first, then the big one.
 __device__ __forceinline__ void gemm_mma(const float* __restrict__ As, const uint32_t* __restrict__ Bb,
                                          const uint32_t* __restrict__ Bs, int ld, int s_begin, int s_end, int wr, int lane,
                                          float (&c)[2][4]) {
@@ -100,6 +111,11 @@ __device__ __forceinline__ void gemm_mma(const float* __restrict__ As, const uin
     const float* a_hi = a_lo + 8 * ld;
     const uint32_t* bb = Bb + g * ld + t;
     const uint32_t* bs = Bs + g * ld + t;
+    float c1[2][4], c2[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c1[nt][e] = 0.f, c2[nt][e] = 0.f;
 #pragma unroll 4
     for (int s = s_begin; s < s_end; ++s) {
         const int k0 = 8 * s;
@@ -111,9 +127,15 @@ __device__ __forceinline__ void gemm_mma(const float* __restrict__ As, const uin
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
             const int o = 8 * nt * ld + k0;
-            mma_3x(c[nt], ab, as, bb[o], bb[o + 4], bs[o], bs[o + 4]);
+            mma_tf32(c1[nt], as, bb[o], bb[o + 4]);
+            mma_tf32(c2[nt], ab, bs[o], bs[o + 4]);
+            mma_tf32(c[nt], ab, bb[o], bb[o + 4]);
         }
     }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[nt][e] += c1[nt][e] + c2[nt][e];
 }
 
 // The two warps that share a row block (w and w ^ 8) each hold a partial 16 x 16 tile over half of the reduction
@@ -136,6 +158,11 @@ __device__ __forceinline__ void wgrad_mma(const float* __restrict__ Gs, const fl
                                           int warp, int lane, float (&c)[2][4]) {
     const int g = lane >> 2, t = lane & 3;
     if (warp >= n_tiles) return;
+    float c1[2][4], c2[2][4];  // (the two small TF32 products: independent accumulators, as in gemm_mma)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c1[q][e] = 0.f, c2[q][e] = 0.f;
 #pragma unroll 2
     for (int k0 = 0; k0 < MF_ROWS; k0 += 8) {
         uint32_t ab[4], as[4];
@@ -150,10 +177,16 @@ __device__ __forceinline__ void wgrad_mma(const float* __restrict__ Gs, const fl
                 uint32_t bb0, bs0, bb1, bs1;
                 split_tf32(In[(k0 + t) * ld + 8 * nt + g], bb0, bs0);
                 split_tf32(In[(k0 + t + 4) * ld + 8 * nt + g], bb1, bs1);
-                mma_3x(c[q], ab, as, bb0, bb1, bs0, bs1);
+                mma_tf32(c1[q], as, bb0, bb1);
+                mma_tf32(c2[q], ab, bs0, bs1);
+                mma_tf32(c[q], ab, bb0, bb1);
             }
         }
     }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[q][e] += c1[q][e] + c2[q][e];
 }
 
 // column totals over the 128 rows of per-thread partials v[j] (columns 8 (j >> 1) + 2 t + (j & 1)): lanes of a warp
@@ -241,8 +274,10 @@ __device__ __forceinline__ void stage_split(uint32_t* Bb, uint32_t* Bs, int ld, 
     }
 }
 
-// shared-memory carve-up of the forward kernels: A [128][ld] | Bt big, small [16][ld] each | exchange | red
+// shared-memory carve-up of the forward kernels: barrier (16 B) | A [128][ld] | Bt big, small [16][ld] each |
+// exchange | red
 struct FwdSmem {
+    uint64_t* bar;
     float* As;
     uint32_t *Bb, *Bs;
     float (*xch)[32][4];
@@ -250,14 +285,15 @@ struct FwdSmem {
 };
 __device__ __forceinline__ FwdSmem carve_fwd(float* smem, int ld) {
     FwdSmem S;
-    S.As = smem;
+    S.bar = reinterpret_cast<uint64_t*>(smem);
+    S.As = smem + 4;
     S.Bb = reinterpret_cast<uint32_t*>(S.As + MF_ROWS * ld);
     S.Bs = S.Bb + MF_COLS * ld;
     S.xch = reinterpret_cast<float(*)[32][4]>(S.Bs + MF_COLS * ld);
     S.red = reinterpret_cast<float(*)[MF_COLS]>(S.xch + MF_THREADS / 32);
     return S;
 }
-constexpr int MF_AUX_FLOATS = (MF_THREADS / 32) * (32 * 4 + MF_COLS);  // exchange + red
+constexpr int MF_AUX_FLOATS = 4 + (MF_THREADS / 32) * (32 * 4 + MF_COLS);  // barrier + exchange + red
 
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const HidFwd a) {
     extern __shared__ __align__(16) float smem[];
@@ -266,14 +302,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
-    stage_rows(S.As, ld, a.Din, k, MF_ROWS, [&](int r) { return r < a.B ? a.in + (long long)r * a.ld_in : nullptr; });
-    cp_async_commit();
+    init_bar(S.bar);
+    stage_rows(S.As, ld, a.Din, k, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, S.bar, false);
     stage_split(S.Bb, S.Bs, ld, a.Din, k,
                 [&](int r) { return c0 + r < a.H ? a.W + (long long)(c0 + r) * a.Din : nullptr; });
     // per-column parameters of my 4 columns (requested before the product is waited for)
     bool cok[4];
     int col[4];
-    float bias[4], gam[4], bet[4];
+    float bias[4], gam[4], bet[4], rmean[4], rvar[4];
+    const bool stat_writer = warp == 0 && g == 0;  // lanes 0 .. 3 of warp 0: the 16 columns
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         col[j] = c0 + 8 * (j >> 1) + 2 * t + (j & 1);
@@ -281,11 +318,13 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
         bias[j] = cok[j] ? a.bias[col[j]] : 0.f;
         gam[j] = (cok[j] && a.gamma) ? a.gamma[col[j]] : 0.f;
         bet[j] = (cok[j] && a.gamma) ? a.beta[col[j]] : 0.f;
+        rmean[j] = (stat_writer && cok[j] && a.running_mean) ? a.running_mean[col[j]] : 0.f;
+        rvar[j] = (stat_writer && cok[j] && a.running_var) ? a.running_var[col[j]] : 0.f;
     }
     const bool drop = a.p > 0.f && a.rng != nullptr;
     unsigned long long seed = 0, call = 0;
     if (drop) seed = a.rng[0], call = a.rng[1];
-    cp_async_wait<0>();
+    tc::mbar_wait(S.bar, 0);
     __syncthreads();
     float acc[2][4];
 #pragma unroll
@@ -320,13 +359,12 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
         for (int j = 0; j < 4; ++j) {
             const float var = q[j] * invB;
             const float rstd = rsqrtf(var + a.eps);
-            if (warp == 0 && g == 0 && cok[j]) {
+            if (stat_writer && cok[j]) {  // (the old running statistics were requested before the product)
                 if (a.save_mean) a.save_mean[col[j]] = s[j], a.save_rstd[col[j]] = rstd;
-                if (a.running_mean)
-                    a.running_mean[col[j]] = fmaf(a.momentum, s[j] - a.running_mean[col[j]], a.running_mean[col[j]]);
+                if (a.running_mean) a.running_mean[col[j]] = fmaf(a.momentum, s[j] - rmean[j], rmean[j]);
                 if (a.running_var) {
                     const float unbiased = a.B > 1 ? var * ((float)a.B / (float)(a.B - 1)) : var;
-                    a.running_var[col[j]] = fmaf(a.momentum, unbiased - a.running_var[col[j]], a.running_var[col[j]]);
+                    a.running_var[col[j]] = fmaf(a.momentum, unbiased - rvar[j], rvar[j]);
                 }
             }
             y[j] = fmaf(y[j] - s[j], gam[j] * rstd, bet[j]);
@@ -378,15 +416,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_fwd_kernel(const Head
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
-    stage_rows(S.As, ld, a.H, k, MF_ROWS, [&](int r) { return r < a.B ? a.in + (long long)r * a.ld_in : nullptr; });
-    cp_async_commit();
+    init_bar(S.bar);
+    stage_rows(S.As, ld, a.H, k, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, S.bar, false);
     stage_split(S.Bb, S.Bs, ld, a.H, k, [&](int r) -> const float* {
         const int c = c0 + r;
         if (c < a.O) return a.Wloc + (long long)c * a.H;
         if (c < 2 * a.O) return a.Wstd + (long long)(c - a.O) * a.H;
         return nullptr;
     });
-    cp_async_wait<0>();
+    tc::mbar_wait(S.bar, 0);
     __syncthreads();
     float acc[2][4];
 #pragma unroll
@@ -447,12 +485,13 @@ struct HeadBwd {
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_bwd_kernel(const HeadBwd a) {
     extern __shared__ __align__(16) float smem[];
     const int k = round8(a.H), ld = pitch8(k);
-    float* In = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    float* In = smem + 4;
     float* Gs = In + MF_ROWS * ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c0 = blockIdx.x * MF_COLS;
-    stage_rows(In, ld, a.H, k, MF_ROWS, [&](int r) { return r < a.B ? a.h + (long long)r * a.ld_h : nullptr; });
-    cp_async_commit();
+    init_bar(bar);
+    stage_rows(In, ld, a.H, k, a.B, [&](int r) { return a.h + (long long)r * a.ld_h; }, bar, false);
 #pragma unroll
     for (int m = 0; m < MF_ROWS * MF_COLS / MF_THREADS; ++m) {
         const int idx = tid + m * MF_THREADS;
@@ -470,7 +509,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_bwd_kernel(const Head
         }
         Gs[r * MF_GS_LD + cl] = v;
     }
-    cp_async_wait<0>();
+    tc::mbar_wait(bar, 0);
     __syncthreads();
     float acc[2][4];
 #pragma unroll
@@ -519,7 +558,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
     extern __shared__ __align__(16) float smem[];
     const int ka = round8(a.Kab), lda = pitch4(ka), ki = round8(a.Din), ldi = pitch8(ki), k8 = ka >> 3;
     const int a_floats = MF_ROWS * (lda > ldi ? lda : ldi);
-    float* As = smem;  // G_above, later this block's input
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    float* As = smem + 4;  // G_above, later this block's input
     uint32_t* Bb = reinterpret_cast<uint32_t*>(As + a_floats);  // W_above[:, columns of this CTA], transposed, split
     uint32_t* Bs = Bb + MF_COLS * lda;
     float* Gs = reinterpret_cast<float*>(Bs + MF_COLS * lda);  // dz slab [128][MF_GS_LD]
@@ -528,8 +568,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
-    stage_rows(As, lda, a.Kab, ka, MF_ROWS, [&](int r) { return r < a.B ? a.Gab + (long long)r * a.Kab : nullptr; });
-    cp_async_commit();
+    init_bar(bar);
+    stage_rows(As, lda, a.Kab, ka, a.B, [&](int r) { return a.Gab + (long long)r * a.Kab; }, bar, false);
     // Bt[o][j] = W_above[j][c0 + o] (64-byte runs along o), zero beyond Kab; loads first, then split + store
     {
         constexpr int PER = MF_KMAX * MF_COLS / MF_THREADS;  // 8
@@ -572,7 +612,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
         rstd[j] = bn ? a.save_rstd[col[j]] : 0.f;
         gam[j] = bn ? a.gamma[col[j]] : 0.f;
     }
-    cp_async_wait<0>();
+    tc::mbar_wait(bar, 0);
     __syncthreads();
     float acc[2][4];
 #pragma unroll
@@ -624,9 +664,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
             if (cok[j] && a.db) a.db[col[j]] = sdz[j];
     }
     // weight gradient: dW[c0 + o][i] = sum_r dz[r][o] in[r][i]
-    stage_rows(As, ldi, a.Din, ki, MF_ROWS, [&](int r) { return r < a.B ? a.in + (long long)r * a.ld_in : nullptr; });
-    cp_async_commit();
-    cp_async_wait<0>();
+    stage_rows(As, ldi, a.Din, ki, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, bar, true);
+    tc::mbar_wait(bar, 1);
     __syncthreads();
     float wacc[2][4];
 #pragma unroll
@@ -696,7 +735,7 @@ extern "C" int glue_mlp_heads_bwd(const float* h, int64_t ld_h, const float* d_l
     HeadBwd a;
     a.h = h, a.ld_h = ld_h, a.d_loc = d_loc, a.d_std = d_std, a.spre = spre, a.G = G;
     a.dWloc = dWloc, a.dbloc = dbloc, a.dWstd = dWstd, a.dbstd = dbstd, a.B = (int)B, a.H = H, a.O = O;
-    const size_t smem = ((size_t)MF_ROWS * pitch8(round8(H)) + (size_t)MF_ROWS * MF_GS_LD) * sizeof(float);
+    const size_t smem = (4 + (size_t)MF_ROWS * pitch8(round8(H)) + (size_t)MF_ROWS * MF_GS_LD) * sizeof(float);
     GLUE_SMEM_ONCE(mlp_heads_bwd_kernel, 227 * 1024);
     mlp_heads_bwd_kernel<<<(2 * O + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
     GLUE_CHECK_LAUNCH();
@@ -723,7 +762,7 @@ extern "C" int glue_mlp_hidden_bwd(const float* g_above, int32_t k_above, const 
     a.B = (int)B, a.H = H, a.slope = negative_slope, a.p = p_drop;
     const int lda = pitch4(round8(k_above)), ldi = pitch8(round8(Din));
     const size_t smem = ((size_t)MF_ROWS * (lda > ldi ? lda : ldi) + (size_t)2 * MF_COLS * lda +
-                         (size_t)MF_ROWS * MF_GS_LD + MF_AUX_FLOATS) * sizeof(float);
+                         (size_t)MF_ROWS * MF_GS_LD + MF_AUX_FLOATS) * sizeof(float);  // (the 4 barrier words included)
     if (smem > 227 * 1024) return GLUE_E_UNSUPPORTED;
     GLUE_SMEM_ONCE(mlp_hidden_bwd_kernel, 227 * 1024);
     mlp_hidden_bwd_kernel<<<(H + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
