@@ -106,6 +106,8 @@ class SCGLUETrainer(GLUETrainer):
         self.graphs = StepGraphs(self)
         self._side_streams: List[torch.cuda.Stream] = []
         self._dsc_stream: Optional[torch.cuda.Stream] = None
+        self._nll_stream: Optional[torch.cuda.Stream] = None
+        self._nll_pending = False
         self.capturing = False
         self.anneal_buffer = torch.zeros((), dtype=torch.float32, device=net.device)
 
@@ -274,8 +276,35 @@ class SCGLUETrainer(GLUETrainer):
             v = g2v(self.eidx, self.enorm, self.esgn)
             vsamp = v.mean + self.noise(v.mean, "v") * v.stddev
             g_kl = _kl_to_prior(v, prior) / vsamp.shape[0]
-        g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+        g_nll = self._graph_nll(vsamp, eidx, esgn, ewt)
         return vsamp, g_nll, g_kl
+
+    def _graph_nll(self, vsamp, eidx, esgn, ewt):
+        r"""Edge reconstruction term (``scglue.py:331-338``).  Only the objective's last line reads it,
+        while the data decoders wait for ``vsamp``: it is issued on a stream of its own, forked where
+        ``vsamp`` is complete, so that the branch that produced ``vsamp`` can be joined -- and the
+        decoders can start -- without waiting for the edge kernels and the incidence sort of their
+        backward pass.  ``_join_graph_nll`` is called before the value is read."""
+        net = self.net
+        device = net.device
+        if device.type != "cuda" or not config.MULTI_STREAM:
+            return net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+        if self._nll_stream is None:
+            self._nll_stream = torch.cuda.Stream(device)
+        side = self._nll_stream
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            vsamp.record_stream(side)
+            g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+        self._nll_pending = True
+        return g_nll
+
+    def _join_graph_nll(self, g_nll):
+        if self._nll_pending:
+            cur = torch.cuda.current_stream(self.net.device)
+            cur.wait_stream(self._nll_stream)
+            g_nll.record_stream(cur)
+            self._nll_pending = False
 
     def _data_nll(self, k: str, usamp, vsamp, xbch, l, x, reduce: str,
                   row_weight: Optional[torch.Tensor] = None,
@@ -348,6 +377,15 @@ class SCGLUETrainer(GLUETrainer):
         # parameters and run as ONE fused launch sequence (the feature table is staged once, the
         # observations are read from HBM once); the modalities run side by side, so the small one
         # (16 CTAs for 2 000 genes) fills the SMs that the tail of the large one leaves idle
+        # the alignment term needs the encoders' posteriors and the updated discriminator, not the
+        # decoders: issued on the discriminator stream (behind the update), it runs beside them
+        main = torch.cuda.current_stream(net.device) if net.device.type == "cuda" else None
+        if dsc_stream is not None:
+            dsc_stream.wait_stream(main)
+            with torch.cuda.stream(dsc_stream):
+                for k in net.keys:
+                    u[k].mean.record_stream(dsc_stream)
+                u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
         self._prepare_extra(usamp)
         results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
         x_nll, self._extra_parts = {}, {k: {} for k in net.keys}
@@ -358,9 +396,12 @@ class SCGLUETrainer(GLUETrainer):
                 else:
                     parts = self._extra_parts[k]
                     parts[kind] = res if kind not in parts else parts[kind] + res
-        if dsc_stream is not None:  # the alignment term needs the updated discriminator
-            torch.cuda.current_stream(net.device).wait_stream(dsc_stream)
-        u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
+        if dsc_stream is not None:
+            main.wait_stream(dsc_stream)
+            u_cat.record_stream(main), dsc_loss.record_stream(main)
+        else:
+            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
+        self._join_graph_nll(g_nll)
         sup_loss = self._supervision(u_cat, xlbl)
         x_kl = {k: self._data_kl(u[k], prior, x[k].shape[1]) for k in net.keys}
         extra_comps, extra_terms = self._extra_losses(data, usamp, vsamp, l)
