@@ -125,12 +125,31 @@ class StepGraphs:
             self._capture(entry, engine, data)
             if entry["graph"] is None:
                 return tr.eager_train_step(engine, data)
-        for static, fresh in zip(entry["inputs"], data):
-            static.copy_(fresh, non_blocking=True)
+        self._load_inputs(entry["inputs"], data)
         tr.anneal_buffer.fill_(anneal)
         entry["graph"].replay()
         self.replays += 1
         return entry["outputs"]
+
+    @staticmethod
+    def _load_inputs(statics: List[torch.Tensor], data: List[torch.Tensor]) -> None:
+        r"""Minibatch -> static input buffers of the captured step.  Tensors that already live on the
+        device and are small go through one multi-tensor copy per dtype (a paired PBMC step has 14
+        inputs: as individual copies they were 60 us of launch latency in front of every replay); count
+        matrices and host tensors are copied one by one (asynchronously when pinned)."""
+        groups: Dict[torch.dtype, Any] = {}
+        for static, fresh in zip(statics, data):
+            small = static.numel() * static.element_size() <= (1 << 20)  # (large ones: the copy engine is faster)
+            if small and fresh.device == static.device and fresh.dtype == static.dtype and fresh.shape == static.shape:
+                dst, src = groups.setdefault(static.dtype, ([], []))
+                dst.append(static), src.append(fresh)
+            else:
+                static.copy_(fresh, non_blocking=True)
+        for dst, src in groups.values():
+            if len(dst) > 1:
+                torch._foreach_copy_(dst, src)
+            else:
+                dst[0].copy_(src[0], non_blocking=True)
 
     @staticmethod
     def _recover_generator(device: torch.device, state: Optional[torch.Tensor]) -> None:

@@ -140,8 +140,8 @@ class EdgeBernoulli:
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
         return -F.binary_cross_entropy_with_logits(self.logits, value, reduction="none")
 
-    def balanced_nll(self, value: torch.Tensor) -> torch.Tensor:
+    def balanced_nll(self, value: torch.Tensor, upstream: float = None) -> torch.Tensor:
         r"""Mean NLL of positive and of negative edges, averaged
         (``scglue/models/scglue.py:331-338``), fused with the gather-dot and free of
-        the reference's ``.item()`` host synchronisation."""
-        return ops.graph_nll(self.v, self.eidx, self.esgn, value)
+        the reference's ``.item()`` host synchronisation.  ``upstream``: see ``ops.graph_nll``."""
+        return ops.graph_nll(self.v, self.eidx, self.esgn, value, upstream=upstream)

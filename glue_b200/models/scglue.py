@@ -208,14 +208,13 @@ class SCGLUETrainer(GLUETrainer):
         by side; returns ``(u, l, usamp[, extra_result])``."""
         keys = self.net.keys
         thunks = [lambda k=k: self._encode_one(k, x, xrep, dsc_only) for k in keys]
-        if extra is not None:
-            thunks.append(extra)
-        out = self._parallel(thunks)
+        extras = [] if extra is None else (list(extra) if isinstance(extra, (list, tuple)) else [extra])
+        out = self._parallel(thunks + extras)
         u = {k: o[0] for k, o in zip(keys, out)}
         l = {k: o[1] for k, o in zip(keys, out)}
         usamp = {k: o[2] for k, o in zip(keys, out)}
         if extra is not None:
-            return u, l, usamp, out[len(keys)]
+            return u, l, usamp, out[len(keys)]  # (further branches are run for their side effects)
         return u, l, usamp
 
     def burnin_anneal(self, epoch: int) -> float:
@@ -259,6 +258,10 @@ class SCGLUETrainer(GLUETrainer):
         ce = F.cross_entropy(net.u2c(u_cat), xlbl_cat.clamp(min=0), reduction="none")
         return (ce * labelled).sum() / labelled.sum().clamp(min=1)
 
+    def _input_branches(self, data):
+        r"""Thunks that depend on the minibatch only; they run beside the encoders."""
+        return []
+
     def _graph_terms(self, eidx, ewt, esgn, prior):
         net = self.net
         g2v = net.g2v
@@ -287,15 +290,18 @@ class SCGLUETrainer(GLUETrainer):
         backward pass.  ``_join_graph_nll`` is called before the value is read."""
         net = self.net
         device = net.device
+        # inside a training step the term's coefficient in gen_loss is known: its gradient is computed with
+        # the forward kernels (see ``ops.graph_nll``), off the critical path of the backward pass
+        up = self.lam_graph * len(net.keys) if device.type == "cuda" else None
         if device.type != "cuda" or not config.MULTI_STREAM:
-            return net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+            return net.v2g(vsamp, eidx, esgn).balanced_nll(ewt, upstream=up)
         if self._nll_stream is None:
             self._nll_stream = torch.cuda.Stream(device)
         side = self._nll_stream
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             vsamp.record_stream(side)
-            g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt)
+            g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt, upstream=up)
         self._nll_pending = True
         return g_nll
 
@@ -371,7 +377,7 @@ class SCGLUETrainer(GLUETrainer):
         # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
         # the data encoders: it runs beside them
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
-            x, xrep, dsc_only, extra=lambda: self._graph_terms(eidx, ewt, esgn, prior))
+            x, xrep, dsc_only, extra=[lambda: self._graph_terms(eidx, ewt, esgn, prior)] + self._input_branches(data))
         # one stream per modality: the reconstruction term and, for paired data, the joint-cross /
         # real-cross terms of a modality share its observations, feature embeddings and decoder
         # parameters and run as ONE fused launch sequence (the feature table is staged once, the
@@ -407,7 +413,7 @@ class SCGLUETrainer(GLUETrainer):
         extra_comps, extra_terms = self._extra_losses(data, usamp, vsamp, l)
         # nothing that carries an autograd graph may outlive the step on `self`: it would keep
         # this step's AccumulateGrad nodes (bound to the current streams) alive into a capture
-        self._extra_parts = self._shared_extra = None
+        self._extra_parts = self._shared_extra = self._pair_w = None
 
         # The objective and every reported term are fixed linear combinations of a dozen scalar
         # components (``scglue.py:349-376``; paired terms ``scglue.py:654-672``).  Evaluated one
@@ -593,6 +599,26 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         return super().compute_losses((x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn),
                                       epoch, dsc_only=dsc_only, dsc_update=dsc_update)
 
+    def _input_branches(self, data):
+        return [lambda: self._pair_weights(data[0])]
+
+    def _pair_weights(self, x) -> None:
+        r"""Per-cell weights ``mask / (n_masked * n_features)`` of the joint-cross and real-cross terms
+        (see :meth:`_extra_terms_for`).  They depend on the pairing mask only -- a dozen tiny launches
+        that used to sit between the encoders and the decoders: computed beside the encoders instead."""
+        keys = self.net.keys
+        pf = self._pmsk.T.to(torch.float32)
+        weight = lambda maskf, k: maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
+        table = {}
+        for i, k in enumerate(keys):
+            if self.lam_joint_cross:
+                table[(i,)] = weight(pf[i], k)
+            if self.lam_real_cross:
+                for j in range(len(keys)):
+                    if i != j:
+                        table[(i, j)] = weight(pf[i] * pf[j], k)
+        self._pair_w = table
+
     def _prepare_extra(self, usamp) -> None:
         self._shared_extra = self._umean(usamp)
 
@@ -634,14 +660,16 @@ class PairedSCGLUETrainer(SCGLUETrainer):
         keys = net.keys
         i = keys.index(k)
         _, umean, pf, _ = self._shared_extra
-        weight = lambda maskf: maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
+        table = getattr(self, "_pair_w", None) or {}
+        weight = lambda maskf, key: table[key] if key in table else \
+            maskf / (maskf.sum().clamp(min=1.0) * x[k].shape[1])
         terms = []
         if self.lam_joint_cross:
-            terms.append(("joint", umean, weight(pf[i]), self.lam_joint_cross * self.modality_weight[k]))
+            terms.append(("joint", umean, weight(pf[i], (i,)), self.lam_joint_cross * self.modality_weight[k]))
         if self.lam_real_cross:
             for j, ks in enumerate(keys):
                 if i != j:
-                    terms.append(("real", usamp[ks], weight(pf[i] * pf[j]),
+                    terms.append(("real", usamp[ks], weight(pf[i] * pf[j], (i, j)),
                                   self.lam_real_cross * self.modality_weight[k]))
         return terms
 

@@ -599,9 +599,23 @@ def _graphdec_ws(n_edges: int, vnum: int, device) -> torch.Tensor:
     return _workspace(_lib.lib().glue_graphdec_workspace_bytes(n_edges, vnum), device)
 
 
+_UPSTREAM_SCALARS: dict = {}
+
+
+def _upstream_scalar(value: float, device) -> torch.Tensor:
+    """Device scalar holding a loss coefficient (cached: inside a captured step no tensor is built)."""
+    key = (float(value), str(device))
+    hit = _UPSTREAM_SCALARS.get(key)
+    if hit is None:
+        if len(_UPSTREAM_SCALARS) > 64:
+            _UPSTREAM_SCALARS.clear()
+        hit = _UPSTREAM_SCALARS[key] = torch.full((), float(value), dtype=torch.float32, device=device)
+    return hit
+
+
 class _GraphNllFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, v, eidx, esgn, ewt, grad_enabled):
+    def forward(ctx, v, eidx, esgn, ewt, grad_enabled, upstream):
         dev = v.device
         n_edges, (vnum, k) = eidx.shape[1], v.shape
         loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -617,12 +631,24 @@ class _GraphNllFn(torch.autograd.Function):
             ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), n_edges, vnum, k, ptr(loss),
             ptr(coef) if need_grad else None, 1 if need_grad else 0, ptr(ws), ws.numel(),
             current_stream(dev)), "graph_nll_fwd")
-        if need_grad:
+        ctx.eager = None
+        if need_grad and upstream is not None:
+            # the coefficient of this term in the differentiated objective is known: its gradient is
+            # computed here, beside the forward pass of everything else, and handed over as it is
+            grad_v = torch.empty_like(v)
+            check(_lib.lib().glue_graph_nll_bwd(
+                ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), ptr(coef), ptr(upstream), n_edges, vnum, k, ptr(grad_v),
+                ptr(ws), ws.numel(), current_stream(dev)), "graph_nll_bwd")
+            ctx.eager = grad_v
+        elif need_grad:
             ctx.save_for_backward(v, eidx, esgn, ewt, coef, ws)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.eager is not None:
+            grad_v, ctx.eager = ctx.eager, None
+            return grad_v, None, None, None, None, None
         v, eidx, esgn, ewt, coef, ws = ctx.saved_tensors
         dev = v.device
         n_edges, (vnum, k) = eidx.shape[1], v.shape
@@ -631,7 +657,7 @@ class _GraphNllFn(torch.autograd.Function):
         check(_lib.lib().glue_graph_nll_bwd(
             ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), ptr(coef), ptr(up), n_edges, vnum, k, ptr(grad_v),
             ptr(ws), ws.numel(), current_stream(dev)), "graph_nll_bwd")
-        return grad_v, None, None, None, None
+        return grad_v, None, None, None, None, None
 
 
 class _GraphLogitsFn(torch.autograd.Function):
@@ -675,11 +701,18 @@ def _graph_args(v, eidx, esgn, ewt=None):
     return v, eidx, esgn, ewt
 
 
-def graph_nll(v, eidx, esgn, ewt) -> torch.Tensor:
+def graph_nll(v, eidx, esgn, ewt, upstream: Optional[float] = None) -> torch.Tensor:
     r"""Balanced Bernoulli NLL of the sampled edges -- replaces ``GraphDecoder.forward``
     + ``Bernoulli.log_prob`` + the pos/neg averaging of ``scglue/models/scglue.py:331-338``
-    (without its ``.item()`` host sync)."""
-    return _GraphNllFn.apply(*_graph_args(v, eidx, esgn, ewt), torch.is_grad_enabled())
+    (without its ``.item()`` host sync).
+
+    ``upstream`` (as for the data decoders): the coefficient with which the caller adds this term to the
+    objective it differentiates.  The gradient ``upstream * d nll / d v`` is then computed right behind the
+    forward kernels and the backward pass hands it over unchanged -- only valid when exactly that objective
+    is back-propagated, once (``SCGLUETrainer.train_step``: ``gen_loss``)."""
+    args = _graph_args(v, eidx, esgn, ewt)
+    up = None if upstream is None else _upstream_scalar(upstream, args[0].device)
+    return _GraphNllFn.apply(*args, torch.is_grad_enabled(), up)
 
 
 def graph_logits(v, eidx, esgn) -> torch.Tensor:

@@ -57,6 +57,13 @@ starts = [e for e in ev if "Memcpy DtoD" in e["name"] or "memcpy" in e["name"].l
 last0 = ev[len(ev) * 2 // 3]["ts"]
 lastev = [e for e in ev if e["ts"] >= last0]
 base = lastev[0]["ts"]
+all_until = float(os.environ.get("ALL_UNTIL", "0"))  # list every activity that starts before this time (us)
+all_from = float(os.environ.get("ALL_FROM", "0"))
+if all_until:
+    print(f"\nlast step, every activity starting in [{all_from:.0f}, {all_until:.0f}) us:")
+    for e in lastev:
+        if all_from <= e["ts"] - base < all_until:
+            print(f"  {e['ts'] - base:7.1f} {e['dur']:6.1f}  s{e['args'].get('stream')}  {e['name'][:100]}")
 print("\nlast step, activities >= 5 us (start us, dur us, stream, name):")
 for e in lastev:
     if e["dur"] >= 5:
