@@ -66,29 +66,38 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// rows [0, 128) x k floats into dst[row][ld]: the first n_rows rows come from row_ptr(r) as ONE bulk copy each
-// (cp.async.bulk, k4 floats, completing on `bar`; a first version issued 16-byte cp.async and spent 4 k cycles on
-// issuing them), the padding columns [k4, k) and the rows beyond n_rows are zero-filled with plain stores.
-// Every thread then waits on `bar` (phase `parity`).  `reuse`: the destination was read through the generic proxy
-// before (the caller has synchronised the CTA): order those reads before the asynchronous writes.
+// rows [0, 128) x k floats into dst[row][ld] (kc real columns, the rest zeros; rows beyond n_rows zeros), completing
+// phase `bar`.  `bulk` (kc a multiple of 4, 16-byte aligned rows): ONE bulk copy per row (cp.async.bulk, completing
+// on `bar`; a first version issued 16-byte cp.async and spent 4 k cycles on issuing them), padding by plain stores.
+// Otherwise (e.g. the 50-wide input of the discriminator): plain loads and stores by all threads.  Every thread then
+// waits on `bar` and the CTA synchronises.  `reuse`: the destination was read through the generic proxy before (the
+// caller has synchronised the CTA): order those reads before the asynchronous writes.
 template <typename RowPtr>
-__device__ __forceinline__ void stage_rows(float* dst, int ld, int k4, int k, int n_rows, RowPtr row_ptr, uint64_t* bar,
-                                           bool reuse) {
+__device__ __forceinline__ void stage_rows(float* dst, int ld, int kc, int k, int n_rows, RowPtr row_ptr, uint64_t* bar,
+                                           bool reuse, bool bulk) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)n_rows * (uint32_t)k4 * 4u);
+    if (!bulk) {
+        if (tid == 0) tc::mbar_arrive(bar);
+        for (int idx = tid; idx < MF_ROWS * k; idx += MF_THREADS) {
+            const int r = idx / k, j = idx - r * k;
+            dst[r * ld + j] = (r < n_rows && j < kc) ? __ldg(row_ptr(r) + j) : 0.f;
+        }
+        return;
+    }
+    if (tid == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)(n_rows < MF_ROWS ? n_rows : MF_ROWS) * (uint32_t)kc * 4u);
     if (lane < 8) {  // row = 16 lane + warp: 8 copies per warp (a warp issues its bulk copies one lane at a time)
         const int r = 16 * lane + warp;
         float* d = dst + r * ld;
         if (r < n_rows) {
             if (reuse) tc::fence_proxy_async();
-            tc::bulk_load(d, row_ptr(r), (uint32_t)k4 * 4u, bar);
+            tc::bulk_load(d, row_ptr(r), (uint32_t)kc * 4u, bar);
         } else {
             for (int q = 0; q < k; q += 4) *reinterpret_cast<float4*>(d + q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else if (lane < 16 && k > k4) {
+    } else if (lane < 16 && k > kc) {
         const int r = 16 * (lane - 8) + warp;
         if (r < n_rows)
-            for (int q = k4; q < k; q += 4) *reinterpret_cast<float4*>(dst + r * ld + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = kc; q < k; q += 4) *reinterpret_cast<float4*>(dst + r * ld + q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 __device__ __forceinline__ void init_bar(uint64_t* bar) {
@@ -248,19 +257,31 @@ struct HidFwd {
     unsigned char* keep;  // [B, H] (NULL: not kept)
     int B, Din, H;
     float slope, eps, momentum, p;
+    int bulk;  // rows of `in` can be fetched with bulk copies
 };
 
 // Bt slab of a Linear: rows = output columns c0 .. c0 + 15 of W [H, K] (row_ptr(r) NULL: zeros), pre-split.
-// 32 threads per row, 4 floats each per sweep; every load of a thread is issued before the first use.
+// 32 threads per row, 4 floats each per sweep; every load of a thread is issued before the first use.  Rows that
+// are not 16-byte aligned (K not a multiple of 4) are read with scalar loads.
 template <typename RowPtr>
-__device__ __forceinline__ void stage_split(uint32_t* Bb, uint32_t* Bs, int ld, int k4, int k, RowPtr row_ptr) {
+__device__ __forceinline__ void stage_split(uint32_t* Bb, uint32_t* Bs, int ld, int kc, int k, RowPtr row_ptr) {
     const int r = threadIdx.x >> 5, q = threadIdx.x & 31;  // (MF_THREADS / 32 = MF_COLS rows)
     const float* src = row_ptr(r);
+    const bool vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (kc & 3) == 0;
     float4 v[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
         const int j = 4 * (q + 32 * m);
-        v[m] = (src != nullptr && j < k4) ? __ldg(reinterpret_cast<const float4*>(src + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src == nullptr || j >= kc) continue;
+        if (vec) {
+            v[m] = __ldg(reinterpret_cast<const float4*>(src + j));
+        } else {
+            v[m].x = __ldg(src + j);
+            if (j + 1 < kc) v[m].y = __ldg(src + j + 1);
+            if (j + 2 < kc) v[m].z = __ldg(src + j + 2);
+            if (j + 3 < kc) v[m].w = __ldg(src + j + 3);
+        }
     }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -302,8 +323,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
+    const int row_base = blockIdx.y * MF_ROWS;  // (several row tiles only without BatchNorm: rows are independent)
+    const int n_rows = min(MF_ROWS, a.B - row_base);
     init_bar(S.bar);
-    stage_rows(S.As, ld, a.Din, k, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, S.bar, false);
+    stage_rows(S.As, ld, a.Din, k, n_rows, [&](int r) { return a.in + (long long)(row_base + r) * a.ld_in; }, S.bar,
+               false, a.bulk != 0);
     stage_split(S.Bb, S.Bs, ld, a.Din, k,
                 [&](int r) { return c0 + r < a.H ? a.W + (long long)(c0 + r) * a.Din : nullptr; });
     // per-column parameters of my 4 columns (requested before the product is waited for)
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
     gemm_mma(S.As, S.Bb, S.Bs, ld, h ? s_mid : 0, h ? k8 : s_mid, wr, lane, acc);
     float zv[4], y[4];
     combine_halves(acc, S.xch, warp, lane, zv);
-    const int row = 16 * wr + g + 8 * h;
+    const int row = row_base + 16 * wr + g + 8 * h;
     const bool rok = row < a.B;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -390,11 +414,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_fwd_kernel(const Hid
     }
     // the last block to finish advances the call counter (every block has read it by then)
     if (tid == 0) {
-        if (blockIdx.x == 0 && a.num_batches) a.num_batches[0] += 1;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && a.num_batches) a.num_batches[0] += 1;
         if (drop) {
             __threadfence();
             const unsigned long long tk = atomicAdd(a.rng + 2, 1ull);
-            if (tk == gridDim.x - 1) a.rng[2] = 0ull, a.rng[1] = call + 1ull;
+            if (tk == (unsigned long long)gridDim.x * gridDim.y - 1) a.rng[2] = 0ull, a.rng[1] = call + 1ull;
         }
     }
 }
@@ -407,6 +431,8 @@ struct HeadFwd {
     float* std;                              // [B, O]  softplus(.) + EPS
     float* spre;                             // [B, O]  pre-activation of the std head (NULL: not kept)
     int B, H, O;
+    int bulk;
+    // Wstd == NULL: a single plain head (the discriminator's `pred`)
 };
 
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_fwd_kernel(const HeadFwd a) {
@@ -416,12 +442,16 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_fwd_kernel(const Head
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
+    const int row_base = blockIdx.y * MF_ROWS;
+    const int n_rows = min(MF_ROWS, a.B - row_base);
+    const int n_cols = a.Wstd ? 2 * a.O : a.O;
     init_bar(S.bar);
-    stage_rows(S.As, ld, a.H, k, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, S.bar, false);
+    stage_rows(S.As, ld, a.H, k, n_rows, [&](int r) { return a.in + (long long)(row_base + r) * a.ld_in; }, S.bar,
+               false, a.bulk != 0);
     stage_split(S.Bb, S.Bs, ld, a.H, k, [&](int r) -> const float* {
         const int c = c0 + r;
         if (c < a.O) return a.Wloc + (long long)c * a.H;
-        if (c < 2 * a.O) return a.Wstd + (long long)(c - a.O) * a.H;
+        if (c < n_cols) return a.Wstd + (long long)(c - a.O) * a.H;
         return nullptr;
     });
     tc::mbar_wait(S.bar, 0);
@@ -435,12 +465,12 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_fwd_kernel(const Head
     gemm_mma(S.As, S.Bb, S.Bs, ld, h ? s_mid : 0, h ? k8 : s_mid, wr, lane, acc);
     float v[4];
     combine_halves(acc, S.xch, warp, lane, v);
-    const int row = 16 * wr + g + 8 * h;
+    const int row = row_base + 16 * wr + g + 8 * h;
     if (row >= a.B) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int c = c0 + 8 * (j >> 1) + 2 * t + (j & 1);
-        if (c >= 2 * a.O) continue;
+        if (c >= n_cols) continue;
         const bool is_loc = c < a.O;
         const int oc = is_loc ? c : c - a.O;
         const float val = v[j] + (is_loc ? a.bloc[oc] : a.bstd[oc]);
@@ -475,11 +505,12 @@ struct HeadBwd {
     const float* h;  // [B, H] input of the heads
     long long ld_h;
     const float* d_loc;  // [B, O]
-    const float* d_std;  // [B, O]
+    const float* d_std;  // [B, O]  (NULL: a single plain head)
     const float* spre;   // [B, O]
-    float* G;            // [B, 2 O] = [d loc | d std sigmoid(spre)]
+    float* G;            // [B, n_heads O] = [d loc | d std sigmoid(spre)]
     float *dWloc, *dbloc, *dWstd, *dbstd;
     int B, H, O;
+    int bulk;
 };
 
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_bwd_kernel(const HeadBwd a) {
@@ -490,44 +521,58 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_heads_bwd_kernel(const Head
     float* Gs = In + MF_ROWS * ld;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c0 = blockIdx.x * MF_COLS;
+    const int n_cols = a.d_std ? 2 * a.O : a.O;
     init_bar(bar);
-    stage_rows(In, ld, a.H, k, a.B, [&](int r) { return a.h + (long long)r * a.ld_h; }, bar, false);
-#pragma unroll
-    for (int m = 0; m < MF_ROWS * MF_COLS / MF_THREADS; ++m) {
-        const int idx = tid + m * MF_THREADS;
-        const int r = idx >> 4, cl = idx & 15, c = c0 + cl;
-        float v = 0.f;
-        if (r < a.B && c < 2 * a.O) {
-            if (c < a.O) {
-                v = a.d_loc[(long long)r * a.O + c];
-            } else {
-                const long long off = (long long)r * a.O + c - a.O;
-                const float pre = a.spre[off];
-                v = a.d_std[off] * (pre > 20.f ? 1.f : sigmoidf(pre));  // (torch's softplus threshold)
-            }
-            a.G[(long long)r * (2 * a.O) + c] = v;
-        }
-        Gs[r * MF_GS_LD + cl] = v;
-    }
-    tc::mbar_wait(bar, 0);
-    __syncthreads();
     float acc[2][4];
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-    wgrad_mma(Gs, In, ld, k >> 3, warp, lane, acc);
+    float db = 0.f;
+    const int n_tiles = (a.B + MF_ROWS - 1) / MF_ROWS;
+    for (int rt = 0; rt < n_tiles; ++rt) {  // (row tiles: the weight gradients accumulate in registers)
+        const int row_base = rt * MF_ROWS;
+        // rows left, NOT clamped to the tile: with min(MF_ROWS, .) inside this loop nvcc 12.9 drops the whole
+        // `r < n_rows` branch of stage_rows, bulk copies included (tests/test_abi.py checks the SASS for them)
+        const int n_rows = a.B - row_base;
+        if (rt) __syncthreads();  // (the previous tile has been consumed)
+        stage_rows(In, ld, a.H, k, n_rows, [&](int r) { return a.h + (long long)(row_base + r) * a.ld_h; }, bar, rt > 0,
+                   a.bulk != 0);
+#pragma unroll
+        for (int m = 0; m < MF_ROWS * MF_COLS / MF_THREADS; ++m) {
+            const int idx = tid + m * MF_THREADS;
+            const int r = idx >> 4, cl = idx & 15, c = c0 + cl, row = row_base + r;
+            float v = 0.f;
+            if (r < n_rows && c < n_cols) {
+                if (c < a.O) {
+                    v = a.d_loc[(long long)row * a.O + c];
+                } else {
+                    const long long off = (long long)row * a.O + c - a.O;
+                    const float pre = a.spre[off];
+                    v = a.d_std[off] * (pre > 20.f ? 1.f : sigmoidf(pre));  // (torch's softplus threshold)
+                }
+                a.G[(long long)row * n_cols + c] = v;
+            }
+            Gs[r * MF_GS_LD + cl] = v;
+        }
+        tc::mbar_wait(bar, rt & 1);
+        __syncthreads();
+        wgrad_mma(Gs, In, ld, k >> 3, warp, lane, acc);
+        if (tid < MF_COLS) {
+            float s = 0.f;
+            for (int r = 0; r < MF_ROWS; ++r) s += Gs[r * MF_GS_LD + tid];
+            db += s;
+        }
+    }
     store_wgrad(acc, a.H, warp, lane, [&](int o) -> float* {
         const int c = c0 + o;
         if (c < a.O) return a.dWloc + (long long)c * a.H;
-        if (c < 2 * a.O) return a.dWstd + (long long)(c - a.O) * a.H;
+        if (c < n_cols) return a.dWstd + (long long)(c - a.O) * a.H;
         return nullptr;
     });
-    if (tid < MF_COLS && c0 + tid < 2 * a.O) {
-        float s = 0.f;
-        for (int r = 0; r < MF_ROWS; ++r) s += Gs[r * MF_GS_LD + tid];
+    if (tid < MF_COLS && c0 + tid < n_cols) {
         const int c = c0 + tid;
-        if (c < a.O) a.dbloc[c] = s; else a.dbstd[c - a.O] = s;
+        if (c < a.O) a.dbloc[c] = db; else a.dbstd[c - a.O] = db;
     }
 }
 
@@ -552,6 +597,7 @@ struct HidBwd {
     float* dbeta;
     int B, H;
     float slope, p;
+    int bulk_g, bulk_in;  // rows of Gab / of `in` can be fetched with bulk copies
 };
 
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const HidBwd a) {
@@ -569,7 +615,6 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
     const int wr = warp & 7, h = warp >> 3;
     const int c0 = blockIdx.x * MF_COLS;
     init_bar(bar);
-    stage_rows(As, lda, a.Kab, ka, a.B, [&](int r) { return a.Gab + (long long)r * a.Kab; }, bar, false);
     // Bt[o][j] = W_above[j][c0 + o] (64-byte runs along o), zero beyond Kab; loads first, then split + store
     {
         constexpr int PER = MF_KMAX * MF_COLS / MF_THREADS;  // 8
@@ -592,93 +637,114 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_hidden_bwd_kernel(const Hid
             Bb[o * lda + j] = b, Bs[o * lda + j] = s;
         }
     }
-    // saved activations and statistics of my 4 elements (requested before the product is waited for)
-    const int row = 16 * wr + g + 8 * h;
-    const bool rok = row < a.B;
     bool cok[4];
     int col[4];
-    float zv[4], mean[4], rstd[4], gam[4];
-    unsigned char kp[4];
+    float mean[4], rstd[4], gam[4], db_acc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         col[j] = c0 + 8 * (j >> 1) + 2 * t + (j & 1);
         cok[j] = col[j] < a.H;
-        const bool ok = rok && cok[j];
-        const long long off = (long long)row * a.H + col[j];
-        zv[j] = ok ? a.z[off] : 0.f;
-        kp[j] = (ok && a.keep) ? a.keep[off] : (unsigned char)1;
         const bool bn = cok[j] && a.gamma != nullptr;
         mean[j] = bn ? a.save_mean[col[j]] : 0.f;
         rstd[j] = bn ? a.save_rstd[col[j]] : 0.f;
         gam[j] = bn ? a.gamma[col[j]] : 0.f;
+        db_acc[j] = 0.f;
     }
-    tc::mbar_wait(bar, 0);
-    __syncthreads();
-    float acc[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-    const int s_mid = (k8 + 1) >> 1;
-    gemm_mma(As, Bb, Bs, lda, h ? s_mid : 0, h ? k8 : s_mid, wr, lane, acc);  // d L / d (block output)
-    float gout[4], dzv[4];
-    combine_halves(acc, xch, warp, lane, gout);
-    const float keep_scale = a.keep ? 1.f / (1.f - a.p) : 1.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) gout[j] = (rok && cok[j] && kp[j]) ? gout[j] * keep_scale : 0.f;
-    if (a.gamma != nullptr) {
-        float sg[4], sgx[4], xhat[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            xhat[j] = (leaky(zv[j], a.slope) - mean[j]) * rstd[j];
-            sg[j] = gout[j];
-            sgx[j] = gout[j] * xhat[j];
-        }
-        col_reduce4(sg, red, warp, lane);
-        col_reduce4(sgx, red, warp, lane);
-        const float invB = 1.f / (float)a.B;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (warp == 0 && g == 0 && cok[j]) {
-                if (a.dgamma) a.dgamma[col[j]] = sgx[j];
-                if (a.dbeta) a.dbeta[col[j]] = sg[j];
-            }
-            const float ga = gam[j] * rstd[j] * (gout[j] - invB * (sg[j] + xhat[j] * sgx[j]));
-            dzv[j] = (rok && cok[j]) ? (zv[j] > 0.f ? ga : a.slope * ga) : 0.f;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dzv[j] = zv[j] > 0.f ? gout[j] : a.slope * gout[j];
-    }
-    float sdz[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        sdz[j] = dzv[j];
-        Gs[row * MF_GS_LD + 8 * (j >> 1) + 2 * t + (j & 1)] = dzv[j];
-        if (a.dz && rok && cok[j]) a.dz[(long long)row * a.H + col[j]] = dzv[j];
-    }
-    col_reduce4(sdz, red, warp, lane);  // (its barriers also separate the product above from the restaging below)
-    if (warp == 0 && g == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (cok[j] && a.db) a.db[col[j]] = sdz[j];
-    }
-    // weight gradient: dW[c0 + o][i] = sum_r dz[r][o] in[r][i]
-    stage_rows(As, ldi, a.Din, ki, a.B, [&](int r) { return a.in + (long long)r * a.ld_in; }, bar, true);
-    tc::mbar_wait(bar, 1);
-    __syncthreads();
     float wacc[2][4];
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int e = 0; e < 4; ++e) wacc[q][e] = 0.f;
-    wgrad_mma(Gs, As, ldi, ki >> 3, warp, lane, wacc);
+    const float keep_scale = a.keep ? 1.f / (1.f - a.p) : 1.f;
+    const int s_mid = (k8 + 1) >> 1;
+    const int n_tiles = (a.B + MF_ROWS - 1) / MF_ROWS;  // (more than one only without BatchNorm)
+    for (int rt = 0; rt < n_tiles; ++rt) {
+        const int row_base = rt * MF_ROWS;
+        // rows left, NOT clamped to the tile: with min(MF_ROWS, .) inside this loop nvcc 12.9 drops the whole
+        // `r < n_rows` branch of stage_rows, bulk copies included (tests/test_abi.py checks the SASS for them)
+        const int n_rows = a.B - row_base;
+        if (rt) __syncthreads();  // (the previous tile's weight-gradient product is done with As and Gs)
+        stage_rows(As, lda, a.Kab, ka, n_rows, [&](int r) { return a.Gab + (long long)(row_base + r) * a.Kab; }, bar,
+                   rt > 0, a.bulk_g != 0);
+        // saved activations of my 4 elements (requested before the product is waited for)
+        const int row = row_base + 16 * wr + g + 8 * h;
+        const bool rok = row < a.B;
+        float zv[4];
+        unsigned char kp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool ok = rok && cok[j];
+            const long long off = (long long)row * a.H + col[j];
+            zv[j] = ok ? a.z[off] : 0.f;
+            kp[j] = (ok && a.keep) ? a.keep[off] : (unsigned char)1;
+        }
+        tc::mbar_wait(bar, 0);  // (two phases per tile: parities 0, 1)
+        __syncthreads();
+        float acc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+        gemm_mma(As, Bb, Bs, lda, h ? s_mid : 0, h ? k8 : s_mid, wr, lane, acc);  // d L / d (block output)
+        float gout[4], dzv[4];
+        combine_halves(acc, xch, warp, lane, gout);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gout[j] = (rok && cok[j] && kp[j]) ? gout[j] * keep_scale : 0.f;
+        if (a.gamma != nullptr) {
+            float sg[4], sgx[4], xhat[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                xhat[j] = (leaky(zv[j], a.slope) - mean[j]) * rstd[j];
+                sg[j] = gout[j];
+                sgx[j] = gout[j] * xhat[j];
+            }
+            col_reduce4(sg, red, warp, lane);
+            col_reduce4(sgx, red, warp, lane);
+            const float invB = 1.f / (float)a.B;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (warp == 0 && g == 0 && cok[j]) {
+                    if (a.dgamma) a.dgamma[col[j]] = sgx[j];
+                    if (a.dbeta) a.dbeta[col[j]] = sg[j];
+                }
+                const float ga = gam[j] * rstd[j] * (gout[j] - invB * (sg[j] + xhat[j] * sgx[j]));
+                dzv[j] = (rok && cok[j]) ? (zv[j] > 0.f ? ga : a.slope * ga) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dzv[j] = zv[j] > 0.f ? gout[j] : a.slope * gout[j];
+        }
+        float sdz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sdz[j] = dzv[j];
+            Gs[(16 * wr + g + 8 * h) * MF_GS_LD + 8 * (j >> 1) + 2 * t + (j & 1)] = dzv[j];
+            if (a.dz && rok && cok[j]) a.dz[(long long)row * a.H + col[j]] = dzv[j];
+        }
+        col_reduce4(sdz, red, warp, lane);  // (its barriers also separate the product above from the restaging below)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) db_acc[j] += sdz[j];
+        // weight gradient: dW[c0 + o][i] += sum_r dz[r][o] in[r][i]
+        stage_rows(As, ldi, a.Din, ki, n_rows, [&](int r) { return a.in + (long long)(row_base + r) * a.ld_in; }, bar, true,
+                   a.bulk_in != 0);
+        tc::mbar_wait(bar, 1);
+        __syncthreads();
+        wgrad_mma(Gs, As, ldi, ki >> 3, warp, lane, wacc);
+    }
+    if (warp == 0 && g == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (cok[j] && a.db) a.db[col[j]] = db_acc[j];
+    }
     store_wgrad(wacc, a.Din, warp, lane,
                 [&](int o) -> float* { return c0 + o < a.H ? a.dW + (long long)(c0 + o) * a.Din : nullptr; });
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline bool dim_ok(int k) { return k > 0 && k <= MF_KMAX && (k & 3) == 0; }
+inline bool dim_ok(int k) { return k > 0 && k <= MF_KMAX && (k & 1) == 0; }
+// rows of a [*, k] fp32 matrix with pitch ld can be fetched with cp.async.bulk
+inline int bulk_ok(const void* p, int64_t ld, int k) { return (aligned16(p) && (ld & 3) == 0 && (k & 3) == 0) ? 1 : 0; }
+constexpr int64_t MF_MAX_ROWS = 8 * MF_ROWS;  // row tiles (only without BatchNorm)
 
 }  // namespace
 }  // namespace glue
@@ -693,17 +759,19 @@ extern "C" int glue_mlp_hidden_fwd(const float* in, int64_t ld_in, const float* 
     if (!in || !W || !bias || !out || B <= 0 || H <= 0) return GLUE_E_BADARG;
     if (gamma && (!beta)) return GLUE_E_BADARG;
     if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && !rng_state)) return GLUE_E_BADARG;
-    if (B > MF_ROWS || !dim_ok(Din) || (ld_in & 3) || !aligned16(in) || !aligned16(W)) return GLUE_E_UNSUPPORTED;
+    if (B > (gamma ? (int64_t)MF_ROWS : MF_MAX_ROWS) || !dim_ok(Din)) return GLUE_E_UNSUPPORTED;
     HidFwd a;
     a.in = in, a.ld_in = ld_in, a.W = W, a.bias = bias, a.gamma = gamma, a.beta = beta;
     a.running_mean = running_mean, a.running_var = running_var, a.num_batches = (long long*)num_batches_tracked;
     a.rng = p_drop > 0.f ? (unsigned long long*)rng_state : nullptr;
     a.z = z, a.out = out, a.save_mean = save_mean, a.save_rstd = save_rstd, a.keep = p_drop > 0.f ? keep_mask : nullptr;
     a.B = (int)B, a.Din = Din, a.H = H, a.slope = negative_slope, a.eps = eps, a.momentum = momentum, a.p = p_drop;
+    a.bulk = bulk_ok(in, ld_in, Din);
     const int ld = pitch4(round8(Din));
     const size_t smem = ((size_t)(MF_ROWS + 2 * MF_COLS) * ld + MF_AUX_FLOATS) * sizeof(float);
     GLUE_SMEM_ONCE(mlp_hidden_fwd_kernel, 227 * 1024);
-    mlp_hidden_fwd_kernel<<<(H + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
+    const dim3 grid((H + MF_COLS - 1) / MF_COLS, (unsigned)((B + MF_ROWS - 1) / MF_ROWS));
+    mlp_hidden_fwd_kernel<<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
@@ -711,16 +779,19 @@ extern "C" int glue_mlp_hidden_fwd(const float* in, int64_t ld_in, const float* 
 extern "C" int glue_mlp_heads_fwd(const float* in, int64_t ld_in, const float* Wloc, const float* bloc,
                                   const float* Wstd, const float* bstd, int64_t B, int32_t H, int32_t O, float* loc,
                                   float* std, float* spre, void* stream) {
-    if (!in || !Wloc || !bloc || !Wstd || !bstd || !loc || !std || B <= 0 || O <= 0) return GLUE_E_BADARG;
-    if (B > MF_ROWS || !dim_ok(H) || (ld_in & 3) || !aligned16(in) || !aligned16(Wloc) || !aligned16(Wstd))
-        return GLUE_E_UNSUPPORTED;
+    if (!in || !Wloc || !bloc || !loc || B <= 0 || O <= 0) return GLUE_E_BADARG;
+    if (Wstd && (!bstd || !std)) return GLUE_E_BADARG;
+    if (B > MF_MAX_ROWS || !dim_ok(H)) return GLUE_E_UNSUPPORTED;
     HeadFwd a;
     a.in = in, a.ld_in = ld_in, a.Wloc = Wloc, a.bloc = bloc, a.Wstd = Wstd, a.bstd = bstd;
     a.loc = loc, a.std = std, a.spre = spre, a.B = (int)B, a.H = H, a.O = O;
+    a.bulk = bulk_ok(in, ld_in, H);
     const int ld = pitch4(round8(H));
     const size_t smem = ((size_t)(MF_ROWS + 2 * MF_COLS) * ld + MF_AUX_FLOATS) * sizeof(float);
     GLUE_SMEM_ONCE(mlp_heads_fwd_kernel, 227 * 1024);
-    mlp_heads_fwd_kernel<<<(2 * O + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
+    const int n_cols = Wstd ? 2 * O : O;
+    const dim3 grid((n_cols + MF_COLS - 1) / MF_COLS, (unsigned)((B + MF_ROWS - 1) / MF_ROWS));
+    mlp_heads_fwd_kernel<<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
@@ -728,16 +799,17 @@ extern "C" int glue_mlp_heads_fwd(const float* in, int64_t ld_in, const float* W
 extern "C" int glue_mlp_heads_bwd(const float* h, int64_t ld_h, const float* d_loc, const float* d_std,
                                   const float* spre, int64_t B, int32_t H, int32_t O, float* G, float* dWloc,
                                   float* dbloc, float* dWstd, float* dbstd, void* stream) {
-    if (!h || !d_loc || !d_std || !spre || !G || !dWloc || !dbloc || !dWstd || !dbstd || B <= 0 || O <= 0)
-        return GLUE_E_BADARG;
-    if (B > MF_ROWS || !dim_ok(H) || (ld_h & 3) || !aligned16(h) || ((uintptr_t)dWloc & 7) || ((uintptr_t)dWstd & 7))
-        return GLUE_E_UNSUPPORTED;
+    if (!h || !d_loc || !G || !dWloc || !dbloc || B <= 0 || O <= 0) return GLUE_E_BADARG;
+    if (d_std && (!spre || !dWstd || !dbstd)) return GLUE_E_BADARG;
+    if (B > MF_MAX_ROWS || !dim_ok(H) || ((uintptr_t)dWloc & 7) || ((uintptr_t)dWstd & 7)) return GLUE_E_UNSUPPORTED;
     HeadBwd a;
     a.h = h, a.ld_h = ld_h, a.d_loc = d_loc, a.d_std = d_std, a.spre = spre, a.G = G;
     a.dWloc = dWloc, a.dbloc = dbloc, a.dWstd = dWstd, a.dbstd = dbstd, a.B = (int)B, a.H = H, a.O = O;
+    a.bulk = bulk_ok(h, ld_h, H);
     const size_t smem = (4 + (size_t)MF_ROWS * pitch8(round8(H)) + (size_t)MF_ROWS * MF_GS_LD) * sizeof(float);
     GLUE_SMEM_ONCE(mlp_heads_bwd_kernel, 227 * 1024);
-    mlp_heads_bwd_kernel<<<(2 * O + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
+    const int n_cols = d_std ? 2 * O : O;
+    mlp_heads_bwd_kernel<<<(n_cols + MF_COLS - 1) / MF_COLS, MF_THREADS, smem, (cudaStream_t)stream>>>(a);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
@@ -752,7 +824,7 @@ extern "C" int glue_mlp_hidden_bwd(const float* g_above, int32_t k_above, const 
     if (n0 < k_above && !w_above1) return GLUE_E_BADARG;
     if (gamma && (!save_mean || !save_rstd)) return GLUE_E_BADARG;
     if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && !keep_mask)) return GLUE_E_BADARG;
-    if (B > MF_ROWS || !dim_ok(Din) || !dim_ok(k_above) || (ld_in & 3) || !aligned16(in) || !aligned16(g_above) ||
+    if (B > (gamma ? (int64_t)MF_ROWS : MF_MAX_ROWS) || !dim_ok(Din) || k_above <= 0 || k_above > MF_KMAX ||
         ((uintptr_t)dW & 7))
         return GLUE_E_UNSUPPORTED;
     HidBwd a;
@@ -760,6 +832,7 @@ extern "C" int glue_mlp_hidden_bwd(const float* g_above, int32_t k_above, const 
     a.save_mean = save_mean, a.save_rstd = save_rstd, a.keep = p_drop > 0.f ? keep_mask : nullptr;
     a.in = in, a.ld_in = ld_in, a.Din = Din, a.dz = dz, a.dW = dW, a.db = db, a.dgamma = dgamma, a.dbeta = dbeta;
     a.B = (int)B, a.H = H, a.slope = negative_slope, a.p = p_drop;
+    a.bulk_g = bulk_ok(g_above, k_above, k_above), a.bulk_in = bulk_ok(in, ld_in, Din);
     const int lda = pitch4(round8(k_above)), ldi = pitch8(round8(Din));
     const size_t smem = ((size_t)MF_ROWS * (lda > ldi ? lda : ldi) + (size_t)2 * MF_COLS * lda +
                          (size_t)MF_ROWS * MF_GS_LD + MF_AUX_FLOATS) * sizeof(float);  // (the 4 barrier words included)

@@ -307,12 +307,46 @@ class Discriminator(torch.nn.Sequential, glue.Discriminator):
         layers["pred"] = torch.nn.Linear(width, out_features)
         super().__init__(layers)
 
+    def _dropout_state(self, layer: int, device: torch.device) -> torch.Tensor:
+        r"""Philox state of block ``layer``'s dropout for the fused kernels (as ``DataEncoder``)."""
+        name = f"_dropout_state_{layer}"
+        state = getattr(self, name, None)
+        if state is None or state.device != device:
+            state = ops.new_dropout_state(device)
+            self.register_buffer(name, state, persistent=False)
+        return state
+
+    def _fused_forward(self, x: torch.Tensor):
+        r"""All blocks + ``pred`` in ``h_depth + 1`` launches each way (``ops.discriminator_mlp``) when the
+        shapes allow it; ``None`` otherwise."""
+        if not (config.USE_FUSED_MLP and config.USE_FUSED_ENCODER and x.is_cuda and x.dtype == torch.float32):
+            return None
+        names = [n for n, _ in self.named_children()]
+        depth = sum(1 for n in names if n.startswith("linear_"))
+        if depth < 1 or names != [f"{kind}_{i}" for i in range(depth) for kind in ("linear", "act", "dropout")] + ["pred"]:
+            return None
+        lins = [getattr(self, f"linear_{i}") for i in range(depth)]
+        acts = [getattr(self, f"act_{i}") for i in range(depth)]
+        drops = [getattr(self, f"dropout_{i}") for i in range(depth)]
+        if any(type(a) is not torch.nn.LeakyReLU for a in acts) or len({a.negative_slope for a in acts}) != 1:
+            return None
+        ps = {d.p if d.training else 0.0 for d in drops}
+        if len(ps) != 1:
+            return None
+        x = x.contiguous()
+        if not ops.discriminator_mlp_supported(x, [lin.weight for lin in lins], self.pred.out_features):
+            return None
+        p = ps.pop()
+        rngs = [self._dropout_state(i, x.device) if p > 0 else None for i in range(depth)]
+        return ops.discriminator_mlp(x, lins, self.pred, p, rngs, negative_slope=acts[0].negative_slope)
+
     def forward(self, x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         if self.norm:
             x = (x - x.mean(dim=0)) / (x.std(dim=0) + EPS)
         if self.n_batches:
             x = torch.cat([x, F.one_hot(b, num_classes=self.n_batches)], dim=1)
-        return super().forward(x)
+        fused = self._fused_forward(x)
+        return fused if fused is not None else super().forward(x)
 
 
 class Classifier(torch.nn.Linear):

@@ -390,20 +390,32 @@ def act_bn_dropout(z: torch.Tensor, bn: torch.nn.BatchNorm1d, p: float, rng_stat
 # ------------------------------------------------------------- whole data-encoder MLP
 
 
+def _mlp_widths_ok(x: torch.Tensor, weights, n_head_cols: int, max_rows: int) -> bool:
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or not (2 <= x.shape[0] <= max_rows):
+        return False
+    widths = [x.shape[1]] + [w.shape[0] for w in weights] + [n_head_cols]
+    if any(w % 2 or w > 256 or w <= 0 for w in widths):
+        return False
+    return x.stride(1) == 1 and x.data_ptr() % 8 == 0
+
+
 def encoder_mlp_supported(x: torch.Tensor, weights, n_out: int) -> bool:
-    r"""Shapes the fused encoder kernels take (``include/glue_b200.h``): at most 128 rows, every
-    operand width a multiple of 4 and at most 256, fp32, 16-byte aligned rows."""
-    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] > 128 or x.shape[0] < 2:
-        return False
-    widths = [x.shape[1]] + [w.shape[0] for w in weights] + [2 * n_out]
-    if any(w % 4 or w > 256 or w <= 0 for w in widths):
-        return False
-    return x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+    r"""Shapes the fused encoder kernels take (``include/glue_b200.h``): at most 128 rows (BatchNorm needs the
+    whole batch in one CTA), every operand width even and at most 256, fp32."""
+    return _mlp_widths_ok(x, weights, 2 * n_out, 128)
 
 
-class _EncoderMlpFn(torch.autograd.Function):
-    r"""``h_depth`` hidden blocks + both heads; tensors: x, then per block (W, b, gamma, beta), then
-    (Wloc, bloc, Wstd, bstd).  ``blocks`` carries the per-block BatchNorm buffers / dropout states."""
+def discriminator_mlp_supported(x: torch.Tensor, weights, n_out: int) -> bool:
+    r"""As :func:`encoder_mlp_supported` for blocks without BatchNorm: up to 1024 rows (row tiles); any
+    number of outputs."""
+    return 0 < n_out <= 256 and _mlp_widths_ok(x, weights, 2, 1024)
+
+
+class _MlpFn(torch.autograd.Function):
+    r"""``depth`` hidden blocks + head(s).  Tensors: x, then per block (W, b, gamma, beta) -- gamma / beta
+    ``None`` for blocks without BatchNorm --, then (W0, b0, W1, b1) of the heads (W1 / b1 ``None``: a single
+    plain head).  ``blocks`` carries the per-block BatchNorm buffers / dropout states.  Returns
+    ``(loc, std)``; ``std`` is ``None`` for a single head."""
 
     @staticmethod
     def forward(ctx, grad_enabled, blocks, slope, p, x, *params):
@@ -412,75 +424,89 @@ class _EncoderMlpFn(torch.autograd.Function):
         depth = len(blocks)
         B = x.shape[0]
         wloc, bloc, wstd, bstd = params[4 * depth:]
-        need_grad = bool(grad_enabled and any(t.requires_grad for t in params))
-        saved, aux = [], []
+        two_heads = wstd is not None
+        need_grad = bool(grad_enabled and (x.requires_grad or any(t is not None and t.requires_grad for t in params)))
+        saved, keeps = [], []
         cur = x
         for i, blk in enumerate(blocks):
             W, b, gamma, beta = params[4 * i:4 * i + 4]
             H, Din = W.shape
+            bn = gamma is not None
             out = torch.empty(B, H, dtype=torch.float32, device=dev)
             z = torch.empty(B, H, dtype=torch.float32, device=dev) if need_grad else None
-            mean = torch.empty(H, dtype=torch.float32, device=dev) if need_grad else None
-            rstd = torch.empty(H, dtype=torch.float32, device=dev) if need_grad else None
+            mean = torch.empty(H, dtype=torch.float32, device=dev) if (need_grad and bn) else None
+            rstd = torch.empty(H, dtype=torch.float32, device=dev) if (need_grad and bn) else None
             keep = torch.empty(B, H, dtype=torch.uint8, device=dev) if (need_grad and p > 0) else None
             check(L.glue_mlp_hidden_fwd(
-                ptr(cur), cur.stride(0), ptr(W), ptr(b), ptr(gamma), ptr(beta), ptr(blk["running_mean"]),
-                ptr(blk["running_var"]), ptr(blk["num_batches_tracked"]), ptr(blk["rng"]) if p > 0 else None,
-                B, Din, H, slope, blk["eps"], blk["momentum"], p, ptr(z), ptr(out), ptr(mean), ptr(rstd),
-                ptr(keep), st), "mlp_hidden_fwd")
+                ptr(cur), cur.stride(0), ptr(W), ptr(b), ptr(gamma), ptr(beta), ptr(blk.get("running_mean")),
+                ptr(blk.get("running_var")), ptr(blk.get("num_batches_tracked")), ptr(blk["rng"]) if p > 0 else None,
+                B, Din, H, slope, blk.get("eps", 0.0), blk.get("momentum", 0.0), p, ptr(z), ptr(out), ptr(mean),
+                ptr(rstd), ptr(keep), st), "mlp_hidden_fwd")
             saved += [cur, z, mean, rstd]
-            aux.append(keep)
+            keeps.append(keep)
             cur = out
         O, H = wloc.shape
         loc = torch.empty(B, O, dtype=torch.float32, device=dev)
-        std = torch.empty(B, O, dtype=torch.float32, device=dev)
-        spre = torch.empty(B, O, dtype=torch.float32, device=dev) if need_grad else None
+        std = torch.empty(B, O, dtype=torch.float32, device=dev) if two_heads else None
+        spre = torch.empty(B, O, dtype=torch.float32, device=dev) if (need_grad and two_heads) else None
         check(L.glue_mlp_heads_fwd(ptr(cur), cur.stride(0), ptr(wloc), ptr(bloc), ptr(wstd), ptr(bstd), B, H, O,
                                    ptr(loc), ptr(std), ptr(spre), st), "mlp_heads_fwd")
-        if need_grad:
-            ctx.save_for_backward(cur, spre, *saved, *[k for k in aux if k is not None], *params)
-            ctx.depth, ctx.slope, ctx.p, ctx.has_keep = depth, slope, p, p > 0
         ctx.need_grad = need_grad
+        if need_grad:
+            # (None entries are fine for save_for_backward)
+            ctx.save_for_backward(cur, spre, *saved, *keeps, *params)
+            ctx.depth, ctx.slope, ctx.p = depth, slope, p
+            ctx.x_grad = x.requires_grad
+        if not two_heads:
+            ctx.mark_non_differentiable()
         return loc, std
 
     @staticmethod
     def backward(ctx, g_loc, g_std):
         if not ctx.need_grad:
-            raise RuntimeError("encoder_mlp was run without gradient buffers")
+            raise RuntimeError("the fused MLP was run without gradient buffers")
         L = _lib.lib()
         t = ctx.saved_tensors
         depth, slope, p = ctx.depth, ctx.slope, ctx.p
         h, spre = t[0], t[1]
         saved = t[2:2 + 4 * depth]
-        n_keep = depth if ctx.has_keep else 0
-        keeps = t[2 + 4 * depth:2 + 4 * depth + n_keep]
-        params = t[2 + 4 * depth + n_keep:]
+        keeps = t[2 + 4 * depth:2 + 5 * depth]
+        params = t[2 + 5 * depth:]
         wloc, bloc, wstd, bstd = params[4 * depth:]
+        two_heads = wstd is not None
         dev, st = h.device, current_stream(h.device)
         B, (O, H) = h.shape[0], wloc.shape
         g_loc = torch.zeros(B, O, dtype=torch.float32, device=dev) if g_loc is None else _f32(g_loc, "grad_loc")
-        g_std = torch.zeros(B, O, dtype=torch.float32, device=dev) if g_std is None else _f32(g_std, "grad_std")
-        G = torch.empty(B, 2 * O, dtype=torch.float32, device=dev)
-        g_wloc, g_bloc, g_wstd, g_bstd = (torch.empty_like(w) for w in (wloc, bloc, wstd, bstd))
-        check(L.glue_mlp_heads_bwd(ptr(h), h.stride(0), ptr(g_loc), ptr(g_std), ptr(spre), B, H, O, ptr(G),
-                                   ptr(g_wloc), ptr(g_bloc), ptr(g_wstd), ptr(g_bstd), st), "mlp_heads_bwd")
+        if two_heads:
+            g_std = torch.zeros(B, O, dtype=torch.float32, device=dev) if g_std is None else _f32(g_std, "grad_std")
+        n_cols = 2 * O if two_heads else O
+        G = torch.empty(B, n_cols, dtype=torch.float32, device=dev)
+        g_wloc, g_bloc = torch.empty_like(wloc), torch.empty_like(bloc)
+        g_wstd = torch.empty_like(wstd) if two_heads else None
+        g_bstd = torch.empty_like(bstd) if two_heads else None
+        check(L.glue_mlp_heads_bwd(ptr(h), h.stride(0), ptr(g_loc), ptr(g_std) if two_heads else None, ptr(spre), B, H, O,
+                                   ptr(G), ptr(g_wloc), ptr(g_bloc), ptr(g_wstd), ptr(g_bstd), st), "mlp_heads_bwd")
         grads = [None] * (4 * depth)
-        above, k_above, wa0, wa1, n0 = G, 2 * O, wloc, wstd, O
+        above, k_above, wa0, wa1, n0 = G, n_cols, wloc, wstd, O
+        g_x = None
         for i in reversed(range(depth)):
             W, b, gamma, beta = params[4 * i:4 * i + 4]
             inp, z, mean, rstd = saved[4 * i:4 * i + 4]
             Hi, Din = W.shape
-            dz = torch.empty(B, Hi, dtype=torch.float32, device=dev) if i > 0 else None
+            want_dz = i > 0 or ctx.x_grad
+            dz = torch.empty(B, Hi, dtype=torch.float32, device=dev) if want_dz else None
             gW, gb = torch.empty_like(W), torch.empty_like(b)
             gg = torch.empty_like(gamma) if gamma is not None else None
             gbeta = torch.empty_like(beta) if beta is not None else None
             check(L.glue_mlp_hidden_bwd(
                 ptr(above), k_above, ptr(wa0), ptr(wa1), n0, ptr(z), ptr(gamma), ptr(mean), ptr(rstd),
-                ptr(keeps[i]) if n_keep else None, ptr(inp), inp.stride(0), Din, B, Hi, slope, p, ptr(dz), ptr(gW),
+                ptr(keeps[i]) if p > 0 else None, ptr(inp), inp.stride(0), Din, B, Hi, slope, p, ptr(dz), ptr(gW),
                 ptr(gb), ptr(gg), ptr(gbeta), st), "mlp_hidden_bwd")
             grads[4 * i:4 * i + 4] = [gW, gb, gg, gbeta]
+            if i == 0 and ctx.x_grad:
+                g_x = dz @ W  # (the input gradient of the first Linear: one small library product)
             above, k_above, wa0, wa1, n0 = dz, Hi, W, None, Hi
-        return (None, None, None, None, None, *grads, g_wloc, g_bloc, g_wstd, g_bstd)
+        return (None, None, None, None, g_x, *grads, g_wloc, g_bloc, g_wstd, g_bstd)
 
 
 def encoder_mlp(x: torch.Tensor, linears, bns, heads, p: float, rng_states, negative_slope: float = 0.2):
@@ -502,7 +528,20 @@ def encoder_mlp(x: torch.Tensor, linears, bns, heads, p: float, rng_states, nega
                        "rng": rng, "eps": float(bn.eps), "momentum": float(bn.momentum)})
         params += [lin.weight, lin.bias, bn.weight, bn.bias]
     params += [heads[0].weight, heads[0].bias, heads[1].weight, heads[1].bias]
-    return _EncoderMlpFn.apply(torch.is_grad_enabled(), blocks, float(negative_slope), float(p), x, *params)
+    return _MlpFn.apply(torch.is_grad_enabled(), blocks, float(negative_slope), float(p), x, *params)
+
+
+def discriminator_mlp(x: torch.Tensor, linears, pred, p: float, rng_states, negative_slope: float = 0.2):
+    r"""Logits of the modality discriminator (``scglue/models/sc.py:576-624``: ``h_depth`` x [Linear ->
+    LeakyReLU -> Dropout], then ``pred``) in ``h_depth + 1`` launches each way; differentiable in ``x``
+    (the generator's alignment term back-propagates into the encoders)."""
+    require_cuda(x)
+    blocks, params = [], []
+    for lin, rng in zip(linears, rng_states):
+        blocks.append({"rng": rng})
+        params += [lin.weight, lin.bias, None, None]
+    params += [pred.weight, pred.bias, None, None]
+    return _MlpFn.apply(torch.is_grad_enabled(), blocks, float(negative_slope), float(p), x, *params)[0]
 
 
 def new_dropout_state(device, generator: Optional[torch.Generator] = None) -> torch.Tensor:

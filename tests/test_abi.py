@@ -49,3 +49,25 @@ def test_bad_arguments_return_codes(native_lib):
     args = _lib.DecoderArgs()
     assert native_lib.glue_decoder_nll_fwd(ctypes.byref(args), None) == -1
     assert native_lib.glue_graphconv_csr(None, None, None, None, None, 10, 50, None) == -1
+
+
+def test_fused_mlp_kernels_keep_their_bulk_copies(native_lib):
+    """Every fused-MLP kernel stages its row operand with cp.async.bulk (SASS: UBLKCP).  nvcc 12.9 was seen to
+    drop that branch silently (a row count clamped with min() inside the row-tile loop): the barrier then never
+    completes and the bounded wait traps.  Checked on the shipped library."""
+    import shutil
+    import pytest
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    counts, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line
+        elif "UBLKCP" in line and cur is not None:
+            counts[cur] = counts.get(cur, 0) + 1
+    want = {"mlp_hidden_fwd_kernel": 1, "mlp_heads_fwd_kernel": 1, "mlp_heads_bwd_kernel": 1, "mlp_hidden_bwd_kernel": 2}
+    for name, n in want.items():
+        got = sum(v for k, v in counts.items() if name in k)
+        assert got >= n, f"{name}: {got} bulk copies in SASS, expected {n}"

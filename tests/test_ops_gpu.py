@@ -767,3 +767,53 @@ def test_fused_encoder_mlp_with_dropout(ops, B, monkeypatch):
     launches = ops.kernel_launches()
     fused(x, x)
     assert ops.kernel_launches() == launches
+
+
+# ------------------------------------------------------------------ discriminator MLP
+@pytest.mark.parametrize("rows,in_dim,n_batches,n_out,p", [(256, 50, 0, 2, 0.0), (384, 50, 0, 3, 0.0),
+                                                           (256, 50, 20, 2, 0.0), (100, 50, 0, 2, 0.0),
+                                                           (256, 50, 0, 2, 0.2), (300, 50, 20, 3, 0.2)])
+def test_fused_discriminator_vs_torch_modules(ops, rows, in_dim, n_batches, n_out, p, monkeypatch):
+    """Discriminator blocks + `pred` as h_depth + 1 launches each way (row tiles of 128, the 50-wide input staged
+    without bulk copies) against a float64 restatement of scglue/models/sc.py:576-624 under the same dropout masks:
+    logits, input gradient (the alignment term back-propagates into the encoders) and parameter gradients."""
+    import torch.nn.functional as F
+    from glue_b200.models import sc
+    from glue_b200.utils import config
+    torch.manual_seed(rows + n_out)
+    dsc = sc.Discriminator(in_dim, n_out, n_batches=n_batches, h_depth=2, h_dim=256, dropout=p).to(DEV)
+    dev = torch.device(DEV)
+    gen = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, in_dim, generator=gen)).to(DEV).requires_grad_(True)
+    b = torch.randint(0, max(n_batches, 1), (rows,), generator=gen).to(DEV)
+    wout = torch.randn(rows, n_out, generator=gen).to(DEV)
+    width = in_dim + n_batches
+    keeps = []
+    for i in range(2):
+        if p > 0:
+            state = dsc._dropout_state(i, dev).clone()
+            keeps.append(ops.act_bn_dropout(torch.zeros(rows, 256, device=DEV), torch.nn.BatchNorm1d(256).to(DEV), p,
+                                            state, return_aux=True)[3].double())
+        else:
+            keeps.append(torch.ones(rows, 256, device=DEV, dtype=torch.float64))
+    params = {n: q.detach().double().requires_grad_(True) for n, q in dsc.named_parameters()}
+    x64 = x.detach().double().requires_grad_(True)
+    h = torch.cat([x64, F.one_hot(b, num_classes=n_batches).double()], dim=1) if n_batches else x64
+    assert h.shape[1] == width
+    for i in range(2):
+        h = F.leaky_relu(h @ params[f"linear_{i}.weight"].T + params[f"linear_{i}.bias"], 0.2) * keeps[i] / (1 - p)
+    ref = h @ params["pred.weight"].T + params["pred.bias"]
+    ref_g = torch.autograd.grad((ref * wout.double()).sum(), [x64] + list(params.values()))
+    launches = ops.kernel_launches()
+    out = dsc(x, b)
+    got_g = torch.autograd.grad((out * wout).sum(), [x] + list(dsc.parameters()))
+    assert ops.kernel_launches() - launches == 6 + (2 if p > 0 else 0) * 0, "three launches each way"
+    assert_close(out, ref.float(), 1e-5, "logits")
+    for name, a, r in zip(["x"] + list(params), got_g, ref_g):
+        assert_close(a, r.float(), 1e-4, f"d / d {name}")
+    if p > 0:
+        assert dsc._dropout_state(0, dev).tolist()[1:] == [1, 0]
+    # the per-op path (torch modules) gives the same values when nothing is dropped
+    if p == 0:
+        monkeypatch.setattr(config, "USE_FUSED_ENCODER", False)
+        assert_close(dsc(x, b), out, 1e-5, "per-op logits")
