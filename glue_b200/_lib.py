@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_log_prob",
     "glue_decoder_mean",
     "glue_rmsprop_flat",
+    "glue_multi_copy",
     "glue_kl_unit_normal_fwd",
     "glue_kl_unit_normal_bwd",
     "glue_paired_mean_cos_fwd",
@@ -211,6 +212,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         ctypes.c_uint32, c_void_p, c_void_p]
 
 
+    lib.glue_multi_copy.restype = c_int32
+    lib.glue_multi_copy.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.glue_rmsprop_flat.restype = c_int32
     lib.glue_rmsprop_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                       c_float, c_void_p]

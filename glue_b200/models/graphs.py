@@ -134,22 +134,20 @@ class StepGraphs:
     @staticmethod
     def _load_inputs(statics: List[torch.Tensor], data: List[torch.Tensor]) -> None:
         r"""Minibatch -> static input buffers of the captured step.  Tensors that already live on the
-        device and are small go through one multi-tensor copy per dtype (a paired PBMC step has 14
-        inputs: as individual copies they were 60 us of launch latency in front of every replay); count
-        matrices and host tensors are copied one by one (asynchronously when pinned)."""
-        groups: Dict[torch.dtype, Any] = {}
+        device go through ONE launch (``ops.multi_copy``; a paired PBMC step has 14 inputs: as
+        individual copies they were 60 us of launch latency in front of every replay); host tensors
+        are copied one by one (asynchronously when pinned)."""
+        dsts, srcs = [], []
         for static, fresh in zip(statics, data):
-            small = static.numel() * static.element_size() <= (1 << 20)  # (large ones: the copy engine is faster)
-            if small and fresh.device == static.device and fresh.dtype == static.dtype and fresh.shape == static.shape:
-                dst, src = groups.setdefault(static.dtype, ([], []))
-                dst.append(static), src.append(fresh)
+            if (fresh.device == static.device and fresh.dtype == static.dtype and fresh.shape == static.shape
+                    and fresh.is_contiguous() and static.is_contiguous() and static.numel()):
+                dsts.append(static), srcs.append(fresh)
             else:
                 static.copy_(fresh, non_blocking=True)
-        for dst, src in groups.values():
-            if len(dst) > 1:
-                torch._foreach_copy_(dst, src)
-            else:
-                dst[0].copy_(src[0], non_blocking=True)
+        if len(dsts) > 1:
+            ops.multi_copy(dsts, srcs)
+        elif dsts:
+            dsts[0].copy_(srcs[0], non_blocking=True)
 
     @staticmethod
     def _recover_generator(device: torch.device, state: Optional[torch.Tensor]) -> None:

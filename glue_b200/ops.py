@@ -77,6 +77,22 @@ def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def multi_copy(dsts, srcs) -> None:
+    r"""``dst.copy_(src)`` for up to 16 pairs of contiguous device tensors of equal byte size in one
+    launch (``glue_multi_copy``): the minibatch of a captured step going into its static input buffers."""
+    n = len(dsts)
+    if n == 0:
+        return
+    if n > 16:
+        multi_copy(dsts[:16], srcs[:16])
+        return multi_copy(dsts[16:], srcs[16:])
+    dev = require_cuda(*dsts, *srcs)
+    arr = ctypes.c_void_p * n
+    nbytes = (ctypes.c_int64 * n)(*[d.numel() * d.element_size() for d in dsts])
+    check(_lib.lib().glue_multi_copy(n, arr(*[s.data_ptr() for s in srcs]), arr(*[d.data_ptr() for d in dsts]),
+                                     nbytes, current_stream(dev)), "multi_copy")
+
+
 # ------------------------------------------------------------------------ CSR
 
 

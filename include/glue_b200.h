@@ -283,6 +283,13 @@ int glue_decoder_nll_multi_fwd(const glue_decoder_multi_args *args, void *stream
 int glue_rmsprop_flat(float *param, const float *grad, float *square_avg, int64_t n, float lr,
                       float alpha, float eps, void *stream);
 
+/* n <= 16 device-to-device copies (dst[s] <- src[s], bytes[s] bytes) in one launch: the minibatch of a
+ * captured training step going into the step's static input buffers (the reference's
+ * SCGLUETrainer.format_data, scglue/models/scglue.py:255-289, moves each tensor separately).  The three
+ * arrays are host arrays. */
+int glue_multi_copy(int32_t n, const void *const *src, void *const *dst, const int64_t *bytes,
+                    void *stream);
+
 /* ------------------------------------------------------------------------- *
  * KL( N(mean, std) || N(0, 1) ) of a data encoder's posterior.
  * Replaces  D.kl_divergence(u, prior).sum(dim=1).mean() / n_features

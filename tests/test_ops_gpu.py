@@ -817,3 +817,21 @@ def test_fused_discriminator_vs_torch_modules(ops, rows, in_dim, n_batches, n_ou
     if p == 0:
         monkeypatch.setattr(config, "USE_FUSED_ENCODER", False)
         assert_close(dsc(x, b), out, 1e-5, "per-op logits")
+
+
+def test_multi_copy(ops):
+    """One launch moves a whole minibatch into the static input buffers of a captured step: mixed dtypes, sizes
+    from 1 byte to tens of MB, misaligned views, more than 16 tensors."""
+    gen = torch.Generator().manual_seed(0)
+    big = torch.randn(128, 50000, generator=gen).to(DEV)
+    srcs = [big, torch.randint(0, 9, (2, 35861), generator=gen).to(DEV), torch.rand(128, generator=gen).to(DEV) > 0.5,
+            torch.randn(1001, generator=gen).to(DEV)[1:], torch.randn(3, generator=gen).to(DEV)[1:2],
+            torch.randint(0, 255, (7,), generator=gen).to(torch.uint8).to(DEV)]
+    srcs += [torch.randn(37 + i, generator=gen).to(DEV) for i in range(14)]  # 20 tensors: two launches
+    dsts = [torch.zeros_like(s).contiguous() for s in srcs]
+    srcs = [s.contiguous() if i != 3 else s for i, s in enumerate(srcs)]  # (index 3 stays a 4-byte-offset view)
+    launches = ops.kernel_launches()
+    ops.multi_copy(dsts, srcs)
+    assert ops.kernel_launches() - launches == 2
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
