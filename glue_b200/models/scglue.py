@@ -550,10 +550,21 @@ class SCGLUETrainer(GLUETrainer):
             return losses.detach()
         return {name: value.detach() for name, value in losses.items()}
 
-    @torch.no_grad()
     def val_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
+        r"""Validation step (``scglue.py:403-408``); replayed from a captured graph like the training
+        step once its input signature has been seen."""
+        data = self.unpack_data(data)
+        if self.graphs.usable():
+            return self.graphs.step(engine, data, mode="val")
+        return self.eager_val_step(engine, data)
+
+    @torch.no_grad()
+    def eager_val_step(self, engine, data: List[torch.Tensor]) -> Mapping[str, torch.Tensor]:
         self.net.eval()
-        return self.compute_losses(self.format_data(data), engine.state.epoch)
+        losses = self.compute_losses(self.format_data(data), engine.state.epoch)
+        if isinstance(losses, LossVector):
+            return losses.detach()
+        return {name: value.detach() for name, value in losses.items()}
 
     def __repr__(self) -> str:
         indent = lambda o: repr(o).replace("    ", "  ").replace("\n", "\n  ")
