@@ -117,7 +117,7 @@ class DecoderMultiArgs(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLUE_B200_ABI_VERSION 3
+#define GLUE_B200_ABI_VERSION 4
 
 #define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
 #define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */

@@ -1,2 +1,7 @@
-python -m pytest tests/test_step_gpu.py -x -q -m gpu > gpurun_out/r4a_step.log 2>&1; echo rc=$? >> gpurun_out/r4a_step.log
-python bench.py --steps 100 --warmup 24 > gpurun_out/r4a_bench.json 2> gpurun_out/r4a_bench.err
+for c in cfg1 cfg3 cfg4 cfg5; do
+  python bench.py --config $c --steps 40 --warmup 12 --skip-cpu-baseline --no-fit > gpurun_out/r4c_bench_$c.json 2> gpurun_out/r4c_bench_$c.err
+done
+bash tools/profile_bench.sh r4c > gpurun_out/r4c_profile.log 2>&1
+python tools/step_profile.py > gpurun_out/r4c_timeline.txt 2>&1
+python tools/gnll_bench.py > gpurun_out/r4c_gnll.json 2>/dev/null
+python tools/mlp_bench.py > gpurun_out/r4c_mlp.json 2>/dev/null

@@ -8,6 +8,11 @@ skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 lines = [l for l in open(path) if not l.startswith("==")]
 rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
 rows = rows[skip:]
+marker = sys.argv[4] if len(sys.argv) > 4 else None
+if marker:  # one replayed step: the launches between the last two occurrences of the marker kernel
+    at = [i for i, r in enumerate(rows) if marker in r["Kernel Name"]]
+    if len(at) >= 2:
+        rows = rows[at[-2]:at[-1]]
 tot, agg = 0.0, defaultdict(lambda: [0, 0.0])
 for r in rows:
     ns = float(r["Metric Value"].replace(",", ""))
@@ -23,5 +28,5 @@ print("| share | total us | launches | us/launch | kernel |\n|---|---|---|---|--
 for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"| {100 * us / tot:.1f}% | {us:.0f} | {n} | {us / n:.2f} | `{name[:110]}` |")
 ours = sum(us for name, (n, us) in agg.items() if "glue::" in name)
-dec = sum(us for name, (n, us) in agg.items() if "glue::" in name and ("tc_" in name or "dec_" in name))
+dec = sum(us for name, (n, us) in agg.items() if "glue::" in name and ("tc_" in name or "dec_" in name or "v3::" in name))
 print(f"\nKernels of libglue_b200.so: {100 * ours / tot:.1f}% of kernel time; fused decoder kernels: {100 * dec / tot:.1f}%.")
