@@ -147,12 +147,14 @@ class GLUETrainer(Trainer):
         return getattr(torch.optim, self.optim_name)(params, lr=self.lr, **kwargs)
 
     # -- data-parallel gradient exchange -------------------------------------------------
-    def _sync_grads(self, which: str) -> None:
+    def _sync_grads(self, which: str, skip=None) -> None:
+        r"""``skip``: flat range of the optimizer's gradient buffer that has been exchanged already
+        (``FlatRMSprop.all_reduce_subset``)."""
         if not gdist.is_distributed():
             return
         optim = self.vae_optim if which == "vae" else self.dsc_optim
         if hasattr(optim, "all_reduce_mean"):  # FlatRMSprop: gradients already live in one buffer
-            optim.all_reduce_mean()
+            optim.all_reduce_mean(skip=skip)
             return
         attr = f"_{which}_bucket"
         if getattr(self, attr) is None:

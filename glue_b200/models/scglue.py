@@ -23,6 +23,7 @@ import torch
 import torch.distributions as D
 import torch.nn.functional as F
 
+from .. import dist as gdist
 from ..num import normalize_edges
 from ..utils import AUTO, config, logged
 from . import sc
@@ -108,6 +109,10 @@ class SCGLUETrainer(GLUETrainer):
         self._dsc_stream: Optional[torch.cuda.Stream] = None
         self._nll_stream: Optional[torch.cuda.Stream] = None
         self._nll_pending = False
+        self._early_stream: Optional[torch.cuda.Stream] = None
+        self._early_pending = False
+        self._early_reduced = None
+        self._in_generator_step = False
         self.capturing = False
         self.anneal_buffer = torch.zeros((), dtype=torch.float32, device=net.device)
 
@@ -275,6 +280,14 @@ class SCGLUETrainer(GLUETrainer):
             vsamp, kl_sum = g2v.sample_with_kl(self.eidx, self.enorm, self.esgn,
                                                self.noise(g2v.vrepr, "v"))
             g_kl = kl_sum / (vsamp.shape[0] * vsamp.shape[0])
+            from .. import ops
+            if ops.V_GRAD_SINK is not None:
+                # early backward pass (see compute_losses): the consumers of the vertex embeddings see a fresh
+                # leaf, so that no autograd edge leads from the objective back into the graph branch -- its
+                # gradient arrives through ``ops.V_GRAD_SINK`` instead
+                self._graph_branch = (vsamp, kl_sum)
+                vsamp = vsamp.detach().requires_grad_(True)
+                g_kl = g_kl.detach()
         else:
             v = g2v(self.eidx, self.enorm, self.esgn)
             vsamp = v.mean + self.noise(v.mean, "v") * v.stddev
@@ -304,6 +317,60 @@ class SCGLUETrainer(GLUETrainer):
             g_nll = net.v2g(vsamp, eidx, esgn).balanced_nll(ewt, upstream=up)
         self._nll_pending = True
         return g_nll
+
+    def _early_backward_ok(self) -> bool:
+        r"""Whether the graph branch can be back-propagated right behind the decoders: a training step's
+        generator pass on CUDA, the fused Gaussian head, and every decoder one of the kernel-backed ones
+        with a non-zero coefficient -- then every gradient with respect to ``vsamp`` is computed in the
+        forward pass with its coefficient folded in (``ops.V_GRAD_SINK``), none flows back through autograd."""
+        net = self.net
+        if not (self._in_generator_step and torch.is_grad_enabled() and net.device.type == "cuda"
+                and config.MULTI_STREAM and config.EARLY_GRAPH_BACKWARD):
+            return False
+        g2v = net.g2v
+        if not (hasattr(g2v, "sample_with_kl") and hasattr(g2v, "vrepr") and g2v.vrepr.shape[1] <= 64
+                and g2v.vrepr.shape[1] % 2 == 0 and getattr(self, "_unit_prior", None)):
+            return False
+        if not self.lam_graph or not self.lam_data:
+            return False
+        return all(isinstance(net.u2x[k], sc._FusedDecoder) and self.modality_weight[k] for k in net.keys)
+
+    def _early_graph_backward(self, v_grads, vnum: int) -> None:
+        r"""``vsamp.backward(sum of the handed-out gradients)`` and the KL term of the vertex posterior, on a
+        stream of its own: autograd replays the graph branch's backward kernels (Gaussian head, weight-gradient
+        reduce, transposed GraphConv) on that branch's stream; the stream this is called from only forks."""
+        from .. import ops
+        net = self.net
+        branch = self._graph_branch
+        self._graph_branch = None
+        if not v_grads or branch is None:
+            raise RuntimeError("early graph backward: no gradient was handed out")
+        device = net.device
+        main = torch.cuda.current_stream(device)
+        if self._early_stream is None:
+            self._early_stream = torch.cuda.Stream(device)
+        side = self._early_stream
+        side.wait_stream(main)
+        vsamp, kl_sum = branch
+        coeff = self.lam_graph * len(net.keys) * self.lam_kl / (vnum * vnum)  # d gen_loss / d kl_sum
+        with torch.cuda.stream(side):
+            total = v_grads[0]
+            total.record_stream(side)
+            for g in v_grads[1:]:
+                g.record_stream(side)
+                total.add_(g)
+            torch.autograd.backward([vsamp, kl_sum], [total, ops._upstream_scalar(coeff, device).reshape(kl_sum.shape)])
+            # data parallel: the vertex embeddings are 10 of the 12 MB of generator gradients -- exchanged
+            # here, beside the discriminator's and the encoders' backward passes, instead of behind them
+            self._early_reduced = None
+            if gdist.is_distributed() and hasattr(self.vae_optim, "all_reduce_subset"):
+                self._early_reduced = self.vae_optim.all_reduce_subset(list(net.g2v.parameters()))
+        self._early_pending = True
+
+    def _join_early_backward(self) -> None:
+        if self._early_pending:
+            torch.cuda.current_stream(self.net.device).wait_stream(self._early_stream)
+            self._early_pending = False
 
     def _join_graph_nll(self, g_nll):
         if self._nll_pending:
@@ -376,6 +443,10 @@ class SCGLUETrainer(GLUETrainer):
             return {"dsc_loss": self.lam_align * dsc_loss}
         # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
         # the data encoders: it runs beside them
+        from .. import ops
+        early = self._early_backward_ok()
+        self._graph_branch = None
+        ops.V_GRAD_SINK = [] if early else None
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
             x, xrep, dsc_only, extra=[lambda: self._graph_terms(eidx, ewt, esgn, prior)] + self._input_branches(data))
         # one stream per modality: the reconstruction term and, for paired data, the joint-cross /
@@ -393,7 +464,15 @@ class SCGLUETrainer(GLUETrainer):
                     u[k].mean.record_stream(dsc_stream)
                 u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
         self._prepare_extra(usamp)
-        results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
+        try:
+            results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
+        finally:
+            v_grads, ops.V_GRAD_SINK = ops.V_GRAD_SINK, None
+        if early:
+            # every gradient that reaches `vsamp` exists by now: the graph branch's backward pass starts here,
+            # beside the alignment term, the objective tail and the discriminator / encoder backward passes
+            self._join_graph_nll(g_nll)
+            self._early_graph_backward(v_grads, vsamp.shape[0])
         x_nll, self._extra_parts = {}, {k: {} for k in net.keys}
         for k, terms in zip(net.keys, results):
             for kind, res in terms:  # (several real-cross terms add up in term order)
@@ -522,6 +601,7 @@ class SCGLUETrainer(GLUETrainer):
         data = self.format_data(data)
         epoch = engine.state.epoch
         dsc_update = None
+        self.net.zero_grad(set_to_none=True)  # (the generator pass may start accumulating before its backward())
         if self.freeze_u:
             self.net.x2u.apply(freeze_running_stats)
             self.net.du.apply(freeze_running_stats)
@@ -539,10 +619,25 @@ class SCGLUETrainer(GLUETrainer):
                 losses["dsc_loss"].backward()  # already scaled by lam_align
                 self._sync_grads("dsc")
                 self.dsc_optim.step()
-        losses = self.compute_losses(data, epoch, dsc_update=dsc_update)  # generator step
-        self.net.zero_grad(set_to_none=True)
+        self._in_generator_step = True
+        try:
+            losses = self.compute_losses(data, epoch, dsc_update=dsc_update)  # generator step
+        finally:
+            self._in_generator_step = False
+            from .. import ops
+            ops.V_GRAD_SINK = None
+            self._graph_branch = None
+        if self._early_pending:
+            # the graph branch's gradients are already accumulating: only the discriminator's (left over
+            # from its own update, not part of the generator's optimizer) are cleared
+            for p in self.net.du.parameters():
+                p.grad = None
+        else:
+            self.net.zero_grad(set_to_none=True)
         losses["gen_loss"].backward()
-        self._sync_grads("vae")
+        self._join_early_backward()
+        self._sync_grads("vae", skip=self._early_reduced)
+        self._early_reduced = None
         self.vae_optim.step()
         # detached: the returned values feed metrics only, and a live autograd graph would keep
         # this step's AccumulateGrad nodes (bound to this stream) alive into a later capture

@@ -654,6 +654,13 @@ def _graphdec_ws(n_edges: int, vnum: int, device) -> torch.Tensor:
     return _workspace(_lib.lib().glue_graphdec_workspace_bytes(n_edges, vnum), device)
 
 
+# While this is a list, the loss functions whose gradients are computed in their forward pass with a folded
+# coefficient (decoder_nll / decoder_nll_multi / graph_nll with ``upstream``) append their gradient with
+# respect to the vertex table ``v`` to it instead of returning it from ``backward``: the caller (the training
+# step) adds those pieces up and back-propagates them through the graph branch right away, beside the rest of
+# the forward pass, instead of waiting for the objective's backward pass.
+V_GRAD_SINK: Optional[list] = None
+
 _UPSTREAM_SCALARS: dict = {}
 
 
@@ -694,13 +701,19 @@ class _GraphNllFn(torch.autograd.Function):
             check(_lib.lib().glue_graph_nll_bwd(
                 ptr(v), ptr(eidx), ptr(esgn), ptr(ewt), ptr(coef), ptr(upstream), n_edges, vnum, k, ptr(grad_v),
                 ptr(ws), ws.numel(), current_stream(dev)), "graph_nll_bwd")
-            ctx.eager = grad_v
+            if V_GRAD_SINK is not None:
+                V_GRAD_SINK.append(grad_v)
+                ctx.eager = False  # (handed out: nothing flows to `v` from here)
+            else:
+                ctx.eager = grad_v
         elif need_grad:
             ctx.save_for_backward(v, eidx, esgn, ewt, coef, ws)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.eager is False:
+            return None, None, None, None, None, None
         if ctx.eager is not None:
             grad_v, ctx.eager = ctx.eager, None
             return grad_v, None, None, None, None, None
@@ -891,6 +904,9 @@ class _DecoderNllFn(torch.autograd.Function):
             ev = TIMER.start(f"decoder_fwd_bwd_{family}_F{call.F}_B{call.B}", call.device)
             check(L.glue_decoder_nll_fwd_bwd(ctypes.byref(a), call.stream()), "decoder_nll_fwd_bwd")
             TIMER.stop(ev, call.device)
+            if V_GRAD_SINK is not None and unit_upstream and gv is not None:
+                V_GRAD_SINK.append(gv)
+                gv = None
             ctx.grads = (gu, gv, gs, gb, gd, gz)
         else:
             a = call.args(loss=loss)
@@ -984,6 +1000,9 @@ class _DecoderNllMultiFn(torch.autograd.Function):
         fn = L.glue_decoder_nll_multi_fwd_bwd if need_grad else L.glue_decoder_nll_multi_fwd
         check(fn(ctypes.byref(m), call.stream()), "decoder_nll_multi")
         TIMER.stop(ev, dev)
+        if need_grad and V_GRAD_SINK is not None and gv is not None:
+            V_GRAD_SINK.append(gv)
+            gv = None
         ctx.grads = (gv, gs, gb, gd, gz, gus) if need_grad else None
         ctx.n_terms = n_terms
         return losses

@@ -107,22 +107,53 @@ class FlatRMSprop(torch.optim.Optimizer):
         self._packed = self._ranges(active)
         return self._packed
 
+    @staticmethod
+    def _all_reduce_avg(flat: torch.Tensor) -> None:
+        if td.is_available() and td.is_initialized() and td.get_world_size() > 1 and flat.numel():
+            if td.get_backend() == "nccl":
+                td.all_reduce(flat, op=td.ReduceOp.AVG)
+            else:
+                td.all_reduce(flat, op=td.ReduceOp.SUM)
+                flat.div_(td.get_world_size())
+
     @torch.no_grad()
-    def all_reduce_mean(self) -> None:
-        r"""Data-parallel gradient exchange on the flat buffer (one message).  Ranks must agree
-        on the message, so parameters without a gradient on this rank contribute zeros and take
-        part in the update."""
+    def all_reduce_subset(self, params) -> Optional[Tuple[int, int]]:
+        r"""Exchange the gradients of ``params`` -- a contiguous run of this optimizer's parameters whose
+        gradients are already final (the graph branch, back-propagated ahead of the rest of the objective) --
+        on the current stream, and return their flat range for :meth:`all_reduce_mean` to skip.  ``None``
+        (nothing done) when the parameters are not contiguous in the flat buffer."""
+        index = {id(p): i for i, p in enumerate(self._plist)}
+        idx = sorted(index[id(p)] for p in params if id(p) in index)
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return None
+        self._adopt_parameters()
+        for i in idx:
+            p, v = self._plist[i], self._gviews[i]
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            p.grad = v
+        start = self._offsets[idx[0]]
+        stop = self._offsets[idx[-1]] + (self._plist[idx[-1]].numel() + 3) // 4 * 4
+        self._all_reduce_avg(self.flat_grad[start:stop])
+        return start, stop
+
+    @torch.no_grad()
+    def all_reduce_mean(self, skip: Optional[Tuple[int, int]] = None) -> None:
+        r"""Data-parallel gradient exchange on the flat buffer (one message; two around ``skip``, a flat
+        range that :meth:`all_reduce_subset` has exchanged already).  Ranks must agree on the message, so
+        parameters without a gradient on this rank contribute zeros and take part in the update."""
         for v, p in zip(self._gviews, self._plist):
             if p.requires_grad and p.grad is None:
                 v.zero_()
                 p.grad = v
         self.pack_grads()
-        if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
-            if td.get_backend() == "nccl":
-                td.all_reduce(self.flat_grad, op=td.ReduceOp.AVG)
-            else:
-                td.all_reduce(self.flat_grad, op=td.ReduceOp.SUM)
-                self.flat_grad.div_(td.get_world_size())
+        if skip is None:
+            self._all_reduce_avg(self.flat_grad)
+        else:
+            self._all_reduce_avg(self.flat_grad[:skip[0]])
+            self._all_reduce_avg(self.flat_grad[skip[1]:])
 
     # ---------------------------------------------------------------------------------- step
     @torch.no_grad()

@@ -71,6 +71,9 @@ class _Settings:
         # the whole data-encoder MLP (Linear layers included) in h_depth + 1 launches each way
         # (training-mode minibatches of <= 128 cells, layer widths <= 256; needs USE_FUSED_MLP)
         USE_FUSED_ENCODER=True,
+        # back-propagate the graph branch right behind the decoders (every gradient with respect to the
+        # vertex embeddings is computed in the forward pass) instead of in the objective's backward pass
+        EARLY_GRAPH_BACKWARD=True,
     )
 
     def __init__(self) -> None:

@@ -835,3 +835,34 @@ def test_multi_copy(ops):
     assert ops.kernel_launches() - launches == 2
     for d, s in zip(dsts, srcs):
         assert torch.equal(d, s)
+
+
+def test_flat_rmsprop_partial_exchange(native_lib):
+    """The graph branch's gradients are exchanged ahead of the rest (all_reduce_subset on a contiguous run of
+    parameters, all_reduce_mean(skip=...) for the others): the flat buffer ends up holding every gradient, the
+    update equals the one of a plain step (world size 1: the exchanges themselves are no-ops)."""
+    from glue_b200.optim import FlatRMSprop
+    gen = torch.Generator().manual_seed(11)
+    shapes = [(500, 50), (50, 50), (50,), (7, 3), (9,)]
+    init = [torch.randn(s, generator=gen) for s in shapes]
+    grads = [torch.randn(s, generator=gen).to(DEV) for s in shapes]
+    outs = []
+    for split in (False, True):
+        ps = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+        opt = FlatRMSprop(ps, lr=2e-3)
+        for p, g in zip(ps[:3], grads[:3]):
+            p.grad = g.clone()
+        skip = opt.all_reduce_subset(ps[:3]) if split else None
+        if split:
+            assert skip == (0, opt._offsets[3])
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(ps[:3], opt._gviews[:3]))
+            assert opt.all_reduce_subset([ps[0], ps[2]]) is None  # not contiguous: nothing done
+        for p, g in zip(ps[3:], grads[3:]):
+            p.grad = g.clone()
+        opt.all_reduce_mean(skip=skip)
+        for v, g in zip(opt._gviews, grads):
+            assert torch.equal(v, g)
+        opt.step()
+        outs.append([p.detach().clone() for p in ps])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
