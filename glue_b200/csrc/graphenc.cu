@@ -637,10 +637,18 @@ __global__ void graphenc_wgrad_reduce_kernel(EncArgs a, int ncta) {
 
 int pick_kp(int K) { return K <= 52 ? 52 : (K <= 64 ? 64 : 0); }
 
+// Persistent CTAs, tiles strided over them.  The kernels' shared memory admits one CTA per SM, so more CTAs than
+// SMs only queue a second wave -- and while a kernel has blocks waiting to be dispatched, the blocks of every
+// kernel launched after it (the objective tail, which runs beside the graph branch's backward pass) wait behind
+// them.  The fewest CTAs with the makespan of a full grid (813 tiles: 6 per CTA with 148 CTAs and with 136) also
+// leave a dozen SMs to the discriminator / encoder backward kernels, which need whole SMs, and halve the number
+// of weight-gradient partials.
 int enc_grid(int64_t V) {
     const int64_t ntiles = (V + TR - 1) / TR;
-    const int cap = 2 * sm_count();
-    return (int)(ntiles < cap ? ntiles : cap);
+    const int64_t sms = sm_count();
+    if (ntiles <= sms) return (int)ntiles;
+    const int64_t per_cta = (ntiles + sms - 1) / sms;
+    return (int)((ntiles + per_cta - 1) / per_cta);
 }
 
 size_t enc_ws_layout(int64_t V, int KP, char* base, EncArgs* a) {

@@ -1,2 +1,3 @@
-python -m pytest tests/test_step_gpu.py tests/test_ops_gpu.py -x -q -m gpu -k "step or fit or rmsprop or graph" > gpurun_out/r4g_tests.log 2>&1; echo rc=$? >> gpurun_out/r4g_tests.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 60 --warmup 16 --skip-cpu-baseline --no-fit > gpurun_out/r4g_bench_n2.json 2> gpurun_out/r4g_bench_n2.err
+python -m pytest tests -x -q -m gpu > gpurun_out/r4h_tests.log 2>&1; echo rc=$? >> gpurun_out/r4h_tests.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r4h_smoke.log 2>&1
+python bench.py --steps 100 --warmup 24 > gpurun_out/r4h_bench.json 2> gpurun_out/r4h_bench.err
