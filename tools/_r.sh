@@ -1,3 +1,3 @@
-python -m pytest tests -x -q -m gpu > gpurun_out/r4h_tests.log 2>&1; echo rc=$? >> gpurun_out/r4h_tests.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r4h_smoke.log 2>&1
-python bench.py --steps 100 --warmup 24 > gpurun_out/r4h_bench.json 2> gpurun_out/r4h_bench.err
+python -m pytest tests/test_ops_gpu.py tests/test_step_gpu.py -x -q -m gpu -k "graph_encoder or step or fit" > gpurun_out/r4i_tests.log 2>&1; echo rc=$? >> gpurun_out/r4i_tests.log
+python bench.py --steps 60 --warmup 16 --skip-cpu-baseline --no-fit > gpurun_out/r4i_bench.json 2> gpurun_out/r4i_bench.err
+python tools/step_profile.py > gpurun_out/r4i_timeline.txt 2>&1
