@@ -146,11 +146,24 @@ class SCGLUETrainer(GLUETrainer):
         rest = data[5 * K:]
         pmsk = move(rest[0])
         eidx, ewt, esgn = (move(t) for t in rest[1:])
-        xflag = {k: torch.full((x[k].shape[0],), i, dtype=torch.int64, device=device)
-                 for i, k in enumerate(keys)}
+        xflag = {k: self._modality_flag(x[k].shape[0], i, device) for i, k in enumerate(keys)}
         if self.PAIRED:
             return x, xrep, xbch, xlbl, xdwt, xflag, pmsk, eidx, ewt, esgn
         return x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn
+
+    def _modality_flag(self, n: int, index: int, device) -> torch.Tensor:
+        r"""``[n]`` int64 tensor filled with the modality index (the discriminator's target); constant, so built
+        once per (n, index) -- outside any capture: the first steps of a signature run eagerly."""
+        cache = self.__dict__.setdefault("_xflag_cache", {})
+        key = (n, index, str(device))
+        flag = cache.get(key)
+        if flag is None:
+            if self.capturing:
+                return torch.full((n,), index, dtype=torch.int64, device=device)
+            if len(cache) > 32:
+                cache.clear()
+            flag = cache[key] = torch.full((n,), index, dtype=torch.int64, device=device)
+        return flag
 
     def prepare_capture(self) -> None:
         r"""Build, outside the capture, what the step looks up in process-wide caches: the CSR of the
@@ -208,12 +221,23 @@ class SCGLUETrainer(GLUETrainer):
             usamp = F.normalize(usamp, dim=1)
         return u, l, usamp
 
-    def _encode(self, x, xrep, dsc_only: bool, extra=None):
+    def _encode(self, x, xrep, dsc_only: bool, extra=None, before_join=None):
         r"""Per-modality encoders (and optionally one more independent branch, ``extra``) side
         by side; returns ``(u, l, usamp[, extra_result])``."""
         keys = self.net.keys
         thunks = [lambda k=k: self._encode_one(k, x, xrep, dsc_only) for k in keys]
         extras = [] if extra is None else (list(extra) if isinstance(extra, (list, tuple)) else [extra])
+        # (`before_join`: work for the forking stream while the branches run: it is issued behind branch 0,
+        # which shares that stream, and ahead of the join)
+        self._encode_aux = None
+        if before_join is not None:
+            first = thunks[0]
+
+            def first_then_aux():
+                res = first()
+                self._encode_aux = before_join()
+                return res
+            thunks = [first_then_aux] + thunks[1:]
         out = self._parallel(thunks + extras)
         u = {k: o[0] for k, o in zip(keys, out)}
         l = {k: o[1] for k, o in zip(keys, out)}
@@ -412,13 +436,14 @@ class SCGLUETrainer(GLUETrainer):
         net = self.net
         x, xrep, xbch, xlbl, xdwt, xflag, eidx, ewt, esgn = data
         prior = net.prior()
-        cat_inputs = self._alignment_inputs(xbch, xdwt, xflag)
         dsc_stream = None
+        cat_inputs = None
         if dsc_update is not None:
             # encoders, discriminator pass first: BatchNorm statistics and dropout streams advance
             # in the reference's order because each modality keeps its stream for both passes
             with torch.no_grad():
-                u_d, _, _ = self._encode(x, xrep, True)
+                u_d, _, _ = self._encode(x, xrep, True, before_join=lambda: self._alignment_inputs(xbch, xdwt, xflag))
+            cat_inputs = self._encode_aux
             main = torch.cuda.current_stream(net.device)
             if self._dsc_stream is None:
                 self._dsc_stream = torch.cuda.Stream(net.device)
@@ -432,6 +457,8 @@ class SCGLUETrainer(GLUETrainer):
                 _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
                 dsc_update(self.lam_align * dsc_loss_d)
             del u_d, dsc_loss_d
+        if cat_inputs is None:
+            cat_inputs = self._alignment_inputs(xbch, xdwt, xflag)
         if dsc_only:
             # only the discriminator is updated in this pass: the encoders run forward (BatchNorm
             # statistics and dropout streams advance as in the reference) but are not
