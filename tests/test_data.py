@@ -612,3 +612,28 @@ def test_balancing_arithmetic_matches_reference_restatement_given_clusters():
             assert abs(got.mean() - 1) < 1e-9
     with pytest.raises(ValueError, match="cannot be found"):
         estimate_balancing_weight(*[a for a, _ in sets[:2]], use_rep="X_emb", use_clusters="nope")
+
+
+def test_fast_loader_iteration_equals_torch_iterator(monkeypatch):
+    """config.FAST_LOADER iterates the (torch) samplers directly; the batch stream over several epochs --
+    including the draw torch's iterator takes from the generator for its base seed -- is the one torch's
+    DataLoader iterator yields, for the constructor forms the trainer and the tests use."""
+    from glue_b200.utils import config
+
+    def stream(fast, explicit):
+        monkeypatch.setattr(config, "FAST_LOADER", fast)
+        ds = ArrayDataset(np.arange(94).reshape(47, 2), getitem_size=2)
+        ds.prepare_shuffle(num_workers=0, random_seed=7)
+        gen = torch.Generator().manual_seed(7)
+        if explicit:
+            bs = torch.utils.data.BatchSampler(torch.utils.data.RandomSampler(ds, generator=gen), 4, False)
+            dl = DataLoader(ds, reshuffle=True, batch_sampler=bs, generator=gen)
+        else:
+            dl = DataLoader(ds, batch_size=4, shuffle=True, drop_last=True, generator=gen)
+        out = [b[0].clone() for _ in range(3) for b in dl]
+        return out, gen.get_state()
+
+    for explicit in (True, False):
+        (a, sa), (b, sb) = stream(True, explicit), stream(False, explicit)
+        assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+        assert torch.equal(sa, sb), "the generator must end in the same state"
