@@ -7,7 +7,7 @@ is asked to run on a non-CUDA tensor, the caller gets a ``RuntimeError``.
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from typing import Optional
 
 import torch
@@ -46,6 +46,7 @@ EXPORTED_SYMBOLS = (
     "glue_decoder_mean",
     "glue_rmsprop_flat",
     "glue_multi_copy",
+    "glue_sample_graph_epoch",
     "glue_kl_unit_normal_fwd",
     "glue_kl_unit_normal_bwd",
     "glue_paired_mean_cos_fwd",
@@ -117,7 +118,7 @@ class DecoderMultiArgs(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -214,6 +215,10 @@ def _declare(lib: ctypes.CDLL) -> None:
 
     lib.glue_multi_copy.restype = c_int32
     lib.glue_multi_copy.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.glue_sample_graph_epoch.restype = c_int32
+    lib.glue_sample_graph_epoch.argtypes = [
+        c_uint32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+        c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.glue_rmsprop_flat.restype = c_int32
     lib.glue_rmsprop_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                       c_float, c_void_p]

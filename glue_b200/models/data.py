@@ -547,7 +547,7 @@ class _CdfSampler:
         cdf = np.asarray(p, dtype=np.float64).cumsum()
         cdf /= cdf[-1]
         self.cdf = cdf
-        bits = min(22, max(10, int(np.ceil(np.log2(cdf.size))) + 4))
+        self.bits = bits = min(22, max(10, int(np.ceil(np.log2(cdf.size))) + 4))
         self.m = 1 << bits
         self.lut = np.searchsorted(cdf, np.arange(self.m + 1) / self.m, side="right").astype(np.int64)
 
@@ -571,7 +571,7 @@ class _KeyFilter:
     MULT = np.uint64(0x9E3779B97F4A7C15)
 
     def __init__(self, keys: np.ndarray) -> None:
-        bits = min(26, max(12, int(np.ceil(np.log2(max(keys.size, 1)))) + 6))
+        self.bits = bits = min(26, max(12, int(np.ceil(np.log2(max(keys.size, 1)))) + 6))
         self.shift = np.uint64(64 - bits)
         self.table = np.zeros(1 << bits, dtype=np.uint8)
         self.table[self._slot(keys)] = 1
@@ -582,6 +582,30 @@ class _KeyFilter:
 
     def maybe(self, keys: np.ndarray) -> np.ndarray:
         return self.table[self._slot(keys)] != 0
+
+
+class _PinnedSlabs:
+    r"""Process-wide pool of pinned host slabs for the sampled graph epochs.  ``cudaHostAlloc`` / ``cudaFreeHost``
+    of the 27 MB a graph epoch of the PBMC shape takes cost milliseconds each and stall kernel launches while
+    they run, so slabs are recycled across graph epochs, datasets and fits instead of going back to torch's
+    host allocator (whose cache ``torch.cuda.empty_cache()`` at the end of every fit would free again)."""
+
+    _free: Dict[Tuple[str, int], List[torch.Tensor]] = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def take(cls, device: torch.device, nbytes: int) -> torch.Tensor:
+        with cls._lock:
+            free = cls._free.get((str(device), nbytes))
+            if free:
+                return free.pop()
+        with torch.cuda.device(device):  # (a look-ahead thread starts on device 0: pin in the dataset's context)
+            return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+    @classmethod
+    def give(cls, device: torch.device, slab: torch.Tensor) -> None:
+        with cls._lock:
+            cls._free.setdefault((str(device), slab.numel()), []).append(slab)
 
 
 @logged
@@ -677,6 +701,64 @@ class GraphDataset(Dataset):
         return [self.samp_eidx[:, s], self.samp_ewt[s], self.samp_esgn[s]]
 
     def propose_shuffle(self, seed: int):
+        r"""One graph epoch of sampled edges ``(eidx int64 [2, n], ewt [n], esgn [n])`` for ``seed``.  By
+        default one native call (``glue_sample_graph_epoch``, ``csrc/sampler.cu``) that runs without the
+        interpreter lock, so the look-ahead threads scale with the host cores; the numpy restatement below
+        gives the same arrays bit for bit (``tests/test_data.py``) and takes over for a float64 default
+        dtype."""
+        if config.NATIVE_SAMPLER and self.esgn.dtype == np.float32 and self.size < 2 ** 32 \
+                and isinstance(seed, (int, np.integer)) and 0 <= seed < 2 ** 32:
+            return self._propose_shuffle_native(int(seed))
+        return self._propose_shuffle_numpy(seed)
+
+    def _native_sampler_tables(self):
+        r"""Arrays ``glue_sample_graph_epoch`` reads (``include/glue_b200.h``), built once: contiguous edge
+        triplets, 32-bit bucket tables of the two cumulative distributions (a quarter of a bucket per entry keeps
+        them cache-resident) and the bit filter over the edge keys."""
+        tables = self.__dict__.get("_native_tables")
+        if tables is None:
+            def lut(cdf):
+                bits = min(22, max(10, int(np.ceil(np.log2(cdf.size))) + 2))
+                grid = np.arange((1 << bits) + 1) / (1 << bits)
+                return np.searchsorted(cdf, grid, side="right").astype(np.int32), bits
+            keys = np.ascontiguousarray(self._edge_keys, dtype=np.int64)
+            fbits = min(30, max(12, int(np.ceil(np.log2(max(keys.size, 1)))) + 5))
+            with np.errstate(over="ignore"):
+                slots = ((keys.astype(np.uint64) * _KeyFilter.MULT) >> np.uint64(64 - fbits)).astype(np.int64)
+            flags = np.zeros(1 << fbits, dtype=np.uint8)
+            flags[slots] = 1
+            tables = self._native_tables = dict(
+                esrc=np.ascontiguousarray(self.eidx[0], dtype=np.int64),
+                edst=np.ascontiguousarray(self.eidx[1], dtype=np.int64),
+                esgn=np.ascontiguousarray(self.esgn, dtype=np.float32), keys=keys,
+                elut=lut(self._esampler.cdf), vlut=lut(self._vsampler.cdf),
+                filter=(np.packbits(flags, bitorder="little"), fbits))
+        return tables
+
+    def _propose_shuffle_native(self, seed: int):
+        from .. import _lib
+        t = self._native_sampler_tables()
+        n = self.size
+        if self.device is not None and self.device.type == "cuda":
+            # pinned, so that the upload of the epoch is asynchronous; the slab goes back to the pool once the
+            # upload has run (`accept_shuffle`) or when the look-ahead is dropped (`clean`)
+            slab = _PinnedSlabs.take(self.device, 24 * n)
+            idx = slab[:16 * n].view(torch.int64).view(2, n)
+            wt, sgn = slab[16 * n:20 * n].view(torch.float32), slab[20 * n:].view(torch.float32)
+            self.__dict__.setdefault("_slabs", {})[idx.data_ptr()] = slab
+        else:
+            idx = torch.empty((2, n), dtype=torch.int64)
+            wt, sgn = torch.empty(n, dtype=torch.float32), torch.empty(n, dtype=torch.float32)
+        (elut, ebits), (vlut, vbits), (flt, fbits) = t["elut"], t["vlut"], t["filter"]
+        _lib.check(_lib.lib().glue_sample_graph_epoch(
+            seed, t["esrc"].ctypes.data, t["edst"].ctypes.data, t["esgn"].ctypes.data, t["esrc"].size,
+            self._esampler.cdf.ctypes.data, elut.ctypes.data, ebits,
+            self._vsampler.cdf.ctypes.data, vlut.ctypes.data, vbits, self.vnum,
+            t["keys"].ctypes.data, t["keys"].size, flt.ctypes.data, fbits, self.effective_enum, self.neg_samples,
+            idx[0].data_ptr(), idx[1].data_ptr(), wt.data_ptr(), sgn.data_ptr()), "sample_graph_epoch")
+        return idx.numpy(), wt.numpy(), sgn.numpy()
+
+    def _propose_shuffle_numpy(self, seed: int):
         rs = get_rs(seed)
         # (``_CdfSampler.choice`` == ``rs.choice(n, size, replace=True, p=p)``, draw for draw)
         pick = self._esampler.choice(rs, self.effective_enum)
@@ -702,7 +784,32 @@ class GraphDataset(Dataset):
         eidx, ewt, esgn = (torch.as_tensor(np.ascontiguousarray(a)) for a in shuffled)
         if self.device is not None:  # one upload per graph epoch; minibatches are slices
             eidx, ewt, esgn = (t.to(self.device, non_blocking=True) for t in (eidx, ewt, esgn))
+            slab = self.__dict__.get("_slabs", {}).pop(shuffled[0].ctypes.data, None)
+            if slab is not None:  # pinned by the native sampler: the upload is asynchronous
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(self.device))
+                self._recycle_uploads(wait=False)
+                self._uploads.append((done, slab))
         self.samp_eidx, self.samp_ewt, self.samp_esgn = eidx, ewt, esgn
+
+
+    def _recycle_uploads(self, wait: bool) -> None:
+        pending = []
+        for done, slab in self.__dict__.get("_uploads", []):
+            if wait:
+                done.synchronize()
+            if wait or done.query():
+                _PinnedSlabs.give(self.device, slab)
+            else:
+                pending.append((done, slab))
+        self._uploads = pending
+
+    def clean(self) -> None:
+        super().clean()  # (joins the look-ahead threads: nobody writes a slab any more)
+        if self.__dict__.get("_uploads"):
+            self._recycle_uploads(wait=True)
+        for slab in self.__dict__.pop("_slabs", {}).values():  # proposed, never accepted
+            _PinnedSlabs.give(self.device, slab)
 
 
 # ------------------------------------------------------------------------ loaders

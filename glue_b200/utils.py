@@ -77,6 +77,9 @@ class _Settings:
         # single-process loaders without pinned memory iterate their (torch) samplers directly instead of
         # through torch's DataLoader iterator: same index streams, a fraction of the per-minibatch host time
         FAST_LOADER=True,
+        # negative sampling of a graph epoch as one native call (same MT19937 draws, no interpreter lock) instead
+        # of the numpy restatement
+        NATIVE_SAMPLER=True,
     )
 
     def __init__(self) -> None:

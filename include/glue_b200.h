@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLUE_B200_ABI_VERSION 4
+#define GLUE_B200_ABI_VERSION 5
 
 #define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
 #define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */
@@ -289,6 +289,30 @@ int glue_rmsprop_flat(float *param, const float *grad, float *square_avg, int64_
  * arrays are host arrays. */
 int glue_multi_copy(int32_t n, const void *const *src, void *const *dst, const int64_t *bytes,
                     void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Host side of the data path: one graph epoch of the guidance-graph negative sampler.
+ * Replaces  GraphDataset.propose_shuffle  (scglue/models/data.py:794-822): n_pos = round(sum(ewt)) positive
+ * edges drawn with replacement (p = ewt / sum), neg_samples corrupted copies of each whose target is redrawn
+ * from the vertex distribution until (src, dst, sign) is not a real edge, weights 1 / 0, then one permutation --
+ * draw for draw on the legacy MT19937 stream of numpy.random.RandomState(seed), so the edge stream is the
+ * reference's bit for bit.  All pointers are HOST pointers; no device work, no stream.
+ *   esrc / edst [n_edges] int64, esgn [n_edges] fp32   the graph's edge triplets
+ *   ecdf [n_edges], vcdf [n_vertices] fp64             cumulative distributions, normalised so the last entry is 1
+ *   elut [2^elut_bits + 1], vlut [...] int32           lut[b] = number of cdf entries <= b / 2^bits
+ *   edge_keys [n_keys] int64, sorted, unique           (src * n_vertices + dst) * 2 + (sign > 0) of every real edge
+ *   key_filter [2^filter_bits / 8] u8                  bit (slot & 7) of byte (slot >> 3) set for slot =
+ *                                                      (key * 0x9E3779B97F4A7C15 mod 2^64) >> (64 - filter_bits)
+ *                                                      of every real edge (a filter without false negatives)
+ *   out_src / out_dst [n] int64, out_wt / out_sgn [n] fp32,  n = n_pos * (1 + neg_samples) < 2^32
+ * Thread-safe (no shared state): the look-ahead threads of the data side call it concurrently.
+ * ------------------------------------------------------------------------- */
+int glue_sample_graph_epoch(uint32_t seed, const int64_t *esrc, const int64_t *edst, const float *esgn,
+                            int64_t n_edges, const double *ecdf, const int32_t *elut, int32_t elut_bits,
+                            const double *vcdf, const int32_t *vlut, int32_t vlut_bits, int64_t n_vertices,
+                            const int64_t *edge_keys, int64_t n_keys, const uint8_t *key_filter,
+                            int32_t filter_bits, int64_t n_pos, int32_t neg_samples, int64_t *out_src,
+                            int64_t *out_dst, float *out_wt, float *out_sgn);
 
 /* ------------------------------------------------------------------------- *
  * KL( N(mean, std) || N(0, 1) ) of a data encoder's posterior.

@@ -637,3 +637,55 @@ def test_fast_loader_iteration_equals_torch_iterator(monkeypatch):
         (a, sa), (b, sb) = stream(True, explicit), stream(False, explicit)
         assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
         assert torch.equal(sa, sb), "the generator must end in the same state"
+
+
+@pytest.mark.parametrize("n_v,n_e,neg,weighted", [(40, 500, 10, True), (40, 500, 1, False), (3000, 9000, 10, True),
+                                                  (25, 200, 0, True)])
+def test_native_negative_sampler_equals_numpy_restatement(n_v, n_e, neg, weighted):
+    """``glue_sample_graph_epoch`` (one native call per graph epoch, the default) against the numpy restatement of
+    scglue/models/data.py:794-822, bit for bit: dense little graphs (a third of all vertex pairs are edges, so
+    the redraw loop runs several rounds), a graph large enough for the bucket tables, no negatives at all; the
+    same arrays from concurrent look-ahead threads."""
+    import threading
+    import networkx as nx
+    from glue_b200.utils import config
+    rs0 = np.random.RandomState(n_v + neg)
+    g = nx.Graph()
+    names = [f"v{i}" for i in range(n_v)]
+    g.add_nodes_from(names)
+    for s, t, w in zip(rs0.randint(0, n_v, n_e), rs0.randint(0, n_v, n_e), rs0.uniform(0.05, 1, n_e)):
+        g.add_edge(names[s], names[t], weight=float(w), sign=1 if (s + t) % 3 else -1)
+    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in names)
+    ds = GraphDataset(g, names, neg_samples=neg, weighted_sampling=weighted)
+    assert config.NATIVE_SAMPLER
+    seeds = (0, 1, 77, 2 ** 32 - 1)
+    want = {seed: ds._propose_shuffle_numpy(seed) for seed in seeds}
+    for seed in seeds:
+        got = ds.propose_shuffle(seed)
+        for a, b in zip(got, want[seed]):
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    got = {}
+    threads = [threading.Thread(target=lambda s=seed: got.__setitem__(s, ds.propose_shuffle(s))) for seed in seeds]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert all(np.array_equal(a, b) for seed in seeds for a, b in zip(got[seed], want[seed]))
+    # the look-ahead machinery on top of it
+    ds.prepare_shuffle(num_workers=2, random_seed=76)
+    ds.shuffle(), ds.shuffle()
+    assert np.array_equal(ds.samp_eidx.numpy(), want[77][0]) and np.array_equal(ds.samp_ewt.numpy(), want[77][1])
+    ds.clean()
+
+
+def test_native_sampler_argument_errors():
+    from glue_b200 import _lib
+    lib = _lib.lib()
+    a = np.zeros(4, dtype=np.int64)
+    assert lib.glue_sample_graph_epoch(0, None, a.ctypes.data, a.ctypes.data, 4, a.ctypes.data, a.ctypes.data, 10,
+                                       a.ctypes.data, a.ctypes.data, 10, 4, a.ctypes.data, 4, a.ctypes.data, 12, 1, 1,
+                                       a.ctypes.data, a.ctypes.data, a.ctypes.data, a.ctypes.data) == -1
+    assert lib.glue_sample_graph_epoch(0, a.ctypes.data, a.ctypes.data, a.ctypes.data, 4, a.ctypes.data,
+                                       a.ctypes.data, 10, a.ctypes.data, a.ctypes.data, 10, 4, a.ctypes.data, 4,
+                                       a.ctypes.data, 12, 2 ** 31, 3, a.ctypes.data, a.ctypes.data, a.ctypes.data,
+                                       a.ctypes.data) == -2
