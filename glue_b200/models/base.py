@@ -10,7 +10,10 @@ differences, both to keep the GPU queue free of host synchronisation:
 * running loss averages are accumulated **on the device** and read back once per epoch
   (ignite's ``Average`` reads every step);
 * the non-finite-loss check (``TerminateOnNan``) therefore fires at the end of the
-  offending epoch instead of at the offending iteration.
+  offending epoch instead of at the offending iteration;
+* the read-back itself waits until somebody looks at the numbers (:class:`DeferredMetrics`), and the
+  validation pass is issued before anybody does: its steps queue up behind the last training steps
+  instead of starting on an idle device.
 """
 
 import os
@@ -64,6 +67,33 @@ class LossVector(Mapping):
 
     def detach(self) -> "LossVector":
         return LossVector(self.names, self.values.detach())
+
+
+class DeferredMetrics(Mapping):
+    r"""Epoch means ``{name: float}`` that stay on the device until the first read (one device -> host copy,
+    one synchronisation, then a plain dict)."""
+
+    def __init__(self, tracked: List[str], names: List[str], means: torch.Tensor) -> None:
+        self._tracked, self._names, self._means, self._host = list(tracked), list(names), means, None
+
+    def resolve(self) -> Dict[str, float]:
+        if self._host is None:
+            host = self._means.tolist()
+            self._host = {key: host[self._names.index(key)] for key in self._tracked}
+            self._means = None
+        return self._host
+
+    def __getitem__(self, name: str) -> float:
+        return self.resolve()[name]
+
+    def __iter__(self):
+        return iter(self._tracked)
+
+    def __len__(self) -> int:
+        return len(self._tracked)
+
+    def __repr__(self) -> str:
+        return repr(self.resolve())
 
 
 class Engine:
@@ -129,9 +159,8 @@ class Engine:
                 self.fire(ITERATION_COMPLETED)
                 if self.should_terminate:
                     break
-            if vec_sum is not None:  # one device->host read per epoch
-                host = (vec_sum.float() / max(count, 1)).tolist()
-                state.metrics = {key: host[vec_names.index(key)] for key in self.tracked}
+            if vec_sum is not None:  # one device->host read per epoch, when the numbers are looked at
+                state.metrics = DeferredMetrics(self.tracked, vec_names, vec_sum.float() / max(count, 1))
             elif sums:
                 keys = list(sums)
                 host = (torch.stack([sums[k].float() for k in keys]) / max(count, 1)).tolist()
@@ -187,17 +216,17 @@ class Trainer:
         train_engine = Engine(self.train_step, self.required_losses, sync_metrics=sync)
         val_engine = Engine(self.val_step, self.required_losses, sync_metrics=sync) if val_loader else None
 
+        if val_engine:  # (first: nothing has read the epoch's metrics yet, the device is still busy)
+            @train_engine.on(EPOCH_COMPLETED)
+            def _validate(engine):
+                val_engine.run(val_loader, max_epochs=engine.state.epoch)
+
         @train_engine.on(EPOCH_COMPLETED)
         def _nonfinite_guard(engine):  # TerminateOnNan, at epoch granularity
             if any(v != v or v in (float("inf"), float("-inf"))
                    for v in engine.state.metrics.values()):
                 self.logger.warning("Non-finite loss encountered, terminating training...")
                 engine.terminate()
-
-        if val_engine:
-            @train_engine.on(EPOCH_COMPLETED)
-            def _validate(engine):
-                val_engine.run(val_loader, max_epochs=engine.state.epoch)
 
         @train_engine.on(EPOCH_COMPLETED)
         def _report(engine):
@@ -223,7 +252,7 @@ class Trainer:
     def get_losses(self, loader: Iterable) -> Mapping[str, float]:
         engine = Engine(self.val_step, self.required_losses)
         engine.run(loader, max_epochs=1)
-        return engine.state.metrics
+        return dict(engine.state.metrics)
 
     def state_dict(self) -> Mapping[str, Any]:
         return {}

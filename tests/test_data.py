@@ -689,3 +689,25 @@ def test_native_sampler_argument_errors():
                                        a.ctypes.data, 10, a.ctypes.data, a.ctypes.data, 10, 4, a.ctypes.data, 4,
                                        a.ctypes.data, 12, 2 ** 31, 3, a.ctypes.data, a.ctypes.data, a.ctypes.data,
                                        a.ctypes.data) == -2
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_anndataset_shuffle_with_cached_indexers_equals_the_literal_form(paired):
+    """``propose_shuffle`` permutes cached row numbers instead of looking the permuted cell ids up again; the
+    literal form of scglue/models/data.py:617-620 (permute the ids, ``get_indexer``, random fill on the same
+    RandomState) gives the same rows and masks, on the full view and on a split."""
+    from tests.synth import make_synthetic
+    from glue_b200.utils import get_rs
+    adatas, _ = make_synthetic(n_cells=(96, 80), n_feat=(12, 30), n_pairs=40, seed=1, rep_dim=6, paired=paired)
+    for a in adatas.values():
+        models.configure_dataset(a, "NB", use_highly_variable=False, use_rep="X_rep", use_obs_names=paired)
+    ds = AnnDataset(list(adatas.values()), [a.uns[config.ANNDATA_KEY] for a in adatas.values()], mode="train",
+                    getitem_size=8)
+    train, val = ds.random_split([0.8, 0.2], random_state=3)
+    for sub in (ds, train, val):
+        for seed in (0, 9):
+            rs = get_rs(seed)
+            want = sub._get_idx_pmsk(rs.permutation(sub.view_idx), random_fill=True, random_state=rs)
+            got = sub.propose_shuffle(seed)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert train._view_indexers()[0].size == train.size and ds._view_indexers()[0].size == ds.size
