@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "glue_rmsprop_flat",
     "glue_multi_copy",
     "glue_sample_graph_epoch",
+    "glue_weighted_ce_fwd",
     "glue_kl_unit_normal_fwd",
     "glue_kl_unit_normal_bwd",
     "glue_paired_mean_cos_fwd",
@@ -118,7 +119,7 @@ class DecoderMultiArgs(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -215,6 +216,9 @@ def _declare(lib: ctypes.CDLL) -> None:
 
     lib.glue_multi_copy.restype = c_int32
     lib.glue_multi_copy.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.glue_weighted_ce_fwd.restype = c_int32
+    lib.glue_weighted_ce_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p,
+                                         c_void_p, c_void_p]
     lib.glue_sample_graph_epoch.restype = c_int32
     lib.glue_sample_graph_epoch.argtypes = [
         c_uint32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,

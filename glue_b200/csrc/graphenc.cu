@@ -18,6 +18,8 @@
 // (thread <-> (out = t >> 2, in = ig + 4 ii)), written as per-CTA partials and reduced in a fixed
 // order => bit-reproducible.  Bound: FFMA / shared-memory issue (10 000 FMA per vertex fwd + bwd
 // against 1 KB of HBM traffic per vertex).
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace glue {
@@ -651,6 +653,23 @@ int enc_grid(int64_t V) {
     return (int)((ntiles + per_cta - 1) / per_cta);
 }
 
+// Backward pass: beside it run the discriminator's and the data encoders' backward kernels, 16 CTAs each that need a
+// whole SM (mlp_fused.cu).  With the dozen SMs enc_grid leaves they take two waves; 30 free SMs hold two of them at
+// once.  The head kernel then works through at most a sixth more tiles per CTA (813 tiles: 7 instead of 6 on 117
+// CTAs) -- it has that slack, the chain discriminator -> encoder backward -> optimizer ends the step (measured:
+// 0.645 -> 0.620 ms per step at the PBMC shape; the same reserve on the forward kernel, which is the long pole of
+// its phase, bought nothing).
+int enc_grid_bwd(int64_t V) {
+    static const int fwd_like = getenv("GLUE_ENC_BWD_FULL_GRID") ? atoi(getenv("GLUE_ENC_BWD_FULL_GRID")) : 0;
+    const int64_t ntiles = (V + TR - 1) / TR;
+    const int64_t sms = sm_count();
+    if (fwd_like || ntiles <= sms - 30 || sms <= 60) return enc_grid(V);
+    const int64_t full = (ntiles + sms - 1) / sms;
+    if (full < 4) return enc_grid(V);  // (one more tile per CTA would cost more than a quarter of the makespan)
+    const int64_t per_cta = std::min((ntiles + sms - 31) / (sms - 30), full + std::max<int64_t>(1, full / 6));
+    return (int)((ntiles + per_cta - 1) / per_cta);
+}
+
 size_t enc_ws_layout(int64_t V, int KP, char* base, EncArgs* a) {
     const int ncta = enc_grid(V);
     size_t off = 0;
@@ -684,7 +703,7 @@ int run_fwd(EncArgs a, cudaStream_t st, int impl) {
 
 template <int KP>
 int run_bwd(EncArgs a, cudaStream_t st, int impl) {
-    const int ncta = enc_grid(a.V);
+    const int ncta = enc_grid_bwd(a.V);
     // impl: 0 = default (warp-level tensor cores, TF32 x 3), 1 = FFMA kernel, 2 = tensor cores
     const bool use_mma = impl != 1;
     if (use_mma) {

@@ -46,6 +46,55 @@ __global__ void __launch_bounds__(256) kl_unit_normal_bwd_kernel(const float* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// Discriminator loss (scglue/models/scglue.py:326-329): F.cross_entropy(logits, target, reduction="none"),
+// times the per-cell weight, summed, over the number of cells -- and its gradient in the same launch, with the
+// coefficient the objective gives the term folded in (the generator's -lam_align, the discriminator update's
+// +lam_align).  Through torch ops: five launches forward, five backward, on the serial stretch between the
+// discriminator's forward and backward kernels at the end of the step.  One block, rows strided over the
+// threads, fixed summation order.
+// ---------------------------------------------------------------------------------------------
+constexpr int CE_THREADS = 256;
+constexpr int CE_MAX_CLASSES = 32;
+
+__global__ void __launch_bounds__(CE_THREADS) weighted_ce_kernel(const float* __restrict__ logits,
+                                                                 const int64_t* __restrict__ target,
+                                                                 const float* __restrict__ weight, int64_t n, int C,
+                                                                 float scale, float coef, float* __restrict__ out,
+                                                                 float* __restrict__ grad) {
+    __shared__ float red[CE_THREADS / 32];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += CE_THREADS) {
+        const float* row = logits + i * C;
+        float x[CE_MAX_CLASSES];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CE_MAX_CLASSES; ++c)
+            if (c < C) x[c] = row[c], mx = fmaxf(mx, x[c]);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CE_MAX_CLASSES; ++c)
+            if (c < C) x[c] = expf(x[c] - mx), sum += x[c];
+        const int t = (int)target[i];
+        const float w = weight[i];
+        acc += w * (mx + logf(sum) - row[t]);
+        if (grad) {
+            const float g = coef * scale * w, inv = 1.f / sum;
+#pragma unroll
+            for (int c = 0; c < CE_MAX_CLASSES; ++c)
+                if (c < C) grad[i * C + c] = g * (x[c] * inv - (c == t ? 1.f : 0.f));
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < CE_THREADS / 32 ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = v * scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Paired cells (scglue/models/scglue.py:618-622, 654-660): mean embedding of every cell over the
 // modalities it is observed in, and the cosine term
 //   cos_loss = sum_k [n_k > 0] (1 - sum_i p_ki cos(u_ki, m_i) / max(n_k, 1)),   n_k = sum_i p_ki,
@@ -195,6 +244,17 @@ extern "C" int glue_kl_unit_normal_bwd(const float* mean, const float* std_, int
     const int grid = (int)(want > cap ? cap : want);
     glue::kl_unit_normal_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mean, std_, n, scale, upstream, grad_mean,
                                                                             grad_std);
+    GLUE_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int glue_weighted_ce_fwd(const float* logits, const int64_t* target, const float* weight, int64_t n,
+                                    int32_t n_classes, float scale, float coef, float* out_loss, float* grad_logits,
+                                    void* stream) {
+    if (!logits || !target || !weight || !out_loss || n <= 0) return GLUE_E_BADARG;
+    if (n_classes < 1 || n_classes > glue::CE_MAX_CLASSES) return GLUE_E_UNSUPPORTED;
+    glue::weighted_ce_kernel<<<1, glue::CE_THREADS, 0, (cudaStream_t)stream>>>(logits, target, weight, n, n_classes,
+                                                                             scale, coef, out_loss, grad_logits);
     GLUE_CHECK_LAUNCH();
     return 0;
 }

@@ -14,7 +14,7 @@ sub-computations through the sm_100a kernels:
 import copy
 from itertools import chain
 from math import ceil
-from typing import Callable, List, Mapping, Optional, Union
+from typing import Callable, List, Mapping, Optional, Tuple, Union
 
 import networkx as nx
 import numpy as np
@@ -190,16 +190,24 @@ class SCGLUETrainer(GLUETrainer):
         return data
 
     # -- shared pieces of the objective ----------------------------------------------------
-    def _parallel(self, thunks):
+    def _parallel(self, thunks, first_join: Optional[Tuple[int, Callable]] = None):
         r"""Run independent branches of the step on forked CUDA streams (branch 0 stays on the
         current stream) and join them.  A step is hundreds of tiny kernels; inside the captured
         graph the forks become parallel branches, so the per-kernel launch latencies of e.g.
         the two data encoders and the graph encoder overlap instead of adding up.  Autograd
         replays every backward node on its forward stream, so the backward pass forks the
-        same way.  Pure scheduling: the arithmetic of each branch is unchanged."""
+        same way.  Pure scheduling: the arithmetic of each branch is unchanged.
+
+        ``first_join = (n, fn)``: the current stream joins the first ``n`` branches, runs
+        ``fn(results[:n])`` and only then joins the rest -- work that needs the short branches only does
+        not wait for the long one."""
         device = self.net.device
+        n_first, fn = first_join if first_join is not None else (len(thunks), None)
         if device.type != "cuda" or not config.MULTI_STREAM or len(thunks) < 2:
-            return [f() for f in thunks]
+            results = [f() for f in thunks]
+            if fn is not None:
+                fn(results[:n_first])
+            return results
         main = torch.cuda.current_stream(device)
         while len(self._side_streams) < len(thunks) - 1:
             self._side_streams.append(torch.cuda.Stream(device))
@@ -210,7 +218,11 @@ class SCGLUETrainer(GLUETrainer):
         for side, f in zip(sides, thunks[1:]):
             with torch.cuda.stream(side):
                 results.append(f())
-        for side in sides:
+        for side in sides[:max(n_first - 1, 0)]:
+            main.wait_stream(side)
+        if fn is not None:
+            fn(results[:n_first])
+        for side in sides[max(n_first - 1, 0):]:
             main.wait_stream(side)
         return results
 
@@ -221,9 +233,10 @@ class SCGLUETrainer(GLUETrainer):
             usamp = F.normalize(usamp, dim=1)
         return u, l, usamp
 
-    def _encode(self, x, xrep, dsc_only: bool, extra=None, before_join=None):
+    def _encode(self, x, xrep, dsc_only: bool, extra=None, before_join=None, after_encoders=None):
         r"""Per-modality encoders (and optionally one more independent branch, ``extra``) side
-        by side; returns ``(u, l, usamp[, extra_result])``."""
+        by side; returns ``(u, l, usamp[, extra_result])``.  ``after_encoders(u, l, usamp)`` is issued on the
+        current stream once the encoders have joined, before the ``extra`` branches are waited for."""
         keys = self.net.keys
         thunks = [lambda k=k: self._encode_one(k, x, xrep, dsc_only) for k in keys]
         extras = [] if extra is None else (list(extra) if isinstance(extra, (list, tuple)) else [extra])
@@ -238,7 +251,11 @@ class SCGLUETrainer(GLUETrainer):
                 self._encode_aux = before_join()
                 return res
             thunks = [first_then_aux] + thunks[1:]
-        out = self._parallel(thunks + extras)
+        first_join = None
+        if after_encoders is not None:
+            first_join = (len(keys), lambda res: after_encoders(*({k: o[i] for k, o in zip(keys, res)}
+                                                                  for i in range(3))))
+        out = self._parallel(thunks + extras, first_join)
         u = {k: o[0] for k, o in zip(keys, out)}
         l = {k: o[1] for k, o in zip(keys, out)}
         usamp = {k: o[2] for k, o in zip(keys, out)}
@@ -257,7 +274,10 @@ class SCGLUETrainer(GLUETrainer):
         return (torch.cat([xbch[k] for k in keys]), torch.cat([xdwt[k] for k in keys]),
                 torch.cat([xflag[k] for k in keys]))
 
-    def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int, cat_inputs=None):
+    def _alignment(self, u, xbch, xdwt, xflag, xlbl, epoch: int, cat_inputs=None, upstream=None):
+        r"""Discriminator loss on the (burn-in jittered) posterior means (``scglue.py:318-329``).  ``upstream``:
+        the coefficient with which the caller back-propagates the result (``ops.weighted_cross_entropy`` folds it
+        into the gradient it computes with the loss; ``None``: plain autograd semantics)."""
         net = self.net
         u_cat = torch.cat([u[k].mean for k in net.keys])
         xbch_cat, xdwt_cat, xflag_cat = cat_inputs or self._alignment_inputs(xbch, xdwt, xflag)
@@ -274,7 +294,12 @@ class SCGLUETrainer(GLUETrainer):
             else:
                 coeff = float(np.float32(anneal) * np.float32(self.BURNIN_NOISE_EXAG))
             u_cat = u_cat + coeff * jitter
-        dsc_loss = F.cross_entropy(net.du(u_cat, xbch_cat), xflag_cat, reduction="none")
+        logits = net.du(u_cat, xbch_cat)
+        if config.USE_FUSED_OBJECTIVE and logits.is_cuda:
+            from .. import ops
+            if ops.weighted_cross_entropy_supported(logits) and xdwt_cat.dtype == torch.float32:
+                return u_cat, ops.weighted_cross_entropy(logits, xflag_cat, xdwt_cat, upstream=upstream)
+        dsc_loss = F.cross_entropy(logits, xflag_cat, reduction="none")
         dsc_loss = (dsc_loss * xdwt_cat).sum() / xdwt_cat.numel()
         return u_cat, dsc_loss
 
@@ -454,7 +479,8 @@ class SCGLUETrainer(GLUETrainer):
                     u_d[k].mean.record_stream(dsc_stream)
                 for t in cat_inputs:
                     t.record_stream(dsc_stream)
-                _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
+                _, dsc_loss_d = self._alignment(u_d, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
+                                                upstream=self.lam_align)
                 dsc_update(self.lam_align * dsc_loss_d)
             del u_d, dsc_loss_d
         if cat_inputs is None:
@@ -466,7 +492,7 @@ class SCGLUETrainer(GLUETrainer):
             # (``scglue.py:386-390``: zero_grad before the generator pass)
             with torch.no_grad():
                 u, l, usamp = self._encode(x, xrep, dsc_only)
-            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
+            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs, upstream=self.lam_align)
             return {"dsc_loss": self.lam_align * dsc_loss}
         # the graph branch (propagation, Gaussian head, edge reconstruction) is independent of
         # the data encoders: it runs beside them
@@ -474,8 +500,18 @@ class SCGLUETrainer(GLUETrainer):
         early = self._early_backward_ok()
         self._graph_branch = None
         ops.V_GRAD_SINK = [] if early else None
+        # what reads the encoders' outputs only -- the paired mean embedding + cosine term, the KL of the
+        # posteriors -- is issued when the encoders have joined: the graph branch is the long one (Gaussian
+        # head), and these two dozen small launches used to sit between its end and the decoders' start
+        # (the mean embedding) and on the objective's tail behind the decoders (the KL)
+        x_kl = {}
+
+        def after_encoders(u, l, usamp):
+            self._prepare_extra(usamp)
+            x_kl.update({k: self._data_kl(u[k], prior, x[k].shape[1]) for k in net.keys})
         u, l, usamp, (vsamp, g_nll, g_kl) = self._encode(
-            x, xrep, dsc_only, extra=[lambda: self._graph_terms(eidx, ewt, esgn, prior)] + self._input_branches(data))
+            x, xrep, dsc_only, extra=[lambda: self._graph_terms(eidx, ewt, esgn, prior)] + self._input_branches(data),
+            after_encoders=after_encoders)
         # one stream per modality: the reconstruction term and, for paired data, the joint-cross /
         # real-cross terms of a modality share its observations, feature embeddings and decoder
         # parameters and run as ONE fused launch sequence (the feature table is staged once, the
@@ -489,8 +525,8 @@ class SCGLUETrainer(GLUETrainer):
             with torch.cuda.stream(dsc_stream):
                 for k in net.keys:
                     u[k].mean.record_stream(dsc_stream)
-                u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
-        self._prepare_extra(usamp)
+                u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
+                                                  upstream=-self.lam_align)
         try:
             results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
         finally:
@@ -512,10 +548,10 @@ class SCGLUETrainer(GLUETrainer):
             main.wait_stream(dsc_stream)
             u_cat.record_stream(main), dsc_loss.record_stream(main)
         else:
-            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs)
+            u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
+                                              upstream=-self.lam_align)
         self._join_graph_nll(g_nll)
         sup_loss = self._supervision(u_cat, xlbl)
-        x_kl = {k: self._data_kl(u[k], prior, x[k].shape[1]) for k in net.keys}
         extra_comps, extra_terms = self._extra_losses(data, usamp, vsamp, l)
         # nothing that carries an autograd graph may outlive the step on `self`: it would keep
         # this step's AccumulateGrad nodes (bound to the current streams) alive into a capture

@@ -300,6 +300,51 @@ def kl_unit_normal(mean: torch.Tensor, std: torch.Tensor, scale: float = 1.0) ->
     return _KlUnitNormalFn.apply(mean, std, float(scale))
 
 
+class _WeightedCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, weight, scale, upstream, grad_enabled):
+        dev = logits.device
+        n, c = logits.shape
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        need_grad = bool(grad_enabled and ctx.needs_input_grad[0])
+        grad = torch.empty_like(logits) if need_grad else None
+        check(_lib.lib().glue_weighted_ce_fwd(ptr(logits), ptr(target), ptr(weight), n, c, scale,
+                                              1.0 if upstream is None else float(upstream), ptr(out), ptr(grad),
+                                              current_stream(dev)), "weighted_ce_fwd")
+        ctx.grad, ctx.folded = grad, upstream is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, ctx.grad = ctx.grad, None
+        if grad is None:
+            raise RuntimeError("weighted_cross_entropy: no gradient was prepared (called under no_grad)")
+        return (grad if ctx.folded else grad * g), None, None, None, None, None
+
+
+def weighted_cross_entropy_supported(logits: torch.Tensor) -> bool:
+    return logits.is_cuda and logits.dim() == 2 and logits.shape[1] <= 32 and logits.dtype == torch.float32
+
+
+def weighted_cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: torch.Tensor,
+                           upstream: Optional[float] = None) -> torch.Tensor:
+    r"""``(F.cross_entropy(logits, target, reduction="none") * weight).sum() / weight.numel()`` -- the
+    discriminator loss of ``scglue/models/scglue.py:326-329`` -- and its gradient in ONE launch.
+
+    ``upstream``: the coefficient with which the caller's objective takes the term (``+lam_align`` in the
+    discriminator update, ``-lam_align`` in the generator's loss).  It is folded into the stored gradient, which
+    autograd then hands on as it is: the caller must back-propagate exactly that multiple of the result, once.
+    Without it the stored gradient is scaled by the incoming one (one more launch)."""
+    require_cuda(logits, target, weight)
+    logits = _f32(logits, "logits")
+    if logits.dim() != 2 or target.shape != (logits.shape[0],) or weight.shape != (logits.shape[0],):
+        raise ValueError("`logits` [n, classes], `target` [n], `weight` [n] expected")
+    if target.dtype != torch.int64:
+        raise TypeError("`target` must be int64")
+    return _WeightedCeFn.apply(logits, target.contiguous(), _f32(weight, "weight"), 1.0 / logits.shape[0],
+                               upstream, torch.is_grad_enabled())
+
+
 class _PairedMeanCosFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ustack, pmask):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GLUE_B200_ABI_VERSION 5
+#define GLUE_B200_ABI_VERSION 6
 
 #define GLUE_E_BADARG (-1)      /* NULL pointer / non-positive size               */
 #define GLUE_E_UNSUPPORTED (-2) /* latent dim > 64, unknown family, ...           */
@@ -328,6 +328,21 @@ int glue_kl_unit_normal_fwd(const float *mean, const float *std_, int64_t n, flo
                             void *stream);
 int glue_kl_unit_normal_bwd(const float *mean, const float *std_, int64_t n, float scale,
                             const float *upstream, float *grad_mean, float *grad_std, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Discriminator loss and its gradient in one launch.
+ * Replaces  (F.cross_entropy(logits, target, reduction="none") * weight).sum() / weight.numel()
+ * (scglue/models/scglue.py:326-329) and its autograd backward:
+ *   out_loss[0]       = scale * sum_i weight_i * (logsumexp(logits_i) - logits[i, target_i])
+ *   grad_logits[i, c] = coef * scale * weight_i * (softmax(logits_i)_c - [c == target_i])   (NULL: not wanted)
+ * coef is the coefficient with which the caller's objective takes the term (+lam_align in the discriminator
+ * update, -lam_align in the generator's loss): folded here, autograd hands grad_logits on as it is.
+ * logits / grad_logits [n, n_classes] fp32 row-major (n_classes <= 32, else GLUE_E_UNSUPPORTED),
+ * target [n] int64 in [0, n_classes), weight [n] fp32.  One block, fixed summation order.
+ * ------------------------------------------------------------------------- */
+int glue_weighted_ce_fwd(const float *logits, const int64_t *target, const float *weight, int64_t n,
+                         int32_t n_classes, float scale, float coef, float *out_loss, float *grad_logits,
+                         void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Paired cells: mean embedding over the modalities a cell is observed in and the

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 
 
 def test_identification(native_lib):
-    assert native_lib.glue_abi_version() == 5
+    assert native_lib.glue_abi_version() == 6
     assert native_lib.glue_arch() == b"sm_100a"
     assert b"workspace" in native_lib.glue_error_string(-3)
 

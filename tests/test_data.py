@@ -711,3 +711,39 @@ def test_anndataset_shuffle_with_cached_indexers_equals_the_literal_form(paired)
             got = sub.propose_shuffle(seed)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
     assert train._view_indexers()[0].size == train.size and ds._view_indexers()[0].size == ds.size
+
+
+@pytest.mark.gpu
+def test_device_graph_dataset_streams_epochs_through_pooled_pinned_slabs():
+    """A device-resident GraphDataset: the native sampler writes each graph epoch into a pinned slab on a
+    look-ahead thread, ``accept_shuffle`` uploads it asynchronously and the slab returns to the process-wide
+    pool once the copy has run.  The edges on the device are the numpy restatement's, epoch after epoch, and
+    slabs are recycled instead of pinned anew."""
+    import networkx as nx
+    from glue_b200.models.data import _PinnedSlabs
+    rs0 = np.random.RandomState(4)
+    n_v, n_e = 3000, 9000
+    g = nx.Graph()
+    names = [f"v{i}" for i in range(n_v)]
+    g.add_nodes_from(names)
+    for s, t, w in zip(rs0.randint(0, n_v, n_e), rs0.randint(0, n_v, n_e), rs0.uniform(0.05, 1, n_e)):
+        g.add_edge(names[s], names[t], weight=float(w), sign=1 if (s + t) % 5 else -1)
+    g.add_edges_from((v, v, {"weight": 1.0, "sign": 1}) for v in names)
+    host = GraphDataset(g, names, neg_samples=10)
+    ds = GraphDataset(g, names, neg_samples=10).to_device(torch.device("cuda:0"))
+    pinned_before = _PinnedSlabs.allocated
+    for fit in range(2):  # two fits' worth: the second one finds its slabs in the pool
+        ds.prepare_shuffle(num_workers=2, random_seed=3)
+        for n in range(6):
+            ds.shuffle()
+            want = host._propose_shuffle_numpy(3 + n)
+            assert ds.samp_eidx.is_cuda and ds.samp_eidx.dtype == torch.int64
+            assert np.array_equal(ds.samp_eidx.cpu().numpy(), want[0])
+            assert np.array_equal(ds.samp_ewt.cpu().numpy(), want[1])
+            assert np.array_equal(ds.samp_esgn.cpu().numpy(), want[2])
+        ds.clean()
+        assert not ds.__dict__.get("_slabs") and not ds.__dict__.get("_uploads")
+        if fit == 0:
+            pinned_first = _PinnedSlabs.allocated - pinned_before
+            assert 0 < pinned_first <= 2 + 3, "look-ahead depth plus the uploads in flight"
+    assert _PinnedSlabs.allocated - pinned_before == pinned_first, "the second fit pinned nothing"

@@ -866,3 +866,32 @@ def test_flat_rmsprop_partial_exchange(native_lib):
         outs.append([p.detach().clone() for p in ps])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,c", [(256, 2), (100, 3), (7, 32)])
+def test_weighted_cross_entropy_matches_torch(ops, n, c):
+    """Discriminator loss (scglue/models/scglue.py:326-329) and its gradient from one launch: against
+    F.cross_entropy * weight, summed, over the number of cells; with the coefficient folded the stored gradient
+    is that multiple of torch's and ignores the incoming one; under no_grad nothing is stored."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(n + c)
+    logits = (4 * torch.randn(n, c, generator=gen)).to(DEV)
+    target = torch.randint(0, c, (n,), generator=gen).to(DEV)
+    weight = torch.rand(n, generator=gen).to(DEV)
+    ref_in = logits.double().requires_grad_(True)
+    ref = (F.cross_entropy(ref_in, target, reduction="none") * weight.double()).sum() / n
+    ref.backward()
+    x = logits.clone().requires_grad_(True)
+    got = ops.weighted_cross_entropy(x, target, weight)
+    (got * 3.0).backward()
+    assert_close(got.detach(), ref.detach().float(), 1e-6, "loss")
+    assert_close(x.grad, 3.0 * ref_in.grad.float(), 1e-5, "d / d logits")
+    y = logits.clone().requires_grad_(True)
+    folded = ops.weighted_cross_entropy(y, target, weight, upstream=-0.05)
+    assert torch.equal(folded, got.detach())
+    folded.backward()  # (the caller back-propagates -0.05 * folded; what arrives here is ignored)
+    assert_close(y.grad, -0.05 * ref_in.grad.float(), 1e-5, "folded d / d logits")
+    with torch.no_grad():
+        assert torch.equal(ops.weighted_cross_entropy(logits, target, weight, upstream=1.0), got.detach())
+    with pytest.raises(RuntimeError, match="UNSUPPORTED|unsupported|-2"):
+        ops.weighted_cross_entropy(torch.zeros(4, 33, device=DEV), target[:4] * 0, weight[:4])
