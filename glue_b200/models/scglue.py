@@ -75,6 +75,37 @@ def _kl_to_prior(q: D.Normal, prior: D.Normal) -> torch.Tensor:
 # --------------------------------------------------------------------- trainers
 
 
+class _Posterior:
+    r"""What :meth:`SCGLUETrainer._alignment` reads of an encoder's posterior: its mean."""
+
+    def __init__(self, mean: torch.Tensor) -> None:
+        self.mean = mean
+
+
+class _InjectGrad(torch.autograd.Function):
+    r"""``forward(streams, leaves, *xs) = 0`` (a scalar that enters the objective with coefficient 1);
+    ``backward`` hands ``leaves[i].grad`` to ``xs[i]``.  ``leaves[i]`` is the detached copy of ``xs[i]`` that a
+    part of the objective was computed from and back-propagated ahead of the rest (the alignment term, see
+    ``compute_losses``): its gradient joins the others that reach ``xs[i]`` when the rest of the objective is
+    back-propagated."""
+
+    @staticmethod
+    def forward(ctx, streams, leaves, *xs):
+        ctx.leaves, ctx.streams = leaves, streams
+        return xs[0].new_zeros(())
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = [leaf.grad for leaf in ctx.leaves]
+        ctx.leaves = None
+        if any(grad is None for grad in grads):
+            raise RuntimeError("early alignment backward: the gradient was not produced")
+        for grad in grads:  # (allocated on this stream, consumed on the encoders')
+            for stream in ctx.streams:
+                grad.record_stream(stream)
+        return (None, None, *grads)
+
+
 @logged
 class SCGLUETrainer(GLUETrainer):
     r"""
@@ -111,6 +142,7 @@ class SCGLUETrainer(GLUETrainer):
         self._nll_pending = False
         self._early_stream: Optional[torch.cuda.Stream] = None
         self._early_pending = False
+        self._early_align_done = False
         self._early_reduced = None
         self._in_generator_step = False
         self.capturing = False
@@ -384,6 +416,14 @@ class SCGLUETrainer(GLUETrainer):
             return False
         return all(isinstance(net.u2x[k], sc._FusedDecoder) and self.modality_weight[k] for k in net.keys)
 
+    def _early_alignment_ok(self) -> bool:
+        r"""The generator's alignment term can be back-propagated as soon as it is computed: training step,
+        coefficient folded into the fused cross-entropy, nothing else reads the concatenated means."""
+        net = self.net
+        return (self._in_generator_step and torch.is_grad_enabled() and net.device.type == "cuda"
+                and config.MULTI_STREAM and config.EARLY_ALIGN_BACKWARD and config.USE_FUSED_OBJECTIVE
+                and not net.u2c and not self.freeze_u and len(net.keys) <= 32)
+
     def _early_graph_backward(self, v_grads, vnum: int) -> None:
         r"""``vsamp.backward(sum of the handed-out gradients)`` and the KL term of the vertex posterior, on a
         stream of its own: autograd replays the graph branch's backward kernels (Gaussian head, weight-gradient
@@ -411,6 +451,8 @@ class SCGLUETrainer(GLUETrainer):
             torch.autograd.backward([vsamp, kl_sum], [total, ops._upstream_scalar(coeff, device).reshape(kl_sum.shape)])
             # data parallel: the vertex embeddings are 10 of the 12 MB of generator gradients -- exchanged
             # here, beside the discriminator's and the encoders' backward passes, instead of behind them
+            # (one GPU: copying them into the flat gradient buffer here instead of with the rest in front of the
+            # optimizer was tried and cost 13 us per step)
             self._early_reduced = None
             if gdist.is_distributed() and hasattr(self.vae_optim, "all_reduce_subset"):
                 self._early_reduced = self.vae_optim.all_reduce_subset(list(net.g2v.parameters()))
@@ -525,8 +567,27 @@ class SCGLUETrainer(GLUETrainer):
             with torch.cuda.stream(dsc_stream):
                 for k in net.keys:
                     u[k].mean.record_stream(dsc_stream)
-                u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
+                # (vi-b) the alignment term's gradient is computed with its forward pass, coefficient folded
+                # (`ops.weighted_cross_entropy`): the discriminator is back-propagated right here, down to
+                # detached copies of the posterior means, while the current stream goes on to the decoders
+                # and the objective's tail; the gradients join the rest at the means (`_InjectGrad`)
+                early_align = self._early_alignment_ok()
+                u_align = {k: _Posterior(u[k].mean.detach().requires_grad_(True)) for k in net.keys} \
+                    if early_align else u
+                u_cat, dsc_loss = self._alignment(u_align, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
                                                   upstream=-self.lam_align)
+                align_inject = None
+                if early_align:
+                    align_inject = _InjectGrad.apply([main] + list(self._side_streams),
+                                                     [u_align[k].mean for k in net.keys], *[u[k].mean for k in net.keys])
+                align_ready = torch.cuda.Event()
+                align_ready.record(dsc_stream)
+                if early_align:
+                    for p in net.du.parameters():  # (this pass's discriminator gradients are not used: no
+                        p.grad = None              # accumulation into the update's)
+                    torch.autograd.backward([dsc_loss])
+                    u_cat, dsc_loss = u_cat.detach(), dsc_loss.detach()
+                    self._early_align_done = True
         try:
             results = self._parallel([lambda k=k: self._modality_nlls(k, data, usamp, vsamp, l) for k in net.keys])
         finally:
@@ -545,9 +606,12 @@ class SCGLUETrainer(GLUETrainer):
                     parts = self._extra_parts[k]
                     parts[kind] = res if kind not in parts else parts[kind] + res
         if dsc_stream is not None:
-            main.wait_stream(dsc_stream)
+            # (the loss value is there once the forward pass is; the early backward pass behind it is joined by
+            # autograd, where its gradients are consumed)
+            main.wait_event(align_ready) if align_inject is not None else main.wait_stream(dsc_stream)
             u_cat.record_stream(main), dsc_loss.record_stream(main)
         else:
+            align_inject = None
             u_cat, dsc_loss = self._alignment(u, xbch, xdwt, xflag, xlbl, epoch, cat_inputs,
                                               upstream=-self.lam_align)
         self._join_graph_nll(g_nll)
@@ -562,6 +626,9 @@ class SCGLUETrainer(GLUETrainer):
         # scalar op at a time that is ~60 tiny launches forward + backward on the serial tail of
         # the step; here: one stack, one matrix-vector product each way.
         comps = {"dsc": dsc_loss, "g_nll": g_nll, "g_kl": g_kl, "sup": sup_loss}
+        if align_inject is not None:
+            align_inject.record_stream(main)
+            comps["align_inject"] = align_inject
         for k in net.keys:
             comps[f"x_{k}_nll"], comps[f"x_{k}_kl"] = x_nll[k], x_kl[k]
         comps.update(extra_comps)
@@ -583,6 +650,8 @@ class SCGLUETrainer(GLUETrainer):
                 vae[comp] = vae.get(comp, 0.0) + weight * coeff
         rows["vae_loss"] = vae
         rows["gen_loss"] = dict(vae, dsc=-self.lam_align)
+        if align_inject is not None:
+            rows["gen_loss"]["align_inject"] = 1.0
         if net.u2c:
             rows["sup_loss"] = {"sup": 1.0}
         return self._combine(comps, rows)
@@ -690,7 +759,11 @@ class SCGLUETrainer(GLUETrainer):
             from .. import ops
             ops.V_GRAD_SINK = None
             self._graph_branch = None
-        if self._early_pending:
+        if self._early_align_done:
+            # the discriminator holds the generator pass's gradients already (cleared before that early
+            # backward pass); nothing else has a gradient but the graph branch, if it went early too
+            self._early_align_done = False
+        elif self._early_pending:
             # the graph branch's gradients are already accumulating: only the discriminator's (left over
             # from its own update, not part of the generator's optimizer) are cleared
             for p in self.net.du.parameters():

@@ -74,6 +74,8 @@ class _Settings:
         # back-propagate the graph branch right behind the decoders (every gradient with respect to the
         # vertex embeddings is computed in the forward pass) instead of in the objective's backward pass
         EARLY_GRAPH_BACKWARD=True,
+        # the generator's alignment term back-propagated through the discriminator right behind its forward pass
+        EARLY_ALIGN_BACKWARD=True,
         # single-process loaders without pinned memory iterate their (torch) samplers directly instead of
         # through torch's DataLoader iterator: same index streams, a fraction of the per-minibatch host time
         FAST_LOADER=True,
