@@ -398,7 +398,12 @@ def main():
         for i in range(warmup):
             step_dev(i)
         launches0, replays0 = ops.kernel_launches(), trainer.graphs.replays
+        if args.profile:  # (`ncu --profile-from-start off`: only the replayed steps are profiled)
+            torch.cuda.synchronize(device)
+            torch.cuda.cudart().cudaProfilerStart()
         ms = timed(step_dev, args.steps)
+        if args.profile:
+            torch.cuda.cudart().cudaProfilerStop()
         ginfo = trainer.graphs.info()
         launches = (ops.kernel_launches() - launches0
                     + (trainer.graphs.replays - replays0) * int(ginfo["kernels_per_step"] or 0))

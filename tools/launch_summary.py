@@ -27,6 +27,11 @@ print(f"{len(rows)} launches, {tot / 1e3:.2f} ms of kernel time (cold-cache, ser
 print("| share | total us | launches | us/launch | kernel |\n|---|---|---|---|---|")
 for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"| {100 * us / tot:.1f}% | {us:.0f} | {n} | {us / n:.2f} | `{name[:110]}` |")
-ours = sum(us for name, (n, us) in agg.items() if "glue::" in name)
-dec = sum(us for name, (n, us) in agg.items() if "glue::" in name and ("tc_" in name or "dec_" in name or "v3::" in name))
-print(f"\nKernels of libglue_b200.so: {100 * ours / tot:.1f}% of kernel time; fused decoder kernels: {100 * dec / tot:.1f}%.")
+native = lambda name: "glue::" in name or "v3::" in name
+ours = sum(us for name, (n, us) in agg.items() if native(name))
+n_ours = sum(n for name, (n, us) in agg.items() if native(name))
+dec = sum(us for name, (n, us) in agg.items() if "v3::" in name or "tc_" in name or "dec_" in name)
+mlp = sum(us for name, (n, us) in agg.items() if "mlp_" in name)
+print(f"\nKernels of libglue_b200.so (names under `glue::` / `v3::`): {n_ours} of the {len(rows)} launches, "
+      f"**{100 * ours / tot:.1f} % of kernel time**; fused data-decoder kernels {100 * dec / tot:.1f} %, "
+      f"encoder / discriminator MLP kernels {100 * mlp / tot:.1f} %.")

@@ -8,7 +8,7 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 STEP_CMD="python bench.py --profile --steps 3 --warmup 3"
 $STEP_CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain step run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $STEP_CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 python tools/launch_summary.py gpurun_out/${TAG}_launches.csv "one replayed training step (cfg2, between two input loads)" 0 multi_copy_kernel \
