@@ -21,6 +21,7 @@ What makes the step capturable (no host synchronisation, static shapes):
 * the burn-in noise coefficient is a device scalar refreshed before every replay.
 """
 
+import gc
 from collections import OrderedDict
 from typing import Any, Dict, List, Mapping, Optional
 
@@ -185,11 +186,19 @@ class StepGraphs:
             graph = torch.cuda.CUDAGraph()
             launches0 = ops.kernel_launches()
             tr.capturing = True
+            # no cyclic garbage collection while the capture is open: a finalizer that releases CUDA memory or
+            # an older graph (a trainer of an earlier fit waiting in a reference cycle) is an operation the
+            # capturing thread may not perform, and it would invalidate the capture
+            gc_was_on = gc.isenabled()
+            gc.collect()
+            gc.disable()
             try:
                 with torch.cuda.graph(graph, pool=self.pool, capture_error_mode="thread_local"):
                     outputs = eager(engine, inputs)
             finally:
                 tr.capturing = False
+                if gc_was_on:
+                    gc.enable()
             entry.update(graph=graph, inputs=inputs,
                          outputs=outputs if isinstance(outputs, LossVector) else dict(outputs),
                          native_kernels=ops.kernel_launches() - launches0)

@@ -4,6 +4,7 @@ training hot path reads: ``config``, ``log``, ``get_rs``, ``AUTO``).
 """
 
 import logging
+import os
 import signal
 from typing import Any, Optional, Union
 
@@ -87,6 +88,12 @@ class _Settings:
     def __init__(self) -> None:
         for key, val in self._DEFAULTS.items():
             object.__setattr__(self, key, list(val) if isinstance(val, list) else val)
+        # boolean switches from the environment, for A/B runs: GLUE_B200_FLAGS="EARLY_ALIGN_BACKWARD=0,FAST_LOADER=1"
+        for item in filter(None, os.environ.get("GLUE_B200_FLAGS", "").split(",")):
+            key, _, val = item.partition("=")
+            if not isinstance(self._DEFAULTS.get(key.strip()), bool):
+                raise AttributeError(f"GLUE_B200_FLAGS: {key!r} is not a boolean configuration key")
+            object.__setattr__(self, key.strip(), bool(int(val)))
 
     def __setattr__(self, key: str, value: Any) -> None:
         if key not in self._DEFAULTS:
