@@ -313,10 +313,12 @@ constexpr int MM_KP = 64;    // padded latent dim (K <= 64)
 constexpr int MM_DS = 68;    // stride of d1 / d2 (A operand of dgrad; 2-way conflicts as A^T of wgrad)
 constexpr int MM_BS = 72;    // stride of x and of the weight matrices (B operands)
 
+constexpr int ENC_BWD_GROUPS = 2;                             // warp groups per CTA, one 64-row tile each per iteration
+constexpr int ENC_BWD_THREADS = ENC_BWD_GROUPS * ENC_THREADS;  // 16 warps: with 8 the kernel waited on its loads
 struct MmaSmem {
-    float x[TR][MM_BS];
-    float d1[TR][MM_DS];
-    float d2[TR][MM_DS];
+    float x[ENC_BWD_GROUPS][TR][MM_BS];
+    float d1[ENC_BWD_GROUPS][TR][MM_DS];
+    float d2[ENC_BWD_GROUPS][TR][MM_DS];
     float wl_big[MM_KP][MM_BS], wl_small[MM_KP][MM_BS];  // [o][i], TF32 split of the weights
     float ws_big[MM_KP][MM_BS], ws_small[MM_KP][MM_BS];
 };
@@ -345,14 +347,20 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ab)[4], c
     mma_tf32(c, ab, bb0, bb1);
 }
 
-__global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a, int KPW /* 52 or 64: partial layout */) {
+__global__ void __launch_bounds__(ENC_BWD_THREADS) graphenc_bwd_mma_kernel(EncArgs a, int KPW /* 52 or 64: partial layout */) {
     extern __shared__ float4 enc_smem_raw[];
     MmaSmem& S = *reinterpret_cast<MmaSmem*>(enc_smem_raw);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+    // two groups of 8 warps; a group works through its own tile exactly as the 8 warps of the one-group kernel did
+    // (same fragments, same summation order per tile), the weights in shared memory serve both
+    const int grp = threadIdx.x / ENC_THREADS, t = threadIdx.x % ENC_THREADS;
+    const int warp = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+    float(&X)[TR][MM_BS] = S.x[grp];
+    float(&D1)[TR][MM_DS] = S.d1[grp];
+    float(&D2)[TR][MM_DS] = S.d2[grp];
     const int K = a.K;
     const int nk8 = (K + 7) >> 3;  // 8-wide tiles covering K
     // weights -> shared memory, split once
-    for (int idx = t; idx < MM_KP * MM_KP; idx += ENC_THREADS) {
+    for (int idx = threadIdx.x; idx < MM_KP * MM_KP; idx += ENC_BWD_THREADS) {
         const int o = idx >> 6, i = idx & 63;
         const bool ok = o < K && i < K;
         uint32_t b, sm;
@@ -369,9 +377,10 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
     for (int n = 0; n < 8; ++n) gw[n][0] = gw[n][1] = gw[n][2] = gw[n][3] = 0.f;
     float gbias = 0.f;  // threads 0..63: column t of d1; 64..127: column t - 64 of d2
     const int64_t ntiles = (a.V + TR - 1) / TR;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t first = (int64_t)ENC_BWD_GROUPS * blockIdx.x; first < ntiles;
+         first += (int64_t)ENC_BWD_GROUPS * gridDim.x) {
         __syncthreads();  // previous tile's reads are done
-        const int64_t row0 = tile * TR;
+        const int64_t row0 = (first + grp) * TR;  // (past the last tile: every row is out of range, zeros flow through)
         // x tile and the two upstream-gradient tiles, zero padded to 64 columns
         for (int idx = t; idx < TR * (MM_KP / 2); idx += ENC_THREADS) {
             const int r = idx >> 5, o = 2 * (idx & 31);
@@ -390,14 +399,14 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
                 const float dsg1 = fmaf(gv.y, nz.y, ckl * (sg.y - 1.f / sg.y));
                 ds = make_float2(dsg0 * (1.f - expf(-(sg.x - GLUE_EPS))), dsg1 * (1.f - expf(-(sg.y - GLUE_EPS))));
             }
-            *reinterpret_cast<float2*>(&S.x[r][o]) = xv;
-            *reinterpret_cast<float2*>(&S.d1[r][o]) = dm;
-            *reinterpret_cast<float2*>(&S.d2[r][o]) = ds;
+            *reinterpret_cast<float2*>(&X[r][o]) = xv;
+            *reinterpret_cast<float2*>(&D1[r][o]) = dm;
+            *reinterpret_cast<float2*>(&D2[r][o]) = ds;
         }
         __syncthreads();
         // ---- bias gradients: column sums of d1 / d2
         if (t < 128) {
-            const float(*d)[MM_DS] = t < 64 ? S.d1 : S.d2;
+            const float(*d)[MM_DS] = t < 64 ? D1 : D2;
             const int col = t & 63;
             float s = 0.f;
 #pragma unroll 8
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
 #pragma unroll
             for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
             for (int mat = 0; mat < 2; ++mat) {
-                const float(*d)[MM_DS] = mat == 0 ? S.d1 : S.d2;
+                const float(*d)[MM_DS] = mat == 0 ? D1 : D2;
                 const float(*wb)[MM_BS] = mat == 0 ? S.wl_big : S.ws_big;
                 const float(*wsm)[MM_BS] = mat == 0 ? S.wl_small : S.ws_small;
                 for (int ks = 0; ks < nk8; ++ks) {
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
         }
         // ---- wgrad: gW_wm[16 mt + ., :] += d_wm^T x over the 64 rows of the tile
         {
-            const float(*d)[MM_DS] = wm == 0 ? S.d1 : S.d2;
+            const float(*d)[MM_DS] = wm == 0 ? D1 : D2;
             const int m0 = 16 * mt;
             for (int ks = 0; ks < TR / 8; ++ks) {
                 const int k0 = 8 * ks;  // rows of the tile
@@ -462,17 +471,18 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
                     if (n < nk8) {
                         const int n0 = 8 * n;
                         uint32_t bb0, bs0, bb1, bs1;  // B[k = r][n = i] = x[r][i]
-                        split_tf32(S.x[k0 + tq][n0 + g], bb0, bs0);
-                        split_tf32(S.x[k0 + tq + 4][n0 + g], bb1, bs1);
+                        split_tf32(X[k0 + tq][n0 + g], bb0, bs0);
+                        split_tf32(X[k0 + tq + 4][n0 + g], bb1, bs1);
                         mma_3x(gw[n], ab, as, bb0, bb1, bs0, bs1);
                     }
                 }
             }
         }
     }
-    // per-CTA partials in the layout of graphenc_wgrad_reduce_kernel<KPW>: [2][KPW][KPW + 1]
+    // per-group partials in the layout of graphenc_wgrad_reduce_kernel<KPW>: [2][KPW][KPW + 1]
     {
-        float* base = a.gwpart + (size_t)blockIdx.x * 2 * KPW * (KPW + 1) + (size_t)wm * KPW * (KPW + 1);
+        const size_t part = (size_t)blockIdx.x * ENC_BWD_GROUPS + grp;
+        float* base = a.gwpart + part * 2 * KPW * (KPW + 1) + (size_t)wm * KPW * (KPW + 1);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
             if (n >= nk8) continue;
@@ -485,8 +495,7 @@ __global__ void __launch_bounds__(ENC_THREADS) graphenc_bwd_mma_kernel(EncArgs a
         }
         if (t < 128) {
             const int col = t & 63, m = t >> 6;
-            if (col < K) a.gwpart[(size_t)blockIdx.x * 2 * KPW * (KPW + 1) + (size_t)m * KPW * (KPW + 1) +
-                                  col * (KPW + 1) + KPW] = gbias;
+            if (col < K) a.gwpart[part * 2 * KPW * (KPW + 1) + (size_t)m * KPW * (KPW + 1) + col * (KPW + 1) + KPW] = gbias;
         }
     }
 }
@@ -655,27 +664,27 @@ int enc_grid(int64_t V) {
 
 // Backward pass: beside it run the discriminator's and the data encoders' backward kernels, 16 CTAs each that need a
 // whole SM (mlp_fused.cu).  With the dozen SMs enc_grid leaves they take two waves; 30 free SMs hold two of them at
-// once.  The head kernel then works through at most a sixth more tiles per CTA (813 tiles: 7 instead of 6 on 117
-// CTAs) -- it has that slack, the chain discriminator -> encoder backward -> optimizer ends the step (measured:
-// 0.645 -> 0.620 ms per step at the PBMC shape; the same reserve on the forward kernel, which is the long pole of
-// its phase, bought nothing).
-int enc_grid_bwd(int64_t V) {
-    static const int fwd_like = getenv("GLUE_ENC_BWD_FULL_GRID") ? atoi(getenv("GLUE_ENC_BWD_FULL_GRID")) : 0;
+// once.  The head kernel then works through one more unit per CTA -- it has that slack when the graph is small
+// (measured at the PBMC shape: 0.645 -> 0.620 ms per step; the same reserve on the forward kernel, which is the long
+// pole of its phase, bought nothing).  `unit_tiles`: 64-row tiles a CTA takes per iteration (2 for the tensor-core
+// kernel with its two warp groups).  Large graphs (200 k vertices): the head kernel is several times longer than
+// the MLP kernels beside it and ends the step itself, so every CTA counts (1.31 -> 1.37 ms per step at the
+// triple-omics shape with the reserve).
+int enc_grid_bwd(int64_t V, int unit_tiles) {
+    static const int full_grid = getenv("GLUE_ENC_BWD_FULL_GRID") ? atoi(getenv("GLUE_ENC_BWD_FULL_GRID")) : 0;
     const int64_t ntiles = (V + TR - 1) / TR;
+    const int64_t units = (ntiles + unit_tiles - 1) / unit_tiles;
     const int64_t sms = sm_count();
-    if (fwd_like || ntiles <= sms - 30 || sms <= 60) return enc_grid(V);
-    const int64_t full = (ntiles + sms - 1) / sms;
-    if (full < 4) return enc_grid(V);  // (one more tile per CTA would cost more than a quarter of the makespan)
-    // Large graphs (200 k vertices: 22 tiles per CTA): the head kernel is several times longer than the MLP
-    // kernels beside it and ends the step itself, so every CTA counts (measured: 1.31 -> 1.37 ms per step at
-    // the triple-omics shape with the reserve).
-    if (full > 8) return enc_grid(V);
-    const int64_t per_cta = std::min((ntiles + sms - 31) / (sms - 30), full + std::max<int64_t>(1, full / 6));
-    return (int)((ntiles + per_cta - 1) / per_cta);
+    if (units <= sms) return (int)units;
+    const int64_t full = (units + sms - 1) / sms;  // units per CTA on a full grid
+    int64_t per_cta = full;
+    if (!full_grid && sms > 60 && full * unit_tiles >= 4 && full * unit_tiles <= 8)
+        per_cta = std::min((units + sms - 31) / (sms - 30), full + 1);
+    return (int)((units + per_cta - 1) / per_cta);
 }
 
 size_t enc_ws_layout(int64_t V, int KP, char* base, EncArgs* a) {
-    const int ncta = enc_grid(V);
+    const int ncta = ENC_BWD_GROUPS * sm_count();  // (upper bound: one weight-gradient partial per warp group of a CTA)
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char* p = base ? base + off : nullptr;
@@ -707,13 +716,14 @@ int run_fwd(EncArgs a, cudaStream_t st, int impl) {
 
 template <int KP>
 int run_bwd(EncArgs a, cudaStream_t st, int impl) {
-    const int ncta = enc_grid_bwd(a.V);
     // impl: 0 = default (warp-level tensor cores, TF32 x 3), 1 = FFMA kernel, 2 = tensor cores
     const bool use_mma = impl != 1;
+    const int ncta = enc_grid_bwd(a.V, use_mma ? ENC_BWD_GROUPS : 1);
+    const int nparts = use_mma ? ENC_BWD_GROUPS * ncta : ncta;
     if (use_mma) {
         const size_t smem = sizeof(MmaSmem);
         GLUE_SMEM_ONCE(graphenc_bwd_mma_kernel, smem);
-        graphenc_bwd_mma_kernel<<<ncta, ENC_THREADS, smem, st>>>(a, KP);
+        graphenc_bwd_mma_kernel<<<ncta, ENC_BWD_THREADS, smem, st>>>(a, KP);
     } else {
         const size_t smem = sizeof(EncSmem<KP>);
         auto k = graphenc_bwd_kernel<KP>;
@@ -722,7 +732,7 @@ int run_bwd(EncArgs a, cudaStream_t st, int impl) {
     }
     GLUE_CHECK_LAUNCH();
     const int total = 2 * KP * (KP + 1);
-    graphenc_wgrad_reduce_kernel<KP><<<(total + 255) / 256, 256, 0, st>>>(a, ncta);
+    graphenc_wgrad_reduce_kernel<KP><<<(total + 255) / 256, 256, 0, st>>>(a, nparts);
     GLUE_CHECK_LAUNCH();
     return 0;
 }
