@@ -747,3 +747,49 @@ def test_device_graph_dataset_streams_epochs_through_pooled_pinned_slabs():
             pinned_first = _PinnedSlabs.allocated - pinned_before
             assert 0 < pinned_first <= 2 + 3, "look-ahead depth plus the uploads in flight"
     assert _PinnedSlabs.allocated - pinned_before == pinned_first, "the second fit pinned nothing"
+
+
+def test_deferred_metrics_resolve_once_and_validation_is_issued_before_they_are_read():
+    """Engine.run keeps the epoch means of LossVector steps on the device until somebody reads them
+    (DeferredMetrics: a Mapping that turns into plain floats at the first access), and Trainer.fit registers the
+    validation pass ahead of every handler that reads the training metrics."""
+    from glue_b200.models.base import DeferredMetrics, Engine, LossVector, Trainer
+    names = ["dsc_loss", "vae_loss", "gen_loss"]
+    vals = [torch.tensor([1.0, 2.0, 3.0]) * (i + 1) for i in range(4)]
+    eng = Engine(lambda e, batch: LossVector(names, batch), tracked=["vae_loss", "gen_loss"])
+    metrics = eng.run(vals, max_epochs=1).metrics
+    assert isinstance(metrics, DeferredMetrics) and metrics._host is None        # nothing read yet
+    assert list(metrics) == ["vae_loss", "gen_loss"] and len(metrics) == 2 and metrics._host is None
+    assert metrics["vae_loss"] == 5.0 and metrics._means is None                 # first read: resolved for good
+    assert dict(metrics) == {"vae_loss": 5.0, "gen_loss": 7.5} and metrics == {"vae_loss": 5.0, "gen_loss": 7.5}
+
+    order = []
+
+    class Stub(Trainer):
+        def __init__(self):
+            super().__init__(torch.nn.Linear(1, 1))
+            self.required_losses = ["vae_loss"]
+
+        def train_step(self, engine, data):
+            return LossVector(["vae_loss"], data)
+
+        def val_step(self, engine, data):
+            order.append("val_step")
+            return LossVector(["vae_loss"], data)
+
+        def report_metrics(self, train_state, val_state):
+            order.append(("report", type(train_state.metrics).__name__, train_state.metrics._host is not None))
+
+    Stub().fit([torch.tensor([2.0])], val_loader=[torch.tensor([4.0])], max_epochs=1)
+    # the validation step ran first; by the time of the report the non-finite guard had read the metrics
+    assert order == ["val_step", ("report", "DeferredMetrics", True)]
+
+
+def test_boolean_config_switches_from_the_environment(monkeypatch):
+    from glue_b200 import utils
+    monkeypatch.setenv("GLUE_B200_FLAGS", "EARLY_ALIGN_BACKWARD=0, FAST_LOADER=1")
+    cfg = type(utils.config)()
+    assert cfg.EARLY_ALIGN_BACKWARD is False and cfg.FAST_LOADER is True and cfg.NATIVE_SAMPLER is True
+    monkeypatch.setenv("GLUE_B200_FLAGS", "TMP_PREFIX=1")
+    with pytest.raises(AttributeError, match="not a boolean"):
+        type(utils.config)()
